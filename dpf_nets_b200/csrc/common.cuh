@@ -1,0 +1,55 @@
+// Shared helpers for the dpf-nets B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DPF_API extern "C" __attribute__((visibility("default")))
+
+// Error codes returned by every C-ABI entry point (0 = ok, >0 = cudaError_t, <0 = argument error).
+#define DPF_OK 0
+#define DPF_ERR_BAD_ARG (-1)
+#define DPF_ERR_NULL_PTR (-2)
+#define DPF_ERR_UNSUPPORTED (-3)
+#define DPF_ERR_ALIGN (-4)
+
+void dpf_set_error(const char* fmt, ...);
+
+static inline int dpf_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    dpf_set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return DPF_OK;
+}
+
+#define DPF_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      dpf_set_error(__VA_ARGS__);     \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int dpf_num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}

@@ -1,0 +1,2 @@
+"""Tensor-level wrappers over the C ABI (device pointers in, device tensors out)."""
+from .chamfer import pairwise_cd  # noqa: F401

@@ -1,0 +1,55 @@
+/*
+ * dpfnets_b200.h — C ABI of libdpfnets_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the data-parallel hot path of Regenerator/dpf-nets.  Every entry point
+ * takes plain device pointers and sizes, runs asynchronously on the given CUDA stream
+ * (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream) on the CURRENT
+ * device, and returns 0 on success, a positive cudaError_t, or a negative DPF_ERR_* code.
+ * dpf_last_error() returns the message of the last failure on the calling thread.
+ * No torch types appear in any signature.  Citations are relative to the reference tree.
+ */
+#ifndef DPFNETS_B200_H
+#define DPFNETS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPF_OK 0
+#define DPF_ERR_BAD_ARG (-1)
+#define DPF_ERR_NULL_PTR (-2)
+#define DPF_ERR_UNSUPPORTED (-3)
+#define DPF_ERR_ALIGN (-4)
+
+const char* dpf_last_error(void);
+int dpf_version(void);
+int dpf_device_check(void);
+
+/* ---- Chamfer / nearest-neighbour distance --------------------------------------------------
+ * dpf_nndistance replaces nndistance() — lib/metrics/pytorch_structural_losses/src/nndistance.cuh:1
+ * (kernel nndistance.cu:2-128; shim structural_loss.cpp:80-99; pybind bind.cpp:13).
+ * xyz (b,n,3), xyz2 (b,m,3) fp32 -> result (b,n) squared NN distance of every xyz point in xyz2,
+ * result_i (b,n) int32 argmin (lowest index on exact ties), result2/result2_i (b,m) the reverse. */
+int dpf_nndistance(int b, int n, const float* xyz, int m, const float* xyz2, float* result,
+                   int* result_i, float* result2, int* result2_i, void* stream);
+
+/* Replaces nndistancegrad() — nndistance.cuh:2, nndistance.cu:129-154, structural_loss.cpp:101-124. */
+int dpf_nndistance_grad(int b, int n, const float* xyz1, int m, const float* xyz2,
+                        const float* grad_dist1, const int* idx1, const float* grad_dist2,
+                        const int* idx2, float* grad_xyz1, float* grad_xyz2, void* stream);
+
+/* Fused replacement of the Python all-pairs loop pairwise_CD — lib/networks/utils.py:90-117
+ * (and _pairwise_EMD_CD_'s CD half, lib/metrics/evaluation_metrics.py:85-121):
+ * out[i*S2+j] = mean_k min_l |A_i[k]-B_j[l]|^2 + mean_l min_k |A_i[k]-B_j[l]|^2
+ * for rows i = row_start + t*row_step, t < n_rows (row sharding across GPUs).
+ * A (S1,n,3), B (S2,m,3), out (S1,S2) fp32.  symmetric != 0 (A == B): only j >= i is written. */
+int dpf_pairwise_cd(int S1, int S2, int n, int m, const float* A, const float* B, float* out,
+                    int row_start, int row_step, int n_rows, int symmetric, void* stream);
+
+/* Mirrors the upper triangle of an (S,S) matrix into the lower one (after dpf_pairwise_cd symmetric). */
+int dpf_symmetrize_upper(float* M, int S, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPFNETS_B200_H */
