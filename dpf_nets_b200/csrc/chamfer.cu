@@ -5,7 +5,8 @@
 // all-pairs loop around them (lib/networks/utils.py:90-117).
 //
 // Arithmetic contract (bit-exact with the reference for finite inputs):
-//   d(q,t) = fma(dz,dz, fma(dy,dy, dx*dx)),  dx = t.x - q.x (fp32, round-to-nearest)
+//   d(q,t) = fma(dz,dz, fma(dx,dx, dy*dy)),  dx = t.x - q.x (fp32, round-to-nearest) - the
+//   contraction nvcc emits for the reference's `x2*x2+y2*y2+z2*z2` (checked in its SASS)
 //   nearest = strict '<' scan in ascending target index  => lowest index wins exact ties.
 //
 // Layout: clouds are (batch, points, 3) fp32 contiguous.  Targets are staged in shared
@@ -22,7 +23,7 @@ __device__ __forceinline__ float sqdist(float4 t, float qx, float qy, float qz) 
   const float dx = __fsub_rn(t.x, qx);
   const float dy = __fsub_rn(t.y, qy);
   const float dz = __fsub_rn(t.z, qz);
-  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 // Cooperative AoS(xyz) -> float4 tile load; reads are fully coalesced over the flat float array.

@@ -4,7 +4,8 @@
  * Plain-C restatement of the reference's structural-loss CUDA kernels
  * (lib/metrics/pytorch_structural_losses/src/nndistance.cu, approxmatch.cu), following the
  * reference's loop order and chunking so that fp32 results are reproducible:
- *   - nvcc contracts x*x+y*y+z*z to fma(z,z,fma(y,y,x*x)); fmaf() reproduces that bit-exactly.
+ *   - nvcc contracts x*x+y*y+z*z to fma(z,z,fma(x,x,y*y)) (FMUL y*y; FFMA x,x; FFMA z,z in the
+ *     reference kernel's sm_100a SASS); fmaf() reproduces that bit-exactly.
  *   - approxmatch sums run in ascending index order like the reference's sequential inner loops;
  *     __expf (GPU fast exp) is restated with expf, so EMD parity is to a tolerance, not bit-exact.
  * Pinned by: the reference kernels themselves built into oracle/_ref (see build_ref.py) and a
@@ -15,7 +16,7 @@
 #include <string.h>
 
 static inline float sq3(float x2, float y2, float z2) {
-  return fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+  return fmaf(z2, z2, fmaf(x2, x2, y2 * y2));
 }
 
 /* NmDistanceKernel (nndistance.cu:2-124): chunks of 512 targets, first element of every chunk
