@@ -1,0 +1,257 @@
+"""TEST INFRASTRUCTURE ONLY - CPU fp32 restatement of the reference's point-flow decoder math.
+
+Explicit tensor formulas (no nn.Module) for:
+  * SharedDot                     lib/networks/layers.py:13-45
+  * CondRealNVPFlow3D             lib/networks/flows.py:10-117     (`coupling_forward`)
+  * CondRealNVPFlow3DTriple       lib/networks/flows.py:120-160    (`triple_warps`)
+  * LocalCondRNVPDecoder          lib/networks/decoders.py:41-72   (`decoder_forward`)
+  * PointFlowNLL                  lib/networks/losses.py:7-15      (`point_flow_nll`)
+  * hand-derived backward of one coupling layer - `coupling_backward`
+    (checked against torch.autograd of `coupling_forward` and of the reference module in tests/).
+
+Parameters are addressed by the reference's own state_dict key names relative to one
+CondRealNVPFlow3D module (e.g. 'T_mu_0.mu_sd0.weight').  Pinned by tests/golden/*.pt, produced by
+importing the reference from /root/reference (tests/golden/make_golden.py).
+"""
+import math
+
+import torch
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+BRANCHES = ("mu", "logvar")
+
+
+def triple_warps(pattern):
+    """warp_inds of nvp1..nvp3 (flows.py:130-148)."""
+    return [[0], [1], [2]] if pattern == 0 else [[0, 1], [0, 2], [1, 2]]
+
+
+def decoder_layer_names(n_flows):
+    """(key prefix, warp_inds) of the 3*n_flows coupling layers in list order (decoders.py:49-52)."""
+    out = []
+    for i in range(n_flows):
+        for j, w in enumerate(triple_warps(i % 2)):
+            out.append(("flows.%d.nvp%d." % (i, j + 1), w))
+    return out
+
+
+def _bn(x, w, b, rm, rv, training, dims):
+    """BatchNorm1d (eps 1e-5, momentum 0.1): returns y, (mean, biased var) used, new running stats."""
+    if training:
+        n = 1
+        for d in dims:
+            n *= x.shape[d]
+        mean = x.mean(dim=dims)
+        var = x.var(dim=dims, unbiased=False)
+        new_rm = (1 - BN_MOMENTUM) * rm + BN_MOMENTUM * mean
+        new_rv = (1 - BN_MOMENTUM) * rv + BN_MOMENTUM * var * (n / max(n - 1, 1))
+    else:
+        mean, var, new_rm, new_rv = rm, rv, rm, rv
+    shape = [1] * x.dim()
+    shape[1] = -1
+    y = (x - mean.view(shape)) / torch.sqrt(var.view(shape) + BN_EPS)
+    if w is not None:
+        y = y * w.view(shape) + b.view(shape)
+    return y, mean, var, new_rm, new_rv
+
+
+def film_net(P, br, kind, g, training, new_stats=None):
+    """T_{br}_0_cond_{kind}: Linear(G->F, no bias) . BN(batch) . Swish . Linear(F->F)  (flows.py:33-45)."""
+    pre = "T_%s_0_cond_%s.%s_sd1_film_%s" % (br, kind, br, kind)
+    u = g @ P[pre + "0.weight"].t()
+    y, _, _, rm, rv = _bn(u, P[pre + "0_bn.weight"], P[pre + "0_bn.bias"], P[pre + "0_bn.running_mean"],
+                          P[pre + "0_bn.running_var"], training, (0,))
+    if new_stats is not None:
+        new_stats[pre + "0_bn.running_mean"] = rm
+        new_stats[pre + "0_bn.running_var"] = rv
+    y = y * torch.sigmoid(y)
+    return y @ P[pre + "1.weight"].t() + P[pre + "1.bias"]
+
+
+def conditioner(P, br, xk, g, training, new_stats=None, keep=None):
+    """One branch (mu or logvar) of the per-point conditioner; returns o (B,w,N) and intermediates."""
+    eps = P["eps"]
+    t0 = "T_%s_0.%s_" % (br, br)
+    h0 = torch.matmul(P[t0 + "sd0.weight"][0], xk)                     # (B,F,N)  SharedDot, no bias
+    z, mean_a, var_a, rm, rv = _bn(h0, P[t0 + "sd0_bn.weight"], P[t0 + "sd0_bn.bias"],
+                                   P[t0 + "sd0_bn.running_mean"], P[t0 + "sd0_bn.running_var"], training, (0, 2))
+    if new_stats is not None:
+        new_stats[t0 + "sd0_bn.running_mean"], new_stats[t0 + "sd0_bn.running_var"] = rm, rv
+    h1 = torch.relu(z)
+    h2pre = torch.matmul(P[t0 + "sd1.weight"][0], h1)
+    h2n, mean_b, var_b, rm, rv = _bn(h2pre, None, None, P[t0 + "sd1_bn.running_mean"],
+                                     P[t0 + "sd1_bn.running_var"], training, (0, 2))
+    if new_stats is not None:
+        new_stats[t0 + "sd1_bn.running_mean"], new_stats[t0 + "sd1_bn.running_var"] = rm, rv
+    wraw = film_net(P, br, "w", g, training, new_stats)
+    s = eps + torch.exp(wraw)                                           # (B,F)
+    t = film_net(P, br, "b", g, training, new_stats)
+    a = s.unsqueeze(2) * h2n + t.unsqueeze(2)
+    h3 = torch.relu(a)
+    t1 = "T_%s_1.%s_sd2." % (br, br)
+    o = torch.matmul(P[t1 + "weight"][0], h3) + P[t1 + "bias"][0].view(1, -1, 1)
+    inter = dict(h0=h0, z=z, h1=h1, h2pre=h2pre, h2n=h2n, a=a, h3=h3, s=s, t=t, wraw=wraw,
+                 mean_a=mean_a, var_a=var_a, mean_b=mean_b, var_b=var_b)
+    return o, inter
+
+
+def coupling_forward(P, p, g, mode, warp_inds, training=False, new_stats=None, return_inter=False):
+    """CondRealNVPFlow3D.forward (flows.py:95-117).  p (B,3,N), g (B,G) -> p_out, mu, logvar."""
+    keep = [c for c in (0, 1, 2) if c not in warp_inds]
+    eps = P["eps"]
+    xk = p[:, keep, :].contiguous()
+    logvar = torch.zeros_like(p)
+    mu = torch.zeros_like(p)
+    o_lv, i_lv = conditioner(P, "logvar", xk, g, training, new_stats)
+    logvar[:, warp_inds, :] = o_lv / (1 + o_lv.abs())                   # softsign
+    o_mu, i_mu = conditioner(P, "mu", xk, g, training, new_stats)
+    mu[:, warp_inds, :] = o_mu
+    sigma = torch.sqrt(eps + torch.exp(logvar))
+    if mode == "direct":
+        p_out = sigma * p + mu
+    elif mode == "inverse":
+        p_out = (p - mu) / sigma
+    else:
+        raise ValueError(mode)
+    if return_inter:
+        return p_out, mu, logvar, dict(mu=i_mu, logvar=i_lv, o_mu=o_mu, o_logvar=o_lv, sigma=sigma, keep=keep)
+    return p_out, mu, logvar
+
+
+def decoder_forward(layers, p, g, mode, training=False, new_stats=None):
+    """LocalCondRNVPDecoder.forward (decoders.py:54-72).  `layers` = list of (param dict, warp_inds)
+    in list order [flows[0].nvp1, flows[0].nvp2, ...]; returns lists indexed like the reference."""
+    L = len(layers)
+    ps, mus, lvs = [None] * L, [None] * L, [None] * L
+    order = range(L) if mode == "direct" else range(L - 1, -1, -1)
+    cur = p
+    for l in order:
+        P, warp = layers[l]
+        ns = None
+        if new_stats is not None:
+            ns = {}
+        cur, mus[l], lvs[l] = coupling_forward(P, cur, g, mode, warp, training, ns)
+        if new_stats is not None:
+            new_stats[l] = ns
+        ps[l] = cur
+    return ps, mus, lvs
+
+
+def point_flow_nll(samples, mus, logvars):
+    """PointFlowNLL (losses.py:7-15)."""
+    s0 = samples[0]
+    acc = logvars[0]
+    for lv in logvars[1:]:
+        acc = acc + lv
+    return 0.5 * (torch.sum(acc + (s0 - mus[0]) ** 2 / torch.exp(logvars[0])) / s0.shape[0]
+                  + math.log(2.0 * math.pi) * s0.shape[1] * s0.shape[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# Hand-derived backward of one coupling layer in TRAIN mode (batch-stat BN), the formulas the
+# fused CUDA backward implements.  Returns grads keyed like the parameters + dp + dg.
+# ------------------------------------------------------------------------------------------------
+def _bn_train_backward(dy, xhat, istd, dims):
+    n = 1
+    for d in dims:
+        n *= dy.shape[d]
+    shape = [1] * dy.dim()
+    shape[1] = -1
+    m1 = dy.sum(dim=dims) / n
+    m2 = (dy * xhat).sum(dim=dims) / n
+    return istd.view(shape) * (dy - m1.view(shape) - xhat * m2.view(shape))
+
+
+def film_net_backward(P, br, kind, g, dout, training, grads):
+    """Backward of film_net; accumulates parameter grads into `grads`, returns dg."""
+    pre = "T_%s_0_cond_%s.%s_sd1_film_%s" % (br, kind, br, kind)
+    W0, W1 = P[pre + "0.weight"], P[pre + "1.weight"]
+    u = g @ W0.t()
+    if training:
+        mean, var = u.mean(0), u.var(0, unbiased=False)
+    else:
+        mean, var = P[pre + "0_bn.running_mean"], P[pre + "0_bn.running_var"]
+    istd = 1.0 / torch.sqrt(var + BN_EPS)
+    xhat = (u - mean) * istd
+    gam, bet = P[pre + "0_bn.weight"], P[pre + "0_bn.bias"]
+    y = xhat * gam + bet
+    sg = torch.sigmoid(y)
+    sw = y * sg
+    grads[pre + "1.weight"] = dout.t() @ sw
+    grads[pre + "1.bias"] = dout.sum(0)
+    dsw = dout @ W1
+    dy = dsw * (sg + y * sg * (1 - sg))
+    grads[pre + "0_bn.weight"] = (dy * xhat).sum(0)
+    grads[pre + "0_bn.bias"] = dy.sum(0)
+    dxhat = dy * gam
+    if training:
+        du = _bn_train_backward(dxhat, xhat, istd, (0,))
+    else:
+        du = dxhat * istd
+    grads[pre + "0.weight"] = du.t() @ g
+    return du @ W0
+
+
+def coupling_backward(P, p, g, mode, warp_inds, dy, dmu_ext=None, dlv_ext=None, training=True):
+    """Gradients of a scalar loss given dy = dL/dp_out, dmu_ext = dL/dmu, dlv_ext = dL/dlogvar
+    (each (B,3,N) or None).  Returns (dp, dg, grads dict)."""
+    eps = P["eps"]
+    p_out, mu, logvar, I = coupling_forward(P, p, g, mode, warp_inds, training, None, return_inter=True)
+    keep = I["keep"]
+    B, _, N = p.shape
+    sigma = I["sigma"]
+    grads = {}
+    dp = torch.zeros_like(p)
+    if mode == "inverse":
+        dp[:] = dy / sigma                                  # kept channels: sigma = sqrt(eps+1)
+        dmu = -dy / sigma
+        dl = -dy * p_out * torch.exp(logvar) / (2 * sigma * sigma)
+    else:
+        dp[:] = dy * sigma
+        dmu = dy.clone()
+        dl = dy * p * torch.exp(logvar) / (2 * sigma)
+    if dmu_ext is not None:
+        dmu = dmu + dmu_ext
+    if dlv_ext is not None:
+        dl = dl + dlv_ext
+    do = {"mu": dmu[:, warp_inds, :], "logvar": dl[:, warp_inds, :] / (1 + I["o_logvar"].abs()) ** 2}
+    xk = p[:, keep, :]
+    dg = torch.zeros_like(g)
+    for br in BRANCHES:
+        it = I[br]
+        t0 = "T_%s_0.%s_" % (br, br)
+        t1 = "T_%s_1.%s_sd2." % (br, br)
+        W0, W1, W2 = P[t0 + "sd0.weight"][0], P[t0 + "sd1.weight"][0], P[t1 + "weight"][0]
+        d_o = do[br]
+        grads[t1 + "bias"] = d_o.sum(dim=(0, 2)).view(1, -1)
+        grads[t1 + "weight"] = torch.einsum("bwn,bcn->wc", d_o, it["h3"]).unsqueeze(0)
+        dh3 = torch.einsum("wc,bwn->bcn", W2, d_o)
+        da = dh3 * (it["a"] > 0)
+        dt = da.sum(2)                                       # (B,F)
+        ds = (da * it["h2n"]).sum(2)
+        dh2n = da * it["s"].unsqueeze(2)
+        istd_b = 1.0 / torch.sqrt(it["var_b"] + BN_EPS)
+        if training:
+            dh2pre = _bn_train_backward(dh2n, it["h2n"], istd_b, (0, 2))
+        else:
+            dh2pre = dh2n * istd_b.view(1, -1, 1)
+        grads[t0 + "sd1.weight"] = torch.einsum("bcn,bjn->cj", dh2pre, it["h1"]).unsqueeze(0)
+        dh1 = torch.einsum("cj,bcn->bjn", W1, dh2pre)
+        dz = dh1 * (it["z"] > 0)
+        istd_a = 1.0 / torch.sqrt(it["var_a"] + BN_EPS)
+        xhat = (it["h0"] - it["mean_a"].view(1, -1, 1)) * istd_a.view(1, -1, 1)
+        gam = P[t0 + "sd0_bn.weight"]
+        grads[t0 + "sd0_bn.weight"] = (dz * xhat).sum(dim=(0, 2))
+        grads[t0 + "sd0_bn.bias"] = dz.sum(dim=(0, 2))
+        dxhat = dz * gam.view(1, -1, 1)
+        if training:
+            dh0 = _bn_train_backward(dxhat, xhat, istd_a, (0, 2))
+        else:
+            dh0 = dxhat * istd_a.view(1, -1, 1)
+        grads[t0 + "sd0.weight"] = torch.einsum("bcn,bjn->cj", dh0, xk).unsqueeze(0)
+        dp[:, keep, :] += torch.einsum("cj,bcn->bjn", W0, dh0)
+        # FiLM nets: s = eps + exp(wraw) -> dwraw = ds * exp(wraw) = ds * (s - eps)
+        dg = dg + film_net_backward(P, br, "w", g, ds * (it["s"] - eps), training, grads)
+        dg = dg + film_net_backward(P, br, "b", g, dt, training, grads)
+    return dp, dg, grads
