@@ -1,0 +1,94 @@
+// Host-side orchestration of the coupling stack behind the C ABI: one call runs all L layers
+// (FiLM pre-compute, per-layer statistics + apply launches) on the caller's stream, so the Python
+// side pays one FFI call per decoder pass and the whole pass can be captured in a CUDA graph.
+#include "coupling.cuh"
+
+// launchers (coupling_fwd.cu / coupling_bwd.cu / coupling_tc.cu)
+int launch_film_forward(const float* arena, float* stats, const LayerMeta* meta_dev, const float* g, float* film,
+                        int L, int B, int G, int training, int update_stats, float eps, cudaStream_t s);
+int launch_moments(const float* x, int B, int N, double* mom, cudaStream_t s);
+int launch_coupling_fwd_fp32(const CouplingArgs& a, int mode, bool stats_pass, cudaStream_t s);
+
+static int validate_common(const long long* meta_host, int L, int G, int B, int N, int mode, int precision) {
+  DPF_REQUIRE(meta_host, DPF_ERR_NULL_PTR, "decoder: layer table is null");
+  DPF_REQUIRE(L > 0 && G > 0 && B > 0 && N > 0, DPF_ERR_BAD_ARG, "decoder: L, G, B, N must be positive");
+  DPF_REQUIRE(mode == 0 || mode == 1, DPF_ERR_BAD_ARG, "decoder: mode must be 0 (direct) or 1 (inverse)");
+  DPF_REQUIRE(precision == 0 || precision == 1, DPF_ERR_BAD_ARG, "decoder: precision must be 0 (fp32) or 1 (bf16 tensor)");
+  for (int l = 0; l < L; ++l) {
+    const LayerMeta& m = reinterpret_cast<const LayerMeta*>(meta_host)[l];
+    DPF_REQUIRE((m.k == 1 && m.w == 2) || (m.k == 2 && m.w == 1), DPF_ERR_BAD_ARG, "decoder: layer %d has k=%lld w=%lld", l, m.k, m.w);
+  }
+  return DPF_OK;
+}
+
+DPF_API int dpf_decoder_workspace_bytes(int L, int G, int B, int N, long long* bytes) {
+  DPF_REQUIRE(bytes, DPF_ERR_NULL_PTR, "dpf_decoder_workspace_bytes: null out pointer");
+  DPF_REQUIRE(L > 0 && G > 0 && B > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_decoder_workspace_bytes: bad sizes");
+  *bytes = (long long)carve_workspace(nullptr, L, G, B, N).bytes;
+  return DPF_OK;
+}
+
+static CouplingArgs make_args(const LayerMeta& m, const float* arena, float* stats, const DecoderWorkspace& ws,
+                              int l, int q, int G, int B, int N, int training, int update_stats, float eps) {
+  CouplingArgs a{};
+  a.prm = arena + m.param_off;
+  a.stat = stats + m.stat_off;
+  a.film = ws.film + (size_t)l * 4 * B * DPF_F;
+  a.mom_in = ws.moments + (size_t)q * 16;
+  a.mom_out = training ? ws.moments + (size_t)(q + 1) * 16 : nullptr;
+  a.bnb_sums = ws.bnb_sums + (size_t)l * 2 * DPF_F * 2;
+  a.B = B; a.N = N; a.G = G;
+  a.k = (int)m.k; a.w = (int)m.w;
+  a.keep0 = (int)m.keep0; a.keep1 = (int)m.keep1; a.warp0 = (int)m.warp0; a.warp1 = (int)m.warp1;
+  a.training = training; a.update_stats = update_stats; a.eps = eps;
+  a.tiles_per_b = (N + DPF_TILE - 1) / DPF_TILE;
+  a.n_tiles = a.tiles_per_b * B;
+  return a;
+}
+
+// Forward of the whole stack: LocalCondRNVPDecoder.forward (decoders.py:54-72) over
+// CondRealNVPFlow3D.forward (flows.py:95-117).  mode 0 = 'direct' (layer 0 first), 1 = 'inverse'
+// (layer L-1 first); outputs are indexed by LAYER, like the reference's lists.
+DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* meta_dev, const float* arena,
+                                float* stats, const float* p, const float* g, float* P_out, float* MU, float* LV,
+                                void* workspace, int L, int G, int B, int N, int mode, int training,
+                                int update_stats, int precision, float eps, void* stream) {
+  int rc = validate_common(meta_host, L, G, B, N, mode, precision);
+  if (rc) return rc;
+  DPF_REQUIRE(meta_dev && arena && stats && p && g && P_out && MU && LV && workspace, DPF_ERR_NULL_PTR,
+              "dpf_decoder_forward: null pointer");
+  DPF_REQUIRE(!training || B <= 256, DPF_ERR_UNSUPPORTED, "dpf_decoder_forward: train-mode FiLM BatchNorm supports B <= 256 (got %d)", B);
+  DPF_REQUIRE(!training || ((long long)B * N > 1 && B > 1), DPF_ERR_BAD_ARG, "dpf_decoder_forward: BatchNorm in training mode needs more than 1 value per channel");
+  DPF_REQUIRE(precision == 0, DPF_ERR_UNSUPPORTED, "dpf_decoder_forward: bf16 tensor path not built yet");
+  cudaStream_t s = (cudaStream_t)stream;
+  const LayerMeta* meta = reinterpret_cast<const LayerMeta*>(meta_host);
+  DecoderWorkspace ws = carve_workspace(workspace, L, G, B, N);
+  const size_t plane = (size_t)B * 3 * N;
+
+  rc = launch_film_forward(arena, stats, reinterpret_cast<const LayerMeta*>(meta_dev), g, ws.film, L, B, G, training,
+                           update_stats, eps, s);
+  if (rc) return rc;
+  if (training) {
+    cudaMemsetAsync(ws.moments, 0, sizeof(double) * (size_t)(L + 1) * 16, s);
+    cudaMemsetAsync(ws.bnb_sums, 0, sizeof(double) * (size_t)L * 2 * DPF_F * 2, s);
+    rc = launch_moments(p, B, N, ws.moments, s);
+    if (rc) return rc;
+  }
+  const float* x = p;
+  for (int q = 0; q < L; ++q) {
+    const int l = mode == 0 ? q : L - 1 - q;
+    CouplingArgs a = make_args(meta[l], arena, stats, ws, l, q, G, B, N, training, update_stats, eps);
+    a.x = x;
+    a.y = P_out + (size_t)l * plane;
+    a.mu = MU + (size_t)l * plane;
+    a.lv = LV + (size_t)l * plane;
+    if (training) {
+      rc = launch_coupling_fwd_fp32(a, mode, true, s);
+      if (rc) return rc;
+    }
+    rc = launch_coupling_fwd_fp32(a, mode, false, s);
+    if (rc) return rc;
+    x = a.y;
+  }
+  return DPF_OK;
+}

@@ -1,0 +1,61 @@
+"""autograd bridge between the arena-backed coupling stack and the C ABI
+(dpf_decoder_forward / dpf_decoder_backward in include/dpfnets_b200.h)."""
+import ctypes
+
+import torch
+
+from ... import _lib
+
+MODES = {"direct": 0, "inverse": 1}
+PRECISIONS = {"fp32": 0, "bf16": 1}
+
+
+def _workspace(L, G, B, N, device):
+    n = ctypes.c_longlong(0)
+    _lib.check(_lib.lib().dpf_decoder_workspace_bytes(L, G, B, N, ctypes.byref(n)), "dpf_decoder_workspace_bytes")
+    return torch.empty(int(n.value), dtype=torch.uint8, device=device)
+
+
+def _meta_host_ptr(stack):
+    return ctypes.c_void_p(stack.layout.meta.ctypes.data)
+
+
+class CouplingStackFunction(torch.autograd.Function):
+    """(p, g, arena) -> stacked (P, MU, LV) of shape (L, B, 3, N), indexed by layer like the
+    reference's output lists."""
+
+    @staticmethod
+    def forward(ctx, p, g, arena, stack, mode, training):
+        _lib.require_cuda(p, g, arena)
+        L, G = stack.layout.L, stack.g_n_features
+        B, C, N = p.shape
+        if C != 3 or g.shape != (B, G) or p.dtype != torch.float32 or g.dtype != torch.float32:
+            raise _lib.DpfNativeError("coupling stack expects p (B,3,N) and g (B,%d) float32; got %s, %s"
+                                      % (G, tuple(p.shape), tuple(g.shape)))
+        dev = p.device
+        out = torch.empty((3, L, B, 3, N), dtype=torch.float32, device=dev)
+        ws = _workspace(L, G, B, N, dev)
+        update = bool(training)
+        with torch.cuda.device(dev):
+            _lib.call("dpf_decoder_forward", _meta_host_ptr(stack), stack.layer_meta, arena, stack.stats, p, g,
+                      out[0], out[1], out[2], ws, L, G, B, N, MODES[mode], bool(training), update,
+                      PRECISIONS[stack.precision], ctypes.c_float(stack.eps_value), device=dev)
+        if training:
+            stack.num_batches_tracked += 1
+        ctx.stack, ctx.mode, ctx.training, ctx.ws = stack, mode, bool(training), ws
+        ctx.save_for_backward(p, g, arena, out)
+        ctx.set_materialize_grads(False)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, dP, dMU, dLV):
+        from ._flowbwd import run_backward
+        return run_backward(ctx, dP, dMU, dLV)
+
+
+def run_stack(stack, p, g, mode):
+    if mode not in MODES:
+        raise ValueError("mode must be 'direct' or 'inverse', got %r" % (mode,))
+    p = p.contiguous()
+    g = g.contiguous()
+    return CouplingStackFunction.apply(p, g, stack.arena, stack, mode, stack.training)

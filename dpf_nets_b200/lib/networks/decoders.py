@@ -1,0 +1,32 @@
+"""Point decoder = stack of 3*n_flows conditional coupling layers (reference:
+lib/networks/decoders.py:41-72).  Output lists are indexed by layer - index 0 is always
+flows[0].nvp1 - in both modes, exactly like the reference."""
+from ._arena import CouplingStack
+from ._flowfn import run_stack
+from .flows import _triple_warps
+
+
+class FlowOutputs(list):
+    """A plain list of per-layer tensors that also carries the stacked (L,B,3,N) tensor it was
+    unbound from, so that losses can reduce over layers in one op."""
+    stacked = None
+
+
+def _as_list(stacked):
+    out = FlowOutputs(stacked.unbind(0))
+    out.stacked = stacked
+    return out
+
+
+class LocalCondRNVPDecoder(CouplingStack):
+    def __init__(self, n_flows, f_n_features, g_n_features, weight_std=0.01):
+        specs = []
+        for i in range(n_flows):
+            for j, w in enumerate(_triple_warps(i % 2)):
+                specs.append(("flows.%d.nvp%d." % (i, j + 1), w))
+        super().__init__(specs, f_n_features, g_n_features, weight_std=weight_std)
+        self.n_flows = n_flows
+
+    def forward(self, p, g, mode="direct"):
+        P, MU, LV = run_stack(self, p, g, mode)
+        return _as_list(P), _as_list(MU), _as_list(LV)

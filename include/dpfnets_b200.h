@@ -49,6 +49,23 @@ int dpf_pairwise_cd(int S1, int S2, int n, int m, const float* A, const float* B
 /* Mirrors the upper triangle of an (S,S) matrix into the lower one (after dpf_pairwise_cd symmetric). */
 int dpf_symmetrize_upper(float* M, int S, void* stream);
 
+/* ---- Point decoder: stack of conditional affine-coupling layers ------------------------------
+ * The reference has no native interface here; the replaceable unit is the nn.Module
+ * (LocalCondRNVPDecoder.forward, lib/networks/decoders.py:54-72, over CondRealNVPFlow3D.forward,
+ * lib/networks/flows.py:95-117).  These entry points are what that module's forward/backward bind.
+ *
+ * layer table: L rows of 8 int64 {param_off, stat_off, k, w, keep0, keep1, warp0, warp1}
+ *   (meta_host = host copy, meta_dev = device copy); arena / stats layouts: csrc/coupling.cuh.
+ * p (B,3,N), g (B,G) fp32; P_out, MU, LV (L,B,3,N) fp32 indexed by layer like the reference lists.
+ * mode 0 = 'direct' (sampling), 1 = 'inverse' (training NLL); training != 0 = BatchNorm batch
+ * statistics (+ running-stat update when update_stats != 0); precision 0 = fp32 CUDA cores,
+ * 1 = bf16 tcgen05 tensor cores with fp32 accumulation. */
+int dpf_decoder_workspace_bytes(int L, int G, int B, int N, long long* bytes);
+int dpf_decoder_forward(const long long* meta_host, const long long* meta_dev, const float* arena,
+                        float* stats, const float* p, const float* g, float* P_out, float* MU, float* LV,
+                        void* workspace, int L, int G, int B, int N, int mode, int training,
+                        int update_stats, int precision, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -255,3 +255,105 @@ def coupling_backward(P, p, g, mode, warp_inds, dy, dmu_ext=None, dlv_ext=None, 
         dg = dg + film_net_backward(P, br, "w", g, ds * (it["s"] - eps), training, grads)
         dg = dg + film_net_backward(P, br, "b", g, dt, training, grads)
     return dp, dg, grads
+
+
+# ------------------------------------------------------------------------------------------------
+# The SAME backward, restated in the two-pass + deferred-correction form the CUDA kernels use
+# (DESIGN.md "training backward"): BN_a's batch-statistics terms are not applied per point; they
+# collapse into per-layer sums (dbeta, E) plus an affine correction  dx[keep] -= cvec + Q x[keep]
+# that the next backward step applies when it loads its dy.  Used by tests to validate the algebra.
+# ------------------------------------------------------------------------------------------------
+def coupling_backward_two_pass(P, p, g, mode, warp_inds, dy_stored, pending=None, dmu_ext=None,
+                               dlv_ext=None, training=True):
+    """Returns (dp_stored, new_pending, dg, grads).  `pending` = (keep_idx, cvec (k,), Q (k,k)) of the
+    layer whose input is this layer's output; dp_true[keep] = dp_stored[keep] - cvec - Q p[keep]."""
+    eps = P["eps"]
+    p_out, mu, logvar, I = coupling_forward(P, p, g, mode, warp_inds, training, None, return_inter=True)
+    keep = I["keep"]
+    B, _, N = p.shape
+    M = B * N
+    dy = dy_stored.clone()
+    if pending is not None:
+        kidx, cvec, Q = pending
+        dy[:, kidx, :] -= cvec.view(1, -1, 1) + torch.einsum("jk,bkn->bjn", Q, p_out[:, kidx, :])
+    sigma = I["sigma"]
+    if mode == "inverse":
+        dp = dy / sigma
+        dmu = -dy / sigma
+        dl = -dy * p_out * torch.exp(logvar) / (2 * sigma * sigma)
+    else:
+        dp = dy * sigma
+        dmu = dy.clone()
+        dl = dy * p * torch.exp(logvar) / (2 * sigma)
+    if dmu_ext is not None:
+        dmu = dmu + dmu_ext
+    if dlv_ext is not None:
+        dl = dl + dlv_ext
+    do = {"mu": dmu[:, warp_inds, :], "logvar": dl[:, warp_inds, :] / (1 + I["o_logvar"].abs()) ** 2}
+    xk = p[:, keep, :].double()
+    S1 = xk.sum(dim=(0, 2))                                   # input moments of this layer
+    S2 = torch.einsum("bjn,bkn->jk", xk, xk)
+    grads = {}
+    dg = torch.zeros_like(g)
+    k = len(keep)
+    cv_new = torch.zeros(k, dtype=torch.float64)
+    Q_new = torch.zeros((k, k), dtype=torch.float64)
+    for br in BRANCHES:
+        it = I[br]
+        t0 = "T_%s_0.%s_" % (br, br)
+        t1 = "T_%s_1.%s_sd2." % (br, br)
+        W0, W1, W2 = P[t0 + "sd0.weight"][0], P[t0 + "sd1.weight"][0], P[t1 + "weight"][0]
+        gam = P[t0 + "sd0_bn.weight"]
+        d_o = do[br]
+        # ---- pass 1: per-(b,c) FiLM sums, W2 grads ----
+        dh3 = torch.einsum("wc,bwn->bcn", W2, d_o)
+        da = dh3 * (it["a"] > 0)
+        dt = da.sum(2)
+        ds = (da * it["h2n"]).sum(2)
+        grads[t1 + "bias"] = d_o.sum(dim=(0, 2)).view(1, -1)
+        grads[t1 + "weight"] = torch.einsum("bwn,bcn->wc", d_o, it["h3"]).unsqueeze(0)
+        istd_b = 1.0 / torch.sqrt(it["var_b"] + BN_EPS)
+        if training:
+            m1 = (it["s"] * dt).sum(0) / M
+            m2 = (it["s"] * ds).sum(0) / M
+        else:
+            m1 = m2 = torch.zeros_like(istd_b)
+        # ---- pass 2 ----
+        dh2pre = istd_b.view(1, -1, 1) * (da * it["s"].unsqueeze(2) - m1.view(1, -1, 1) - it["h2n"] * m2.view(1, -1, 1))
+        grads[t0 + "sd1.weight"] = torch.einsum("bcn,bjn->cj", dh2pre, it["h1"]).unsqueeze(0)
+        dh1 = torch.einsum("cj,bcn->bjn", W1, dh2pre)
+        dz = dh1 * (it["z"] > 0)
+        istd_a = (1.0 / torch.sqrt(it["var_a"] + BN_EPS))
+        A0 = (gam * istd_a).view(-1, 1) * W0                   # folded BN_a slope, (F,k)
+        T1 = torch.einsum("cj,bcn->bjn", A0, dz)               # per-point term
+        dp[:, keep, :] += T1
+        dbeta = dz.double().sum(dim=(0, 2))
+        E = torch.einsum("bcn,bjn->cj", dz.double(), xk)       # (F,k)
+        # ---- finalize (per layer, tiny) ----
+        W0d, ia, mean_a, gd = W0.double(), istd_a.double(), it["mean_a"].double(), gam.double()
+        dgamma = ia * ((W0d * E).sum(1) - mean_a * dbeta)
+        grads[t0 + "sd0_bn.bias"] = dbeta.float()
+        grads[t0 + "sd0_bn.weight"] = dgamma.float()
+        if training:
+            n1 = gd * dbeta / M
+            n2 = gd * dgamma / M
+        else:
+            n1 = n2 = torch.zeros_like(dbeta)
+        sx = ia.view(-1, 1) * (W0d @ S2 - mean_a.view(-1, 1) * S1.view(1, -1))      # sum_p xhat_c x_k
+        grads[t0 + "sd0.weight"] = (ia.view(-1, 1) * (gd.view(-1, 1) * E - n1.view(-1, 1) * S1.view(1, -1)
+                                                      - n2.view(-1, 1) * sx)).float().unsqueeze(0)
+        u = (W0d * (ia * n1).view(-1, 1)).sum(0)
+        r = (W0d * (ia * ia * n2 * mean_a).view(-1, 1)).sum(0)
+        cv_new += u - r
+        Q_new += torch.einsum("c,cj,ck->jk", ia * ia * n2, W0d, W0d)
+        dg = dg + film_net_backward(P, br, "w", g, ds * (it["s"] - eps), training, grads)
+        dg = dg + film_net_backward(P, br, "b", g, dt, training, grads)
+    return dp, (keep, cv_new.float(), Q_new.float()), dg, grads
+
+
+def apply_pending(dp_stored, p, pending):
+    """Resolves the deferred BN_a correction on a stored input gradient."""
+    kidx, cvec, Q = pending
+    dp = dp_stored.clone()
+    dp[:, kidx, :] -= cvec.view(1, -1, 1) + torch.einsum("jk,bkn->bjn", Q, p[:, kidx, :])
+    return dp
