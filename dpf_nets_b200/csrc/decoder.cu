@@ -92,3 +92,76 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
   }
   return DPF_OK;
 }
+
+int launch_coupling_bwd_fp32(const BwdArgs& a, int mode, cudaStream_t s);
+int launch_coupling_bwd_final(const BwdArgs& a, const float* p_in, const float* dx_stored, float* dp, cudaStream_t s);
+int launch_film_backward(const float* arena, const float* stats, float* darena, const LayerMeta* meta_dev,
+                         const float* g, const float* film, const float* dfilm, float* dg, int L, int B, int G,
+                         int training, float eps, cudaStream_t s);
+
+// Backward of dpf_decoder_forward (what torch.autograd does for the reference modules; formulas in
+// SURVEY.md Appendix F).  `workspace` must be the one the forward call used (FiLM outputs, input
+// moments and BN_b sums live there).  dP / dMU / dLV are the cotangents of the stacked outputs
+// (nullable; *_stride = elements between consecutive layers, 0 = the same (B,3,N) block for every
+// layer).  darena (n_params) and dg (B,G) are overwritten; dp (B,3,N) is optional.
+DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* meta_dev, const float* arena,
+                                 float* stats, const float* p, const float* g, const float* P_out, const float* LV,
+                                 const float* dP, long long dP_stride, const float* dMU, long long dMU_stride,
+                                 const float* dLV, long long dLV_stride, float* darena, long long n_params,
+                                 float* dg, float* dp, void* workspace, int L, int G, int B, int N, int mode,
+                                 int training, int precision, float eps, void* stream) {
+  int rc = validate_common(meta_host, L, G, B, N, mode, precision);
+  if (rc) return rc;
+  DPF_REQUIRE(meta_dev && arena && stats && p && g && P_out && LV && darena && dg && workspace, DPF_ERR_NULL_PTR,
+              "dpf_decoder_backward: null pointer");
+  DPF_REQUIRE(precision == 0, DPF_ERR_UNSUPPORTED, "dpf_decoder_backward: bf16 tensor path not built yet");
+  cudaStream_t s = (cudaStream_t)stream;
+  const LayerMeta* meta = reinterpret_cast<const LayerMeta*>(meta_host);
+  DecoderWorkspace ws = carve_workspace(workspace, L, G, B, N);
+  const size_t plane = (size_t)B * 3 * N;
+  cudaMemsetAsync(darena, 0, sizeof(float) * (size_t)n_params, s);
+  cudaMemsetAsync(dg, 0, sizeof(float) * (size_t)B * G, s);
+  cudaMemsetAsync(ws.dfilm, 0, sizeof(float) * (size_t)L * 4 * B * DPF_F, s);
+  cudaMemsetAsync(ws.bna_sums, 0, sizeof(double) * (size_t)L * 2 * DPF_F * 4, s);
+
+  auto layer_of = [&](int q) { return mode == 0 ? q : L - 1 - q; };
+  auto set_pending = [&](BwdArgs& a, int qn) {   // correction owed by the layer of step qn
+    const int ln = layer_of(qn);
+    const LayerMeta& mn = meta[ln];
+    a.has_pending = 1;
+    a.nprm = arena + mn.param_off;
+    a.nstat = stats + mn.stat_off;
+    a.ndprm = darena + mn.param_off;
+    a.n_bna_sums = ws.bna_sums + (size_t)ln * 2 * DPF_F * 4;
+    a.n_mom = ws.moments + (size_t)qn * 16;
+    a.nk = (int)mn.k; a.nw = (int)mn.w; a.nkeep0 = (int)mn.keep0; a.nkeep1 = (int)mn.keep1;
+  };
+  for (int q = L - 1; q >= 0; --q) {
+    const int l = layer_of(q);
+    BwdArgs a{};
+    a.f = make_args(meta[l], arena, stats, ws, l, q, G, B, N, training, 0, eps);
+    a.f.x = q == 0 ? p : P_out + (size_t)layer_of(q - 1) * plane;
+    a.yv = P_out + (size_t)l * plane;
+    a.lvv = LV + (size_t)l * plane;
+    a.dy_chain = q == L - 1 ? nullptr : ws.dx[(q + 1) & 1];
+    a.dP = dP ? dP + (size_t)l * dP_stride : nullptr;
+    a.dMU = dMU ? dMU + (size_t)l * dMU_stride : nullptr;
+    a.dLV = dLV ? dLV + (size_t)l * dLV_stride : nullptr;
+    a.dx_out = ws.dx[q & 1];
+    a.dfilm = ws.dfilm + (size_t)l * 4 * B * DPF_F;
+    a.dprm = darena + meta[l].param_off;
+    a.bna_sums = ws.bna_sums + (size_t)l * 2 * DPF_F * 4;
+    if (q < L - 1) set_pending(a, q + 1);
+    rc = launch_coupling_bwd_fp32(a, mode, s);
+    if (rc) return rc;
+  }
+  {
+    BwdArgs a{};
+    a.f.B = B; a.f.N = N; a.f.G = G; a.f.training = training; a.f.eps = eps;
+    set_pending(a, 0);
+    rc = launch_coupling_bwd_final(a, p, ws.dx[0], dp, s);
+    if (rc) return rc;
+  }
+  return launch_film_backward(arena, stats, darena, reinterpret_cast<const LayerMeta*>(meta_dev), g, ws.film,
+                              ws.dfilm, dg, L, B, G, training, eps, s);
+}

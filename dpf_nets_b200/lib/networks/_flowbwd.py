@@ -1,5 +1,41 @@
-"""Backward of the coupling stack (filled in with dpf_decoder_backward)."""
+"""Backward of the coupling stack through dpf_decoder_backward."""
+import ctypes
+
+import torch
+
+from ... import _lib
+from ._flowfn import MODES, PRECISIONS, _meta_host_ptr
+
+
+def _cotangent(t, L, plane):
+    """(tensor or None) -> (pointer-able tensor or None, layer stride in elements).  A cotangent
+    that is the same (B,3,N) block for every layer (stride 0 on dim 0, e.g. from `.sum(0)`) is
+    passed without materialising L copies."""
+    if t is None:
+        return None, 0
+    if t.dim() == 4 and t.stride(0) == 0 and t[0].is_contiguous():
+        return t[0], 0
+    t = t.contiguous()
+    return t, plane
 
 
 def run_backward(ctx, dP, dMU, dLV):
-    raise NotImplementedError("coupling-stack backward is not built yet")
+    stack, mode = ctx.stack, ctx.mode
+    p, g, arena, out = ctx.saved_tensors
+    L, G = stack.layout.L, stack.g_n_features
+    B, _, N = p.shape
+    dev = p.device
+    plane = B * 3 * N
+    dP_t, dP_s = _cotangent(dP, L, plane)
+    dMU_t, dMU_s = _cotangent(dMU, L, plane)
+    dLV_t, dLV_s = _cotangent(dLV, L, plane)
+    darena = torch.empty_like(arena)
+    dg = torch.empty_like(g)
+    dp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+    with torch.cuda.device(dev):
+        _lib.call("dpf_decoder_backward", _meta_host_ptr(stack), stack.layer_meta, arena, stack.stats, p, g,
+                  out[0], out[2], dP_t, ctypes.c_longlong(dP_s), dMU_t, ctypes.c_longlong(dMU_s),
+                  dLV_t, ctypes.c_longlong(dLV_s), darena, ctypes.c_longlong(arena.numel()), dg, dp, ctx.ws,
+                  L, G, B, N, MODES[mode], ctx.training, PRECISIONS[stack.precision],
+                  ctypes.c_float(stack.eps_value), device=dev)
+    return dp, dg, darena, None, None, None

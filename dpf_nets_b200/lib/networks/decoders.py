@@ -30,3 +30,14 @@ class LocalCondRNVPDecoder(CouplingStack):
     def forward(self, p, g, mode="direct"):
         P, MU, LV = run_stack(self, p, g, mode)
         return _as_list(P), _as_list(MU), _as_list(LV)
+
+
+class TailedList(list):
+    """[base] + decoder list: keeps a handle on the decoder's stacked tensor for fused reductions."""
+    tail_stacked = None
+
+
+def prepend(base, flow_list):
+    out = TailedList([base] + list(flow_list))
+    out.tail_stacked = getattr(flow_list, "stacked", None)
+    return out

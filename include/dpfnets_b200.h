@@ -66,6 +66,18 @@ int dpf_decoder_forward(const long long* meta_host, const long long* meta_dev, c
                         void* workspace, int L, int G, int B, int N, int mode, int training,
                         int update_stats, int precision, float eps, void* stream);
 
+/* Backward of dpf_decoder_forward = what torch.autograd derives for flows.py:95-117 (the reference
+ * has no hand-written backward; formulas: SURVEY.md Appendix F).  `workspace` must be the buffer
+ * the forward call used.  dP/dMU/dLV: cotangents of the stacked outputs (nullable), *_stride =
+ * elements between layers (0 = one (B,3,N) block shared by all layers).  darena (n_params, arena
+ * layout) and dg (B,G) are overwritten; dp (B,3,N) is optional (NULL = not needed). */
+int dpf_decoder_backward(const long long* meta_host, const long long* meta_dev, const float* arena,
+                         float* stats, const float* p, const float* g, const float* P_out, const float* LV,
+                         const float* dP, long long dP_stride, const float* dMU, long long dMU_stride,
+                         const float* dLV, long long dLV_stride, float* darena, long long n_params,
+                         float* dg, float* dp, void* workspace, int L, int G, int B, int N, int mode,
+                         int training, int precision, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

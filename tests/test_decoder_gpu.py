@@ -140,3 +140,58 @@ def test_rejects_cpu_tensors_and_bad_width(mods):
         m(torch.zeros(2, 3, 5), torch.zeros(2, 8))
     with pytest.raises(ValueError):
         flows.CondRealNVPFlow3D(32, 8)
+
+
+# ---------------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------------
+TOLG = 1e-3   # gradients: fp32 re-association noise through BN backward (reference vs its own fp64 ~3e-4)
+
+
+@pytest.mark.parametrize("name", ["coupling_w0.pt", "coupling_w02.pt", "coupling_w1_g128.pt"])
+@pytest.mark.parametrize("mode", ["inverse", "direct"])
+def test_coupling_layer_backward_vs_reference_autograd(mods, cuda, name, mode):
+    flows, _ = mods
+    fx = load(name)
+    t = fx["train_" + mode]
+    m = flows.CondRealNVPFlow3D(64, fx["G"], warp_inds=fx["warp"]).to(cuda)
+    m.load_state_dict(fx["state"])
+    m.train()
+    p = fx["p"].to(cuda).requires_grad_(True)
+    g = fx["g"].to(cuda).requires_grad_(True)
+    p_out, mu, lv = m(p, g, mode=mode)
+    cy, cm, cl = [c.to(cuda) for c in t["cot"]]
+    ((p_out * cy).sum() + (mu * cm).sum() + (lv * cl).sum()).backward()
+    assert rel(p.grad, t["dp"]) < TOLG, rel(p.grad, t["dp"])
+    assert rel(g.grad, t["dg"]) < TOLG, rel(g.grad, t["dg"])
+    gv = m.named_views(grad=True)
+    worst = max((rel(gv[k], v), k) for k, v in t["grads"].items())
+    assert worst[0] < TOLG, worst
+
+
+def test_decoder_nll_backward_vs_reference_autograd(mods, cuda):
+    _, decoders = mods
+    from dpf_nets_b200.lib.networks.losses import PointFlowNLL
+    fx = load("decoder_f2.pt")
+    t = fx["train_inverse"]
+    m = decoders.LocalCondRNVPDecoder(fx["n_flows"], 64, fx["G"]).to(cuda)
+    m.load_state_dict(fx["state"])
+    m.train()
+    p = fx["p"].to(cuda)
+    g = fx["g"].to(cuda).requires_grad_(True)
+    ps, mus, lvs = m(p, g, mode="inverse")
+    base_mu, base_lv = torch.zeros_like(p), torch.full_like(p, t["base_logvar"])
+    nll = PointFlowNLL()(decoders.prepend(None, ps)[1:] + [p], decoders.prepend(base_mu, mus), decoders.prepend(base_lv, lvs))
+    assert abs(nll.item() - t["nll"].item()) < 5e-3 * abs(t["nll"].item())
+    nll.backward()
+    gv = m.named_views(grad=True)
+    errs = sorted(((rel(gv[k], v), k) for k, v in t["grads"].items()), reverse=True)
+    assert errs[0][0] < 5e-3, errs[:5]
+    assert rel(g.grad, t["dg"]) < 5e-3
+    # same loss through the plain-list path (63 separate adds like the reference's sum())
+    m.zero_grad()
+    g2 = fx["g"].to(cuda).requires_grad_(True)
+    ps, mus, lvs = m(p, g2, mode="inverse")
+    nll2 = PointFlowNLL()(list(ps) + [p], [base_mu] + list(mus), [base_lv] + list(lvs))
+    nll2.backward()
+    assert rel(g2.grad, g.grad) < 2e-3   # two runs differ by atomic-order noise on this ill-conditioned fixture
