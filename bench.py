@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the DPF-Nets hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host CPU
+
+Metric (BASELINE.json): decoder points/s, train forward+backward, on the chair generation config
+(configs/generation/chair.yaml: 21 triples = 63 coupling layers, F=64, G=128), synthetic batch
+32 x 2048 points per GPU, random-init weights.  One "step" = LocalCondRNVPDecoder(p, g, 'inverse')
+in train mode + PointFlowNLL + backward to every decoder parameter and g (the
+optimizer is not part of this metric).  N > 1: batch-sharded (weak scaling), NCCL all-reduce of
+the gradient arena inside the step.  Also reported: sampling points/s, Chamfer pair-evals/s,
+roofline of the dominant kernel, and the oracle port timed on the host cores (cpu_baseline).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_FLOWS, F_WIDTH, G_LATENT = 21, 64, 128
+BASE_LOGVAR = -3.6990                    # configs/generation/chair.yaml:51 p_decoder_base_var
+FLOP_PER_POINT_LAYER_FWD = 17152         # 2 branches x (2k64 + 2*64*64 + 2*64w), k+w=3
+KERNEL_CLASSES = ["film_fwd", "moments", "fwd_stats", "fwd_apply", "bwd_p1", "bwd_p2", "bwd_final", "film_bwd"]
+# algorithmic (non-recompute) GEMM FLOP per point per layer each kernel class is responsible for
+ALGO_FLOP = {"fwd_stats": 0, "fwd_apply": FLOP_PER_POINT_LAYER_FWD, "bwd_p1": 2 * 2 * 64 * 3,
+             "bwd_p2": 2 * FLOP_PER_POINT_LAYER_FWD - 2 * 2 * 64 * 3}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("DPF_PRECISION", "auto"))
+    ap.add_argument("--batch", type=int, default=32, help="shapes per GPU")
+    ap.add_argument("--points", type=int, default=2048)
+    ap.add_argument("--no-extras", action="store_true", help="skip sampling / Chamfer / cpu_baseline legs")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def synth_inputs(B, N, G, rank, pin=False):
+    gen = torch.Generator().manual_seed(1234 + rank)
+    p = torch.rand((B, 3, N), generator=gen) - 0.5
+    g = torch.randn((B, G), generator=gen)
+    if pin:
+        p, g = p.pin_memory(), g.pin_memory()
+    return p, g
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (profiling recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port (CPU restatement of the reference algorithm)
+# --------------------------------------------------------------------------------------------
+def oracle_train_step_factory(B, N, rank=0):
+    """Builds the oracle decoder (reference init through our module's reference-faithful
+    initialiser, same state_dict layout) and returns step() -> loss running fwd+bwd on CPU."""
+    from oracle import flow_oracle as fo
+    from dpf_nets_b200.lib.networks._arena import ArenaLayout, init_arena, init_stats
+    specs = fo.decoder_layer_names(N_FLOWS)
+    lay = ArenaLayout(specs, G_LATENT)
+    torch.manual_seed(0)
+    arena, stats = init_arena(lay, 0.01), init_stats(lay)
+    arena.requires_grad_(True)
+    layers = []
+    for pre, warp in specs:
+        P = {"eps": torch.tensor([1e-6])}
+        for key, (off, shape) in lay.param_index.items():
+            if key.startswith(pre):
+                n = 1
+                for s in shape:
+                    n *= s
+                P[key[len(pre):]] = arena[off:off + n].view(shape)
+        for key, (off, shape) in lay.stat_index.items():
+            if key.startswith(pre):
+                P[key[len(pre):]] = stats[off:off + 64]
+        layers.append((P, warp))
+    p, g = synth_inputs(B, N, G_LATENT, rank)
+    g.requires_grad_(True)
+    base_mu, base_lv = torch.zeros_like(p), torch.full_like(p, BASE_LOGVAR)
+
+    def step():
+        arena.grad = None
+        g.grad = None
+        ps, mus, lvs = fo.decoder_forward(layers, p, g, "inverse", training=True)
+        nll = fo.point_flow_nll(ps + [p], [base_mu] + mus, [base_lv] + lvs)
+        nll.backward()
+        return float(nll.detach())
+    return step
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, N = args.batch, args.points
+    step = oracle_train_step_factory(B, N)
+    t0 = time.perf_counter()
+    step()
+    est = time.perf_counter() - t0
+    sample = "full batch %dx%d per step" % (B, N)
+    if est * (args.steps + args.warmup) > 240.0 and B > 8:
+        B = 8
+        step = oracle_train_step_factory(B, N)
+        sample = "bounded sample: %d of %d shapes x %d points per step" % (B, args.batch, N)
+    ts = time_cpu(step, args.steps, args.warmup)
+    ms = 1e3 * sum(ts) / len(ts)
+    val = B * N / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": "decoder points/s (train fwd+bwd)", "value": val, "unit": "points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "fp32"),
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, precision):
+    return {"workload": "chair generation config (configs/generation/chair.yaml): point decoder, 63 coupling "
+                        "layers F=64 G=128, train-mode inverse pass + PointFlowNLL + backward",
+            "batch_per_gpu": args.batch, "points": args.points, "global_batch": args.batch * args.gpus,
+            "precision": precision, "parallelism": "dp%d" % args.gpus,
+            "l2": "256 MiB flush write between timed steps (untimed)",
+            "optimizer": "not part of the metric (SURVEY.md 8d)"}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from dpf_nets_b200 import _lib
+    from dpf_nets_b200.lib.networks.decoders import LocalCondRNVPDecoder, prepend
+    from dpf_nets_b200.lib.networks.losses import PointFlowNLL
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    _lib.check(lib.dpf_device_check(), "dpf_device_check")
+    pk = peaks()
+
+    precision = args.precision
+    torch.manual_seed(0)
+    model = LocalCondRNVPDecoder(N_FLOWS, F_WIDTH, G_LATENT).to(dev)
+    if precision == "auto":
+        precision = getattr(model, "default_precision", "fp32")
+    model.precision = precision
+    model.train()
+    B, N = args.batch, args.points
+    p_host, g_host = synth_inputs(B, N, G_LATENT, rank, pin=True)
+    p_dev, g_dev = p_host.to(dev), g_host.to(dev).requires_grad_(True)
+    base_mu, base_lv = torch.zeros_like(p_dev), torch.full_like(p_dev, BASE_LOGVAR)
+    crit = PointFlowNLL()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(p, g):
+        model.arena.grad = None
+        g.grad = None
+        ps, mus, lvs = model(p, g, mode="inverse")
+        nll = crit(prepend(None, ps)[1:] + [p], prepend(base_mu, mus), prepend(base_lv, lvs))
+        nll.backward()
+        if world > 1:
+            dist.all_reduce(model.arena.grad, op=dist.ReduceOp.AVG)
+        return nll
+
+    def launches():
+        n = ctypes.c_longlong(0)
+        lib.dpf_launch_count(ctypes.byref(n))
+        return n.value
+
+    for _ in range(args.warmup):
+        step(p_dev, g_dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- timed region: device-resident inputs ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = launches()
+    torch.cuda.synchronize()
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        step(p_dev, g_dev)
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l1 = launches()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the loss, every step ----
+    g_e2e = torch.empty_like(g_dev).requires_grad_(True)
+    p_e2e = torch.empty_like(p_dev)
+    evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    loss_val = 0.0
+    for a, b in evs2:
+        flush.zero_()
+        a.record()
+        p_e2e.copy_(p_host, non_blocking=True)
+        with torch.no_grad():
+            g_e2e.copy_(g_host, non_blocking=True)
+        loss_val = float(step(p_e2e, g_e2e).item())
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in evs2)
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = world * B * N / (ms_per_step * 1e-3)
+    e2e_val = world * B * N / (e2e_ms / args.steps * 1e-3)
+
+    # ---- per-kernel-class timing (separate pass, CUDA events on the launching stream) ----
+    lib.dpf_profile_enable(1)
+    prof_steps = max(2, min(args.steps, 5))
+    for _ in range(prof_steps):
+        flush.zero_()
+        step(p_dev, g_dev)
+    torch.cuda.synchronize()
+    ms = (ctypes.c_double * 8)()
+    cnt = (ctypes.c_longlong * 8)()
+    lib.dpf_profile_collect(ms, cnt, 8)
+    lib.dpf_profile_enable(0)
+    classes = {k: {"ms_per_step": ms[i] / prof_steps, "launches_per_step": cnt[i] / prof_steps,
+                   "us_per_launch": (1e3 * ms[i] / cnt[i]) if cnt[i] else None} for i, k in enumerate(KERNEL_CLASSES)}
+    dom = max(("fwd_stats", "fwd_apply", "bwd_p1", "bwd_p2"), key=lambda k: classes[k]["ms_per_step"])
+    dom_us = classes[dom]["us_per_launch"] or float("inf")
+    tensor_peak = pk["bf16_tflops_sustained"]
+    achieved = ALGO_FLOP[dom] * B * N / (dom_us * 1e-6) / 1e12
+    whole = 3 * FLOP_PER_POINT_LAYER_FWD * 3 * N_FLOWS * B * N / (ms_per_step * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": achieved / tensor_peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+                "algorithmic_flop_per_launch": ALGO_FLOP[dom] * B * N,
+                "whole_step": {"achieved": whole, "frac": whole / tensor_peak,
+                               "flop_per_point": 3 * FLOP_PER_POINT_LAYER_FWD * 3 * N_FLOWS},
+                "kernel_classes": classes}
+
+    line = {
+        "metric": "decoder points/s (train fwd+bwd)", "value": value, "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32",
+        "data": "synthetic", "config": workload_config(args, precision),
+        "e2e": {"value": e2e_val, "unit": "points/s", "h2d_bytes_per_step": p_host.numel() * 4 + g_host.numel() * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "loss": loss_val},
+        "gpu_launches": l1 - l0, "clocks": clocks, "roofline": roofline,
+    }
+
+    if rank == 0 and not args.no_extras:
+        line["extra"] = extras(model, dev, B, N, pk, flush)
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cstep = oracle_train_step_factory(B, N)
+        ts = time_cpu(cstep, 2, 1)
+        cms = 1e3 * sum(ts) / len(ts)
+        line["cpu_baseline"] = {"value": B * N / (cms * 1e-3), "unit": "points/s", "cores": cores, "kind": "port",
+                                "sample": "full batch %dx%d, 1 warm-up + 2 timed steps of the oracle port "
+                                          "(torch CPU fp32 restatement of the reference modules)" % (B, N),
+                                "ms_per_step": cms}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(model, dev, B, N, pk, flush):
+    """Secondary metrics BASELINE.json names: sampling points/s and Chamfer pair-evals/s."""
+    from dpf_nets_b200.ops import pairwise_cd
+    out = {}
+    model.eval()
+    gen = torch.Generator().manual_seed(7)
+    z = torch.randn((B, 3, N), generator=gen).to(dev)
+    g = torch.randn((B, G_LATENT), generator=gen).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            model(z, g, mode="direct")
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); model(z, g, mode="direct"); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+    ms = sum(ts) / len(ts)
+    samp = B * N / (ms * 1e-3)
+    out["sampling"] = {"value": samp, "unit": "points/s", "ms_per_pass": ms,
+                       "tensor_frac": samp * FLOP_PER_POINT_LAYER_FWD * 3 * N_FLOWS / 1e12 / pk["bf16_tflops_sustained"]}
+    model.train()
+    S = 256
+    A = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
+    Bc = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
+    pairwise_cd(A, Bc)
+    ts = []
+    for _ in range(3):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); pairwise_cd(A, Bc); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    sec = sum(ts) / len(ts) * 1e-3
+    pairs = S * S / sec
+    fp32_issue_peak = 148 * 128 * 1.965e9 / 7.0          # distance evals/s at 7 FP32 issue slots each
+    out["chamfer"] = {"value": pairs, "unit": "cloud-pair CD evals/s", "clouds": "%dx%d of %d points" % (S, S, N),
+                      "point_pair_evals_per_s": pairs * N * N,
+                      "hbm": {"achieved_gbs": pairs * (2 * N * 12 + 4) / 1e9, "peak_gbs": pk["hbm_gbs"],
+                              "frac": pairs * (2 * N * 12 + 4) / 1e9 / pk["hbm_gbs"]},
+                      "fp32_issue": {"achieved_dist_evals_per_s": 2 * pairs * N * N, "bound": fp32_issue_peak,
+                                     "frac": 2 * pairs * N * N / fp32_issue_peak}}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,7 @@
 #include <cstdio>
 
 static thread_local char g_err[512] = "";
+long long g_dpf_launches = 0;
 
 void dpf_set_error(const char* fmt, ...) {
   va_list ap;
@@ -31,5 +32,12 @@ DPF_API int dpf_device_check(void) {
     dpf_set_error("dpf_device_check: device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
     return DPF_ERR_UNSUPPORTED;
   }
+  return DPF_OK;
+}
+
+// Number of kernels this library has launched since load (bench.py's gpu_launches evidence).
+DPF_API int dpf_launch_count(long long* count) {
+  if (!count) { dpf_set_error("dpf_launch_count: null pointer"); return DPF_ERR_NULL_PTR; }
+  *count = g_dpf_launches;
   return DPF_OK;
 }

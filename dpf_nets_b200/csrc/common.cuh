@@ -14,7 +14,10 @@
 
 void dpf_set_error(const char* fmt, ...);
 
+extern long long g_dpf_launches;   // kernels launched by this library (api.cu)
+
 static inline int dpf_check_launch(const char* what) {
+  ++g_dpf_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     dpf_set_error("%s: %s", what, cudaGetErrorString(e));

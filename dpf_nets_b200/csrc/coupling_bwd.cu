@@ -676,26 +676,27 @@ film_backward_kernel(const float* __restrict__ arena, const float* __restrict__ 
 }
 
 template <int K, int MODE>
-int launch_bwd_t(const BwdArgs& a, int grid, cudaStream_t st) {
+int launch_bwd_t(const BwdArgs& a, int grid, int pass, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(coupling_bwd_p1_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P1Smem));
     cudaFuncSetAttribute(coupling_bwd_p2_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2Smem));
     attr = true;
   }
-  coupling_bwd_p1_kernel<K, MODE><<<grid, DPF_TILE, sizeof(P1Smem), st>>>(a);
-  int rc = dpf_check_launch("coupling_bwd_p1_kernel");
-  if (rc) return rc;
+  if (pass == 1) {
+    coupling_bwd_p1_kernel<K, MODE><<<grid, DPF_TILE, sizeof(P1Smem), st>>>(a);
+    return dpf_check_launch("coupling_bwd_p1_kernel");
+  }
   coupling_bwd_p2_kernel<K, MODE><<<grid, DPF_TILE, sizeof(P2Smem), st>>>(a);
   return dpf_check_launch("coupling_bwd_p2_kernel");
 }
 
 }  // namespace
 
-int launch_coupling_bwd_fp32(const BwdArgs& a, int mode, cudaStream_t s) {
+int launch_coupling_bwd_fp32(const BwdArgs& a, int mode, int pass, cudaStream_t s) {
   const int grid = min(a.f.n_tiles, dpf_num_sms());
-  if (a.f.k == 2) return mode == 0 ? launch_bwd_t<2, 0>(a, grid, s) : launch_bwd_t<2, 1>(a, grid, s);
-  return mode == 0 ? launch_bwd_t<1, 0>(a, grid, s) : launch_bwd_t<1, 1>(a, grid, s);
+  if (a.f.k == 2) return mode == 0 ? launch_bwd_t<2, 0>(a, grid, pass, s) : launch_bwd_t<2, 1>(a, grid, pass, s);
+  return mode == 0 ? launch_bwd_t<1, 0>(a, grid, pass, s) : launch_bwd_t<1, 1>(a, grid, pass, s);
 }
 
 int launch_coupling_bwd_final(const BwdArgs& a, const float* p_in, const float* dx_stored, float* dp, cudaStream_t s) {

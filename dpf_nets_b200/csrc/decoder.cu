@@ -2,6 +2,52 @@
 // (FiLM pre-compute, per-layer statistics + apply launches) on the caller's stream, so the Python
 // side pays one FFI call per decoder pass and the whole pass can be captured in a CUDA graph.
 #include "coupling.cuh"
+#include <vector>
+
+// ---- optional per-kernel-class timing (CUDA events on the launching stream; bench.py roofline) ----
+namespace {
+enum { CAT_FILM_FWD = 0, CAT_MOMENTS, CAT_FWD_STATS, CAT_FWD_APPLY, CAT_BWD_P1, CAT_BWD_P2, CAT_BWD_FINAL, CAT_FILM_BWD, CAT_COUNT };
+struct ProfRec { int cat; cudaEvent_t a, b; };
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<ProfRec> recs;
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+} g_prof;
+struct ProfScope {
+  int cat; cudaStream_t s; cudaEvent_t a;
+  ProfScope(int c, cudaStream_t st) : cat(c), s(st), a(nullptr) { if (g_prof.on) { a = g_prof.get(); cudaEventRecord(a, s); } }
+  ~ProfScope() { if (g_prof.on) { cudaEvent_t b = g_prof.get(); cudaEventRecord(b, s); g_prof.recs.push_back({cat, a, b}); } }
+};
+}  // namespace
+
+// Enables (and clears) / disables per-kernel-class event timing of the decoder entry points.
+DPF_API int dpf_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  g_prof.recs.clear();
+  return DPF_OK;
+}
+
+// Sums the recorded durations: ms[c], counts[c] for the n (<= 8) kernel classes
+// {film_fwd, moments, fwd_stats, fwd_apply, bwd_p1, bwd_p2, bwd_final, film_bwd}.
+DPF_API int dpf_profile_collect(double* ms, long long* counts, int n) {
+  DPF_REQUIRE(ms && counts && n > 0, DPF_ERR_BAD_ARG, "dpf_profile_collect: bad arguments");
+  for (int i = 0; i < n; ++i) { ms[i] = 0.0; counts[i] = 0; }
+  for (const ProfRec& r : g_prof.recs) {
+    cudaEventSynchronize(r.b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (r.cat < n) { ms[r.cat] += t; counts[r.cat] += 1; }
+  }
+  g_prof.used = 0;
+  g_prof.recs.clear();
+  return DPF_OK;
+}
 
 // launchers (coupling_fwd.cu / coupling_bwd.cu / coupling_tc.cu)
 int launch_film_forward(const float* arena, float* stats, const LayerMeta* meta_dev, const float* g, float* film,
@@ -65,12 +111,16 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
   DecoderWorkspace ws = carve_workspace(workspace, L, G, B, N);
   const size_t plane = (size_t)B * 3 * N;
 
-  rc = launch_film_forward(arena, stats, reinterpret_cast<const LayerMeta*>(meta_dev), g, ws.film, L, B, G, training,
-                           update_stats, eps, s);
+  {
+    ProfScope ps(CAT_FILM_FWD, s);
+    rc = launch_film_forward(arena, stats, reinterpret_cast<const LayerMeta*>(meta_dev), g, ws.film, L, B, G, training,
+                             update_stats, eps, s);
+  }
   if (rc) return rc;
   if (training) {
     cudaMemsetAsync(ws.moments, 0, sizeof(double) * (size_t)(L + 1) * 16, s);
     cudaMemsetAsync(ws.bnb_sums, 0, sizeof(double) * (size_t)L * 2 * DPF_F * 2, s);
+    ProfScope ps(CAT_MOMENTS, s);
     rc = launch_moments(p, B, N, ws.moments, s);
     if (rc) return rc;
   }
@@ -83,17 +133,21 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
     a.mu = MU + (size_t)l * plane;
     a.lv = LV + (size_t)l * plane;
     if (training) {
+      ProfScope ps(CAT_FWD_STATS, s);
       rc = launch_coupling_fwd_fp32(a, mode, true, s);
       if (rc) return rc;
     }
-    rc = launch_coupling_fwd_fp32(a, mode, false, s);
+    {
+      ProfScope ps(CAT_FWD_APPLY, s);
+      rc = launch_coupling_fwd_fp32(a, mode, false, s);
+    }
     if (rc) return rc;
     x = a.y;
   }
   return DPF_OK;
 }
 
-int launch_coupling_bwd_fp32(const BwdArgs& a, int mode, cudaStream_t s);
+int launch_coupling_bwd_fp32(const BwdArgs& a, int mode, int pass, cudaStream_t s);
 int launch_coupling_bwd_final(const BwdArgs& a, const float* p_in, const float* dx_stored, float* dp, cudaStream_t s);
 int launch_film_backward(const float* arena, const float* stats, float* darena, const LayerMeta* meta_dev,
                          const float* g, const float* film, const float* dfilm, float* dg, int L, int B, int G,
@@ -152,16 +206,26 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     a.dprm = darena + meta[l].param_off;
     a.bna_sums = ws.bna_sums + (size_t)l * 2 * DPF_F * 4;
     if (q < L - 1) set_pending(a, q + 1);
-    rc = launch_coupling_bwd_fp32(a, mode, s);
+    {
+      ProfScope ps(CAT_BWD_P1, s);
+      rc = launch_coupling_bwd_fp32(a, mode, 1, s);
+    }
+    if (rc) return rc;
+    {
+      ProfScope ps(CAT_BWD_P2, s);
+      rc = launch_coupling_bwd_fp32(a, mode, 2, s);
+    }
     if (rc) return rc;
   }
   {
     BwdArgs a{};
     a.f.B = B; a.f.N = N; a.f.G = G; a.f.training = training; a.f.eps = eps;
     set_pending(a, 0);
+    ProfScope ps(CAT_BWD_FINAL, s);
     rc = launch_coupling_bwd_final(a, p, ws.dx[0], dp, s);
     if (rc) return rc;
   }
+  ProfScope ps(CAT_FILM_BWD, s);
   return launch_film_backward(arena, stats, darena, reinterpret_cast<const LayerMeta*>(meta_dev), g, ws.film,
                               ws.dfilm, dg, L, B, G, training, eps, s);
 }

@@ -24,6 +24,12 @@ extern "C" {
 const char* dpf_last_error(void);
 int dpf_version(void);
 int dpf_device_check(void);
+/* Kernels launched by this library since load (evidence for bench.py's gpu_launches). */
+int dpf_launch_count(long long* count);
+/* Per-kernel-class CUDA-event timing of the decoder entry points (off by default).
+ * classes: 0 film_fwd, 1 moments, 2 fwd_stats, 3 fwd_apply, 4 bwd_p1, 5 bwd_p2, 6 bwd_final, 7 film_bwd */
+int dpf_profile_enable(int on);
+int dpf_profile_collect(double* ms, long long* counts, int n);
 
 /* ---- Chamfer / nearest-neighbour distance --------------------------------------------------
  * dpf_nndistance replaces nndistance() — lib/metrics/pytorch_structural_losses/src/nndistance.cuh:1
