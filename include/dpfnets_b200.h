@@ -84,6 +84,13 @@ int dpf_decoder_backward(const long long* meta_host, const long long* meta_dev, 
                          float* dg, float* dp, void* workspace, int L, int G, int B, int N, int mode,
                          int training, int precision, float eps, void* stream);
 
+/* tcgen05 self-test (tests/test_umma_gpu.py): D[128,ncols] = sum_k A_k B_k from raw shared-memory
+ * operand images and descriptor fields; validates the UMMA layouts the coupling kernels rely on. */
+int dpf_umma_selftest(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
+                      unsigned long long a_templ, unsigned long long b_templ, unsigned int idesc,
+                      int num_k, int a_kstep, int b_kstep, int ncols, int use_bulk, float* d_out,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
