@@ -232,10 +232,11 @@ def run_ours(args):
     precision = args.precision
     torch.manual_seed(0)
     model = LocalCondRNVPDecoder(N_FLOWS, F_WIDTH, G_LATENT).to(dev)
-    if precision == "auto":
-        precision = getattr(model, "default_precision", "fp32")
     model.precision = precision
     model.train()
+    if precision == "auto":   # what the module resolves 'auto' to in train mode (plain bf16 in eval)
+        from dpf_nets_b200.lib.networks._flowfn import resolve_precision
+        precision = resolve_precision(model)
     B, N = args.batch, args.points
     p_host, g_host = synth_inputs(B, N, G_LATENT, rank, pin=True)
     p_dev, g_dev = p_host.to(dev), g_host.to(dev).requires_grad_(True)
@@ -334,7 +335,7 @@ def run_ours(args):
     line = {
         "metric": "decoder points/s (train fwd+bwd)", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if precision.startswith("bf16") else "f32",
         "data": "synthetic", "config": workload_config(args, precision),
         "e2e": {"value": e2e_val, "unit": "points/s", "h2d_bytes_per_step": p_host.numel() * 4 + g_host.numel() * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "loss": loss_val},

@@ -62,7 +62,7 @@ struct DecoderWorkspace {
   float* dfilm;       // [L][4][B][F]   backward: ds_raw_mu, dt_mu, ds_raw_lv, dt_lv
   double* bna_sums;   // [L][2][F][4]   backward: dbeta, E0, E1, pad
   float* dx[2];       // [B][3][N]      ping-pong stored input gradients
-  unsigned short* w1_bf16;  // [L][2][2][F*F] bf16 W1 / W1^T images in UMMA smem layout (tensor path)
+  unsigned short* w1_bf16;  // [L][2][3][F*F] bf16 images {W1 hi, W1^T hi, W1 lo} in UMMA smem layout (tensor path)
   size_t bytes;
 };
 
@@ -80,7 +80,7 @@ __host__ inline DecoderWorkspace carve_workspace(void* base, int L, int G, int B
   w.bna_sums = (double*)take(sizeof(double) * (size_t)L * 2 * DPF_F * 4);
   w.dx[0] = (float*)take(sizeof(float) * (size_t)B * 3 * N);
   w.dx[1] = (float*)take(sizeof(float) * (size_t)B * 3 * N);
-  w.w1_bf16 = (unsigned short*)take(sizeof(unsigned short) * (size_t)L * 4 * DPF_F * DPF_F);
+  w.w1_bf16 = (unsigned short*)take(sizeof(unsigned short) * (size_t)L * 6 * DPF_F * DPF_F);
   w.bytes = off;
   (void)G;
   return w;

@@ -1,0 +1,901 @@
+// Tensor-core (tcgen05 / TMEM) kernels of the conditional coupling stack - the BF16 path.
+//
+// Tile = 128 consecutive points of one shape = the 128 TMEM lanes of one CTA (thread t owns point
+// t and TMEM lane t).  Per tile and branch the 64x64 SharedDot is a UMMA chain
+//     D[128 x 64] (TMEM, fp32) = H1[128 x 64] (smem, bf16, K-major SW128) x W1^T (smem, bf16)
+// whose A operand the CUDA cores produce in place (first SharedDot + folded BN_a + ReLU -> bf16 ->
+// swizzled st.shared), and whose accumulator row each thread reads back with tcgen05.ld for the
+// fused epilogue (BN_b x FiLM fold, ReLU, last SharedDot, softsign, exp, sqrt, affine transform,
+// log-det output) - no activation ever goes to HBM.  Weight images (pre-swizzled bf16, packed per
+// step by pack_w1_kernel) are staged with TMA bulk copies (cp.async.bulk + mbarrier).
+//
+// SPLIT (precision "bf16x3"): both operands are carried as bf16 hi + bf16 lo and the product is
+// accumulated from three chains hi*hi + lo*hi + hi*lo (fp32-class accuracy, ~2^-17 per operand).
+// Train-mode BatchNorm divides by small batch deviations and amplifies single-bf16 rounding beyond
+// the 2e-2 budget (measured: tests/test_decoder_gpu.py), so training defaults to SPLIT; plain
+// "bf16" stays available (sampling / eval: ~1e-3).
+//
+// Backward pass 2 chains three UMMAs per tile: the forward recompute, dgrad
+//     DH1[128 x 64] = DH2[128 x 64] x W1          (K-major operands, W1^T image)
+// and wgrad accumulated in TMEM across all tiles of the CTA
+//     DW1[c, j] += sum_p DH2[p, c] * H1[p, j]      (the SAME smem tiles read as MN-major operands).
+// Per-channel reductions over points (BN statistics, FiLM / BN / W2 gradients) go through a
+// shared-memory transpose (colreduce) instead of warp shuffles.
+#include "coupling.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int F = DPF_F;
+constexpr uint32_t IMG_W = F * F * 2;           // 8 KB  : one 64x64 bf16 weight image
+constexpr uint32_t IMG_H = DPF_TILE * F * 2;    // 16 KB : one 128x64 bf16 activation tile
+constexpr int N_IMG = 3;                         // weight images per (layer, branch): W1 hi, W1^T hi, W1 lo
+constexpr uint64_t DESC_K = umma::make_desc_template(16, 1024, umma::LAYOUT_SW128);        // K-major SW128
+constexpr uint64_t DESC_MN = umma::make_desc_template(IMG_H, 1024, umma::LAYOUT_SW128);    // MN-major, 64-blocks IMG_H apart
+constexpr uint32_t IDESC_GEMM = umma::make_idesc_bf16(128, 64, 0, 0);
+constexpr uint32_t IDESC_WGRAD = umma::make_idesc_bf16(128, 128, 1, 1);
+
+__device__ __forceinline__ float pick3(const float v[3], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing: fp32 W1 (arena) -> bf16 128B-swizzled images per (layer, branch)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_w1_kernel(const float* __restrict__ arena, const LayerMeta* __restrict__ meta, int G, unsigned short* __restrict__ out) {
+  const int l = blockIdx.x >> 1, br = blockIdx.x & 1;
+  const LayerMeta m = meta[l];
+  const BranchLayout lay = branch_layout((int)m.k, (int)m.w, G);
+  const float* W1 = arena + m.param_off + (size_t)br * lay.size + lay.W1;
+  unsigned char* img = reinterpret_cast<unsigned char*>(out) + (size_t)(l * 2 + br) * N_IMG * IMG_W;
+  for (int e = threadIdx.x; e < N_IMG * F * 8; e += 256) {
+    const int t = e / (F * 8), r = (e / 8) % F, q = e & 7;   // image t (0: W1 hi, 1: W1^T hi, 2: W1 lo), row r, chunk q
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = q * 8 + 2 * i;
+      float lo = t == 1 ? W1[c0 * F + r] : W1[r * F + c0];
+      float hi = t == 1 ? W1[(c0 + 1) * F + r] : W1[r * F + c0 + 1];
+      if (t == 2) {   // residual of the bf16 rounding: W1 = hi + lo to ~2^-17
+        lo -= __bfloat162float(__float2bfloat16_rn(lo));
+        hi -= __bfloat162float(__float2bfloat16_rn(hi));
+      }
+      w[i] = umma::pack_bf16(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(img + t * IMG_W + umma::sw128_offset(r, q)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared building blocks
+// ---------------------------------------------------------------------------------------------
+struct TcCommon {                       // small per-CTA tables (after the 1024-aligned image area)
+  float4 A0[2][F];                      // folded BN_a: {A00, A01, c0, -}
+  float4 epi[2][F];                     // per tile: {S, T, W2_0, W2_1},  a = S*acc + T
+  float mb[2][F], ib[2][F], sraw[2][F];
+  float W2[2][2][F];
+  float b2[2][2];
+  double pend[20];
+  uint64_t bar_mma, bar_load;
+  uint32_t tmem_base;
+};
+
+// this thread's h1 row of one branch -> row `tid` of the swizzled K-major bf16 tile(s):
+// hi = bf16(h1); with SPLIT also lo = bf16(h1 - hi)
+template <int K, bool SPLIT>
+__device__ __forceinline__ void write_h1_row(unsigned char* tile_hi, unsigned char* tile_lo, const float4* A0, float xk0,
+                                             float xk1, int tid) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint32_t w[4], wl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 Aa = A0[q * 8 + 2 * i], Ab = A0[q * 8 + 2 * i + 1];
+      float va = fmaf(Aa.x, xk0, Aa.z), vb = fmaf(Ab.x, xk0, Ab.z);
+      if (K == 2) { va = fmaf(Aa.y, xk1, va); vb = fmaf(Ab.y, xk1, vb); }
+      va = fmaxf(va, 0.f);
+      vb = fmaxf(vb, 0.f);
+      w[i] = umma::pack_bf16(va, vb);
+      if (SPLIT) {
+        const float ra = va - __uint_as_float(w[i] << 16);
+        const float rb = vb - __uint_as_float(w[i] & 0xffff0000u);
+        wl[i] = umma::pack_bf16(ra, rb);
+      }
+    }
+    const uint32_t off = umma::sw128_offset(tid, q);
+    *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (SPLIT) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+  }
+}
+
+// forward UMMA chain of ONE branch into TMEM columns [tcol, tcol+64): K = 64 in 4 steps,
+// SPLIT: hi*hi + lo*hi + hi*lo
+template <bool SPLIT>
+__device__ __forceinline__ void issue_gemm1(uint32_t tcol, const unsigned char* Hhi, const unsigned char* Hlo,
+                                            const unsigned char* Whi, const unsigned char* Wlo) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma::mma_bf16(tcol, umma::desc_at(DESC_K, umma::smem_u32(Hhi) + 32 * k), umma::desc_at(DESC_K, umma::smem_u32(Whi) + 32 * k),
+                   IDESC_GEMM, k > 0);
+  if (SPLIT) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma::mma_bf16(tcol, umma::desc_at(DESC_K, umma::smem_u32(Hlo) + 32 * k), umma::desc_at(DESC_K, umma::smem_u32(Whi) + 32 * k),
+                     IDESC_GEMM, 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma::mma_bf16(tcol, umma::desc_at(DESC_K, umma::smem_u32(Hhi) + 32 * k), umma::desc_at(DESC_K, umma::smem_u32(Wlo) + 32 * k),
+                     IDESC_GEMM, 1u);
+  }
+}
+
+// Column sums over the 128 rows of the tile for 32 columns x 2 quantities: thread t returns the
+// partial over rows [32*(t/32), 32*(t/32)+32) of column (t%32).  scratch = float[2][128][33].
+__device__ __forceinline__ void colreduce32x2(float* scratch, const float va[32], const float vb[32], int tid, float& ra, float& rb) {
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    scratch[tid * 33 + i] = va[i];
+    scratch[DPF_TILE * 33 + tid * 33 + i] = vb[i];
+  }
+  __syncthreads();
+  const int col = tid & 31, r0 = (tid >> 5) * 32;
+  float sa = 0.f, sb = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    sa += scratch[(r0 + r) * 33 + col];
+    sb += scratch[DPF_TILE * 33 + (r0 + r) * 33 + col];
+  }
+  ra = sa;
+  rb = sb;
+}
+
+// sum and sum of squares of ONE quantity (scratch = float[128][33])
+__device__ __forceinline__ void colreduce32_sq(float* scratch, const float va[32], int tid, float& rs, float& rq) {
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) scratch[tid * 33 + i] = va[i];
+  __syncthreads();
+  const int col = tid & 31, r0 = (tid >> 5) * 32;
+  float sa = 0.f, sb = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    const float v = scratch[(r0 + r) * 33 + col];
+    sa += v;
+    sb = fmaf(v, v, sb);
+  }
+  rs = sa;
+  rq = sb;
+}
+
+__device__ __forceinline__ void tc_prologue_tables(const CouplingArgs& a, const BranchLayout& lay, TcCommon& s, bool writer, bool need_bnb) {
+  const int tid = threadIdx.x, br = tid >> 6, c = tid & 63;
+  float A00, A01, c0;
+  fold_bn_a(a, lay, br, c, writer, A00, A01, c0, nullptr, nullptr);
+  s.A0[br][c] = make_float4(A00, A01, c0, 0.f);
+  if (need_bnb) {
+    float mean, istd;
+    bn_b_stats(a, br, c, writer, mean, istd);
+    s.mb[br][c] = mean;
+    s.ib[br][c] = istd;
+    const float* prm = a.prm + (size_t)br * lay.size;
+    s.W2[br][0][c] = prm[lay.W2 + c];
+    s.W2[br][1][c] = (a.w == 2) ? prm[lay.W2 + F + c] : 0.f;
+    if (c < 2) s.b2[br][c] = (c < a.w) ? prm[lay.b2 + c] : 0.f;
+  }
+}
+
+__device__ __forceinline__ void tc_tile_film(const CouplingArgs& a, TcCommon& s, int b) {
+  const int tid = threadIdx.x, br = tid >> 6, c = tid & 63;
+  const float sc = a.film[((size_t)(br * 2 + 0) * a.B + b) * F + c];
+  const float sh = a.film[((size_t)(br * 2 + 1) * a.B + b) * F + c];
+  const float S = sc * s.ib[br][c];
+  s.sraw[br][c] = sc;
+  s.epi[br][c] = make_float4(S, fmaf(-S, s.mb[br][c], sh), s.W2[br][0][c], s.W2[br][1][c]);
+}
+
+// CTA setup: barriers and TMEM allocation (the weight images are TMA-bulk-loaded by the caller).
+__device__ __forceinline__ uint32_t tc_setup(TcCommon& s, uint32_t tmem_cols) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    umma::mbar_init(&s.bar_mma, 1);
+    umma::mbar_init(&s.bar_load, 1);
+    umma::mbar_fence_init();
+  }
+  if ((tid >> 5) == 0) umma::tmem_alloc(&s.tmem_base, tmem_cols);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  return s.tmem_base;
+}
+
+// TMA bulk load of this layer's weight images: all N_IMG images of both branches, contiguous.
+__device__ __forceinline__ void tc_load_weights(TcCommon& s, unsigned char* W, const unsigned short* wimg) {
+  if (threadIdx.x == 0) {
+    umma::mbar_expect_tx(&s.bar_load, 2 * N_IMG * IMG_W);
+    umma::bulk_g2s(W, wimg, 2 * N_IMG * IMG_W, &s.bar_load);
+  }
+}
+// image t of branch br inside the staged block
+__device__ __forceinline__ const unsigned char* wimg_at(const unsigned char* W, int br, int t) { return W + (br * N_IMG + t) * IMG_W; }
+
+__device__ __forceinline__ void tile_range(int n_tiles, int& t0, int& t1) {   // contiguous tiles per CTA
+  const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  t0 = blockIdx.x * per;
+  t1 = min(n_tiles, t0 + per);
+}
+
+// =============================================================================================
+// Forward: STATS (BN_b batch statistics) or APPLY.  Branches are processed one after the other so
+// that a single pair of (hi, lo) activation tiles is live: 2 CTAs per SM.
+// =============================================================================================
+struct TcFwdSmem {
+  unsigned char W[2 * N_IMG * IMG_W];   // 48 KB
+  unsigned char H[2 * IMG_H];           // hi, lo tile of the branch in flight (32 KB)
+  TcCommon c;
+  float scratch[DPF_TILE * 33];
+  float fin[2][2 * F];
+  double mom[9][4];
+};
+
+template <int K, int MODE, bool STATS, bool SPLIT>
+__global__ void __launch_bounds__(DPF_TILE)
+coupling_fwd_tc_kernel(const CouplingArgs a, const unsigned short* __restrict__ wimg) {
+  extern __shared__ unsigned char smraw[];
+  TcFwdSmem& s = *reinterpret_cast<TcFwdSmem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const BranchLayout lay = branch_layout(a.k, a.w, a.G);
+  const bool writer = (blockIdx.x == 0) && a.update_stats && !STATS;
+  const uint32_t tmem = tc_setup(s.c, 128);
+  tc_load_weights(s.c, s.W, wimg);
+  tc_prologue_tables(a, lay, s.c, writer, !STATS);
+  float sacc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sacc[i][0] = sacc[i][1] = 0.f;
+  float macc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) macc[i] = 0.f;
+  umma::mbar_wait(&s.c.bar_load, 0);
+  __syncthreads();
+
+  int t0, t1;
+  tile_range(a.n_tiles, t0, t1);
+  uint32_t phase = 0;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int tile = t0; tile < t1; ++tile) {
+    const int b = tile / a.tiles_per_b;
+    const int n = (tile - b * a.tiles_per_b) * DPF_TILE + tid;
+    const bool valid = n < a.N;
+    if (!STATS) tc_tile_film(a, s.c, b);
+    const float* px = a.x + (size_t)b * 3 * a.N + n;
+    float xin[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) xin[ch] = valid ? px[(size_t)ch * a.N] : 0.f;
+    const float xk0 = pick3(xin, a.keep0);
+    const float xk1 = (K == 2) ? pick3(xin, a.keep1) : 0.f;
+    float o[2][2];
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      write_h1_row<K, SPLIT>(s.H, s.H + IMG_H, s.c.A0[br], xk0, xk1, tid);
+      umma::fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        issue_gemm1<SPLIT>(tmem + br * F, s.H, s.H + IMG_H, wimg_at(s.W, br, 0), wimg_at(s.W, br, 2));
+        umma::mma_commit(&s.c.bar_mma);
+      }
+      umma::mbar_wait(&s.c.bar_mma, phase);
+      phase ^= 1;
+      umma::fence_after_sync();
+      if (STATS) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          umma::tmem_ld32(lane_addr + br * F + half * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] : 0.f;
+          float rs, rq;
+          colreduce32_sq(s.scratch, v, tid, rs, rq);
+          sacc[br * 2 + half][0] += rs;
+          sacc[br * 2 + half][1] += rq;
+        }
+      } else {
+        float o0 = s.c.b2[br][0], o1 = s.c.b2[br][1];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          umma::tmem_ld32(lane_addr + br * F + half * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 e = s.c.epi[br][half * 32 + i];
+            const float h3 = fmaxf(fmaf(e.x, v[i], e.y), 0.f);
+            o0 = fmaf(e.z, h3, o0);
+            o1 = fmaf(e.w, h3, o1);
+          }
+        }
+        o[br][0] = o0;
+        o[br][1] = o1;
+      }
+      umma::fence_before_sync();
+      __syncthreads();     // activation tiles, this branch's TMEM columns and (br == 1) the epi table are free again
+    }
+    if (!STATS) {
+      float yv[3], muv[3] = {0.f, 0.f, 0.f}, lvv[3] = {0.f, 0.f, 0.f};
+      const float sig1 = sqrtf(a.eps + 1.0f);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) yv[ch] = (MODE == 0) ? sig1 * xin[ch] : xin[ch] / sig1;
+#pragma unroll
+      for (int wi = 0; wi < 2; ++wi) {
+        if (wi < a.w) {
+          const int ch = wi == 0 ? a.warp0 : a.warp1;
+          const float l = softsign(o[1][wi]);
+          const float sig = sqrtf(a.eps + expf(l));
+          const float m = o[0][wi];
+          const float xv = pick3(xin, ch);
+          const float r = (MODE == 0) ? fmaf(sig, xv, m) : (xv - m) / sig;
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (q == ch) { yv[q] = r; muv[q] = m; lvv[q] = l; }
+        }
+      }
+      if (valid) {
+        const size_t base = (size_t)b * 3 * a.N + n;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          a.y[base + (size_t)ch * a.N] = yv[ch];
+          a.mu[base + (size_t)ch * a.N] = muv[ch];
+          a.lv[base + (size_t)ch * a.N] = lvv[ch];
+        }
+        macc[0] += yv[0]; macc[1] += yv[1]; macc[2] += yv[2];
+        macc[3] = fmaf(yv[0], yv[0], macc[3]); macc[4] = fmaf(yv[0], yv[1], macc[4]); macc[5] = fmaf(yv[0], yv[2], macc[5]);
+        macc[6] = fmaf(yv[1], yv[1], macc[6]); macc[7] = fmaf(yv[1], yv[2], macc[7]); macc[8] = fmaf(yv[2], yv[2], macc[8]);
+      }
+    }
+  }
+  if (STATS) {
+    // combine the 4 row-quarters of every column, then one double atomic per (branch, channel, stat)
+    float* fin = &s.fin[0][0];
+    for (int i = tid; i < 4 * F; i += DPF_TILE) fin[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      atomicAdd(&s.fin[0][ch * 32 + (tid & 31)], sacc[ch][0]);
+      atomicAdd(&s.fin[1][ch * 32 + (tid & 31)], sacc[ch][1]);
+    }
+    __syncthreads();
+    atomicAdd(&a.bnb_sums[tid * 2 + 0], (double)s.fin[0][tid]);   // tid == br*F + c
+    atomicAdd(&a.bnb_sums[tid * 2 + 1], (double)s.fin[1][tid]);
+  } else if (a.mom_out) {
+    const int lane = tid & 31;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double v = warp_sum_d((double)macc[i]);
+      if (lane == 0) s.mom[i][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 9) atomicAdd(a.mom_out + tid, s.mom[tid][0] + s.mom[tid][1] + s.mom[tid][2] + s.mom[tid][3]);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+}
+
+// =============================================================================================
+// Backward helpers (same math as coupling_bwd.cu)
+// =============================================================================================
+__device__ Pending tc_compute_pending(const BwdArgs& a, bool writer, double* red) {
+  Pending P{0.f, 0.f, 0.f, 0.f, 0.f};
+  if (!a.has_pending) return P;
+  const int tid = threadIdx.x, br = tid >> 6, c = tid & 63;
+  const BranchLayout nlay = branch_layout(a.nk, a.nw, a.f.G);
+  const double M = (double)a.f.B * (double)a.f.N;
+  const BnA bn = bn_a_of(a.nprm, a.nstat, nlay, a.n_mom, M, a.nk, a.nkeep0, a.nkeep1, a.f.training, br, c);
+  const double dbeta = a.n_bna_sums[(br * F + c) * 4 + 0];
+  const double E0 = a.n_bna_sums[(br * F + c) * 4 + 1];
+  const double E1 = a.n_bna_sums[(br * F + c) * 4 + 2];
+  const double istd = bn.istd, mean = bn.mean, w0 = bn.w0, w1 = bn.w1, gam = bn.gamma;
+  const double dgamma = istd * (w0 * E0 + w1 * E1 - mean * dbeta);
+  const double n1 = a.f.training ? gam * dbeta / M : 0.0;
+  const double n2 = a.f.training ? gam * dgamma / M : 0.0;
+  const double i2n2 = istd * istd * n2;
+  double v[5] = {w0 * istd * n1 - i2n2 * mean * w0, w1 * istd * n1 - i2n2 * mean * w1, i2n2 * w0 * w0, i2n2 * w0 * w1, i2n2 * w1 * w1};
+  if (writer) {
+    float* d = a.ndprm + (size_t)br * nlay.size;
+    d[nlay.bnA_b + c] = (float)dbeta;
+    d[nlay.bnA_w + c] = (float)dgamma;
+    double S1[2] = {0.0, 0.0}, S2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    if (a.f.training) {
+      S1[0] = a.n_mom[a.nkeep0];
+      S2[0][0] = a.n_mom[mom2_index(a.nkeep0, a.nkeep0)];
+      if (a.nk == 2) {
+        S1[1] = a.n_mom[a.nkeep1];
+        S2[0][1] = S2[1][0] = a.n_mom[mom2_index(a.nkeep0, a.nkeep1)];
+        S2[1][1] = a.n_mom[mom2_index(a.nkeep1, a.nkeep1)];
+      }
+    }
+    const double E[2] = {E0, E1};
+    for (int j = 0; j < a.nk; ++j) {
+      const double sx = istd * (w0 * S2[0][j] + w1 * S2[1][j] - mean * S1[j]);
+      d[nlay.W0 + c * a.nk + j] = (float)(istd * (gam * E[j] - n1 * S1[j] - n2 * sx));
+    }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const double sm = warp_sum_d(v[i]);
+    if (lane == 0) red[i * 4 + warp] = sm;
+  }
+  __syncthreads();
+  P.c0 = (float)(red[0] + red[1] + red[2] + red[3]);
+  P.c1 = (float)(red[4] + red[5] + red[6] + red[7]);
+  P.q00 = (float)(red[8] + red[9] + red[10] + red[11]);
+  P.q01 = (float)(red[12] + red[13] + red[14] + red[15]);
+  P.q11 = (float)(red[16] + red[17] + red[18] + red[19]);
+  __syncthreads();
+  return P;
+}
+
+struct TcPoint { float x[3], dy[3], sig[2], do_mu[2], do_lv[2]; };
+
+template <int MODE>
+__device__ __forceinline__ TcPoint tc_load_point(const BwdArgs& a, const Pending& P, int b, int n, bool valid) {
+  TcPoint g;
+  const int N = a.f.N;
+  const size_t base = (size_t)b * 3 * N + n;
+  float y[3], lv[3], dmu[3], dlv[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const size_t o = base + (size_t)ch * N;
+    g.x[ch] = valid ? a.f.x[o] : 0.f;
+    y[ch] = valid ? a.yv[o] : 0.f;
+    lv[ch] = valid ? a.lvv[o] : 0.f;
+    float d = 0.f;
+    if (valid && a.dy_chain) d += a.dy_chain[o];
+    if (valid && a.dP) d += a.dP[o];
+    g.dy[ch] = d;
+    dmu[ch] = (valid && a.dMU) ? a.dMU[o] : 0.f;
+    dlv[ch] = (valid && a.dLV) ? a.dLV[o] : 0.f;
+  }
+  if (a.has_pending && valid) {
+    const float y0 = pick3(y, a.nkeep0);
+    const float y1 = a.nk == 2 ? pick3(y, a.nkeep1) : 0.f;
+    const float corr0 = P.c0 + P.q00 * y0 + P.q01 * y1;
+    const float corr1 = P.c1 + P.q01 * y0 + P.q11 * y1;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if (ch == a.nkeep0) g.dy[ch] -= corr0;
+      if (a.nk == 2 && ch == a.nkeep1) g.dy[ch] -= corr1;
+    }
+  }
+#pragma unroll
+  for (int wi = 0; wi < 2; ++wi) {
+    g.sig[wi] = 1.f; g.do_mu[wi] = 0.f; g.do_lv[wi] = 0.f;
+    if (wi < a.f.w) {
+      const int ch = wi == 0 ? a.f.warp0 : a.f.warp1;
+      const float l = pick3(lv, ch), dyv = pick3(g.dy, ch);
+      const float e = expf(l);
+      const float s2 = a.f.eps + e;
+      const float sg = sqrtf(s2);
+      g.sig[wi] = sg;
+      float dm, dl;
+      if (MODE == 1) {
+        dm = -dyv / sg;
+        dl = -dyv * pick3(y, ch) * e / (2.f * s2);
+      } else {
+        dm = dyv;
+        dl = dyv * pick3(g.x, ch) * e / (2.f * sg);
+      }
+      dm += pick3(dmu, ch);
+      dl += pick3(dlv, ch);
+      const float om = 1.f - fabsf(l);
+      g.do_mu[wi] = valid ? dm : 0.f;
+      g.do_lv[wi] = valid ? dl * om * om : 0.f;
+    }
+  }
+  return g;
+}
+
+// =============================================================================================
+// Backward pass 1: FiLM sums (dt, ds), dW2, db2
+// =============================================================================================
+struct TcP1Smem {
+  unsigned char W[2 * N_IMG * IMG_W];
+  unsigned char H[2 * IMG_H];
+  TcCommon c;
+  float scratch[2 * DPF_TILE * 33];
+  float fin[4][2 * F];          // dt, ds (per shape) ; dW2_0, dW2_1 (per CTA)
+  float b2fin[2][2];
+};
+
+template <int K, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(DPF_TILE)
+coupling_bwd_p1_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wimg) {
+  extern __shared__ unsigned char smraw[];
+  TcP1Smem& s = *reinterpret_cast<TcP1Smem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
+  const uint32_t tmem = tc_setup(s.c, 128);
+  tc_load_weights(s.c, s.W, wimg);
+  tc_prologue_tables(a.f, lay, s.c, false, true);
+  for (int i = tid; i < 4 * 2 * F; i += DPF_TILE) (&s.fin[0][0])[i] = 0.f;
+  if (tid < 4) (&s.b2fin[0][0])[tid] = 0.f;
+  __syncthreads();
+  const Pending P = tc_compute_pending(a, blockIdx.x == 0, s.c.pend);
+  float acc_t[4], acc_s[4], acc_w0[4], acc_w1[4];   // per chunk (branch, half); column = lane, row-quarter = warp
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc_t[i] = acc_s[i] = acc_w0[i] = acc_w1[i] = 0.f;
+  float b2acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  umma::mbar_wait(&s.c.bar_load, 0);
+  __syncthreads();
+
+  int t0, t1;
+  tile_range(a.f.n_tiles, t0, t1);
+  uint32_t phase = 0;
+  int cur_b = -1;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  auto flush_film = [&](int b) {   // dt / ds of shape b -> global (all threads)
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      atomicAdd(&s.fin[0][ch * 32 + lane], acc_t[ch]);
+      atomicAdd(&s.fin[1][ch * 32 + lane], acc_s[ch]);
+      acc_t[ch] = acc_s[ch] = 0.f;
+    }
+    __syncthreads();
+    const int br = tid >> 6, c = tid & 63;
+    atomicAdd(&a.dfilm[((size_t)(br * 2 + 0) * a.f.B + b) * F + c], s.fin[1][tid]);   // ds_raw
+    atomicAdd(&a.dfilm[((size_t)(br * 2 + 1) * a.f.B + b) * F + c], s.fin[0][tid]);   // dt
+    s.fin[0][tid] = 0.f;
+    s.fin[1][tid] = 0.f;
+  };
+  for (int tile = t0; tile < t1; ++tile) {
+    const int b = tile / a.f.tiles_per_b;
+    const int n = (tile - b * a.f.tiles_per_b) * DPF_TILE + tid;
+    const bool valid = n < a.f.N;
+    if (b != cur_b) {
+      if (cur_b >= 0) flush_film(cur_b);
+      cur_b = b;
+    }
+    tc_tile_film(a.f, s.c, b);
+    const TcPoint g = tc_load_point<MODE>(a, P, b, n, valid);
+    const float xk0 = pick3(g.x, a.f.keep0);
+    const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      write_h1_row<K, SPLIT>(s.H, s.H + IMG_H, s.c.A0[br], xk0, xk1, tid);
+      umma::fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        issue_gemm1<SPLIT>(tmem + br * F, s.H, s.H + IMG_H, wimg_at(s.W, br, 0), wimg_at(s.W, br, 2));
+        umma::mma_commit(&s.c.bar_mma);
+      }
+      umma::mbar_wait(&s.c.bar_mma, phase);
+      phase ^= 1;
+      umma::fence_after_sync();
+      const float d0 = br == 0 ? g.do_mu[0] : g.do_lv[0];
+      const float d1 = br == 0 ? g.do_mu[1] : g.do_lv[1];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int ch = br * 2 + half;
+        float v[32], q1[32], q2[32];
+        umma::tmem_ld32(lane_addr + ch * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = half * 32 + i;
+          const float4 e = s.c.epi[br][c];
+          const float h2n = (v[i] - s.c.mb[br][c]) * s.c.ib[br][c];
+          const float av = fmaf(e.x, v[i], e.y);
+          const float da = av > 0.f ? fmaf(e.z, d0, e.w * d1) : 0.f;
+          q1[i] = da;
+          q2[i] = da * h2n;
+          v[i] = fmaxf(av, 0.f);            // h3
+        }
+        float ra, rb;
+        colreduce32x2(s.scratch, q1, q2, tid, ra, rb);
+        acc_t[ch] += ra;
+        acc_s[ch] += rb;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          q1[i] = d0 * v[i];
+          q2[i] = d1 * v[i];
+        }
+        colreduce32x2(s.scratch, q1, q2, tid, ra, rb);
+        acc_w0[ch] += ra;
+        acc_w1[ch] += rb;
+      }
+      umma::fence_before_sync();
+      __syncthreads();
+    }
+    b2acc[0][0] += g.do_mu[0]; b2acc[0][1] += g.do_mu[1];
+    b2acc[1][0] += g.do_lv[0]; b2acc[1][1] += g.do_lv[1];
+  }
+  if (cur_b >= 0) flush_film(cur_b);
+  __syncthreads();
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    atomicAdd(&s.fin[2][ch * 32 + lane], acc_w0[ch]);
+    atomicAdd(&s.fin[3][ch * 32 + lane], acc_w1[ch]);
+  }
+#pragma unroll
+  for (int br = 0; br < 2; ++br)
+#pragma unroll
+    for (int wi = 0; wi < 2; ++wi) {
+      const float v = warp_sum(b2acc[br][wi]);
+      if (lane == 0) atomicAdd(&s.b2fin[br][wi], v);
+    }
+  __syncthreads();
+  {
+    const int br = tid >> 6, c = tid & 63;
+    float* d = a.dprm + (size_t)br * lay.size;
+    atomicAdd(&d[lay.W2 + c], s.fin[2][tid]);
+    if (a.f.w == 2) atomicAdd(&d[lay.W2 + F + c], s.fin[3][tid]);
+    if (c < a.f.w) atomicAdd(&d[lay.b2 + c], s.b2fin[br][c]);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+}
+
+// =============================================================================================
+// Backward pass 2: BN_b backward, dgrad, wgrad (TMEM-resident across tiles), BN_a sums, dx.
+// Both branches' h1 (hi) and dh2pre tiles are live together: wgrad reads them as one MN-major
+// operand of width 128.  The h1 lo tiles alias the dh2pre tiles (dead once the recompute is done).
+// =============================================================================================
+struct TcP2Smem {
+  unsigned char W[2 * N_IMG * IMG_W];   // [br][W1 hi, W1^T hi, W1 lo]
+  unsigned char H[2 * IMG_H];           // h1 hi tiles (mu, logvar) - contiguous: MN-major N = 128 for wgrad
+  unsigned char D[2 * IMG_H];           // h1 lo tiles during the recompute, then dh2pre tiles (MN-major M = 128)
+  TcCommon c;
+  float m1[2][F], m2[2][F];
+  float scratch[2 * DPF_TILE * 33];
+  float fin[3][2 * F];
+};
+
+template <int K, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(DPF_TILE)
+coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wimg) {
+  extern __shared__ unsigned char smraw[];
+  TcP2Smem& s = *reinterpret_cast<TcP2Smem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
+  const uint32_t tmem = tc_setup(s.c, 512);
+  tc_load_weights(s.c, s.W, wimg);
+  tc_prologue_tables(a.f, lay, s.c, false, true);
+  {
+    const int br = tid >> 6, c = tid & 63;
+    float m1 = 0.f, m2 = 0.f;
+    if (a.f.training) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int b = 0; b < a.f.B; ++b) {
+        const double sc = a.f.film[((size_t)(br * 2 + 0) * a.f.B + b) * F + c];
+        s1 += sc * (double)a.dfilm[((size_t)(br * 2 + 1) * a.f.B + b) * F + c];
+        s2 += sc * (double)a.dfilm[((size_t)(br * 2 + 0) * a.f.B + b) * F + c];
+      }
+      const double M = (double)a.f.B * (double)a.f.N;
+      m1 = (float)(s1 / M);
+      m2 = (float)(s2 / M);
+    }
+    s.m1[br][c] = m1;
+    s.m2[br][c] = m2;
+  }
+  for (int i = tid; i < 3 * 2 * F; i += DPF_TILE) (&s.fin[0][0])[i] = 0.f;
+  __syncthreads();
+  const Pending P = tc_compute_pending(a, false, s.c.pend);
+  const float sig1 = sqrtf(a.f.eps + 1.0f);
+  float acc_b[4], acc_e0[4], acc_e1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc_b[i] = acc_e0[i] = acc_e1[i] = 0.f;
+  umma::mbar_wait(&s.c.bar_load, 0);
+  __syncthreads();
+
+  int t0, t1;
+  tile_range(a.f.n_tiles, t0, t1);
+  uint32_t phase = 0;
+  const uint32_t T_FWD = tmem, T_DG = tmem + 128, T_WG = tmem + 256;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  for (int tile = t0; tile < t1; ++tile) {
+    const int b = tile / a.f.tiles_per_b;
+    const int n = (tile - b * a.f.tiles_per_b) * DPF_TILE + tid;
+    const bool valid = n < a.f.N;
+    tc_tile_film(a.f, s.c, b);
+    const TcPoint g = tc_load_point<MODE>(a, P, b, n, valid);
+    const float xk0 = pick3(g.x, a.f.keep0);
+    const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
+    write_h1_row<K, SPLIT>(s.H, s.D, s.c.A0[0], xk0, xk1, tid);
+    write_h1_row<K, SPLIT>(s.H + IMG_H, s.D + IMG_H, s.c.A0[1], xk0, xk1, tid);
+    umma::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+      issue_gemm1<SPLIT>(T_FWD, s.H, s.D, wimg_at(s.W, 0, 0), wimg_at(s.W, 0, 2));
+      issue_gemm1<SPLIT>(T_FWD + F, s.H + IMG_H, s.D + IMG_H, wimg_at(s.W, 1, 0), wimg_at(s.W, 1, 2));
+      umma::mma_commit(&s.c.bar_mma);
+    }
+    umma::mbar_wait(&s.c.bar_mma, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+    // ---- epilogue A: dh2pre (bf16) -> D tiles (the lo tiles are dead now) ----
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int br = ch >> 1, half = ch & 1;
+      const float d0 = br == 0 ? g.do_mu[0] : g.do_lv[0];
+      const float d1 = br == 0 ? g.do_mu[1] : g.do_lv[1];
+      float v[32];
+      umma::tmem_ld32(T_FWD + lane_off + ch * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int c = half * 32 + i;
+        const float4 e = s.c.epi[br][c];
+        const float h2n = (v[i] - s.c.mb[br][c]) * s.c.ib[br][c];
+        const float av = fmaf(e.x, v[i], e.y);
+        const float da = av > 0.f ? fmaf(e.z, d0, e.w * d1) : 0.f;
+        const float dh = s.c.ib[br][c] * (da * s.c.sraw[br][c] - s.m1[br][c] - h2n * s.m2[br][c]);
+        v[i] = valid ? dh : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                    umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+        *reinterpret_cast<uint4*>(s.D + br * IMG_H + umma::sw128_offset(tid, half * 4 + q)) = pk;
+      }
+    }
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+      // dgrad: DH1[br] = DH2[br] (K-major, K = c) x W1^T image (rows j, K = c)
+#pragma unroll
+      for (int br = 0; br < 2; ++br)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma::mma_bf16(T_DG + br * F, umma::desc_at(DESC_K, umma::smem_u32(s.D + br * IMG_H) + 32 * k),
+                         umma::desc_at(DESC_K, umma::smem_u32(wimg_at(s.W, br, 1)) + 32 * k), IDESC_GEMM, k > 0);
+      // wgrad: [c_mu | c_lv] x [j_mu | j_lv] += sum over the tile's 128 points (MN-major views, K = 16 rows per step)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma::mma_bf16(T_WG, umma::desc_at(DESC_MN, umma::smem_u32(s.D) + 2048 * k), umma::desc_at(DESC_MN, umma::smem_u32(s.H) + 2048 * k),
+                       IDESC_WGRAD, (tile > t0 || k > 0) ? 1u : 0u);
+      umma::mma_commit(&s.c.bar_mma);
+    }
+    umma::mbar_wait(&s.c.bar_mma, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+    // ---- epilogue B: dz, T1, BN_a sums ----
+    float T1_0 = 0.f, T1_1 = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int br = ch >> 1, half = ch & 1;
+      float v[32], q1[32], q2[32];
+      umma::tmem_ld32(T_DG + lane_off + ch * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float4 A = s.c.A0[br][half * 32 + i];
+        float z = fmaf(A.x, xk0, A.z);
+        if (K == 2) z = fmaf(A.y, xk1, z);
+        const float dz = (z > 0.f && valid) ? v[i] : 0.f;
+        T1_0 = fmaf(A.x, dz, T1_0);
+        if (K == 2) T1_1 = fmaf(A.y, dz, T1_1);
+        v[i] = dz;
+        q1[i] = dz * xk0;
+        q2[i] = dz * xk1;
+      }
+      float ra, rb;
+      colreduce32x2(s.scratch, v, q1, tid, ra, rb);
+      acc_b[ch] += ra;
+      acc_e0[ch] += rb;
+      if (K == 2) {
+        colreduce32x2(s.scratch, q2, q2, tid, ra, rb);
+        acc_e1[ch] += ra;
+      }
+    }
+    if (valid) {
+      float dx[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) dx[ch] = (MODE == 1) ? g.dy[ch] / sig1 : g.dy[ch] * sig1;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        if (ch == a.f.keep0) dx[ch] += T1_0;
+        if (K == 2 && ch == a.f.keep1) dx[ch] += T1_1;
+        if (ch == a.f.warp0) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[0] : g.dy[ch] * g.sig[0];
+        if (K == 1 && ch == a.f.warp1) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[1] : g.dy[ch] * g.sig[1];
+      }
+      const size_t base = (size_t)b * 3 * a.f.N + n;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) a.dx_out[base + (size_t)ch * a.f.N] = dx[ch];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+  }
+  // ---- CTA epilogue: BN_a sums and the TMEM-resident wgrad accumulator ----
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    atomicAdd(&s.fin[0][ch * 32 + lane], acc_b[ch]);
+    atomicAdd(&s.fin[1][ch * 32 + lane], acc_e0[ch]);
+    atomicAdd(&s.fin[2][ch * 32 + lane], acc_e1[ch]);
+  }
+  __syncthreads();
+  atomicAdd(&a.bna_sums[tid * 4 + 0], (double)s.fin[0][tid]);
+  atomicAdd(&a.bna_sums[tid * 4 + 1], (double)s.fin[1][tid]);
+  atomicAdd(&a.bna_sums[tid * 4 + 2], (double)s.fin[2][tid]);
+  if (t1 > t0) {
+    // accumulator row = tid: rows 0..63 -> branch mu channel c = tid, its dW1 row lives in columns 0..63;
+    // rows 64..127 -> branch logvar channel c = tid-64, columns 64..127 (off-diagonal blocks are unused)
+    const int br = tid >> 6, c = tid & 63;
+    float* d = a.dprm + (size_t)br * lay.size + lay.W1 + c * F;
+    umma::fence_after_sync();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float v[32];
+      umma::tmem_ld32(T_WG + lane_off + br * F + half * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(&d[half * 32 + i], v[i]);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+template <typename T>
+inline size_t smem_for() { return sizeof(T) + 1024; }
+
+template <int K, int MODE, bool STATS, bool SPLIT>
+int launch_fwd_tc_t(const CouplingArgs& a, const unsigned short* wimg, int grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(coupling_fwd_tc_kernel<K, MODE, STATS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcFwdSmem>());
+    attr = true;
+  }
+  coupling_fwd_tc_kernel<K, MODE, STATS, SPLIT><<<grid, DPF_TILE, smem_for<TcFwdSmem>(), st>>>(a, wimg);
+  return dpf_check_launch("coupling_fwd_tc_kernel");
+}
+
+template <int K, int MODE, bool SPLIT>
+int launch_bwd_tc_t(const BwdArgs& a, const unsigned short* wimg, int pass, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(coupling_bwd_p1_tc_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP1Smem>());
+    cudaFuncSetAttribute(coupling_bwd_p2_tc_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP2Smem>());
+    attr = true;
+  }
+  if (pass == 1) {
+    const int grid = min(a.f.n_tiles, dpf_num_sms() * 2);
+    coupling_bwd_p1_tc_kernel<K, MODE, SPLIT><<<grid, DPF_TILE, smem_for<TcP1Smem>(), st>>>(a, wimg);
+    return dpf_check_launch("coupling_bwd_p1_tc_kernel");
+  }
+  const int grid = min(a.f.n_tiles, dpf_num_sms());
+  coupling_bwd_p2_tc_kernel<K, MODE, SPLIT><<<grid, DPF_TILE, smem_for<TcP2Smem>(), st>>>(a, wimg);
+  return dpf_check_launch("coupling_bwd_p2_tc_kernel");
+}
+
+template <int K, bool SPLIT>
+int launch_fwd_tc_k(const CouplingArgs& a, const unsigned short* wimg, int mode, bool stats_pass, int grid, cudaStream_t s) {
+  if (mode == 0) return stats_pass ? launch_fwd_tc_t<K, 0, true, SPLIT>(a, wimg, grid, s) : launch_fwd_tc_t<K, 0, false, SPLIT>(a, wimg, grid, s);
+  return stats_pass ? launch_fwd_tc_t<K, 1, true, SPLIT>(a, wimg, grid, s) : launch_fwd_tc_t<K, 1, false, SPLIT>(a, wimg, grid, s);
+}
+
+}  // namespace
+
+size_t tc_weight_image_elems_per_layer() { return (size_t)2 * N_IMG * F * F; }
+
+int launch_pack_w1(const float* arena, const LayerMeta* meta_dev, int L, int G, unsigned short* out, cudaStream_t s) {
+  pack_w1_kernel<<<L * 2, 256, 0, s>>>(arena, meta_dev, G, out);
+  return dpf_check_launch("pack_w1_kernel");
+}
+
+// wimg: this layer's images [br][W1 hi, W1^T hi, W1 lo][4096 bf16]; split != 0 = bf16x3
+int launch_coupling_fwd_tc(const CouplingArgs& a, const unsigned short* wimg, int mode, bool stats_pass, int split, cudaStream_t s) {
+  const int grid = min(a.n_tiles, dpf_num_sms() * 2);
+  if (a.k == 2) return split ? launch_fwd_tc_k<2, true>(a, wimg, mode, stats_pass, grid, s) : launch_fwd_tc_k<2, false>(a, wimg, mode, stats_pass, grid, s);
+  return split ? launch_fwd_tc_k<1, true>(a, wimg, mode, stats_pass, grid, s) : launch_fwd_tc_k<1, false>(a, wimg, mode, stats_pass, grid, s);
+}
+
+int launch_coupling_bwd_tc(const BwdArgs& a, const unsigned short* wimg, int mode, int pass, int split, cudaStream_t s) {
+  if (a.f.k == 2) {
+    if (split) return mode == 0 ? launch_bwd_tc_t<2, 0, true>(a, wimg, pass, s) : launch_bwd_tc_t<2, 1, true>(a, wimg, pass, s);
+    return mode == 0 ? launch_bwd_tc_t<2, 0, false>(a, wimg, pass, s) : launch_bwd_tc_t<2, 1, false>(a, wimg, pass, s);
+  }
+  if (split) return mode == 0 ? launch_bwd_tc_t<1, 0, true>(a, wimg, pass, s) : launch_bwd_tc_t<1, 1, true>(a, wimg, pass, s);
+  return mode == 0 ? launch_bwd_tc_t<1, 0, false>(a, wimg, pass, s) : launch_bwd_tc_t<1, 1, false>(a, wimg, pass, s);
+}

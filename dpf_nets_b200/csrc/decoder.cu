@@ -54,12 +54,15 @@ int launch_film_forward(const float* arena, float* stats, const LayerMeta* meta_
                         int L, int B, int G, int training, int update_stats, float eps, cudaStream_t s);
 int launch_moments(const float* x, int B, int N, double* mom, cudaStream_t s);
 int launch_coupling_fwd_fp32(const CouplingArgs& a, int mode, bool stats_pass, cudaStream_t s);
+int launch_pack_w1(const float* arena, const LayerMeta* meta_dev, int L, int G, unsigned short* out, cudaStream_t s);
+int launch_coupling_fwd_tc(const CouplingArgs& a, const unsigned short* wimg, int mode, bool stats_pass, int split, cudaStream_t s);
+size_t tc_weight_image_elems_per_layer();
 
 static int validate_common(const long long* meta_host, int L, int G, int B, int N, int mode, int precision) {
   DPF_REQUIRE(meta_host, DPF_ERR_NULL_PTR, "decoder: layer table is null");
   DPF_REQUIRE(L > 0 && G > 0 && B > 0 && N > 0, DPF_ERR_BAD_ARG, "decoder: L, G, B, N must be positive");
   DPF_REQUIRE(mode == 0 || mode == 1, DPF_ERR_BAD_ARG, "decoder: mode must be 0 (direct) or 1 (inverse)");
-  DPF_REQUIRE(precision == 0 || precision == 1, DPF_ERR_BAD_ARG, "decoder: precision must be 0 (fp32) or 1 (bf16 tensor)");
+  DPF_REQUIRE(precision >= 0 && precision <= 2, DPF_ERR_BAD_ARG, "decoder: precision must be 0 (fp32), 1 (bf16) or 2 (bf16x3)");
   for (int l = 0; l < L; ++l) {
     const LayerMeta& m = reinterpret_cast<const LayerMeta*>(meta_host)[l];
     DPF_REQUIRE((m.k == 1 && m.w == 2) || (m.k == 2 && m.w == 1), DPF_ERR_BAD_ARG, "decoder: layer %d has k=%lld w=%lld", l, m.k, m.w);
@@ -105,7 +108,6 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
               "dpf_decoder_forward: null pointer");
   DPF_REQUIRE(!training || B <= 256, DPF_ERR_UNSUPPORTED, "dpf_decoder_forward: train-mode FiLM BatchNorm supports B <= 256 (got %d)", B);
   DPF_REQUIRE(!training || ((long long)B * N > 1 && B > 1), DPF_ERR_BAD_ARG, "dpf_decoder_forward: BatchNorm in training mode needs more than 1 value per channel");
-  DPF_REQUIRE(precision == 0, DPF_ERR_UNSUPPORTED, "dpf_decoder_forward: bf16 tensor path not built yet");
   cudaStream_t s = (cudaStream_t)stream;
   const LayerMeta* meta = reinterpret_cast<const LayerMeta*>(meta_host);
   DecoderWorkspace ws = carve_workspace(workspace, L, G, B, N);
@@ -117,6 +119,10 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
                              update_stats, eps, s);
   }
   if (rc) return rc;
+  if (precision >= 1) {
+    rc = launch_pack_w1(arena, reinterpret_cast<const LayerMeta*>(meta_dev), L, G, ws.w1_bf16, s);
+    if (rc) return rc;
+  }
   if (training) {
     cudaMemsetAsync(ws.moments, 0, sizeof(double) * (size_t)(L + 1) * 16, s);
     cudaMemsetAsync(ws.bnb_sums, 0, sizeof(double) * (size_t)L * 2 * DPF_F * 2, s);
@@ -132,14 +138,15 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
     a.y = P_out + (size_t)l * plane;
     a.mu = MU + (size_t)l * plane;
     a.lv = LV + (size_t)l * plane;
+    const unsigned short* wimg = ws.w1_bf16 + (size_t)l * tc_weight_image_elems_per_layer();
     if (training) {
       ProfScope ps(CAT_FWD_STATS, s);
-      rc = launch_coupling_fwd_fp32(a, mode, true, s);
+      rc = precision >= 1 ? launch_coupling_fwd_tc(a, wimg, mode, true, precision == 2, s) : launch_coupling_fwd_fp32(a, mode, true, s);
       if (rc) return rc;
     }
     {
       ProfScope ps(CAT_FWD_APPLY, s);
-      rc = launch_coupling_fwd_fp32(a, mode, false, s);
+      rc = precision >= 1 ? launch_coupling_fwd_tc(a, wimg, mode, false, precision == 2, s) : launch_coupling_fwd_fp32(a, mode, false, s);
     }
     if (rc) return rc;
     x = a.y;
@@ -148,6 +155,7 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
 }
 
 int launch_coupling_bwd_fp32(const BwdArgs& a, int mode, int pass, cudaStream_t s);
+int launch_coupling_bwd_tc(const BwdArgs& a, const unsigned short* wimg, int mode, int pass, int split, cudaStream_t s);
 int launch_coupling_bwd_final(const BwdArgs& a, const float* p_in, const float* dx_stored, float* dp, cudaStream_t s);
 int launch_film_backward(const float* arena, const float* stats, float* darena, const LayerMeta* meta_dev,
                          const float* g, const float* film, const float* dfilm, float* dg, int L, int B, int G,
@@ -168,7 +176,6 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
   if (rc) return rc;
   DPF_REQUIRE(meta_dev && arena && stats && p && g && P_out && LV && darena && dg && workspace, DPF_ERR_NULL_PTR,
               "dpf_decoder_backward: null pointer");
-  DPF_REQUIRE(precision == 0, DPF_ERR_UNSUPPORTED, "dpf_decoder_backward: bf16 tensor path not built yet");
   cudaStream_t s = (cudaStream_t)stream;
   const LayerMeta* meta = reinterpret_cast<const LayerMeta*>(meta_host);
   DecoderWorkspace ws = carve_workspace(workspace, L, G, B, N);
@@ -206,14 +213,15 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     a.dprm = darena + meta[l].param_off;
     a.bna_sums = ws.bna_sums + (size_t)l * 2 * DPF_F * 4;
     if (q < L - 1) set_pending(a, q + 1);
+    const unsigned short* wimg = ws.w1_bf16 + (size_t)l * tc_weight_image_elems_per_layer();
     {
       ProfScope ps(CAT_BWD_P1, s);
-      rc = launch_coupling_bwd_fp32(a, mode, 1, s);
+      rc = precision >= 1 ? launch_coupling_bwd_tc(a, wimg, mode, 1, precision == 2, s) : launch_coupling_bwd_fp32(a, mode, 1, s);
     }
     if (rc) return rc;
     {
       ProfScope ps(CAT_BWD_P2, s);
-      rc = launch_coupling_bwd_fp32(a, mode, 2, s);
+      rc = precision >= 1 ? launch_coupling_bwd_tc(a, wimg, mode, 2, precision == 2, s) : launch_coupling_bwd_fp32(a, mode, 2, s);
     }
     if (rc) return rc;
   }

@@ -126,7 +126,9 @@ class CouplingStack(nn.Module):
         self.register_buffer("stats", init_stats(self.layout), persistent=False)
         self.register_buffer("num_batches_tracked", torch.zeros(self.layout.n_bn, dtype=torch.long), persistent=False)
         self.register_buffer("layer_meta", torch.from_numpy(self.layout.meta.copy()), persistent=False)
-        self.precision = "fp32"
+        # 'fp32' (CUDA cores, exact), 'bf16' / 'bf16x3' (tcgen05 tensor cores), or 'auto'
+        # (= bf16x3 while training, bf16 in eval mode); see _flowfn.resolve_precision
+        self.precision = "auto"
 
     # ---- named views ---------------------------------------------------------------------
     def named_views(self, grad=False):

@@ -36,6 +36,6 @@ def run_backward(ctx, dP, dMU, dLV):
         _lib.call("dpf_decoder_backward", _meta_host_ptr(stack), stack.layer_meta, arena, stack.stats, p, g,
                   out[0], out[2], dP_t, ctypes.c_longlong(dP_s), dMU_t, ctypes.c_longlong(dMU_s),
                   dLV_t, ctypes.c_longlong(dLV_s), darena, ctypes.c_longlong(arena.numel()), dg, dp, ctx.ws,
-                  L, G, B, N, MODES[mode], ctx.training, PRECISIONS[stack.precision],
+                  L, G, B, N, MODES[mode], ctx.training, PRECISIONS[ctx.precision],
                   ctypes.c_float(stack.eps_value), device=dev)
-    return dp, dg, darena, None, None, None
+    return dp, dg, darena, None, None, None, None

@@ -7,7 +7,7 @@ import torch
 from ... import _lib
 
 MODES = {"direct": 0, "inverse": 1}
-PRECISIONS = {"fp32": 0, "bf16": 1}
+PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2}
 
 
 def _workspace(L, G, B, N, device):
@@ -25,7 +25,7 @@ class CouplingStackFunction(torch.autograd.Function):
     reference's output lists."""
 
     @staticmethod
-    def forward(ctx, p, g, arena, stack, mode, training):
+    def forward(ctx, p, g, arena, stack, mode, training, precision):
         _lib.require_cuda(p, g, arena)
         L, G = stack.layout.L, stack.g_n_features
         B, C, N = p.shape
@@ -39,10 +39,10 @@ class CouplingStackFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.call("dpf_decoder_forward", _meta_host_ptr(stack), stack.layer_meta, arena, stack.stats, p, g,
                       out[0], out[1], out[2], ws, L, G, B, N, MODES[mode], bool(training), update,
-                      PRECISIONS[stack.precision], ctypes.c_float(stack.eps_value), device=dev)
+                      PRECISIONS[precision], ctypes.c_float(stack.eps_value), device=dev)
         if training:
             stack.num_batches_tracked += 1
-        ctx.stack, ctx.mode, ctx.training, ctx.ws = stack, mode, bool(training), ws
+        ctx.stack, ctx.mode, ctx.training, ctx.ws, ctx.precision = stack, mode, bool(training), ws, precision
         ctx.save_for_backward(p, g, arena, out)
         ctx.set_materialize_grads(False)
         return out[0], out[1], out[2]
@@ -53,9 +53,20 @@ class CouplingStackFunction(torch.autograd.Function):
         return run_backward(ctx, dP, dMU, dLV)
 
 
+def resolve_precision(stack):
+    """'auto' = the tensor-core path: bf16x3 (split operands, fp32-class accuracy) when BatchNorm
+    uses batch statistics, plain bf16 in eval mode (sampling)."""
+    prec = stack.precision
+    if prec == "auto":
+        prec = "bf16x3" if stack.training else "bf16"
+    if prec not in PRECISIONS:
+        raise ValueError("precision must be one of %s or 'auto', got %r" % (sorted(PRECISIONS), prec))
+    return prec
+
+
 def run_stack(stack, p, g, mode):
     if mode not in MODES:
         raise ValueError("mode must be 'direct' or 'inverse', got %r" % (mode,))
     p = p.contiguous()
     g = g.contiguous()
-    return CouplingStackFunction.apply(p, g, stack.arena, stack, mode, stack.training)
+    return CouplingStackFunction.apply(p, g, stack.arena, stack, mode, stack.training, resolve_precision(stack))

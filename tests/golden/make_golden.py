@@ -118,12 +118,45 @@ def decoder_fixture(n_flows, G, B, N, seed):
     return fx
 
 
+def perturb_survey(module, seed):
+    """SURVEY.md 8d recipe: only the last SharedDot of each branch gets std 0.3."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, prm in module.named_parameters():
+            if name.endswith("sd2.weight"):
+                prm.copy_(torch.randn(prm.shape, generator=g) * 0.3)
+
+
+def decoder_survey_fixture(n_flows, G, B, N, seed):
+    """Realistic-weights fixture for the BF16 tolerance (2e-2 / NLL 0.5 %): default init + SURVEY
+    perturbation + 3 train passes; stores only what the gates need."""
+    torch.manual_seed(seed)
+    m = LocalCondRNVPDecoder(n_flows, 64, G, weight_std=0.01)
+    perturb_survey(m, seed + 1)
+    warm_stats(m, G, N, seed, "inverse")
+    p, lat = inputs(B, N, G, seed + 2)
+    fx = {"n_flows": n_flows, "G": G, "state": clone_sd(m), "p": p, "g": lat}
+    m.eval()
+    with torch.no_grad():
+        ps, mus, lvs = m(lat.new_tensor(p), lat, mode="direct")
+        fx["eval_direct"] = {"p_last": ps[-1].clone(), "sum_logvar": torch.stack(lvs).sum(0)}
+        ps, mus, lvs = m(p, lat, mode="inverse")
+        fx["eval_inverse"] = {"p_first": ps[0].clone(), "sum_logvar": torch.stack(lvs).sum(0)}
+    m.train()
+    ps, mus, lvs = m(p, lat, mode="inverse")
+    nll = PointFlowNLL()(ps + [p], [torch.zeros_like(p)] + mus, [torch.full_like(p, -0.5)] + lvs)
+    fx["train_inverse"] = {"p_first": ps[0].detach().clone(), "sum_logvar": torch.stack(lvs).sum(0).detach(),
+                           "nll": nll.detach().clone(), "base_logvar": -0.5}
+    return fx
+
+
 def main():
     torch.set_num_threads(4)
     torch.save(coupling_fixture((0,), 16, 3, 200, 11), os.path.join(HERE, "coupling_w0.pt"))
     torch.save(coupling_fixture((0, 2), 24, 2, 333, 12), os.path.join(HERE, "coupling_w02.pt"))
     torch.save(coupling_fixture((1,), 128, 4, 128, 13), os.path.join(HERE, "coupling_w1_g128.pt"))
     torch.save(decoder_fixture(2, 16, 3, 200, 21), os.path.join(HERE, "decoder_f2.pt"))
+    torch.save(decoder_survey_fixture(6, 16, 6, 384, 31), os.path.join(HERE, "decoder_f6_survey.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
