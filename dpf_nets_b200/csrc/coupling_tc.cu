@@ -29,7 +29,7 @@ namespace {
 constexpr int F = DPF_F;
 constexpr uint32_t IMG_W = F * F * 2;           // 8 KB  : one 64x64 bf16 weight image
 constexpr uint32_t IMG_H = DPF_TILE * F * 2;    // 16 KB : one 128x64 bf16 activation tile
-constexpr int N_IMG = 3;                         // weight images per (layer, branch): W1 hi, W1^T hi, W1 lo
+constexpr int N_IMG = 3;                         // weight images per (layer, branch): W1 hi, W1 lo, W1^T hi
 constexpr uint64_t DESC_K = umma::make_desc_template(16, 1024, umma::LAYOUT_SW128);        // K-major SW128
 constexpr uint64_t DESC_MN = umma::make_desc_template(IMG_H, 1024, umma::LAYOUT_SW128);    // MN-major, 64-blocks IMG_H apart
 constexpr uint32_t IDESC_GEMM = umma::make_idesc_bf16(128, 64, 0, 0);
@@ -48,14 +48,14 @@ pack_w1_kernel(const float* __restrict__ arena, const LayerMeta* __restrict__ me
   const float* W1 = arena + m.param_off + (size_t)br * lay.size + lay.W1;
   unsigned char* img = reinterpret_cast<unsigned char*>(out) + (size_t)(l * 2 + br) * N_IMG * IMG_W;
   for (int e = threadIdx.x; e < N_IMG * F * 8; e += 256) {
-    const int t = e / (F * 8), r = (e / 8) % F, q = e & 7;   // image t (0: W1 hi, 1: W1^T hi, 2: W1 lo), row r, chunk q
+    const int t = e / (F * 8), r = (e / 8) % F, q = e & 7;   // image t (0: W1 hi, 1: W1 lo, 2: W1^T hi), row r, chunk q
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c0 = q * 8 + 2 * i;
-      float lo = t == 1 ? W1[c0 * F + r] : W1[r * F + c0];
-      float hi = t == 1 ? W1[(c0 + 1) * F + r] : W1[r * F + c0 + 1];
-      if (t == 2) {   // residual of the bf16 rounding: W1 = hi + lo to ~2^-17
+      float lo = t == 2 ? W1[c0 * F + r] : W1[r * F + c0];
+      float hi = t == 2 ? W1[(c0 + 1) * F + r] : W1[r * F + c0 + 1];
+      if (t == 1) {   // residual of the bf16 rounding: W1 = hi + lo to ~2^-17
         lo -= __bfloat162float(__float2bfloat16_rn(lo));
         hi -= __bfloat162float(__float2bfloat16_rn(hi));
       }
@@ -208,15 +208,24 @@ __device__ __forceinline__ uint32_t tc_setup(TcCommon& s, uint32_t tmem_cols) {
   return s.tmem_base;
 }
 
-// TMA bulk load of this layer's weight images: all N_IMG images of both branches, contiguous.
+// TMA bulk loads of this layer's weight images.  ALL = {hi, lo, T} of both branches in one copy
+// (backward pass 2); otherwise only {hi, lo} of each branch, packed [br][hi, lo] (32 KB).
+template <bool ALL>
 __device__ __forceinline__ void tc_load_weights(TcCommon& s, unsigned char* W, const unsigned short* wimg) {
   if (threadIdx.x == 0) {
-    umma::mbar_expect_tx(&s.bar_load, 2 * N_IMG * IMG_W);
-    umma::bulk_g2s(W, wimg, 2 * N_IMG * IMG_W, &s.bar_load);
+    if (ALL) {
+      umma::mbar_expect_tx(&s.bar_load, 2 * N_IMG * IMG_W);
+      umma::bulk_g2s(W, wimg, 2 * N_IMG * IMG_W, &s.bar_load);
+    } else {
+      umma::mbar_expect_tx(&s.bar_load, 4 * IMG_W);
+      umma::bulk_g2s(W, wimg, 2 * IMG_W, &s.bar_load);
+      umma::bulk_g2s(W + 2 * IMG_W, reinterpret_cast<const unsigned char*>(wimg) + N_IMG * IMG_W, 2 * IMG_W, &s.bar_load);
+    }
   }
 }
-// image t of branch br inside the staged block
-__device__ __forceinline__ const unsigned char* wimg_at(const unsigned char* W, int br, int t) { return W + (br * N_IMG + t) * IMG_W; }
+// image t (0 hi, 1 lo, 2 T) of branch br inside the staged block
+template <bool ALL>
+__device__ __forceinline__ const unsigned char* wimg_at(const unsigned char* W, int br, int t) { return W + (br * (ALL ? N_IMG : 2) + t) * IMG_W; }
 
 __device__ __forceinline__ void tile_range(int n_tiles, int& t0, int& t1) {   // contiguous tiles per CTA
   const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
@@ -229,7 +238,7 @@ __device__ __forceinline__ void tile_range(int n_tiles, int& t0, int& t1) {   //
 // that a single pair of (hi, lo) activation tiles is live: 2 CTAs per SM.
 // =============================================================================================
 struct TcFwdSmem {
-  unsigned char W[2 * N_IMG * IMG_W];   // 48 KB
+  unsigned char W[4 * IMG_W];           // [br][W1 hi, W1 lo] (32 KB)
   unsigned char H[2 * IMG_H];           // hi, lo tile of the branch in flight (32 KB)
   TcCommon c;
   float scratch[DPF_TILE * 33];
@@ -246,7 +255,7 @@ coupling_fwd_tc_kernel(const CouplingArgs a, const unsigned short* __restrict__ 
   const BranchLayout lay = branch_layout(a.k, a.w, a.G);
   const bool writer = (blockIdx.x == 0) && a.update_stats && !STATS;
   const uint32_t tmem = tc_setup(s.c, 128);
-  tc_load_weights(s.c, s.W, wimg);
+  tc_load_weights<false>(s.c, s.W, wimg);
   tc_prologue_tables(a, lay, s.c, writer, !STATS);
   float sacc[4][2];
 #pragma unroll
@@ -280,7 +289,7 @@ coupling_fwd_tc_kernel(const CouplingArgs a, const unsigned short* __restrict__ 
       __syncthreads();
       if (tid == 0) {
         umma::fence_after_sync();
-        issue_gemm1<SPLIT>(tmem + br * F, s.H, s.H + IMG_H, wimg_at(s.W, br, 0), wimg_at(s.W, br, 2));
+        issue_gemm1<SPLIT>(tmem + br * F, s.H, s.H + IMG_H, wimg_at<false>(s.W, br, 0), wimg_at<false>(s.W, br, 1));
         umma::mma_commit(&s.c.bar_mma);
       }
       umma::mbar_wait(&s.c.bar_mma, phase);
@@ -498,7 +507,7 @@ __device__ __forceinline__ TcPoint tc_load_point(const BwdArgs& a, const Pending
 // Backward pass 1: FiLM sums (dt, ds), dW2, db2
 // =============================================================================================
 struct TcP1Smem {
-  unsigned char W[2 * N_IMG * IMG_W];
+  unsigned char W[4 * IMG_W];           // [br][W1 hi, W1 lo]
   unsigned char H[2 * IMG_H];
   TcCommon c;
   float scratch[2 * DPF_TILE * 33];
@@ -514,15 +523,12 @@ coupling_bwd_p1_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
   const uint32_t tmem = tc_setup(s.c, 128);
-  tc_load_weights(s.c, s.W, wimg);
+  tc_load_weights<false>(s.c, s.W, wimg);
   tc_prologue_tables(a.f, lay, s.c, false, true);
   for (int i = tid; i < 4 * 2 * F; i += DPF_TILE) (&s.fin[0][0])[i] = 0.f;
   if (tid < 4) (&s.b2fin[0][0])[tid] = 0.f;
   __syncthreads();
   const Pending P = tc_compute_pending(a, blockIdx.x == 0, s.c.pend);
-  float acc_t[4], acc_s[4], acc_w0[4], acc_w1[4];   // per chunk (branch, half); column = lane, row-quarter = warp
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc_t[i] = acc_s[i] = acc_w0[i] = acc_w1[i] = 0.f;
   float b2acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   umma::mbar_wait(&s.c.bar_load, 0);
   __syncthreads();
@@ -532,14 +538,7 @@ coupling_bwd_p1_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
   uint32_t phase = 0;
   int cur_b = -1;
   const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-  auto flush_film = [&](int b) {   // dt / ds of shape b -> global (all threads)
-    __syncthreads();
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      atomicAdd(&s.fin[0][ch * 32 + lane], acc_t[ch]);
-      atomicAdd(&s.fin[1][ch * 32 + lane], acc_s[ch]);
-      acc_t[ch] = acc_s[ch] = 0.f;
-    }
+  auto flush_film = [&](int b) {   // dt / ds of shape b (accumulated in smem) -> global (all threads)
     __syncthreads();
     const int br = tid >> 6, c = tid & 63;
     atomicAdd(&a.dfilm[((size_t)(br * 2 + 0) * a.f.B + b) * F + c], s.fin[1][tid]);   // ds_raw
@@ -566,7 +565,7 @@ coupling_bwd_p1_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
       __syncthreads();
       if (tid == 0) {
         umma::fence_after_sync();
-        issue_gemm1<SPLIT>(tmem + br * F, s.H, s.H + IMG_H, wimg_at(s.W, br, 0), wimg_at(s.W, br, 2));
+        issue_gemm1<SPLIT>(tmem + br * F, s.H, s.H + IMG_H, wimg_at<false>(s.W, br, 0), wimg_at<false>(s.W, br, 1));
         umma::mma_commit(&s.c.bar_mma);
       }
       umma::mbar_wait(&s.c.bar_mma, phase);
@@ -592,16 +591,16 @@ coupling_bwd_p1_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
         }
         float ra, rb;
         colreduce32x2(s.scratch, q1, q2, tid, ra, rb);
-        acc_t[ch] += ra;
-        acc_s[ch] += rb;
+        atomicAdd(&s.fin[0][ch * 32 + lane], ra);
+        atomicAdd(&s.fin[1][ch * 32 + lane], rb);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           q1[i] = d0 * v[i];
           q2[i] = d1 * v[i];
         }
         colreduce32x2(s.scratch, q1, q2, tid, ra, rb);
-        acc_w0[ch] += ra;
-        acc_w1[ch] += rb;
+        atomicAdd(&s.fin[2][ch * 32 + lane], ra);
+        atomicAdd(&s.fin[3][ch * 32 + lane], rb);
       }
       umma::fence_before_sync();
       __syncthreads();
@@ -611,11 +610,6 @@ coupling_bwd_p1_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
   }
   if (cur_b >= 0) flush_film(cur_b);
   __syncthreads();
-#pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    atomicAdd(&s.fin[2][ch * 32 + lane], acc_w0[ch]);
-    atomicAdd(&s.fin[3][ch * 32 + lane], acc_w1[ch]);
-  }
 #pragma unroll
   for (int br = 0; br < 2; ++br)
 #pragma unroll
@@ -642,7 +636,7 @@ coupling_bwd_p1_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
 // operand of width 128.  The h1 lo tiles alias the dh2pre tiles (dead once the recompute is done).
 // =============================================================================================
 struct TcP2Smem {
-  unsigned char W[2 * N_IMG * IMG_W];   // [br][W1 hi, W1^T hi, W1 lo]
+  unsigned char W[2 * N_IMG * IMG_W];   // [br][W1 hi, W1 lo, W1^T hi]
   unsigned char H[2 * IMG_H];           // h1 hi tiles (mu, logvar) - contiguous: MN-major N = 128 for wgrad
   unsigned char D[2 * IMG_H];           // h1 lo tiles during the recompute, then dh2pre tiles (MN-major M = 128)
   TcCommon c;
@@ -659,7 +653,7 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
   const uint32_t tmem = tc_setup(s.c, 512);
-  tc_load_weights(s.c, s.W, wimg);
+  tc_load_weights<true>(s.c, s.W, wimg);
   tc_prologue_tables(a.f, lay, s.c, false, true);
   {
     const int br = tid >> 6, c = tid & 63;
@@ -682,9 +676,6 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
   __syncthreads();
   const Pending P = tc_compute_pending(a, false, s.c.pend);
   const float sig1 = sqrtf(a.f.eps + 1.0f);
-  float acc_b[4], acc_e0[4], acc_e1[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc_b[i] = acc_e0[i] = acc_e1[i] = 0.f;
   umma::mbar_wait(&s.c.bar_load, 0);
   __syncthreads();
 
@@ -707,15 +698,15 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
     __syncthreads();
     if (tid == 0) {
       umma::fence_after_sync();
-      issue_gemm1<SPLIT>(T_FWD, s.H, s.D, wimg_at(s.W, 0, 0), wimg_at(s.W, 0, 2));
-      issue_gemm1<SPLIT>(T_FWD + F, s.H + IMG_H, s.D + IMG_H, wimg_at(s.W, 1, 0), wimg_at(s.W, 1, 2));
+      issue_gemm1<SPLIT>(T_FWD, s.H, s.D, wimg_at<true>(s.W, 0, 0), wimg_at<true>(s.W, 0, 1));
+      issue_gemm1<SPLIT>(T_FWD + F, s.H + IMG_H, s.D + IMG_H, wimg_at<true>(s.W, 1, 0), wimg_at<true>(s.W, 1, 1));
       umma::mma_commit(&s.c.bar_mma);
     }
     umma::mbar_wait(&s.c.bar_mma, phase);
     phase ^= 1;
     umma::fence_after_sync();
     // ---- epilogue A: dh2pre (bf16) -> D tiles (the lo tiles are dead now) ----
-#pragma unroll
+#pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
       const int br = ch >> 1, half = ch & 1;
       const float d0 = br == 0 ? g.do_mu[0] : g.do_lv[0];
@@ -750,7 +741,7 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma::mma_bf16(T_DG + br * F, umma::desc_at(DESC_K, umma::smem_u32(s.D + br * IMG_H) + 32 * k),
-                         umma::desc_at(DESC_K, umma::smem_u32(wimg_at(s.W, br, 1)) + 32 * k), IDESC_GEMM, k > 0);
+                         umma::desc_at(DESC_K, umma::smem_u32(wimg_at<true>(s.W, br, 2)) + 32 * k), IDESC_GEMM, k > 0);
       // wgrad: [c_mu | c_lv] x [j_mu | j_lv] += sum over the tile's 128 points (MN-major views, K = 16 rows per step)
 #pragma unroll
       for (int k = 0; k < 8; ++k)
@@ -763,7 +754,7 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
     umma::fence_after_sync();
     // ---- epilogue B: dz, T1, BN_a sums ----
     float T1_0 = 0.f, T1_1 = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
       const int br = ch >> 1, half = ch & 1;
       float v[32], q1[32], q2[32];
@@ -782,11 +773,11 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
       }
       float ra, rb;
       colreduce32x2(s.scratch, v, q1, tid, ra, rb);
-      acc_b[ch] += ra;
-      acc_e0[ch] += rb;
+      atomicAdd(&s.fin[0][ch * 32 + lane], ra);
+      atomicAdd(&s.fin[1][ch * 32 + lane], rb);
       if (K == 2) {
         colreduce32x2(s.scratch, q2, q2, tid, ra, rb);
-        acc_e1[ch] += ra;
+        atomicAdd(&s.fin[2][ch * 32 + lane], ra);
       }
     }
     if (valid) {
@@ -808,12 +799,6 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
     __syncthreads();
   }
   // ---- CTA epilogue: BN_a sums and the TMEM-resident wgrad accumulator ----
-#pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    atomicAdd(&s.fin[0][ch * 32 + lane], acc_b[ch]);
-    atomicAdd(&s.fin[1][ch * 32 + lane], acc_e0[ch]);
-    atomicAdd(&s.fin[2][ch * 32 + lane], acc_e1[ch]);
-  }
   __syncthreads();
   atomicAdd(&a.bna_sums[tid * 4 + 0], (double)s.fin[0][tid]);
   atomicAdd(&a.bna_sums[tid * 4 + 1], (double)s.fin[1][tid]);
@@ -884,7 +869,7 @@ int launch_pack_w1(const float* arena, const LayerMeta* meta_dev, int L, int G, 
   return dpf_check_launch("pack_w1_kernel");
 }
 
-// wimg: this layer's images [br][W1 hi, W1^T hi, W1 lo][4096 bf16]; split != 0 = bf16x3
+// wimg: this layer's images [br][W1 hi, W1 lo, W1^T hi][4096 bf16]; split != 0 = bf16x3
 int launch_coupling_fwd_tc(const CouplingArgs& a, const unsigned short* wimg, int mode, bool stats_pass, int split, cudaStream_t s) {
   const int grid = min(a.n_tiles, dpf_num_sms() * 2);
   if (a.k == 2) return split ? launch_fwd_tc_k<2, true>(a, wimg, mode, stats_pass, grid, s) : launch_fwd_tc_k<2, false>(a, wimg, mode, stats_pass, grid, s);
