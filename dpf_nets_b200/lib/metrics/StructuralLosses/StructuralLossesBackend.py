@@ -43,3 +43,35 @@ def NNDistanceGrad(set_d, set_q, idx1, idx2, grad_dist1, grad_dist2):
         _lib.call("dpf_nndistance_grad", b, n, set_d, m, set_q, grad_dist1, idx1, grad_dist2, idx2,
                   grad1, grad2, device=dev)
     return [grad1, grad2]
+
+
+def ApproxMatch(set_d, set_q):
+    """-> [match (b, m, n), temp (b, 2(n+m))]  (structural_loss.cpp:22-37; temp is unused scratch)."""
+    _check(set_d, set_q)
+    b, n, m = set_d.size(0), set_d.size(1), set_q.size(1)
+    dev = set_d.device
+    match = torch.empty((b, m, n), dtype=torch.float32, device=dev)
+    temp = torch.empty((b, (n + m) * 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dpf_approxmatch", b, n, m, set_d, set_q, match, temp, device=dev)
+    return [match, temp]
+
+
+def MatchCost(set_d, set_q, match):
+    _check(set_d, set_q, match)
+    b, n, m = set_d.size(0), set_d.size(1), set_q.size(1)
+    out = torch.empty((b,), dtype=torch.float32, device=set_d.device)
+    with torch.cuda.device(set_d.device):
+        _lib.call("dpf_matchcost", b, n, m, set_d, set_q, match, out, device=set_d.device)
+    return out
+
+
+def MatchCostGrad(set_d, set_q, match):
+    _check(set_d, set_q, match)
+    b, n, m = set_d.size(0), set_d.size(1), set_q.size(1)
+    dev = set_d.device
+    grad1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
+    grad2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dpf_matchcost_grad", b, n, m, set_d, set_q, match, grad1, grad2, device=dev)
+    return [grad1, grad2]

@@ -1,2 +1,2 @@
 """Tensor-level wrappers over the C ABI (device pointers in, device tensors out)."""
-from .chamfer import pairwise_cd  # noqa: F401
+from .chamfer import pairwise_cd, pairwise_emd  # noqa: F401

@@ -26,3 +26,19 @@ def pairwise_cd(clouds1, clouds2, out=None, row_start=0, row_step=1, n_rows=None
         if symmetric and whole:
             _lib.call("dpf_symmetrize_upper", out, S1, device=dev)
     return out
+
+
+def pairwise_emd(clouds1, clouds2, out=None, row_start=0, row_step=1, n_rows=None):
+    """(S1,n,3),(S2,m,3) -> (S1,S2) un-normalised approximate EMD costs (MatchCost per pair) with the
+    dense match never materialised; divide by n for the reference's emd_approx."""
+    _lib.require_cuda(clouds1, clouds2)
+    S1, n = clouds1.shape[0], clouds1.shape[1]
+    S2, m = clouds2.shape[0], clouds2.shape[1]
+    if out is None:
+        out = torch.zeros((S1, S2), dtype=torch.float32, device=clouds1.device)
+    if n_rows is None:
+        n_rows = max(0, (S1 - row_start + row_step - 1) // row_step)
+    with torch.cuda.device(clouds1.device):
+        _lib.call("dpf_pairwise_emd", S1, S2, n, m, clouds1, clouds2, out, row_start, row_step, n_rows,
+                  device=clouds1.device)
+    return out

@@ -55,6 +55,23 @@ int dpf_pairwise_cd(int S1, int S2, int n, int m, const float* A, const float* B
 /* Mirrors the upper triangle of an (S,S) matrix into the lower one (after dpf_pairwise_cd symmetric). */
 int dpf_symmetrize_upper(float* M, int S, void* stream);
 
+/* ---- Approximate EMD (soft auction, 9 levels) -----------------------------------------------
+ * dpf_approxmatch replaces approxmatch() — src/approxmatch.cuh:6 (kernel approxmatch.cu:3-182, shim
+ * structural_loss.cpp:22-37): xyz1 (b,n,3), xyz2 (b,m,3) -> match (b,m,n).  `temp` (b,2(n+m)) of the
+ * reference signature is accepted and unused (may be NULL).
+ * dpf_matchcost replaces matchcost() — approxmatch.cuh:7 (approxmatch.cu:184-224): out (b).
+ * dpf_matchcost_grad replaces matchcostgrad() — approxmatch.cuh:8 (approxmatch.cu:229-291). */
+int dpf_approxmatch(int b, int n, int m, const float* xyz1, const float* xyz2, float* match, float* temp,
+                    void* stream);
+int dpf_matchcost(int b, int n, int m, const float* xyz1, const float* xyz2, const float* match, float* out,
+                  void* stream);
+int dpf_matchcost_grad(int b, int n, int m, const float* xyz1, const float* xyz2, const float* match,
+                       float* grad1, float* grad2, void* stream);
+/* Fused EMD half of _pairwise_EMD_CD_ (lib/metrics/evaluation_metrics.py:85-121): out[i*S2+j] =
+ * MatchCost(A_i, B_j) without materialising the dense match; rows row_start + t*row_step, t < n_rows. */
+int dpf_pairwise_emd(int S1, int S2, int n, int m, const float* A, const float* B, float* out, int row_start,
+                     int row_step, int n_rows, void* stream);
+
 /* ---- Point decoder: stack of conditional affine-coupling layers ------------------------------
  * The reference has no native interface here; the replaceable unit is the nn.Module
  * (LocalCondRNVPDecoder.forward, lib/networks/decoders.py:54-72, over CondRealNVPFlow3D.forward,
