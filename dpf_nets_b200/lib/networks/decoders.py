@@ -41,3 +41,33 @@ def prepend(base, flow_list):
     out = TailedList([base] + list(flow_list))
     out.tail_stacked = getattr(flow_list, "stacked", None)
     return out
+
+
+import torch.nn as _nn
+
+from .flows import RealNVPFlowCouple as _Couple
+
+
+class GlobalRNVPDecoder(_nn.Module):
+    """Latent prior flow: n_flows couples, list outputs ordered like the reference
+    (lib/networks/decoders.py:7-38)."""
+
+    def __init__(self, n_flows, n_features, g_n_features, weight_std=0.01):
+        super().__init__()
+        self.n_flows, self.n_features, self.g_n_features, self.weight_std = n_flows, n_features, g_n_features, weight_std
+        self.flows = _nn.ModuleList([_Couple(n_features, g_n_features, weight_std=weight_std, pattern=i % 2)
+                                     for i in range(n_flows)])
+
+    def forward(self, g, mode='direct'):
+        gs, mus, logvars = [], [], []
+        cur = g
+        order = range(self.n_flows) if mode == 'direct' else range(self.n_flows - 1, -1, -1)
+        for i in order:
+            o = self.flows[i](cur, mode=mode)
+            if mode == 'direct':
+                gs, mus, logvars = gs + o[0], mus + o[1], logvars + o[2]
+                cur = gs[-1]
+            else:
+                gs, mus, logvars = o[0] + gs, o[1] + mus, o[2] + logvars
+                cur = gs[0]
+        return gs, mus, logvars

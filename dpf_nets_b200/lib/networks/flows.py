@@ -44,3 +44,68 @@ class CondRealNVPFlow3DTriple(CouplingStack):
     def forward(self, p, g, mode="direct"):
         P, MU, LV = run_stack(self, p, g, mode)
         return list(P.unbind(0)), list(MU.unbind(0)), list(LV.unbind(0))
+
+
+# ---- latent-space (per-shape) coupling flows: (B, G) vectors, launch-latency only -------------
+import numpy as _np
+import torch as _torch
+import torch.nn as _nn
+
+from .layers import Swish as _Swish
+
+
+class RealNVPFlow(_nn.Module):
+    """Unconditional coupling layer on the shape latent (reference flows.py:163-213):
+    logvar = log(eps + exp(net(g_keep))), g_out = exp(+-logvar/2) * g (+-) mu."""
+
+    def __init__(self, n_features, g_n_features, weight_std=0.01, warp_inds=[0], eps=1e-6):
+        super().__init__()
+        self.n_features, self.g_n_features, self.weight_std = n_features, g_n_features, weight_std
+        self.warp_inds = [int(i) for i in warp_inds]
+        self.keep_inds = [i for i in range(g_n_features) if i not in set(self.warp_inds)]
+        self.register_buffer('eps', _torch.tensor([eps], dtype=_torch.float32))
+        for br in ('mu', 'logvar'):
+            net = _nn.Sequential()
+            net.add_module(br + '_mlp0', _nn.Linear(len(self.keep_inds), n_features, bias=False))
+            net.add_module(br + '_mlp0_bn', _nn.BatchNorm1d(n_features))
+            net.add_module(br + '_mlp0_swish', _Swish())
+            net.add_module(br + '_mlp1', _nn.Linear(n_features, len(self.warp_inds), bias=True))
+            with _torch.no_grad():
+                net[-1].weight.normal_(std=weight_std)
+                net[-1].bias.zero_()
+            setattr(self, 'T_%s_0' % br, net)
+
+    def forward(self, g, mode='direct'):
+        kept = g[:, self.keep_inds].contiguous()
+        logvar = _torch.zeros_like(g)
+        mu = _torch.zeros_like(g)
+        logvar[:, self.warp_inds] = _torch.log(self.eps + _torch.exp(self.T_logvar_0(kept)))
+        mu[:, self.warp_inds] = self.T_mu_0(kept)
+        if mode == 'direct':
+            g_out = _torch.exp(0.5 * logvar) * g + mu
+        elif mode == 'inverse':
+            g_out = _torch.exp(-0.5 * logvar) * (g - mu)
+        else:
+            raise ValueError(mode)
+        return g_out, mu, logvar
+
+
+class RealNVPFlowCouple(_nn.Module):
+    """Two complementary latent coupling layers: even/odd (pattern 0) or halves (pattern 1)."""
+
+    def __init__(self, n_features, g_n_features, weight_std=0.01, pattern=0):
+        super().__init__()
+        idx = _np.arange(g_n_features)
+        parts = (idx[::2], idx[1::2]) if pattern == 0 else (idx[:g_n_features // 2], idx[g_n_features // 2:])
+        self.pattern = pattern
+        self.nvp1 = RealNVPFlow(n_features, g_n_features, weight_std=weight_std, warp_inds=list(parts[0]))
+        self.nvp2 = RealNVPFlow(n_features, g_n_features, weight_std=weight_std, warp_inds=list(parts[1]))
+
+    def forward(self, g, mode='direct'):
+        if mode == 'direct':
+            a = self.nvp1(g, mode=mode)
+            b = self.nvp2(a[0], mode=mode)
+        else:
+            b = self.nvp2(g, mode=mode)
+            a = self.nvp1(b[0], mode=mode)
+        return [a[0], b[0]], [a[1], b[1]], [a[2], b[2]]

@@ -1,0 +1,74 @@
+"""The reference's custom AMSGrad Adam and cosine LR / beta2 updater (lib/networks/optimizers.py:8-97),
+same state keys ('step', 'exp_avg', 'exp_avg_sq', 'max_exp_avg_sq') and the same non-standard
+update:  denom = sqrt(v_hat) / sqrt(1 - beta2^t) + eps ;  p -= wd * p + lr * (m / (1 - beta1^t)) / denom
+(weight decay NOT scaled by lr).  CUDA tensors take one fused kernel (dpf_adam_step); the decoder is a
+single arena tensor, so the per-parameter Python loop of the reference collapses to a few launches."""
+import math
+
+import numpy as np
+import torch
+from torch.optim import Optimizer
+
+from ... import _lib
+
+
+class Adam(Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for group in self.param_groups:
+            beta1, beta2 = group['betas']
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                if p.grad.is_sparse:
+                    raise RuntimeError('Adam does not support sparse gradients')
+                st = self.state[p]
+                if len(st) == 0:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(p)
+                    st['exp_avg_sq'] = torch.zeros_like(p)
+                    if group['amsgrad']:
+                        st['max_exp_avg_sq'] = torch.zeros_like(p)
+                st['step'] += 1
+                bc1 = 1 - beta1 ** st['step']
+                bc2 = math.sqrt(1 - beta2 ** st['step'])
+                if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous():
+                    mx = st.get('max_exp_avg_sq')
+                    with torch.cuda.device(p.device):
+                        _lib.call("dpf_adam_step", p, p.grad, st['exp_avg'], st['exp_avg_sq'], mx,
+                                  _lib.ctypes.c_longlong(p.numel()), float(group['lr']), float(beta1), float(beta2),
+                                  float(group['eps']), float(group['weight_decay']), float(bc1), float(bc2), device=p.device)
+                    continue
+                g = p.grad
+                st['exp_avg'].mul_(beta1).add_(g, alpha=1 - beta1)
+                st['exp_avg_sq'].mul_(beta2).addcmul_(g, g, value=1 - beta2)
+                if group['amsgrad']:
+                    torch.max(st['max_exp_avg_sq'], st['exp_avg_sq'], out=st['max_exp_avg_sq'])
+                    denom = st['max_exp_avg_sq'].sqrt()
+                else:
+                    denom = st['exp_avg_sq'].sqrt()
+                upd = (st['exp_avg'] / bc1) / (denom / bc2 + group['eps']) * group['lr']
+                if group['weight_decay'] != 0:
+                    upd = upd + p * group['weight_decay']
+                p.sub_(upd)
+        return loss
+
+
+class LRUpdater(object):
+    def __init__(self, epoch_length, **kwargs):
+        self.epoch_length = epoch_length
+        self.cycle_length = kwargs['cycle_length']
+        self.min_lr, self.max_lr = kwargs['min_lr'], kwargs['max_lr']
+        self.beta1 = kwargs['beta1']
+        self.min_beta2, self.max_beta2 = kwargs['min_beta2'], kwargs['max_beta2']
+
+    def __call__(self, optimizer, epoch, iteration):
+        pos = ((epoch % self.cycle_length) * self.epoch_length + iteration) / (self.cycle_length * self.epoch_length)
+        c = 0.5 * (1.0 + np.cos(np.pi * pos))
+        for group in optimizer.param_groups:
+            group['lr'] = self.min_lr + (self.max_lr - self.min_lr) * c
+            group['betas'] = (self.beta1, self.min_beta2 + (self.max_beta2 - self.min_beta2) * c)

@@ -1,0 +1,66 @@
+"""Training epoch loop with the reference's signature and behaviour (lib/networks/training.py:10-87):
+NaN guard, stdout meters every `num_workers` iterations, checkpoint dict
+{'epoch','iter','model_state','optimizer_state'} every 100*num_workers iterations and at epoch end.
+Added: gradient averaging across ranks when torch.distributed is initialised (batch sharding)."""
+import os
+from sys import stdout
+from time import time
+
+import torch
+
+from ... import dist as _dist
+from .utils import AverageMeter, save_model
+
+
+def train(iterator, model, loss_func, optimizer, scheduler, epoch, iter, **kwargs):
+    num_workers = max(1, kwargs.get('num_workers') or 1)
+    train_mode = kwargs.get('train_mode')
+    model_name = os.path.join(kwargs['path2save'], 'models', 'DPFNets', kwargs.get('model_name'))
+    rank, _ = _dist.world()
+    meters = {k: AverageMeter() for k in ('time', 'LB', 'PNLL', 'GNLL', 'GENT')}
+    model.train()
+    torch.set_grad_enabled(True)
+    dev = next(model.parameters()).device
+
+    def checkpoint(ep, it):
+        if rank == 0:
+            os.makedirs(os.path.dirname(model_name), exist_ok=True)
+            save_model({'epoch': ep, 'iter': it, 'model_state': model.state_dict(),
+                        'optimizer_state': optimizer.state_dict()}, model_name)
+
+    end = time()
+    for i, batch in enumerate(iterator):
+        if iter + i >= len(iterator):
+            break
+        scheduler(optimizer, epoch, iter + i)
+        g_clouds = batch['cloud'].to(dev, non_blocking=True)
+        p_clouds = batch['eval_cloud'].to(dev, non_blocking=True)
+        if train_mode == 'p_rnvp_mc_g_rnvp_vae_ic':
+            outputs = model(g_clouds, p_clouds, batch['image'].to(dev, non_blocking=True))
+        else:
+            outputs = model(g_clouds, p_clouds)
+        loss, pnll, gnll, gent = loss_func(g_clouds, p_clouds, outputs)
+        if torch.isnan(loss.detach()):
+            print('Loss is NaN! Stopping without updating the net...')
+            raise SystemExit(1)
+        n = g_clouds.shape[0]
+        meters['PNLL'].update(pnll.item(), n)
+        meters['GNLL'].update(gnll.item(), n)
+        meters['GENT'].update(gent.item(), n)
+        meters['LB'].update((pnll + gnll - gent).item(), n)
+        optimizer.zero_grad()
+        loss.backward()
+        _dist.allreduce_arena_grads(model)
+        optimizer.step()
+        meters['time'].update(time() - end)
+        if rank == 0 and (iter + i + 1) % num_workers == 0:
+            stdout.write('Epoch: [{0}][{1}/{2}]\tTime {t.val:.3f} ({t.avg:.3f})\tLB {lb.val:.2f} ({lb.avg:.2f})'
+                         '\tPNLL {p.val:.2f} ({p.avg:.2f})\tGNLL {g.val:.2f} ({g.avg:.2f})\tGENT {e.val:.2f} ({e.avg:.2f})\n'
+                         .format(epoch + 1, iter + i + 1, len(iterator), t=meters['time'], lb=meters['LB'],
+                                 p=meters['PNLL'], g=meters['GNLL'], e=meters['GENT']))
+            stdout.flush()
+        end = time()
+        if (iter + i + 1) % (100 * num_workers) == 0:
+            checkpoint(epoch, iter + i + 1)
+    checkpoint(epoch + 1, 0)
+    return meters

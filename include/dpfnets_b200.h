@@ -101,6 +101,12 @@ int dpf_decoder_backward(const long long* meta_host, const long long* meta_dev, 
                          float* dg, float* dp, void* workspace, int L, int G, int B, int N, int mode,
                          int training, int precision, float eps, void* stream);
 
+/* Fused AMSGrad step with the reference's exact update (lib/networks/optimizers.py:53-74):
+ * denom = sqrt(max_exp_avg_sq or exp_avg_sq)/bc2 + eps; p -= wd*p + lr*(exp_avg/bc1)/denom.
+ * vmax may be NULL (amsgrad off); bc1 = 1-beta1^t, bc2 = sqrt(1-beta2^t). */
+int dpf_adam_step(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float b1,
+                  float b2, float eps, float wd, float bc1, float bc2, void* stream);
+
 /* tcgen05 self-test (tests/test_umma_gpu.py): D[128,ncols] = sum_k A_k B_k from raw shared-memory
  * operand images and descriptor fields; validates the UMMA layouts the coupling kernels rely on. */
 int dpf_umma_selftest(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
