@@ -405,6 +405,19 @@ def extras(model, dev, B, N, pk, flush):
 
 def main():
     args = parse()
+    # Libraries (NCCL's version banner, torchrun) write to fd 1; keep stdout to the ONE JSON line:
+    # everything else goes to stderr, the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    import builtins
+    _print = builtins.print
+
+    def json_print(*a, **k):
+        k.setdefault("file", real_stdout)
+        _print(*a, **k)
+        real_stdout.flush()
+    builtins.print = json_print
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_n2.log 2>&1; echo "bench n2 rc=$?"
+tail -30 gpurun_out/bench_n2.log | cut -c1-400
