@@ -222,6 +222,7 @@ struct BwdArgs {
   float* dfilm;            // [4][B][F]   ds_raw_mu, dt_mu, ds_raw_lv, dt_lv (accumulated)
   float* dprm;             // this layer's slice of the gradient arena
   double* bna_sums;        // [2][F][4]   dbeta, E0, E1 (accumulated in pass 2)
+  float* dw1_partial;      // tensor path: per-CTA wgrad partials [grid][2][F*F] of this layer (reduced once per pass)
   // deferred BN_a correction owed by the layer processed just before in backward (its input == our y)
   int has_pending;
   const float* nprm;

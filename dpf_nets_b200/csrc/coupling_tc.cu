@@ -659,15 +659,28 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
     const int br = tid >> 6, c = tid & 63;
     float m1 = 0.f, m2 = 0.f;
     if (a.f.training) {
-      double s1 = 0.0, s2 = 0.0;
-      for (int b = 0; b < a.f.B; ++b) {
-        const double sc = a.f.film[((size_t)(br * 2 + 0) * a.f.B + b) * F + c];
-        s1 += sc * (double)a.dfilm[((size_t)(br * 2 + 1) * a.f.B + b) * F + c];
-        s2 += sc * (double)a.dfilm[((size_t)(br * 2 + 0) * a.f.B + b) * F + c];
+      // sum_b s[b,c] * {dt, ds}[b,c]: 4 independent chains so the loads of 4 shapes are in flight together
+      double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+      const float* fs = a.f.film + (size_t)(br * 2 + 0) * a.f.B * F + c;
+      const float* dsr = a.dfilm + (size_t)(br * 2 + 0) * a.f.B * F + c;
+      const float* dtr = a.dfilm + (size_t)(br * 2 + 1) * a.f.B * F + c;
+      int b = 0;
+      for (; b + 4 <= a.f.B; b += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double sc = fs[(size_t)(b + u) * F];
+          s1[u] += sc * (double)dtr[(size_t)(b + u) * F];
+          s2[u] += sc * (double)dsr[(size_t)(b + u) * F];
+        }
+      }
+      for (; b < a.f.B; ++b) {
+        const double sc = fs[(size_t)b * F];
+        s1[0] += sc * (double)dtr[(size_t)b * F];
+        s2[0] += sc * (double)dsr[(size_t)b * F];
       }
       const double M = (double)a.f.B * (double)a.f.N;
-      m1 = (float)(s1 / M);
-      m2 = (float)(s2 / M);
+      m1 = (float)(((s1[0] + s1[1]) + (s1[2] + s1[3])) / M);
+      m2 = (float)(((s2[0] + s2[1]) + (s2[2] + s2[3])) / M);
     }
     s.m1[br][c] = m1;
     s.m2[br][c] = m2;
@@ -803,18 +816,24 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
   atomicAdd(&a.bna_sums[tid * 4 + 0], (double)s.fin[0][tid]);
   atomicAdd(&a.bna_sums[tid * 4 + 1], (double)s.fin[1][tid]);
   atomicAdd(&a.bna_sums[tid * 4 + 2], (double)s.fin[2][tid]);
-  if (t1 > t0) {
+  {
     // accumulator row = tid: rows 0..63 -> branch mu channel c = tid, its dW1 row lives in columns 0..63;
-    // rows 64..127 -> branch logvar channel c = tid-64, columns 64..127 (off-diagonal blocks are unused)
+    // rows 64..127 -> branch logvar channel c = tid-64, columns 64..127 (off-diagonal blocks are unused).
+    // Every CTA stores its partial (zeros if it had no tile); dw1_reduce_kernel sums them once per pass.
     const int br = tid >> 6, c = tid & 63;
-    float* d = a.dprm + (size_t)br * lay.size + lay.W1 + c * F;
+    float4* d = reinterpret_cast<float4*>(a.dw1_partial + ((size_t)blockIdx.x * 2 + br) * (F * F) + c * F);
     umma::fence_after_sync();
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       float v[32];
-      umma::tmem_ld32(T_WG + lane_off + br * F + half * 32, v);
+      if (t1 > t0) {
+        umma::tmem_ld32(T_WG + lane_off + br * F + half * 32, v);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(&d[half * 32 + i], v[i]);
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[half * 8 + i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
   }
   umma::fence_before_sync();
@@ -861,6 +880,32 @@ int launch_fwd_tc_k(const CouplingArgs& a, const unsigned short* wimg, int mode,
 }
 
 }  // namespace
+
+// dW1 of every layer = sum over the pass-2 CTAs' partials (deterministic, no global atomics).
+// grid = (L*2, 16): blockIdx.x = layer*2 + branch, each thread owns one of the 64x64 entries.
+__global__ void __launch_bounds__(256)
+dw1_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ darena, const LayerMeta* __restrict__ meta, int G) {
+  const int l = blockIdx.x >> 1, br = blockIdx.x & 1;
+  const int e = blockIdx.y * 256 + threadIdx.x;
+  const LayerMeta m = meta[l];
+  const BranchLayout lay = branch_layout((int)m.k, (int)m.w, G);
+  const float* p = partial + ((size_t)l * n_cta * 2 + br) * (DPF_F * DPF_F) + e;
+  float s0 = 0.f, s1 = 0.f;
+  int c = 0;
+  for (; c + 2 <= n_cta; c += 2) {
+    s0 += p[(size_t)c * 2 * DPF_F * DPF_F];
+    s1 += p[(size_t)(c + 1) * 2 * DPF_F * DPF_F];
+  }
+  if (c < n_cta) s0 += p[(size_t)c * 2 * DPF_F * DPF_F];
+  darena[m.param_off + (size_t)br * lay.size + lay.W1 + e] = s0 + s1;
+}
+
+int launch_dw1_reduce(const float* partial, int n_cta, float* darena, const LayerMeta* meta_dev, int L, int G, cudaStream_t s) {
+  dw1_reduce_kernel<<<dim3(L * 2, 16), 256, 0, s>>>(partial, n_cta, darena, meta_dev, G);
+  return dpf_check_launch("dw1_reduce_kernel");
+}
+
+int tc_bwd_p2_max_ctas() { return dpf_num_sms(); }
 
 size_t tc_weight_image_elems_per_layer() { return (size_t)2 * N_IMG * F * F; }
 

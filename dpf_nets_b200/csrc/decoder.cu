@@ -156,6 +156,17 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
 
 int launch_coupling_bwd_fp32(const BwdArgs& a, int mode, int pass, cudaStream_t s);
 int launch_coupling_bwd_tc(const BwdArgs& a, const unsigned short* wimg, int mode, int pass, int split, cudaStream_t s);
+int launch_dw1_reduce(const float* partial, int n_cta, float* darena, const LayerMeta* meta_dev, int L, int G, cudaStream_t s);
+int tc_bwd_p2_max_ctas();
+
+// Scratch of the tensor-core backward: per-CTA wgrad partials [L][ctas][2][64*64] fp32.
+DPF_API int dpf_decoder_backward_scratch_bytes(int L, int B, int N, long long* bytes) {
+  DPF_REQUIRE(bytes && L > 0 && B > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_decoder_backward_scratch_bytes: bad arguments");
+  const long long tiles = (long long)B * ((N + DPF_TILE - 1) / DPF_TILE);
+  const long long ctas = tiles < tc_bwd_p2_max_ctas() ? tiles : tc_bwd_p2_max_ctas();
+  *bytes = (long long)sizeof(float) * L * ctas * 2 * DPF_F * DPF_F;
+  return DPF_OK;
+}
 int launch_coupling_bwd_final(const BwdArgs& a, const float* p_in, const float* dx_stored, float* dp, cudaStream_t s);
 int launch_film_backward(const float* arena, const float* stats, float* darena, const LayerMeta* meta_dev,
                          const float* g, const float* film, const float* dfilm, float* dg, int L, int B, int G,
@@ -170,16 +181,19 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
                                  float* stats, const float* p, const float* g, const float* P_out, const float* LV,
                                  const float* dP, long long dP_stride, const float* dMU, long long dMU_stride,
                                  const float* dLV, long long dLV_stride, float* darena, long long n_params,
-                                 float* dg, float* dp, void* workspace, int L, int G, int B, int N, int mode,
-                                 int training, int precision, float eps, void* stream) {
+                                 float* dg, float* dp, void* workspace, void* bwd_scratch, int L, int G, int B, int N,
+                                 int mode, int training, int precision, float eps, void* stream) {
   int rc = validate_common(meta_host, L, G, B, N, mode, precision);
   if (rc) return rc;
   DPF_REQUIRE(meta_dev && arena && stats && p && g && P_out && LV && darena && dg && workspace, DPF_ERR_NULL_PTR,
               "dpf_decoder_backward: null pointer");
+  DPF_REQUIRE(precision == 0 || bwd_scratch, DPF_ERR_NULL_PTR, "dpf_decoder_backward: the tensor path needs bwd_scratch (dpf_decoder_backward_scratch_bytes)");
   cudaStream_t s = (cudaStream_t)stream;
   const LayerMeta* meta = reinterpret_cast<const LayerMeta*>(meta_host);
   DecoderWorkspace ws = carve_workspace(workspace, L, G, B, N);
   const size_t plane = (size_t)B * 3 * N;
+  const long long n_tiles_all = (long long)B * ((N + DPF_TILE - 1) / DPF_TILE);
+  const int p2_ctas = (int)(n_tiles_all < tc_bwd_p2_max_ctas() ? n_tiles_all : tc_bwd_p2_max_ctas());
   cudaMemsetAsync(darena, 0, sizeof(float) * (size_t)n_params, s);
   cudaMemsetAsync(dg, 0, sizeof(float) * (size_t)B * G, s);
   cudaMemsetAsync(ws.dfilm, 0, sizeof(float) * (size_t)L * 4 * B * DPF_F, s);
@@ -212,6 +226,7 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     a.dfilm = ws.dfilm + (size_t)l * 4 * B * DPF_F;
     a.dprm = darena + meta[l].param_off;
     a.bna_sums = ws.bna_sums + (size_t)l * 2 * DPF_F * 4;
+    a.dw1_partial = precision >= 1 ? (float*)bwd_scratch + (size_t)l * p2_ctas * 2 * DPF_F * DPF_F : nullptr;
     if (q < L - 1) set_pending(a, q + 1);
     const unsigned short* wimg = ws.w1_bf16 + (size_t)l * tc_weight_image_elems_per_layer();
     {
@@ -232,6 +247,10 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     ProfScope ps(CAT_BWD_FINAL, s);
     rc = launch_coupling_bwd_final(a, p, ws.dx[0], dp, s);
     if (rc) return rc;
+    if (precision >= 1) {
+      rc = launch_dw1_reduce((const float*)bwd_scratch, p2_ctas, darena, reinterpret_cast<const LayerMeta*>(meta_dev), L, G, s);
+      if (rc) return rc;
+    }
   }
   ProfScope ps(CAT_FILM_BWD, s);
   return launch_film_backward(arena, stats, darena, reinterpret_cast<const LayerMeta*>(meta_dev), g, ws.film,

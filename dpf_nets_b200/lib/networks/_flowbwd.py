@@ -32,10 +32,15 @@ def run_backward(ctx, dP, dMU, dLV):
     darena = torch.empty_like(arena)
     dg = torch.empty_like(g)
     dp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+    scratch = None
+    if PRECISIONS[ctx.precision] >= 1:
+        nb = ctypes.c_longlong(0)
+        _lib.check(_lib.lib().dpf_decoder_backward_scratch_bytes(L, B, N, ctypes.byref(nb)), "dpf_decoder_backward_scratch_bytes")
+        scratch = torch.empty(int(nb.value), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dpf_decoder_backward", _meta_host_ptr(stack), stack.layer_meta, arena, stack.stats, p, g,
                   out[0], out[2], dP_t, ctypes.c_longlong(dP_s), dMU_t, ctypes.c_longlong(dMU_s),
-                  dLV_t, ctypes.c_longlong(dLV_s), darena, ctypes.c_longlong(arena.numel()), dg, dp, ctx.ws,
+                  dLV_t, ctypes.c_longlong(dLV_s), darena, ctypes.c_longlong(arena.numel()), dg, dp, ctx.ws, scratch,
                   L, G, B, N, MODES[mode], ctx.training, PRECISIONS[ctx.precision],
                   ctypes.c_float(stack.eps_value), device=dev)
     return dp, dg, darena, None, None, None, None

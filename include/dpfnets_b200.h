@@ -98,8 +98,10 @@ int dpf_decoder_backward(const long long* meta_host, const long long* meta_dev, 
                          float* stats, const float* p, const float* g, const float* P_out, const float* LV,
                          const float* dP, long long dP_stride, const float* dMU, long long dMU_stride,
                          const float* dLV, long long dLV_stride, float* darena, long long n_params,
-                         float* dg, float* dp, void* workspace, int L, int G, int B, int N, int mode,
-                         int training, int precision, float eps, void* stream);
+                         float* dg, float* dp, void* workspace, void* bwd_scratch, int L, int G, int B, int N,
+                         int mode, int training, int precision, float eps, void* stream);
+/* bwd_scratch: per-CTA wgrad partials of the tensor path (may be NULL for precision 0). */
+int dpf_decoder_backward_scratch_bytes(int L, int B, int N, long long* bytes);
 
 /* Fused AMSGrad step with the reference's exact update (lib/networks/optimizers.py:53-74):
  * denom = sqrt(max_exp_avg_sq or exp_avg_sq)/bc2 + eps; p -= wd*p + lr*(exp_avg/bc1)/denom.
