@@ -63,6 +63,7 @@ struct DecoderWorkspace {
   double* bna_sums;   // [L][2][F][4]   backward: dbeta, E0, E1, pad
   float* dx[2];       // [B][3][N]      ping-pong stored input gradients
   unsigned short* w1_bf16;  // [L][2][3][F*F] bf16 images {W1 hi, W1^T hi, W1 lo} in UMMA smem layout (tensor path)
+  unsigned int* barriers;   // [L][32] grid-barrier counters of the merged train-mode forward (one 128-B line per layer)
   size_t bytes;
 };
 
@@ -81,6 +82,7 @@ __host__ inline DecoderWorkspace carve_workspace(void* base, int L, int G, int B
   w.dx[0] = (float*)take(sizeof(float) * (size_t)B * 3 * N);
   w.dx[1] = (float*)take(sizeof(float) * (size_t)B * 3 * N);
   w.w1_bf16 = (unsigned short*)take(sizeof(unsigned short) * (size_t)L * 6 * DPF_F * DPF_F);
+  w.barriers = (unsigned int*)take(sizeof(unsigned int) * (size_t)L * 32);
   w.bytes = off;
   (void)G;
   return w;

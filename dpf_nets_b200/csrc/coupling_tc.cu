@@ -389,6 +389,222 @@ coupling_fwd_tc_kernel(const CouplingArgs a, const unsigned short* __restrict__ 
 }
 
 // =============================================================================================
+// Train-mode forward, ONE cooperative launch per layer: statistics phase -> grid barrier -> apply
+// phase, with the 64x64 SharedDot accumulators RESIDENT IN TMEM across the barrier (no recompute,
+// one prologue, one weight staging).  Each CTA owns up to RES tiles (RES * 128 TMEM columns; two
+// CTAs per SM use all 512), so this form covers n_tiles <= RES * grid; larger problems use the
+// two-launch form above.
+// =============================================================================================
+constexpr int RES = 2;
+
+// Software grid barrier.  The launch puts exactly as many CTAs on the chip as fit (2 per SM by shared
+// memory and TMEM), so all of them are resident and the barrier completes; should that ever not hold
+// (another tenant on the SMs) the spin gives up after ~2 s and raises counter[1] instead of hanging
+// the GPU - the host side checks it (dpf_decoder_status).
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v < expected) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+          atomicExch(counter + 1, 1u);
+          break;
+        }
+      }
+    } while (v < expected);
+  }
+  __syncthreads();
+}
+
+template <int K, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(DPF_TILE)
+coupling_fwd_train_tc_kernel(const CouplingArgs a, const unsigned short* __restrict__ wimg, unsigned int* __restrict__ barrier_counter) {
+  extern __shared__ unsigned char smraw[];
+  TcFwdSmem& s = *reinterpret_cast<TcFwdSmem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const BranchLayout lay = branch_layout(a.k, a.w, a.G);
+  const bool writer = (blockIdx.x == 0) && a.update_stats;
+  const uint32_t tmem = tc_setup(s.c, RES * 128);
+  tc_load_weights<false>(s.c, s.W, wimg);
+  tc_prologue_tables(a, lay, s.c, writer, false);   // BN_a fold only; BN_b after the barrier
+  {
+    const int br = tid >> 6, c = tid & 63;
+    const float* prm = a.prm + (size_t)br * lay.size;
+    s.c.W2[br][0][c] = prm[lay.W2 + c];
+    s.c.W2[br][1][c] = (a.w == 2) ? prm[lay.W2 + F + c] : 0.f;
+    if (c < 2) s.c.b2[br][c] = (c < a.w) ? prm[lay.b2 + c] : 0.f;
+  }
+  float sacc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sacc[i][0] = sacc[i][1] = 0.f;
+  umma::mbar_wait(&s.c.bar_load, 0);
+  __syncthreads();
+
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t phase = 0;
+  float xin[RES][3];
+  // ---------------- phase 1: h1 -> UMMA -> per-channel sum / sum of squares ----------------
+#pragma unroll
+  for (int ts = 0; ts < RES; ++ts) {
+    const int tile = blockIdx.x + ts * gridDim.x;
+    if (tile < a.n_tiles) {                      // uniform per CTA
+      const int b = tile / a.tiles_per_b;
+      const int n = (tile - b * a.tiles_per_b) * DPF_TILE + tid;
+      const bool valid = n < a.N;
+      const float* px = a.x + (size_t)b * 3 * a.N + n;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) xin[ts][ch] = valid ? px[(size_t)ch * a.N] : 0.f;
+      const float xk0 = pick3(xin[ts], a.keep0);
+      const float xk1 = (K == 2) ? pick3(xin[ts], a.keep1) : 0.f;
+#pragma unroll
+      for (int br = 0; br < 2; ++br) {
+        write_h1_row<K, SPLIT>(s.H, s.H + IMG_H, s.c.A0[br], xk0, xk1, tid);
+        umma::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          umma::fence_after_sync();
+          issue_gemm1<SPLIT>(tmem + ts * 128 + br * F, s.H, s.H + IMG_H, wimg_at<false>(s.W, br, 0), wimg_at<false>(s.W, br, 1));
+          umma::mma_commit(&s.c.bar_mma);
+        }
+        umma::mbar_wait(&s.c.bar_mma, phase);
+        phase ^= 1;
+        umma::fence_after_sync();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          umma::tmem_ld32(lane_addr + ts * 128 + br * F + half * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] : 0.f;
+          float rs, rq;
+          colreduce32_sq(s.scratch, v, tid, rs, rq);
+          sacc[br * 2 + half][0] += rs;
+          sacc[br * 2 + half][1] += rq;
+        }
+        umma::fence_before_sync();
+        __syncthreads();                         // the activation tiles are free again (TMEM columns stay)
+      }
+    }
+  }
+  {
+    float* fin = &s.fin[0][0];
+    for (int i = tid; i < 4 * F; i += DPF_TILE) fin[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      atomicAdd(&s.fin[0][ch * 32 + (tid & 31)], sacc[ch][0]);
+      atomicAdd(&s.fin[1][ch * 32 + (tid & 31)], sacc[ch][1]);
+    }
+    __syncthreads();
+    if (blockIdx.x < a.n_tiles) {
+      atomicAdd(&a.bnb_sums[tid * 2 + 0], (double)s.fin[0][tid]);
+      atomicAdd(&a.bnb_sums[tid * 2 + 1], (double)s.fin[1][tid]);
+    }
+  }
+  // ---------------- grid-wide barrier: every CTA's statistics are in bnb_sums ----------------
+  grid_barrier(barrier_counter, gridDim.x);
+  // ---------------- phase 2: BN_b x FiLM fold, epilogue from the resident accumulators ----------------
+  {
+    const int br = tid >> 6, c = tid & 63;
+    const double M = (double)a.B * (double)a.N;
+    const double sm = __ldcg(&a.bnb_sums[(br * F + c) * 2 + 0]), sq = __ldcg(&a.bnb_sums[(br * F + c) * 2 + 1]);
+    const double dm = sm / M;
+    const double dv = fmax(sq / M - dm * dm, 0.0);
+    s.c.mb[br][c] = (float)dm;
+    s.c.ib[br][c] = 1.f / sqrtf((float)dv + DPF_BN_EPS);
+    if (writer) {
+      float* st = a.stat + (size_t)br * ST_COUNT * F;
+      st[ST_BNB_RM * F + c] = (1.f - DPF_BN_MOM) * st[ST_BNB_RM * F + c] + DPF_BN_MOM * (float)dm;
+      st[ST_BNB_RV * F + c] = (1.f - DPF_BN_MOM) * st[ST_BNB_RV * F + c] + DPF_BN_MOM * (float)(dv * (M / fmax(M - 1.0, 1.0)));
+    }
+  }
+  __syncthreads();
+  float macc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) macc[i] = 0.f;
+  umma::fence_after_sync();
+#pragma unroll
+  for (int ts = 0; ts < RES; ++ts) {
+    const int tile = blockIdx.x + ts * gridDim.x;
+    if (tile < a.n_tiles) {
+      const int b = tile / a.tiles_per_b;
+      const int n = (tile - b * a.tiles_per_b) * DPF_TILE + tid;
+      const bool valid = n < a.N;
+      __syncthreads();                           // previous tile finished with the epi table
+      tc_tile_film(a, s.c, b);
+      __syncthreads();
+      float o[2][2];
+#pragma unroll
+      for (int br = 0; br < 2; ++br) {
+        float o0 = s.c.b2[br][0], o1 = s.c.b2[br][1];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          umma::tmem_ld32(lane_addr + ts * 128 + br * F + half * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 e = s.c.epi[br][half * 32 + i];
+            const float h3 = fmaxf(fmaf(e.x, v[i], e.y), 0.f);
+            o0 = fmaf(e.z, h3, o0);
+            o1 = fmaf(e.w, h3, o1);
+          }
+        }
+        o[br][0] = o0;
+        o[br][1] = o1;
+      }
+      float yv[3], muv[3] = {0.f, 0.f, 0.f}, lvv[3] = {0.f, 0.f, 0.f};
+      const float sig1 = sqrtf(a.eps + 1.0f);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) yv[ch] = (MODE == 0) ? sig1 * xin[ts][ch] : xin[ts][ch] / sig1;
+#pragma unroll
+      for (int wi = 0; wi < 2; ++wi) {
+        if (wi < a.w) {
+          const int ch = wi == 0 ? a.warp0 : a.warp1;
+          const float l = softsign(o[1][wi]);
+          const float sig = sqrtf(a.eps + expf(l));
+          const float m = o[0][wi];
+          const float xv = pick3(xin[ts], ch);
+          const float r = (MODE == 0) ? fmaf(sig, xv, m) : (xv - m) / sig;
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (q == ch) { yv[q] = r; muv[q] = m; lvv[q] = l; }
+        }
+      }
+      if (valid) {
+        const size_t base = (size_t)b * 3 * a.N + n;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          a.y[base + (size_t)ch * a.N] = yv[ch];
+          a.mu[base + (size_t)ch * a.N] = muv[ch];
+          a.lv[base + (size_t)ch * a.N] = lvv[ch];
+        }
+        macc[0] += yv[0]; macc[1] += yv[1]; macc[2] += yv[2];
+        macc[3] = fmaf(yv[0], yv[0], macc[3]); macc[4] = fmaf(yv[0], yv[1], macc[4]); macc[5] = fmaf(yv[0], yv[2], macc[5]);
+        macc[6] = fmaf(yv[1], yv[1], macc[6]); macc[7] = fmaf(yv[1], yv[2], macc[7]); macc[8] = fmaf(yv[2], yv[2], macc[8]);
+      }
+    }
+  }
+  if (a.mom_out) {
+    const int lane = tid & 31;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double v = warp_sum_d((double)macc[i]);
+      if (lane == 0) s.mom[i][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 9) atomicAdd(a.mom_out + tid, s.mom[tid][0] + s.mom[tid][1] + s.mom[tid][2] + s.mom[tid][3]);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, RES * 128);
+}
+
+// =============================================================================================
 // Backward helpers (same math as coupling_bwd.cu)
 // =============================================================================================
 __device__ Pending tc_compute_pending(const BwdArgs& a, bool writer, double* red) {
@@ -873,6 +1089,37 @@ int launch_bwd_tc_t(const BwdArgs& a, const unsigned short* wimg, int pass, cuda
   return dpf_check_launch("coupling_bwd_p2_tc_kernel");
 }
 
+static int g_coop_occupancy = -1;
+
+// cooperative (all CTAs co-resident) launch of the merged train-mode forward; DPF_ERR_UNSUPPORTED when
+// the problem does not fit RES tiles per resident CTA - the caller then uses the two-launch form
+template <int K, int MODE, bool SPLIT>
+int launch_fwd_train_t(const CouplingArgs& a, const unsigned short* wimg, unsigned int* counter, cudaStream_t st) {
+  static int max_grid = -1;
+  auto kern = coupling_fwd_train_tc_kernel<K, MODE, SPLIT>;
+  if (max_grid < 0) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcFwdSmem>());
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DPF_TILE, smem_for<TcFwdSmem>());
+    g_coop_occupancy = per_sm;
+    // shared memory allows 2 CTAs per SM (2 x ~92 KB) and so do the 512 TMEM columns (RES*128 each);
+    // the cooperative launch itself validates co-residency and we fall back if it refuses
+    per_sm = 512 / (RES * 128);
+    max_grid = per_sm * dpf_num_sms();
+  }
+  if (max_grid <= 0 || a.n_tiles > RES * max_grid) {
+    dpf_set_error("merged forward not used: n_tiles=%d max_grid=%d smem=%zu", a.n_tiles, max_grid, smem_for<TcFwdSmem>());
+    return DPF_ERR_UNSUPPORTED;
+  }
+  // Not cudaLaunchCooperativeKernel: the runtime's co-residency check assumes ONE CTA per SM for any
+  // kernel that allocates TMEM (occupancy query returns 1 at every shared-memory size), although two
+  // CTAs with 256 columns each do share an SM.  grid <= 2 * SMs keeps every CTA resident.
+  const int grid = min(a.n_tiles, max_grid);
+  kern<<<grid, DPF_TILE, smem_for<TcFwdSmem>(), st>>>(a, wimg, counter);
+  return dpf_check_launch("coupling_fwd_train_tc_kernel");
+}
+
 template <int K, bool SPLIT>
 int launch_fwd_tc_k(const CouplingArgs& a, const unsigned short* wimg, int mode, bool stats_pass, int grid, cudaStream_t s) {
   if (mode == 0) return stats_pass ? launch_fwd_tc_t<K, 0, true, SPLIT>(a, wimg, grid, s) : launch_fwd_tc_t<K, 0, false, SPLIT>(a, wimg, grid, s);
@@ -919,6 +1166,33 @@ int launch_coupling_fwd_tc(const CouplingArgs& a, const unsigned short* wimg, in
   const int grid = min(a.n_tiles, dpf_num_sms() * 2);
   if (a.k == 2) return split ? launch_fwd_tc_k<2, true>(a, wimg, mode, stats_pass, grid, s) : launch_fwd_tc_k<2, false>(a, wimg, mode, stats_pass, grid, s);
   return split ? launch_fwd_tc_k<1, true>(a, wimg, mode, stats_pass, grid, s) : launch_fwd_tc_k<1, false>(a, wimg, mode, stats_pass, grid, s);
+}
+
+// merged statistics + apply launch of one train-mode layer (DPF_ERR_UNSUPPORTED = does not fit)
+int launch_coupling_fwd_train_tc(const CouplingArgs& a, const unsigned short* wimg, int mode, int split, unsigned int* counter,
+                                 cudaStream_t s) {
+  if (a.k == 2) {
+    if (split) return mode == 0 ? launch_fwd_train_t<2, 0, true>(a, wimg, counter, s) : launch_fwd_train_t<2, 1, true>(a, wimg, counter, s);
+    return mode == 0 ? launch_fwd_train_t<2, 0, false>(a, wimg, counter, s) : launch_fwd_train_t<2, 1, false>(a, wimg, counter, s);
+  }
+  if (split) return mode == 0 ? launch_fwd_train_t<1, 0, true>(a, wimg, counter, s) : launch_fwd_train_t<1, 1, true>(a, wimg, counter, s);
+  return mode == 0 ? launch_fwd_train_t<1, 0, false>(a, wimg, counter, s) : launch_fwd_train_t<1, 1, false>(a, wimg, counter, s);
+}
+
+// occupancy (CTAs per SM) the runtime computes for the merged / the plain apply kernel at `smem` dynamic bytes
+int tc_debug_occupancy(int which, int smem) {
+  int n = -1;
+  if (which == 0) {
+    auto k = coupling_fwd_train_tc_kernel<1, 1, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, DPF_TILE, smem);
+  } else {
+    auto k = coupling_fwd_tc_kernel<1, 1, false, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, DPF_TILE, smem);
+  }
+  return n;
 }
 
 int launch_coupling_bwd_tc(const BwdArgs& a, const unsigned short* wimg, int mode, int pass, int split, cudaStream_t s) {

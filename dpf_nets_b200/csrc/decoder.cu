@@ -57,6 +57,17 @@ int launch_coupling_fwd_fp32(const CouplingArgs& a, int mode, bool stats_pass, c
 int launch_pack_w1(const float* arena, const LayerMeta* meta_dev, int L, int G, unsigned short* out, cudaStream_t s);
 int launch_coupling_fwd_tc(const CouplingArgs& a, const unsigned short* wimg, int mode, bool stats_pass, int split, cudaStream_t s);
 size_t tc_weight_image_elems_per_layer();
+int launch_coupling_fwd_train_tc(const CouplingArgs& a, const unsigned short* wimg, int mode, int split, unsigned int* counter,
+                                 cudaStream_t s);
+
+// The merged (cooperative, TMEM-resident) train-mode forward is on by default; dpf_set_option(0, 0)
+// forces the two-launch form (tests compare both).
+static bool g_merged_forward = true;
+DPF_API int dpf_set_option(int option, int value) {
+  DPF_REQUIRE(option == 0, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
+  g_merged_forward = value != 0;
+  return DPF_OK;
+}
 
 static int validate_common(const long long* meta_host, int L, int G, int B, int N, int mode, int precision) {
   DPF_REQUIRE(meta_host, DPF_ERR_NULL_PTR, "decoder: layer table is null");
@@ -131,6 +142,8 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
     if (rc) return rc;
   }
   const float* x = p;
+  bool merged_ok = g_merged_forward;
+  if (training && precision >= 1) cudaMemsetAsync(ws.barriers, 0, sizeof(unsigned int) * (size_t)L * 32, s);
   for (int q = 0; q < L; ++q) {
     const int l = mode == 0 ? q : L - 1 - q;
     CouplingArgs a = make_args(meta[l], arena, stats, ws, l, q, G, B, N, training, update_stats, eps);
@@ -139,6 +152,14 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
     a.mu = MU + (size_t)l * plane;
     a.lv = LV + (size_t)l * plane;
     const unsigned short* wimg = ws.w1_bf16 + (size_t)l * tc_weight_image_elems_per_layer();
+    if (training && precision >= 1 && merged_ok) {
+      // one cooperative launch: statistics -> grid barrier -> apply from TMEM-resident accumulators
+      ProfScope ps(CAT_FWD_APPLY, s);
+      rc = launch_coupling_fwd_train_tc(a, wimg, mode, precision == 2, ws.barriers + (size_t)l * 32, s);
+      if (rc == DPF_OK) { x = a.y; continue; }
+      if (rc != DPF_ERR_UNSUPPORTED) return rc;
+      merged_ok = false;                        // does not fit: two-launch form for this and later layers
+    }
     if (training) {
       ProfScope ps(CAT_FWD_STATS, s);
       rc = precision >= 1 ? launch_coupling_fwd_tc(a, wimg, mode, true, precision == 2, s) : launch_coupling_fwd_fp32(a, mode, true, s);
@@ -151,6 +172,24 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
     if (rc) return rc;
     x = a.y;
   }
+  return DPF_OK;
+}
+
+// Synchronous health check of a forward workspace: *flag = number of layers whose grid barrier gave up
+// (must be 0; a non-zero value means the merged forward's CTAs were not co-resident and the outputs
+// of that pass are invalid).
+DPF_API int dpf_decoder_status(const void* workspace, int L, int G, int B, int N, int* flag) {
+  DPF_REQUIRE(workspace && flag && L > 0, DPF_ERR_BAD_ARG, "dpf_decoder_status: bad arguments");
+  DecoderWorkspace ws = carve_workspace(const_cast<void*>(workspace), L, G, B, N);
+  std::vector<unsigned int> host((size_t)L * 32);
+  cudaError_t e = cudaMemcpy(host.data(), ws.barriers, host.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    dpf_set_error("dpf_decoder_status: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  int bad = 0;
+  for (int l = 0; l < L; ++l) bad += host[(size_t)l * 32 + 1] != 0;
+  *flag = bad;
   return DPF_OK;
 }
 

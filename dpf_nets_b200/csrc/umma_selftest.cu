@@ -84,3 +84,11 @@ DPF_API int dpf_umma_selftest(const void* a_img, int a_bytes, const void* b_img,
                                                              use_bulk, d_out);
   return dpf_check_launch("umma_selftest_kernel");
 }
+
+int tc_debug_occupancy(int which, int smem);
+// Debug probe: occupancy the runtime reports for the merged (which = 0) / plain (1) forward kernel.
+DPF_API int dpf_debug_occupancy(int which, int smem, int* out) {
+  DPF_REQUIRE(out, DPF_ERR_NULL_PTR, "dpf_debug_occupancy: null pointer");
+  *out = tc_debug_occupancy(which, smem);
+  return DPF_OK;
+}

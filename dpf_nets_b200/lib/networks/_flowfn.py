@@ -43,6 +43,7 @@ class CouplingStackFunction(torch.autograd.Function):
         if training:
             stack.num_batches_tracked += 1
         ctx.stack, ctx.mode, ctx.training, ctx.ws, ctx.precision = stack, mode, bool(training), ws, precision
+        stack._last_pass = (ws, L, G, B, N)
         ctx.save_for_backward(p, g, arena, out)
         ctx.set_materialize_grads(False)
         return out[0], out[1], out[2]
@@ -70,3 +71,12 @@ def run_stack(stack, p, g, mode):
     p = p.contiguous()
     g = g.contiguous()
     return CouplingStackFunction.apply(p, g, stack.arena, stack, mode, stack.training, resolve_precision(stack))
+
+
+def last_pass_status(stack):
+    """Synchronous health check of the stack's most recent forward workspace (0 = fine): number of
+    layers whose merged-forward grid barrier timed out."""
+    ws, L, G, B, N = stack._last_pass
+    flag = ctypes.c_int(-1)
+    _lib.check(_lib.lib().dpf_decoder_status(_lib.ptr(ws), L, G, B, N, ctypes.byref(flag)), "dpf_decoder_status")
+    return flag.value

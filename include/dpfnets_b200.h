@@ -28,6 +28,8 @@ int dpf_device_check(void);
 int dpf_launch_count(long long* count);
 /* Per-kernel-class CUDA-event timing of the decoder entry points (off by default).
  * classes: 0 film_fwd, 1 moments, 2 fwd_stats, 3 fwd_apply, 4 bwd_p1, 5 bwd_p2, 6 bwd_final, 7 film_bwd */
+/* option 0: merged cooperative train-mode forward (1 = on, default; 0 = two launches per layer). */
+int dpf_set_option(int option, int value);
 int dpf_profile_enable(int on);
 int dpf_profile_collect(double* ms, long long* counts, int n);
 
@@ -100,6 +102,9 @@ int dpf_decoder_backward(const long long* meta_host, const long long* meta_dev, 
                          const float* dLV, long long dLV_stride, float* darena, long long n_params,
                          float* dg, float* dp, void* workspace, void* bwd_scratch, int L, int G, int B, int N,
                          int mode, int training, int precision, float eps, void* stream);
+/* Synchronous health check of a forward workspace: *flag = layers whose merged-forward grid barrier
+ * timed out (must be 0). */
+int dpf_decoder_status(const void* workspace, int L, int G, int B, int N, int* flag);
 /* bwd_scratch: per-CTA wgrad partials of the tensor path (may be NULL for precision 0). */
 int dpf_decoder_backward_scratch_bytes(int L, int B, int N, long long* bytes);
 
@@ -115,6 +120,9 @@ int dpf_umma_selftest(const void* a_img, int a_bytes, const void* b_img, int b_b
                       unsigned long long a_templ, unsigned long long b_templ, unsigned int idesc,
                       int num_k, int a_kstep, int b_kstep, int ncols, int use_bulk, float* d_out,
                       void* stream);
+
+/* Debug probe: CTAs/SM the runtime reports for the merged (0) / plain (1) forward kernel at `smem` bytes. */
+int dpf_debug_occupancy(int which, int smem, int* out);
 
 #ifdef __cplusplus
 }

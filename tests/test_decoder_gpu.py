@@ -425,3 +425,32 @@ def test_bf16x3_coupling_layer_vs_reference(mods, cuda, name, mode):
     assert max(errs_out) < 5e-3, errs_out
     assert rel(p.grad, t["dp"]) < 5e-2 and rel(g.grad, t["dg"]) < 5e-2
     assert errs[0][0] < 0.1, errs[:4]
+
+
+def test_merged_cooperative_forward_equals_two_launch_form(mods, cuda, native_lib):
+    """Train-mode forward: the one-launch-per-layer cooperative kernel (TMEM-resident accumulators
+    across a grid barrier) vs the statistics + apply two-launch form, incl. a size that does not fit
+    (falls back) and ragged tiles."""
+    _, decoders = mods
+    torch.manual_seed(5)
+    m = decoders.LocalCondRNVPDecoder(3, 64, 32).to(cuda)
+    m.precision = "bf16x3"
+    m.train()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    gen = torch.Generator().manual_seed(6)
+    for B, N in ((4, 1000), (32, 2048), (5, 16384)):
+        p = (torch.rand((B, 3, N), generator=gen) - 0.5).to(cuda)
+        g = torch.randn((B, 32), generator=gen).to(cuda)
+        outs = []
+        for merged in (1, 0):
+            native_lib.dpf_set_option(0, merged)
+            m.load_state_dict(sd0)
+            with torch.no_grad():
+                ps, mus, lvs = m(p, g, mode="inverse")
+            from dpf_nets_b200.lib.networks._flowfn import last_pass_status
+            assert last_pass_status(m) == 0
+            outs.append((ps.stacked.clone(), lvs.stacked.clone(), {k: v.clone() for k, v in m.state_dict().items() if "running" in k}))
+        native_lib.dpf_set_option(0, 1)
+        assert rel(outs[0][0], outs[1][0]) < 1e-4 and rel(outs[0][1], outs[1][1]) < 1e-4, (B, N)
+        for k in outs[0][2]:
+            assert rel(outs[0][2][k], outs[1][2][k]) < 1e-4, k
