@@ -167,8 +167,11 @@ __device__ __forceinline__ void colreduce32_sq(float* scratch, const float va[32
   rq = sb;
 }
 
+// (all table helpers index by row = threadIdx.x & 127: in the 256-thread kernels both threads of a
+// point compute identical entries; side effects are restricted to threadIdx.x < 128)
 __device__ __forceinline__ void tc_prologue_tables(const CouplingArgs& a, const BranchLayout& lay, TcCommon& s, bool writer, bool need_bnb) {
-  const int tid = threadIdx.x, br = tid >> 6, c = tid & 63;
+  const int tid = threadIdx.x & 127, br = tid >> 6, c = tid & 63;
+  writer = writer && threadIdx.x < 128;
   float A00, A01, c0;
   fold_bn_a(a, lay, br, c, writer, A00, A01, c0, nullptr, nullptr);
   s.A0[br][c] = make_float4(A00, A01, c0, 0.f);
@@ -185,7 +188,7 @@ __device__ __forceinline__ void tc_prologue_tables(const CouplingArgs& a, const 
 }
 
 __device__ __forceinline__ void tc_tile_film(const CouplingArgs& a, TcCommon& s, int b) {
-  const int tid = threadIdx.x, br = tid >> 6, c = tid & 63;
+  const int tid = threadIdx.x & 127, br = tid >> 6, c = tid & 63;
   const float sc = a.film[((size_t)(br * 2 + 0) * a.B + b) * F + c];
   const float sh = a.film[((size_t)(br * 2 + 1) * a.B + b) * F + c];
   const float S = sc * s.ib[br][c];
@@ -610,7 +613,8 @@ coupling_fwd_train_tc_kernel(const CouplingArgs a, const unsigned short* __restr
 __device__ Pending tc_compute_pending(const BwdArgs& a, bool writer, double* red) {
   Pending P{0.f, 0.f, 0.f, 0.f, 0.f};
   if (!a.has_pending) return P;
-  const int tid = threadIdx.x, br = tid >> 6, c = tid & 63;
+  const int tid = threadIdx.x & 127, br = tid >> 6, c = tid & 63;
+  writer = writer && threadIdx.x < 128;
   const BranchLayout nlay = branch_layout(a.nk, a.nw, a.f.G);
   const double M = (double)a.f.B * (double)a.f.N;
   const BnA bn = bn_a_of(a.nprm, a.nstat, nlay, a.n_mom, M, a.nk, a.nkeep0, a.nkeep1, a.f.training, br, c);
@@ -1057,6 +1061,257 @@ coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
+// =============================================================================================
+// Backward pass 2, two threads per point (256 threads per CTA): thread (row = tid & 127, part =
+// tid >> 7) owns channels [32*part, 32*part+32) of BOTH branches of its point - same TMEM lane, half
+// of the columns.  Twice the warps per SM for the same shared memory: the latency-bound phases
+// (TMEM loads, column reductions, tile writes) interleave across 8 warps instead of 4.
+// =============================================================================================
+constexpr int NT2 = 256;
+
+// column sums of ONE quantity per part: scratch = float[2 parts][128][33]; returns the partial over
+// rows [32*q, 32*q+32) (q = warp & 3) of column (lane) of this thread's part
+__device__ __forceinline__ float colreduce32_part(float* scratch, const float va[32], int row, int part, int lane, int quarter) {
+  float* sc = scratch + part * (DPF_TILE * 33);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sc[row * 33 + i] = va[i];
+  __syncthreads();
+  float sa = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) sa += sc[(quarter * 32 + r) * 33 + lane];
+  return sa;
+}
+
+struct TcP2Smem2 {
+  unsigned char W[2 * N_IMG * IMG_W];   // [br][W1 hi, W1 lo, W1^T hi]
+  unsigned char H[2 * IMG_H];           // h1 hi tiles
+  unsigned char D[2 * IMG_H];           // h1 lo tiles, then dh2pre tiles
+  TcCommon c;
+  float m1[2][F], m2[2][F];
+  float scratch[2 * DPF_TILE * 33];
+  float fin[3][2 * F];
+  float t1buf[DPF_TILE][2];
+};
+
+template <int K, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(NT2)
+coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ wimg) {
+  extern __shared__ unsigned char smraw[];
+  TcP2Smem2& s = *reinterpret_cast<TcP2Smem2*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, part = tid >> 7, quarter = warp & 3;
+  const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
+  const uint32_t tmem = tc_setup(s.c, 512);
+  tc_load_weights<true>(s.c, s.W, wimg);
+  tc_prologue_tables(a.f, lay, s.c, false, true);
+  if (tid < 128) {
+    const int br = tid >> 6, c = tid & 63;
+    float m1 = 0.f, m2 = 0.f;
+    if (a.f.training) {
+      double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+      const float* fs = a.f.film + (size_t)(br * 2 + 0) * a.f.B * F + c;
+      const float* dsr = a.dfilm + (size_t)(br * 2 + 0) * a.f.B * F + c;
+      const float* dtr = a.dfilm + (size_t)(br * 2 + 1) * a.f.B * F + c;
+      int b = 0;
+      for (; b + 4 <= a.f.B; b += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double sc = fs[(size_t)(b + u) * F];
+          s1[u] += sc * (double)dtr[(size_t)(b + u) * F];
+          s2[u] += sc * (double)dsr[(size_t)(b + u) * F];
+        }
+      }
+      for (; b < a.f.B; ++b) {
+        const double sc = fs[(size_t)b * F];
+        s1[0] += sc * (double)dtr[(size_t)b * F];
+        s2[0] += sc * (double)dsr[(size_t)b * F];
+      }
+      const double M = (double)a.f.B * (double)a.f.N;
+      m1 = (float)(((s1[0] + s1[1]) + (s1[2] + s1[3])) / M);
+      m2 = (float)(((s2[0] + s2[1]) + (s2[2] + s2[3])) / M);
+    }
+    s.m1[br][c] = m1;
+    s.m2[br][c] = m2;
+  }
+  for (int i = tid; i < 3 * 2 * F; i += NT2) (&s.fin[0][0])[i] = 0.f;
+  __syncthreads();
+  const Pending P = tc_compute_pending(a, false, s.c.pend);
+  const float sig1 = sqrtf(a.f.eps + 1.0f);
+  umma::mbar_wait(&s.c.bar_load, 0);
+  __syncthreads();
+
+  int t0, t1;
+  tile_range(a.f.n_tiles, t0, t1);
+  uint32_t phase = 0;
+  const uint32_t T_FWD = tmem, T_DG = tmem + 128, T_WG = tmem + 256;
+  const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+  for (int tile = t0; tile < t1; ++tile) {
+    const int b = tile / a.f.tiles_per_b;
+    const int n = (tile - b * a.f.tiles_per_b) * DPF_TILE + row;
+    const bool valid = n < a.f.N;
+    tc_tile_film(a.f, s.c, b);
+    const TcPoint g = tc_load_point<MODE>(a, P, b, n, valid);
+    const float xk0 = pick3(g.x, a.f.keep0);
+    const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
+    // h1 (hi / lo) chunks of this part: 4 x 16 B per branch
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const int q = part * 4 + qq;
+        uint32_t w[4], wl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 Aa = s.c.A0[br][q * 8 + 2 * i], Ab = s.c.A0[br][q * 8 + 2 * i + 1];
+          float va = fmaf(Aa.x, xk0, Aa.z), vb = fmaf(Ab.x, xk0, Ab.z);
+          if (K == 2) { va = fmaf(Aa.y, xk1, va); vb = fmaf(Ab.y, xk1, vb); }
+          va = fmaxf(va, 0.f);
+          vb = fmaxf(vb, 0.f);
+          w[i] = umma::pack_bf16(va, vb);
+          if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
+        }
+        const uint32_t off = umma::sw128_offset(row, q);
+        *reinterpret_cast<uint4*>(s.H + br * IMG_H + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (SPLIT) *reinterpret_cast<uint4*>(s.D + br * IMG_H + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      }
+    }
+    umma::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+      issue_gemm1<SPLIT>(T_FWD, s.H, s.D, wimg_at<true>(s.W, 0, 0), wimg_at<true>(s.W, 0, 1));
+      issue_gemm1<SPLIT>(T_FWD + F, s.H + IMG_H, s.D + IMG_H, wimg_at<true>(s.W, 1, 0), wimg_at<true>(s.W, 1, 1));
+      umma::mma_commit(&s.c.bar_mma);
+    }
+    umma::mbar_wait(&s.c.bar_mma, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+    // ---- epilogue A: dh2pre (bf16) of this part's 32 channels of each branch -> D tiles ----
+#pragma unroll 1
+    for (int br = 0; br < 2; ++br) {
+      const float d0 = br == 0 ? g.do_mu[0] : g.do_lv[0];
+      const float d1 = br == 0 ? g.do_mu[1] : g.do_lv[1];
+      float v[32];
+      umma::tmem_ld32(T_FWD + lane_off + br * F + part * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int c = part * 32 + i;
+        const float4 e = s.c.epi[br][c];
+        const float h2n = (v[i] - s.c.mb[br][c]) * s.c.ib[br][c];
+        const float av = fmaf(e.x, v[i], e.y);
+        const float da = av > 0.f ? fmaf(e.z, d0, e.w * d1) : 0.f;
+        const float dh = s.c.ib[br][c] * (da * s.c.sraw[br][c] - s.m1[br][c] - h2n * s.m2[br][c]);
+        v[i] = valid ? dh : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                    umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+        *reinterpret_cast<uint4*>(s.D + br * IMG_H + umma::sw128_offset(row, part * 4 + q)) = pk;
+      }
+    }
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+#pragma unroll
+      for (int br = 0; br < 2; ++br)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma::mma_bf16(T_DG + br * F, umma::desc_at(DESC_K, umma::smem_u32(s.D + br * IMG_H) + 32 * k),
+                         umma::desc_at(DESC_K, umma::smem_u32(wimg_at<true>(s.W, br, 2)) + 32 * k), IDESC_GEMM, k > 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma::mma_bf16(T_WG, umma::desc_at(DESC_MN, umma::smem_u32(s.D) + 2048 * k), umma::desc_at(DESC_MN, umma::smem_u32(s.H) + 2048 * k),
+                       IDESC_WGRAD, (tile > t0 || k > 0) ? 1u : 0u);
+      umma::mma_commit(&s.c.bar_mma);
+    }
+    umma::mbar_wait(&s.c.bar_mma, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+    // ---- epilogue B: dz, T1, BN_a sums over this part's channels ----
+    float T1_0 = 0.f, T1_1 = 0.f;
+#pragma unroll 1
+    for (int br = 0; br < 2; ++br) {
+      float v[32], q1[32];
+      umma::tmem_ld32(T_DG + lane_off + br * F + part * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float4 A = s.c.A0[br][part * 32 + i];
+        float z = fmaf(A.x, xk0, A.z);
+        if (K == 2) z = fmaf(A.y, xk1, z);
+        const float dz = (z > 0.f && valid) ? v[i] : 0.f;
+        T1_0 = fmaf(A.x, dz, T1_0);
+        if (K == 2) T1_1 = fmaf(A.y, dz, T1_1);
+        v[i] = dz;
+        q1[i] = dz * xk0;
+      }
+      const int col = (br * 2 + part) * 32 + lane;
+      float r = colreduce32_part(s.scratch, v, row, part, lane, quarter);
+      atomicAdd(&s.fin[0][col], r);
+      r = colreduce32_part(s.scratch, q1, row, part, lane, quarter);
+      atomicAdd(&s.fin[1][col], r);
+      if (K == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) q1[i] = v[i] * xk1;
+        r = colreduce32_part(s.scratch, q1, row, part, lane, quarter);
+        atomicAdd(&s.fin[2][col], r);
+      }
+    }
+    if (part == 1) {
+      s.t1buf[row][0] = T1_0;
+      s.t1buf[row][1] = T1_1;
+    }
+    __syncthreads();
+    if (part == 0 && valid) {
+      T1_0 += s.t1buf[row][0];
+      T1_1 += s.t1buf[row][1];
+      float dx[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) dx[ch] = (MODE == 1) ? g.dy[ch] / sig1 : g.dy[ch] * sig1;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        if (ch == a.f.keep0) dx[ch] += T1_0;
+        if (K == 2 && ch == a.f.keep1) dx[ch] += T1_1;
+        if (ch == a.f.warp0) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[0] : g.dy[ch] * g.sig[0];
+        if (K == 1 && ch == a.f.warp1) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[1] : g.dy[ch] * g.sig[1];
+      }
+      const size_t base = (size_t)b * 3 * a.f.N + n;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) a.dx_out[base + (size_t)ch * a.f.N] = dx[ch];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+  }
+  // ---- CTA epilogue ----
+  __syncthreads();
+  if (tid < 128) {
+    atomicAdd(&a.bna_sums[tid * 4 + 0], (double)s.fin[0][tid]);
+    atomicAdd(&a.bna_sums[tid * 4 + 1], (double)s.fin[1][tid]);
+    atomicAdd(&a.bna_sums[tid * 4 + 2], (double)s.fin[2][tid]);
+  }
+  {
+    // accumulator row = branch*64 + channel; this thread stores columns [part*32, +32) of its branch's block
+    const int br = row >> 6, c = row & 63;
+    float4* d = reinterpret_cast<float4*>(a.dw1_partial + ((size_t)blockIdx.x * 2 + br) * (F * F) + c * F + part * 32);
+    umma::fence_after_sync();
+    float v[32];
+    if (t1 > t0) {
+      umma::tmem_ld32(T_WG + lane_off + br * F + part * 32, v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
 template <typename T>
 inline size_t smem_for() { return sizeof(T) + 1024; }
 
@@ -1076,7 +1331,7 @@ int launch_bwd_tc_t(const BwdArgs& a, const unsigned short* wimg, int pass, cuda
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(coupling_bwd_p1_tc_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP1Smem>());
-    cudaFuncSetAttribute(coupling_bwd_p2_tc_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP2Smem>());
+    cudaFuncSetAttribute(coupling_bwd_p2_tc2_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP2Smem2>());
     attr = true;
   }
   if (pass == 1) {
@@ -1085,8 +1340,8 @@ int launch_bwd_tc_t(const BwdArgs& a, const unsigned short* wimg, int pass, cuda
     return dpf_check_launch("coupling_bwd_p1_tc_kernel");
   }
   const int grid = min(a.f.n_tiles, dpf_num_sms());
-  coupling_bwd_p2_tc_kernel<K, MODE, SPLIT><<<grid, DPF_TILE, smem_for<TcP2Smem>(), st>>>(a, wimg);
-  return dpf_check_launch("coupling_bwd_p2_tc_kernel");
+  coupling_bwd_p2_tc2_kernel<K, MODE, SPLIT><<<grid, NT2, smem_for<TcP2Smem2>(), st>>>(a, wimg);
+  return dpf_check_launch("coupling_bwd_p2_tc2_kernel");
 }
 
 static int g_coop_occupancy = -1;
