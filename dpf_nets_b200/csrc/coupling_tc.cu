@@ -75,7 +75,7 @@ struct TcCommon {                       // small per-CTA tables (after the 1024-
   float W2[2][2][F];
   float b2[2][2];
   double pend[20];
-  uint64_t bar_mma, bar_load;
+  uint64_t bar_mma, bar_load, bar_aux;
   uint32_t tmem_base;
 };
 
@@ -202,6 +202,7 @@ __device__ __forceinline__ uint32_t tc_setup(TcCommon& s, uint32_t tmem_cols) {
   if (tid == 0) {
     umma::mbar_init(&s.bar_mma, 1);
     umma::mbar_init(&s.bar_load, 1);
+    umma::mbar_init(&s.bar_aux, 1);
     umma::mbar_fence_init();
   }
   if ((tid >> 5) == 0) umma::tmem_alloc(&s.tmem_base, tmem_cols);
@@ -1086,11 +1087,11 @@ __device__ __forceinline__ float colreduce32_part(float* scratch, const float va
 struct TcP2Smem2 {
   unsigned char W[2 * N_IMG * IMG_W];   // [br][W1 hi, W1 lo, W1^T hi]
   unsigned char H[2 * IMG_H];           // h1 hi tiles
-  unsigned char D[2 * IMG_H];           // h1 lo tiles, then dh2pre tiles
+  unsigned char D[2 * IMG_H];           // h1 lo tiles, then dh2pre tiles, then dz tiles
+  unsigned char X[2 * IMG_H];           // per-point weights {1, xk0 hi, xk0 lo, xk1 hi, xk1 lo, 0...} (block 1 = zeros); 1024-aligned
   TcCommon c;
   float m1[2][F], m2[2][F];
-  float scratch[2 * DPF_TILE * 33];
-  float fin[3][2 * F];
+  float bnrow[5][2 * F];                // rows 0..4 of the BN_a-sum accumulator at kernel end
   float t1buf[DPF_TILE][2];
 };
 
@@ -1134,7 +1135,7 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
     s.m1[br][c] = m1;
     s.m2[br][c] = m2;
   }
-  for (int i = tid; i < 3 * 2 * F; i += NT2) (&s.fin[0][0])[i] = 0.f;
+  for (int i = tid; i < (int)(2 * IMG_H / 16); i += NT2) reinterpret_cast<uint4*>(s.X)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   const Pending P = tc_compute_pending(a, false, s.c.pend);
   const float sig1 = sqrtf(a.f.eps + 1.0f);
@@ -1143,8 +1144,8 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
 
   int t0, t1;
   tile_range(a.f.n_tiles, t0, t1);
-  uint32_t phase = 0;
-  const uint32_t T_FWD = tmem, T_DG = tmem + 128, T_WG = tmem + 256;
+  uint32_t phase = 0, phase_aux = 0;
+  const uint32_t T_FWD = tmem, T_DG = tmem + 128, T_WG = tmem + 256, T_BN = tmem + 384;
   const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
   for (int tile = t0; tile < t1; ++tile) {
     const int b = tile / a.f.tiles_per_b;
@@ -1154,6 +1155,10 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
     const TcPoint g = tc_load_point<MODE>(a, P, b, n, valid);
     const float xk0 = pick3(g.x, a.f.keep0);
     const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
+    if (tile > t0) {   // the previous tile's BN-sum UMMAs still read the D / X tiles
+      umma::mbar_wait(&s.c.bar_aux, phase_aux);
+      phase_aux ^= 1;
+    }
     // h1 (hi / lo) chunks of this part: 4 x 16 B per branch
 #pragma unroll
     for (int br = 0; br < 2; ++br) {
@@ -1232,10 +1237,14 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
     phase ^= 1;
     umma::fence_after_sync();
     // ---- epilogue B: dz, T1, BN_a sums over this part's channels ----
+    // The per-channel sums over points  dbeta = sum dz,  E = sum dz * x_keep  run on the tensor cores:
+    // dz (bf16) overwrites the D tiles (their UMMAs are complete) and is multiplied by the per-point
+    // weight tile X = {1, xk0 hi, xk0 lo, xk1 hi, xk1 lo} - the same MN-major operand pair as wgrad,
+    // accumulated in TMEM across all tiles of the CTA.
     float T1_0 = 0.f, T1_1 = 0.f;
 #pragma unroll 1
     for (int br = 0; br < 2; ++br) {
-      float v[32], q1[32];
+      float v[32];
       umma::tmem_ld32(T_DG + lane_off + br * F + part * 32, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -1246,25 +1255,37 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
         T1_0 = fmaf(A.x, dz, T1_0);
         if (K == 2) T1_1 = fmaf(A.y, dz, T1_1);
         v[i] = dz;
-        q1[i] = dz * xk0;
       }
-      const int col = (br * 2 + part) * 32 + lane;
-      float r = colreduce32_part(s.scratch, v, row, part, lane, quarter);
-      atomicAdd(&s.fin[0][col], r);
-      r = colreduce32_part(s.scratch, q1, row, part, lane, quarter);
-      atomicAdd(&s.fin[1][col], r);
-      if (K == 2) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) q1[i] = v[i] * xk1;
-        r = colreduce32_part(s.scratch, q1, row, part, lane, quarter);
-        atomicAdd(&s.fin[2][col], r);
+      for (int q = 0; q < 4; ++q) {
+        const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                    umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+        *reinterpret_cast<uint4*>(s.D + br * IMG_H + umma::sw128_offset(row, part * 4 + q)) = pk;
       }
     }
-    if (part == 1) {
+    if (part == 0) {
+      const float one = valid ? 1.f : 0.f;
+      const uint32_t w0 = umma::pack_bf16(one, xk0);                                   // {1, xk0 hi}
+      const float xk0_lo = xk0 - __uint_as_float(w0 & 0xffff0000u);
+      const uint32_t w1 = umma::pack_bf16(xk0_lo, xk1);                                // {xk0 lo, xk1 hi}
+      const float xk1_lo = xk1 - __uint_as_float(w1 & 0xffff0000u);
+      const uint32_t w2 = umma::pack_bf16(xk1_lo, 0.f);                                // {xk1 lo, 0}
+      *reinterpret_cast<uint4*>(s.X + umma::sw128_offset(row, 0)) = make_uint4(w0, w1, w2, 0u);
+    } else {
       s.t1buf[row][0] = T1_0;
       s.t1buf[row][1] = T1_1;
     }
+    umma::fence_async_smem();
+    umma::fence_before_sync();
     __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma::mma_bf16(T_BN, umma::desc_at(DESC_MN, umma::smem_u32(s.X) + 2048 * k), umma::desc_at(DESC_MN, umma::smem_u32(s.D) + 2048 * k),
+                       IDESC_WGRAD, (tile > t0 || k > 0) ? 1u : 0u);
+      umma::mma_commit(&s.c.bar_aux);
+    }
     if (part == 0 && valid) {
       T1_0 += s.t1buf[row][0];
       T1_1 += s.t1buf[row][1];
@@ -1286,11 +1307,26 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
     __syncthreads();
   }
   // ---- CTA epilogue ----
+  if (t1 > t0) {
+    umma::mbar_wait(&s.c.bar_aux, phase_aux);
+    umma::fence_after_sync();
+    if (quarter == 0) {   // accumulator rows 0..4 live in TMEM lanes 0..4: warps 0 (columns 0..63) and 4 (64..127)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        umma::tmem_ld32(T_BN + part * F + half * 32, v);
+        if (lane < 5) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s.bnrow[lane][part * F + half * 32 + i] = v[i];
+        }
+      }
+    }
+  }
   __syncthreads();
-  if (tid < 128) {
-    atomicAdd(&a.bna_sums[tid * 4 + 0], (double)s.fin[0][tid]);
-    atomicAdd(&a.bna_sums[tid * 4 + 1], (double)s.fin[1][tid]);
-    atomicAdd(&a.bna_sums[tid * 4 + 2], (double)s.fin[2][tid]);
+  if (tid < 128 && t1 > t0) {
+    atomicAdd(&a.bna_sums[tid * 4 + 0], (double)s.bnrow[0][tid]);
+    atomicAdd(&a.bna_sums[tid * 4 + 1], (double)s.bnrow[1][tid] + (double)s.bnrow[2][tid]);
+    atomicAdd(&a.bna_sums[tid * 4 + 2], (double)s.bnrow[3][tid] + (double)s.bnrow[4][tid]);
   }
   {
     // accumulator row = branch*64 + channel; this thread stores columns [part*32, +32) of its branch's block
