@@ -1348,6 +1348,335 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
+// =============================================================================================
+// Forward kernels, two threads per point (256 threads per CTA, same shared memory as the 128-thread
+// form => 16 warps per SM): statistics pass, apply pass, and the merged train-mode launch.
+// =============================================================================================
+struct TcFwdSmem2 {
+  unsigned char W[4 * IMG_W];           // [br][W1 hi, W1 lo]
+  unsigned char H[2 * IMG_H];           // hi, lo tile of the branch in flight
+  TcCommon c;
+  float scratch[2 * DPF_TILE * 33];     // column-sum scratch, one plane per part
+  float fin[2][2 * F];
+  float obuf[DPF_TILE][4];              // part 1 -> part 0 hand-over of the partial last-SharedDot sums
+  double mom[9][4];
+};
+
+// sum and sum of squares over the 128 rows for this part's 32 columns
+__device__ __forceinline__ void colreduce32_sq_part(float* scratch, const float va[32], int row, int part, int lane, int quarter,
+                                                    float& rs, float& rq) {
+  float* sc = scratch + part * (DPF_TILE * 33);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sc[row * 33 + i] = va[i];
+  __syncthreads();
+  float sa = 0.f, sb = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    const float v = sc[(quarter * 32 + r) * 33 + lane];
+    sa += v;
+    sb = fmaf(v, v, sb);
+  }
+  rs = sa;
+  rq = sb;
+}
+
+// h1 chunks of this part for one branch -> tiles, then UMMA chain into TMEM columns [tcol, tcol+64)
+template <int K, bool SPLIT>
+__device__ __forceinline__ void fwd2_gemm(TcFwdSmem2& s, int br, uint32_t tcol, float xk0, float xk1, int row, int part, uint32_t& phase) {
+#pragma unroll
+  for (int qq = 0; qq < 4; ++qq) {
+    const int q = part * 4 + qq;
+    uint32_t w[4], wl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 Aa = s.c.A0[br][q * 8 + 2 * i], Ab = s.c.A0[br][q * 8 + 2 * i + 1];
+      float va = fmaf(Aa.x, xk0, Aa.z), vb = fmaf(Ab.x, xk0, Ab.z);
+      if (K == 2) { va = fmaf(Aa.y, xk1, va); vb = fmaf(Ab.y, xk1, vb); }
+      va = fmaxf(va, 0.f);
+      vb = fmaxf(vb, 0.f);
+      w[i] = umma::pack_bf16(va, vb);
+      if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
+    }
+    const uint32_t off = umma::sw128_offset(row, q);
+    *reinterpret_cast<uint4*>(s.H + off) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (SPLIT) *reinterpret_cast<uint4*>(s.H + IMG_H + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+  }
+  umma::fence_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    umma::fence_after_sync();
+    issue_gemm1<SPLIT>(tcol, s.H, s.H + IMG_H, wimg_at<false>(s.W, br, 0), wimg_at<false>(s.W, br, 1));
+    umma::mma_commit(&s.c.bar_mma);
+  }
+  umma::mbar_wait(&s.c.bar_mma, phase);
+  phase ^= 1;
+  umma::fence_after_sync();
+}
+
+// partial last-SharedDot sums of this part's 32 channels of one branch from TMEM columns [tcol + 32*part, +32)
+__device__ __forceinline__ void fwd2_epilogue(const TcFwdSmem2& s, int br, uint32_t taddr, int part, float& o0, float& o1) {
+  float v[32];
+  umma::tmem_ld32(taddr + part * 32, v);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float4 e = s.c.epi[br][part * 32 + i];
+    const float h3 = fmaxf(fmaf(e.x, v[i], e.y), 0.f);
+    o0 = fmaf(e.z, h3, o0);
+    o1 = fmaf(e.w, h3, o1);
+  }
+}
+
+// transform + outputs + moment accumulation of one point (part 0 threads)
+template <int MODE>
+__device__ __forceinline__ void fwd2_finish(const CouplingArgs& a, const float xin[3], const float o[2][2], int b, int n, bool valid,
+                                            float macc[9]) {
+  float yv[3], muv[3] = {0.f, 0.f, 0.f}, lvv[3] = {0.f, 0.f, 0.f};
+  const float sig1 = sqrtf(a.eps + 1.0f);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) yv[ch] = (MODE == 0) ? sig1 * xin[ch] : xin[ch] / sig1;
+#pragma unroll
+  for (int wi = 0; wi < 2; ++wi) {
+    if (wi < a.w) {
+      const int ch = wi == 0 ? a.warp0 : a.warp1;
+      const float l = softsign(o[1][wi]);
+      const float sig = sqrtf(a.eps + expf(l));
+      const float m = o[0][wi];
+      const float xv = pick3(xin, ch);
+      const float r = (MODE == 0) ? fmaf(sig, xv, m) : (xv - m) / sig;
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (q == ch) { yv[q] = r; muv[q] = m; lvv[q] = l; }
+    }
+  }
+  if (valid) {
+    const size_t base = (size_t)b * 3 * a.N + n;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      a.y[base + (size_t)ch * a.N] = yv[ch];
+      a.mu[base + (size_t)ch * a.N] = muv[ch];
+      a.lv[base + (size_t)ch * a.N] = lvv[ch];
+    }
+    macc[0] += yv[0]; macc[1] += yv[1]; macc[2] += yv[2];
+    macc[3] = fmaf(yv[0], yv[0], macc[3]); macc[4] = fmaf(yv[0], yv[1], macc[4]); macc[5] = fmaf(yv[0], yv[2], macc[5]);
+    macc[6] = fmaf(yv[1], yv[1], macc[6]); macc[7] = fmaf(yv[1], yv[2], macc[7]); macc[8] = fmaf(yv[2], yv[2], macc[8]);
+  }
+}
+
+// apply epilogue of one tile from TMEM columns [tbase, tbase+128): both branches, pair hand-over, finish
+template <int MODE>
+__device__ __forceinline__ void fwd2_apply_tile(const CouplingArgs& a, TcFwdSmem2& s, uint32_t tbase_lane, const float xin[3], int b,
+                                                int n, bool valid, int row, int part, float macc[9]) {
+  float o[2][2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    o[br][0] = part == 0 ? s.c.b2[br][0] : 0.f;
+    o[br][1] = part == 0 ? s.c.b2[br][1] : 0.f;
+    fwd2_epilogue(s, br, tbase_lane + br * F, part, o[br][0], o[br][1]);
+  }
+  if (part == 1) *reinterpret_cast<float4*>(s.obuf[row]) = make_float4(o[0][0], o[0][1], o[1][0], o[1][1]);
+  __syncthreads();
+  if (part == 0) {
+    const float4 t = *reinterpret_cast<const float4*>(s.obuf[row]);
+    o[0][0] += t.x; o[0][1] += t.y; o[1][0] += t.z; o[1][1] += t.w;
+    fwd2_finish<MODE>(a, xin, o, b, n, valid, macc);
+  }
+}
+
+__device__ __forceinline__ void fwd2_flush_stats(const CouplingArgs& a, TcFwdSmem2& s, const float sacc[2][2], int tid, int part, int lane) {
+  float* fin = &s.fin[0][0];
+  for (int i = tid; i < 4 * F; i += NT2) fin[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    atomicAdd(&s.fin[0][br * F + part * 32 + lane], sacc[br][0]);
+    atomicAdd(&s.fin[1][br * F + part * 32 + lane], sacc[br][1]);
+  }
+  __syncthreads();
+  if (tid < 128) {
+    atomicAdd(&a.bnb_sums[tid * 2 + 0], (double)s.fin[0][tid]);   // tid == br*F + c
+    atomicAdd(&a.bnb_sums[tid * 2 + 1], (double)s.fin[1][tid]);
+  }
+}
+
+__device__ __forceinline__ void fwd2_flush_moments(const CouplingArgs& a, TcFwdSmem2& s, const float macc[9], int tid) {
+  // only part-0 threads (warps 0..3) carry moments
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const double v = warp_sum_d((double)macc[i]);
+    if (lane == 0 && warp < 4) s.mom[i][warp] = v;
+  }
+  __syncthreads();
+  if (tid < 9) atomicAdd(a.mom_out + tid, s.mom[tid][0] + s.mom[tid][1] + s.mom[tid][2] + s.mom[tid][3]);
+}
+
+template <int K, int MODE, bool STATS, bool SPLIT>
+__global__ void __launch_bounds__(NT2, 2)
+coupling_fwd_tc2_kernel(const CouplingArgs a, const unsigned short* __restrict__ wimg) {
+  extern __shared__ unsigned char smraw[];
+  TcFwdSmem2& s = *reinterpret_cast<TcFwdSmem2*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, part = tid >> 7, quarter = warp & 3;
+  const BranchLayout lay = branch_layout(a.k, a.w, a.G);
+  const bool writer = (blockIdx.x == 0) && a.update_stats && !STATS;
+  const uint32_t tmem = tc_setup(s.c, 128);
+  tc_load_weights<false>(s.c, s.W, wimg);
+  tc_prologue_tables(a, lay, s.c, writer, !STATS);
+  float sacc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float macc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) macc[i] = 0.f;
+  umma::mbar_wait(&s.c.bar_load, 0);
+  __syncthreads();
+
+  int t0, t1;
+  tile_range(a.n_tiles, t0, t1);
+  uint32_t phase = 0;
+  const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+  for (int tile = t0; tile < t1; ++tile) {
+    const int b = tile / a.tiles_per_b;
+    const int n = (tile - b * a.tiles_per_b) * DPF_TILE + row;
+    const bool valid = n < a.N;
+    if (!STATS) tc_tile_film(a, s.c, b);
+    const float* px = a.x + (size_t)b * 3 * a.N + n;
+    float xin[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) xin[ch] = valid ? px[(size_t)ch * a.N] : 0.f;
+    const float xk0 = pick3(xin, a.keep0);
+    const float xk1 = (K == 2) ? pick3(xin, a.keep1) : 0.f;
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      fwd2_gemm<K, SPLIT>(s, br, tmem + br * F, xk0, xk1, row, part, phase);
+      if (STATS) {
+        float v[32];
+        umma::tmem_ld32(lane_addr + br * F + part * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] : 0.f;
+        float rs, rq;
+        colreduce32_sq_part(s.scratch, v, row, part, lane, quarter, rs, rq);
+        sacc[br][0] += rs;
+        sacc[br][1] += rq;
+        umma::fence_before_sync();
+        __syncthreads();
+      } else if (br == 0) {
+        // branch 1's tiles overwrite H only after this sync; branch 0's accumulator stays in its TMEM columns
+        umma::fence_before_sync();
+        __syncthreads();
+      }
+    }
+    if (!STATS) {
+      fwd2_apply_tile<MODE>(a, s, lane_addr, xin, b, n, valid, row, part, macc);
+      umma::fence_before_sync();
+      __syncthreads();     // TMEM columns, tiles, epi table and obuf are free again
+    }
+  }
+  if (STATS) {
+    fwd2_flush_stats(a, s, sacc, tid, part, lane);
+  } else if (a.mom_out) {
+    fwd2_flush_moments(a, s, macc, tid);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+}
+
+template <int K, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(NT2, 2)
+coupling_fwd_train_tc2_kernel(const CouplingArgs a, const unsigned short* __restrict__ wimg, unsigned int* __restrict__ barrier_counter) {
+  extern __shared__ unsigned char smraw[];
+  TcFwdSmem2& s = *reinterpret_cast<TcFwdSmem2*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, part = tid >> 7, quarter = warp & 3;
+  const BranchLayout lay = branch_layout(a.k, a.w, a.G);
+  const bool writer = (blockIdx.x == 0) && a.update_stats && tid < 128;
+  const uint32_t tmem = tc_setup(s.c, RES * 128);
+  tc_load_weights<false>(s.c, s.W, wimg);
+  tc_prologue_tables(a, lay, s.c, writer, false);
+  if (tid < 128) {
+    const int br = tid >> 6, c = tid & 63;
+    const float* prm = a.prm + (size_t)br * lay.size;
+    s.c.W2[br][0][c] = prm[lay.W2 + c];
+    s.c.W2[br][1][c] = (a.w == 2) ? prm[lay.W2 + F + c] : 0.f;
+    if (c < 2) s.c.b2[br][c] = (c < a.w) ? prm[lay.b2 + c] : 0.f;
+  }
+  float sacc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  umma::mbar_wait(&s.c.bar_load, 0);
+  __syncthreads();
+
+  const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+  uint32_t phase = 0;
+  float xin[RES][3];
+  // ---------------- phase 1: h1 -> UMMA -> per-channel sum / sum of squares ----------------
+#pragma unroll
+  for (int ts = 0; ts < RES; ++ts) {
+    const int tile = blockIdx.x + ts * gridDim.x;
+    if (tile < a.n_tiles) {
+      const int b = tile / a.tiles_per_b;
+      const int n = (tile - b * a.tiles_per_b) * DPF_TILE + row;
+      const bool valid = n < a.N;
+      const float* px = a.x + (size_t)b * 3 * a.N + n;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) xin[ts][ch] = valid ? px[(size_t)ch * a.N] : 0.f;
+      const float xk0 = pick3(xin[ts], a.keep0);
+      const float xk1 = (K == 2) ? pick3(xin[ts], a.keep1) : 0.f;
+#pragma unroll
+      for (int br = 0; br < 2; ++br) {
+        fwd2_gemm<K, SPLIT>(s, br, tmem + ts * 128 + br * F, xk0, xk1, row, part, phase);
+        float v[32];
+        umma::tmem_ld32(lane_addr + ts * 128 + br * F + part * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] : 0.f;
+        float rs, rq;
+        colreduce32_sq_part(s.scratch, v, row, part, lane, quarter, rs, rq);
+        sacc[br][0] += rs;
+        sacc[br][1] += rq;
+        umma::fence_before_sync();
+        __syncthreads();
+      }
+    }
+  }
+  fwd2_flush_stats(a, s, sacc, tid, part, lane);
+  grid_barrier(barrier_counter, gridDim.x);
+  // ---------------- phase 2: BN_b x FiLM fold, epilogue from the resident accumulators ----------------
+  if (tid < 128) {
+    const int br = tid >> 6, c = tid & 63;
+    const double M = (double)a.B * (double)a.N;
+    const double sm = __ldcg(&a.bnb_sums[(br * F + c) * 2 + 0]), sq = __ldcg(&a.bnb_sums[(br * F + c) * 2 + 1]);
+    const double dm = sm / M;
+    const double dv = fmax(sq / M - dm * dm, 0.0);
+    s.c.mb[br][c] = (float)dm;
+    s.c.ib[br][c] = 1.f / sqrtf((float)dv + DPF_BN_EPS);
+    if (writer) {
+      float* st = a.stat + (size_t)br * ST_COUNT * F;
+      st[ST_BNB_RM * F + c] = (1.f - DPF_BN_MOM) * st[ST_BNB_RM * F + c] + DPF_BN_MOM * (float)dm;
+      st[ST_BNB_RV * F + c] = (1.f - DPF_BN_MOM) * st[ST_BNB_RV * F + c] + DPF_BN_MOM * (float)(dv * (M / fmax(M - 1.0, 1.0)));
+    }
+  }
+  __syncthreads();
+  float macc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) macc[i] = 0.f;
+  umma::fence_after_sync();
+#pragma unroll
+  for (int ts = 0; ts < RES; ++ts) {
+    const int tile = blockIdx.x + ts * gridDim.x;
+    if (tile < a.n_tiles) {
+      const int b = tile / a.tiles_per_b;
+      const int n = (tile - b * a.tiles_per_b) * DPF_TILE + row;
+      const bool valid = n < a.N;
+      __syncthreads();
+      tc_tile_film(a, s.c, b);
+      __syncthreads();
+      fwd2_apply_tile<MODE>(a, s, lane_addr + ts * 128, xin[ts], b, n, valid, row, part, macc);
+    }
+  }
+  if (a.mom_out) fwd2_flush_moments(a, s, macc, tid);
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, RES * 128);
+}
+
 template <typename T>
 inline size_t smem_for() { return sizeof(T) + 1024; }
 
@@ -1355,11 +1684,11 @@ template <int K, int MODE, bool STATS, bool SPLIT>
 int launch_fwd_tc_t(const CouplingArgs& a, const unsigned short* wimg, int grid, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(coupling_fwd_tc_kernel<K, MODE, STATS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcFwdSmem>());
+    cudaFuncSetAttribute(coupling_fwd_tc2_kernel<K, MODE, STATS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcFwdSmem2>());
     attr = true;
   }
-  coupling_fwd_tc_kernel<K, MODE, STATS, SPLIT><<<grid, DPF_TILE, smem_for<TcFwdSmem>(), st>>>(a, wimg);
-  return dpf_check_launch("coupling_fwd_tc_kernel");
+  coupling_fwd_tc2_kernel<K, MODE, STATS, SPLIT><<<grid, NT2, smem_for<TcFwdSmem2>(), st>>>(a, wimg);
+  return dpf_check_launch("coupling_fwd_tc2_kernel");
 }
 
 template <int K, int MODE, bool SPLIT>
@@ -1387,12 +1716,12 @@ static int g_coop_occupancy = -1;
 template <int K, int MODE, bool SPLIT>
 int launch_fwd_train_t(const CouplingArgs& a, const unsigned short* wimg, unsigned int* counter, cudaStream_t st) {
   static int max_grid = -1;
-  auto kern = coupling_fwd_train_tc_kernel<K, MODE, SPLIT>;
+  auto kern = coupling_fwd_train_tc2_kernel<K, MODE, SPLIT>;
   if (max_grid < 0) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcFwdSmem>());
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcFwdSmem2>());
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DPF_TILE, smem_for<TcFwdSmem>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT2, smem_for<TcFwdSmem2>());
     g_coop_occupancy = per_sm;
     // shared memory allows 2 CTAs per SM (2 x ~92 KB) and so do the 512 TMEM columns (RES*128 each);
     // the cooperative launch itself validates co-residency and we fall back if it refuses
@@ -1400,14 +1729,14 @@ int launch_fwd_train_t(const CouplingArgs& a, const unsigned short* wimg, unsign
     max_grid = per_sm * dpf_num_sms();
   }
   if (max_grid <= 0 || a.n_tiles > RES * max_grid) {
-    dpf_set_error("merged forward not used: n_tiles=%d max_grid=%d smem=%zu", a.n_tiles, max_grid, smem_for<TcFwdSmem>());
+    dpf_set_error("merged forward not used: n_tiles=%d max_grid=%d smem=%zu", a.n_tiles, max_grid, smem_for<TcFwdSmem2>());
     return DPF_ERR_UNSUPPORTED;
   }
   // Not cudaLaunchCooperativeKernel: the runtime's co-residency check assumes ONE CTA per SM for any
   // kernel that allocates TMEM (occupancy query returns 1 at every shared-memory size), although two
   // CTAs with 256 columns each do share an SM.  grid <= 2 * SMs keeps every CTA resident.
   const int grid = min(a.n_tiles, max_grid);
-  kern<<<grid, DPF_TILE, smem_for<TcFwdSmem>(), st>>>(a, wimg, counter);
+  kern<<<grid, NT2, smem_for<TcFwdSmem2>(), st>>>(a, wimg, counter);
   return dpf_check_launch("coupling_fwd_train_tc_kernel");
 }
 
