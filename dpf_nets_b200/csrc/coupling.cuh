@@ -18,6 +18,7 @@
 #define DPF_BN_EPS 1e-5f
 #define DPF_BN_MOM 0.1f
 #define DPF_TILE 128      // points per tile = threads per CTA (one TMEM lane / one thread per point)
+#define DPF_EVAL_LTAB_BYTES 2112   // sizeof(EvalLayerTab), coupling_tc.cu
 
 struct LayerMeta {        // 8 x int64 per layer, identical on host (numpy int64) and device
   long long param_off, stat_off, k, w, keep0, keep1, warp0, warp1;
@@ -63,6 +64,8 @@ struct DecoderWorkspace {
   double* bna_sums;   // [L][2][F][4]   backward: dbeta, E0, E1, pad
   float* dx[2];       // [B][3][N]      ping-pong stored input gradients
   unsigned short* w1_bf16;  // [L][2][3][F*F] bf16 images {W1 hi, W1^T hi, W1 lo} in UMMA smem layout (tensor path)
+  unsigned char* eval_ltab; // [L] EvalLayerTab (fused eval decoder)
+  float* eval_epi;          // [L][B][2][F] float4 {S, T, W2_0, W2_1} (fused eval decoder)
   unsigned int* barriers;   // [L][32] grid-barrier counters of the merged train-mode forward (one 128-B line per layer)
   size_t bytes;
 };
@@ -83,6 +86,8 @@ __host__ inline DecoderWorkspace carve_workspace(void* base, int L, int G, int B
   w.dx[1] = (float*)take(sizeof(float) * (size_t)B * 3 * N);
   w.w1_bf16 = (unsigned short*)take(sizeof(unsigned short) * (size_t)L * 6 * DPF_F * DPF_F);
   w.barriers = (unsigned int*)take(sizeof(unsigned int) * (size_t)L * 32);
+  w.eval_ltab = (unsigned char*)take((size_t)L * DPF_EVAL_LTAB_BYTES);
+  w.eval_epi = (float*)take(sizeof(float) * (size_t)L * B * 2 * DPF_F * 4);
   w.bytes = off;
   (void)G;
   return w;

@@ -23,19 +23,9 @@
 // shared-memory transpose (colreduce) instead of warp shuffles.
 #include "coupling.cuh"
 #include "umma.cuh"
+#include "tc_tiles.cuh"
 
 namespace {
-
-constexpr int F = DPF_F;
-constexpr uint32_t IMG_W = F * F * 2;           // 8 KB  : one 64x64 bf16 weight image
-constexpr uint32_t IMG_H = DPF_TILE * F * 2;    // 16 KB : one 128x64 bf16 activation tile
-constexpr int N_IMG = 3;                         // weight images per (layer, branch): W1 hi, W1 lo, W1^T hi
-constexpr uint64_t DESC_K = umma::make_desc_template(16, 1024, umma::LAYOUT_SW128);        // K-major SW128
-constexpr uint64_t DESC_MN = umma::make_desc_template(IMG_H, 1024, umma::LAYOUT_SW128);    // MN-major, 64-blocks IMG_H apart
-constexpr uint32_t IDESC_GEMM = umma::make_idesc_bf16(128, 64, 0, 0);
-constexpr uint32_t IDESC_WGRAD = umma::make_idesc_bf16(128, 128, 1, 1);
-
-__device__ __forceinline__ float pick3(const float v[3], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }
 
 // ---------------------------------------------------------------------------------------------
 // Weight packing: fp32 W1 (arena) -> bf16 128B-swizzled images per (layer, branch)
@@ -104,27 +94,6 @@ __device__ __forceinline__ void write_h1_row(unsigned char* tile_hi, unsigned ch
     const uint32_t off = umma::sw128_offset(tid, q);
     *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(w[0], w[1], w[2], w[3]);
     if (SPLIT) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-  }
-}
-
-// forward UMMA chain of ONE branch into TMEM columns [tcol, tcol+64): K = 64 in 4 steps,
-// SPLIT: hi*hi + lo*hi + hi*lo
-template <bool SPLIT>
-__device__ __forceinline__ void issue_gemm1(uint32_t tcol, const unsigned char* Hhi, const unsigned char* Hlo,
-                                            const unsigned char* Whi, const unsigned char* Wlo) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    umma::mma_bf16(tcol, umma::desc_at(DESC_K, umma::smem_u32(Hhi) + 32 * k), umma::desc_at(DESC_K, umma::smem_u32(Whi) + 32 * k),
-                   IDESC_GEMM, k > 0);
-  if (SPLIT) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma::mma_bf16(tcol, umma::desc_at(DESC_K, umma::smem_u32(Hlo) + 32 * k), umma::desc_at(DESC_K, umma::smem_u32(Whi) + 32 * k),
-                     IDESC_GEMM, 1u);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma::mma_bf16(tcol, umma::desc_at(DESC_K, umma::smem_u32(Hhi) + 32 * k), umma::desc_at(DESC_K, umma::smem_u32(Wlo) + 32 * k),
-                     IDESC_GEMM, 1u);
   }
 }
 

@@ -63,9 +63,16 @@ int launch_coupling_fwd_train_tc(const CouplingArgs& a, const unsigned short* wi
 // The merged (cooperative, TMEM-resident) train-mode forward is on by default; dpf_set_option(0, 0)
 // forces the two-launch form (tests compare both).
 static bool g_merged_forward = true;
+// Option 1: the fused all-layer eval decoder (coupling_eval.cu) is on by default for the tensor
+// precisions; dpf_set_option(1, 0) forces one launch per layer (tests compare both).
+static bool g_fused_eval = true;
+int launch_decoder_eval_tc(const float* arena, const float* stats, const LayerMeta* meta_dev, const float* film,
+                           const unsigned short* wimg, unsigned char* ltab, float* epi, const float* p, float* P, float* MU,
+                           float* LV, int L, int G, int B, int N, int mode, int split, float eps, cudaStream_t s);
 DPF_API int dpf_set_option(int option, int value) {
-  DPF_REQUIRE(option == 0, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
-  g_merged_forward = value != 0;
+  DPF_REQUIRE(option == 0 || option == 1, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
+  if (option == 0) g_merged_forward = value != 0;
+  else g_fused_eval = value != 0;
   return DPF_OK;
 }
 
@@ -140,6 +147,12 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
     ProfScope ps(CAT_MOMENTS, s);
     rc = launch_moments(p, B, N, ws.moments, s);
     if (rc) return rc;
+  }
+  if (!training && precision >= 1 && g_fused_eval) {
+    // eval mode has no cross-point reduction: the whole stack is one launch (+ one for its tables)
+    ProfScope ps(CAT_FWD_APPLY, s);
+    return launch_decoder_eval_tc(arena, stats, reinterpret_cast<const LayerMeta*>(meta_dev), ws.film, ws.w1_bf16, ws.eval_ltab,
+                                  ws.eval_epi, p, P_out, MU, LV, L, G, B, N, mode, precision == 2, eps, s);
   }
   const float* x = p;
   bool merged_ok = g_merged_forward;

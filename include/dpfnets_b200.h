@@ -28,7 +28,9 @@ int dpf_device_check(void);
 int dpf_launch_count(long long* count);
 /* Per-kernel-class CUDA-event timing of the decoder entry points (off by default).
  * classes: 0 film_fwd, 1 moments, 2 fwd_stats, 3 fwd_apply, 4 bwd_p1, 5 bwd_p2, 6 bwd_final, 7 film_bwd */
-/* option 0: merged cooperative train-mode forward (1 = on, default; 0 = two launches per layer). */
+/* option 0: merged train-mode forward (1 = on, default; 0 = two launches per layer).
+ * option 1: fused all-layer eval-mode decoder, one launch for the whole stack (1 = on, default;
+ *           0 = one launch per layer).  Both exist so that tests can compare the two forms. */
 int dpf_set_option(int option, int value);
 int dpf_profile_enable(int on);
 int dpf_profile_collect(double* ms, long long* counts, int n);

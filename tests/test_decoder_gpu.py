@@ -454,3 +454,37 @@ def test_merged_cooperative_forward_equals_two_launch_form(mods, cuda, native_li
         assert rel(outs[0][0], outs[1][0]) < 1e-4 and rel(outs[0][1], outs[1][1]) < 1e-4, (B, N)
         for k in outs[0][2]:
             assert rel(outs[0][2][k], outs[1][2][k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_fused_eval_decoder_equals_per_layer_form(mods, cuda, native_lib, precision):
+    """Eval mode (running statistics): the one-launch all-layer decoder (coupling_eval.cu) must give
+    the per-layer kernels' outputs bit for bit - same arithmetic, different scheduling - in both
+    directions, with ragged tiles and with more tiles than resident CTAs."""
+    _, decoders = mods
+    torch.manual_seed(11)
+    m = decoders.LocalCondRNVPDecoder(4, 64, 32).to(cuda)   # 12 coupling layers, both patterns
+    m.precision = precision
+    gen = torch.Generator().manual_seed(12)
+    with torch.no_grad():
+        for prm in m.parameters():
+            prm.add_(0.05 * torch.randn(prm.shape, generator=gen).to(cuda))
+    m.train()
+    with torch.no_grad():   # move the running statistics away from their init
+        for _ in range(2):
+            m((torch.rand((6, 3, 700), generator=gen) - 0.5).to(cuda), torch.randn((6, 32), generator=gen).to(cuda), mode="inverse")
+    m.eval()
+    for B, N in ((3, 1000), (7, 128), (2, 77), (40, 2048)):
+        p = (torch.rand((B, 3, N), generator=gen) - 0.5).to(cuda)
+        g = torch.randn((B, 32), generator=gen).to(cuda)
+        for mode in ("direct", "inverse"):
+            outs = []
+            for fused in (1, 0):
+                native_lib.dpf_set_option(1, fused)
+                with torch.no_grad():
+                    ps, mus, lvs = m(p, g, mode=mode)
+                outs.append((ps.stacked.clone(), mus.stacked.clone(), lvs.stacked.clone()))
+            native_lib.dpf_set_option(1, 1)
+            for a, b in zip(*outs):
+                assert torch.isfinite(a).all()
+                assert torch.equal(a, b), (precision, B, N, mode, rel(a, b))
