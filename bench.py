@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="shapes per GPU")
     ap.add_argument("--points", type=int, default=2048)
     ap.add_argument("--no-extras", action="store_true", help="skip sampling / Chamfer / cpu_baseline legs")
+    ap.add_argument("--lib-option", action="append", default=[], metavar="K=V", help="dpf_set_option(K, V) before the run (A/B tests)")
     return ap.parse_args()
 
 
@@ -227,6 +228,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
     _lib.check(lib.dpf_device_check(), "dpf_device_check")
+    for kv in args.lib_option:      # A/B switches of the library (include/dpfnets_b200.h: dpf_set_option)
+        k, v = kv.split("=")
+        _lib.check(lib.dpf_set_option(int(k), int(v)), "dpf_set_option")
     pk = peaks()
 
     precision = args.precision
@@ -344,6 +348,7 @@ def run_ours(args):
 
     if rank == 0 and not args.no_extras:
         line["extra"] = extras(model, dev, B, N, pk, flush)
+        line["extra"]["full_model_step"] = full_model_step(dev, B, N, precision, flush)
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         cstep = oracle_train_step_factory(B, N)
@@ -401,6 +406,49 @@ def extras(model, dev, B, N, pk, flush):
                       "fp32_issue": {"achieved_dist_evals_per_s": 2 * pairs * N * N, "bound": fp32_issue_peak,
                                      "frac": 2 * pairs * N * N / fp32_issue_peak}}
     return out
+
+
+def full_model_step(dev, B, N, precision, flush, steps=5, warmup=3):
+    """Whole training step of the chair generation model ('also report whole-model step'):
+    PointNet encoder + latent flows + priors + point decoder + VAE loss + backward + AMSGrad Adam."""
+    from dpf_nets_b200 import configs
+    from dpf_nets_b200.lib.networks.losses import Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss
+    from dpf_nets_b200.lib.networks.models import Local_Cond_RNVP_MC_Global_RNVP_VAE
+    from dpf_nets_b200.lib.networks.optimizers import Adam
+    config = configs.load("generation/chair")
+    torch.manual_seed(0)
+    model = Local_Cond_RNVP_MC_Global_RNVP_VAE(**config).to(dev)
+    model.pc_decoder.precision = precision
+    model.train()
+    crit = Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss(**config).to(dev)
+    opt = Adam(model.parameters(), lr=config["max_lr"], weight_decay=config["wd"], betas=(config["beta1"], config["max_beta2"]),
+               amsgrad=True)
+    gen = torch.Generator().manual_seed(99)
+    clouds = [(torch.rand((B, 3, N), generator=gen) - 0.5).pin_memory() for _ in range(2)]
+
+    def step():
+        g_clouds = clouds[0].to(dev, non_blocking=True)
+        p_clouds = clouds[1].to(dev, non_blocking=True)
+        out = model(g_clouds, p_clouds)
+        loss, pnll, gnll, gent = crit(g_clouds, p_clouds, out)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ts, loss = [], None
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); loss = step(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sum(ts) / len(ts)
+    return {"value": B * N / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "loss": float(loss),
+            "model": "generation/chair VAE, %d params" % sum(p.numel() for p in model.parameters()),
+            "includes": "H2D of both clouds, encoder, latent flows, priors, decoder, loss, backward, AMSGrad step"}
 
 
 def main():

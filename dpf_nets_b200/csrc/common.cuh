@@ -56,3 +56,28 @@ static inline int dpf_num_sms() {
   }
   return sms;
 }
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Consecutive per-layer kernels of one pass are launched with programmatic stream serialization:
+// a kernel's CTAs may start (barrier init, TMEM allocation, TMA weight loads) while the previous
+// kernel drains; pdl_wait() blocks until the previous grid has completed and its writes are
+// visible, and MUST precede the first read of anything that grid produced.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern int g_dpf_pdl;   // decoder.cu: dpf_set_option(2, v), default 1
+
+template <typename... KArgs, typename... Args>
+static inline void dpf_launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_dpf_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}

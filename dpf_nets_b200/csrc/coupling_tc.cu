@@ -25,6 +25,8 @@
 #include "umma.cuh"
 #include "tc_tiles.cuh"
 
+extern int g_dpf_p1_tensor_sums;   // decoder.cu: dpf_set_option(3, v)
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -206,168 +208,8 @@ __device__ __forceinline__ void tile_range(int n_tiles, int& t0, int& t1) {   //
   t1 = min(n_tiles, t0 + per);
 }
 
-// =============================================================================================
-// Forward: STATS (BN_b batch statistics) or APPLY.  Branches are processed one after the other so
-// that a single pair of (hi, lo) activation tiles is live: 2 CTAs per SM.
-// =============================================================================================
-struct TcFwdSmem {
-  unsigned char W[4 * IMG_W];           // [br][W1 hi, W1 lo] (32 KB)
-  unsigned char H[2 * IMG_H];           // hi, lo tile of the branch in flight (32 KB)
-  TcCommon c;
-  float scratch[DPF_TILE * 33];
-  float fin[2][2 * F];
-  double mom[9][4];
-};
-
-template <int K, int MODE, bool STATS, bool SPLIT>
-__global__ void __launch_bounds__(DPF_TILE)
-coupling_fwd_tc_kernel(const CouplingArgs a, const unsigned short* __restrict__ wimg) {
-  extern __shared__ unsigned char smraw[];
-  TcFwdSmem& s = *reinterpret_cast<TcFwdSmem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const BranchLayout lay = branch_layout(a.k, a.w, a.G);
-  const bool writer = (blockIdx.x == 0) && a.update_stats && !STATS;
-  const uint32_t tmem = tc_setup(s.c, 128);
-  tc_load_weights<false>(s.c, s.W, wimg);
-  tc_prologue_tables(a, lay, s.c, writer, !STATS);
-  float sacc[4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) sacc[i][0] = sacc[i][1] = 0.f;
-  float macc[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) macc[i] = 0.f;
-  umma::mbar_wait(&s.c.bar_load, 0);
-  __syncthreads();
-
-  int t0, t1;
-  tile_range(a.n_tiles, t0, t1);
-  uint32_t phase = 0;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-  for (int tile = t0; tile < t1; ++tile) {
-    const int b = tile / a.tiles_per_b;
-    const int n = (tile - b * a.tiles_per_b) * DPF_TILE + tid;
-    const bool valid = n < a.N;
-    if (!STATS) tc_tile_film(a, s.c, b);
-    const float* px = a.x + (size_t)b * 3 * a.N + n;
-    float xin[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) xin[ch] = valid ? px[(size_t)ch * a.N] : 0.f;
-    const float xk0 = pick3(xin, a.keep0);
-    const float xk1 = (K == 2) ? pick3(xin, a.keep1) : 0.f;
-    float o[2][2];
-#pragma unroll
-    for (int br = 0; br < 2; ++br) {
-      write_h1_row<K, SPLIT>(s.H, s.H + IMG_H, s.c.A0[br], xk0, xk1, tid);
-      umma::fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        umma::fence_after_sync();
-        issue_gemm1<SPLIT>(tmem + br * F, s.H, s.H + IMG_H, wimg_at<false>(s.W, br, 0), wimg_at<false>(s.W, br, 1));
-        umma::mma_commit(&s.c.bar_mma);
-      }
-      umma::mbar_wait(&s.c.bar_mma, phase);
-      phase ^= 1;
-      umma::fence_after_sync();
-      if (STATS) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          umma::tmem_ld32(lane_addr + br * F + half * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] : 0.f;
-          float rs, rq;
-          colreduce32_sq(s.scratch, v, tid, rs, rq);
-          sacc[br * 2 + half][0] += rs;
-          sacc[br * 2 + half][1] += rq;
-        }
-      } else {
-        float o0 = s.c.b2[br][0], o1 = s.c.b2[br][1];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          umma::tmem_ld32(lane_addr + br * F + half * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float4 e = s.c.epi[br][half * 32 + i];
-            const float h3 = fmaxf(fmaf(e.x, v[i], e.y), 0.f);
-            o0 = fmaf(e.z, h3, o0);
-            o1 = fmaf(e.w, h3, o1);
-          }
-        }
-        o[br][0] = o0;
-        o[br][1] = o1;
-      }
-      umma::fence_before_sync();
-      __syncthreads();     // activation tiles, this branch's TMEM columns and (br == 1) the epi table are free again
-    }
-    if (!STATS) {
-      float yv[3], muv[3] = {0.f, 0.f, 0.f}, lvv[3] = {0.f, 0.f, 0.f};
-      const float sig1 = sqrtf(a.eps + 1.0f);
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) yv[ch] = (MODE == 0) ? sig1 * xin[ch] : xin[ch] / sig1;
-#pragma unroll
-      for (int wi = 0; wi < 2; ++wi) {
-        if (wi < a.w) {
-          const int ch = wi == 0 ? a.warp0 : a.warp1;
-          const float l = softsign(o[1][wi]);
-          const float sig = sqrtf(a.eps + expf(l));
-          const float m = o[0][wi];
-          const float xv = pick3(xin, ch);
-          const float r = (MODE == 0) ? fmaf(sig, xv, m) : (xv - m) / sig;
-#pragma unroll
-          for (int q = 0; q < 3; ++q)
-            if (q == ch) { yv[q] = r; muv[q] = m; lvv[q] = l; }
-        }
-      }
-      if (valid) {
-        const size_t base = (size_t)b * 3 * a.N + n;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          a.y[base + (size_t)ch * a.N] = yv[ch];
-          a.mu[base + (size_t)ch * a.N] = muv[ch];
-          a.lv[base + (size_t)ch * a.N] = lvv[ch];
-        }
-        macc[0] += yv[0]; macc[1] += yv[1]; macc[2] += yv[2];
-        macc[3] = fmaf(yv[0], yv[0], macc[3]); macc[4] = fmaf(yv[0], yv[1], macc[4]); macc[5] = fmaf(yv[0], yv[2], macc[5]);
-        macc[6] = fmaf(yv[1], yv[1], macc[6]); macc[7] = fmaf(yv[1], yv[2], macc[7]); macc[8] = fmaf(yv[2], yv[2], macc[8]);
-      }
-    }
-  }
-  if (STATS) {
-    // combine the 4 row-quarters of every column, then one double atomic per (branch, channel, stat)
-    float* fin = &s.fin[0][0];
-    for (int i = tid; i < 4 * F; i += DPF_TILE) fin[i] = 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      atomicAdd(&s.fin[0][ch * 32 + (tid & 31)], sacc[ch][0]);
-      atomicAdd(&s.fin[1][ch * 32 + (tid & 31)], sacc[ch][1]);
-    }
-    __syncthreads();
-    atomicAdd(&a.bnb_sums[tid * 2 + 0], (double)s.fin[0][tid]);   // tid == br*F + c
-    atomicAdd(&a.bnb_sums[tid * 2 + 1], (double)s.fin[1][tid]);
-  } else if (a.mom_out) {
-    const int lane = tid & 31;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const double v = warp_sum_d((double)macc[i]);
-      if (lane == 0) s.mom[i][warp] = v;
-    }
-    __syncthreads();
-    if (tid < 9) atomicAdd(a.mom_out + tid, s.mom[tid][0] + s.mom[tid][1] + s.mom[tid][2] + s.mom[tid][3]);
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, 128);
-}
-
-// =============================================================================================
-// Train-mode forward, ONE cooperative launch per layer: statistics phase -> grid barrier -> apply
-// phase, with the 64x64 SharedDot accumulators RESIDENT IN TMEM across the barrier (no recompute,
-// one prologue, one weight staging).  Each CTA owns up to RES tiles (RES * 128 TMEM columns; two
-// CTAs per SM use all 512), so this form covers n_tiles <= RES * grid; larger problems use the
-// two-launch form above.
-// =============================================================================================
+// Tiles whose SharedDot accumulators one CTA of the merged train-mode forward keeps resident in TMEM
+// across the grid barrier (RES * 128 columns; two CTAs per SM use all 512).
 constexpr int RES = 2;
 
 // Software grid barrier.  The launch puts exactly as many CTAs on the chip as fit (2 per SM by shared
@@ -393,188 +235,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     } while (v < expected);
   }
   __syncthreads();
-}
-
-template <int K, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(DPF_TILE)
-coupling_fwd_train_tc_kernel(const CouplingArgs a, const unsigned short* __restrict__ wimg, unsigned int* __restrict__ barrier_counter) {
-  extern __shared__ unsigned char smraw[];
-  TcFwdSmem& s = *reinterpret_cast<TcFwdSmem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const BranchLayout lay = branch_layout(a.k, a.w, a.G);
-  const bool writer = (blockIdx.x == 0) && a.update_stats;
-  const uint32_t tmem = tc_setup(s.c, RES * 128);
-  tc_load_weights<false>(s.c, s.W, wimg);
-  tc_prologue_tables(a, lay, s.c, writer, false);   // BN_a fold only; BN_b after the barrier
-  {
-    const int br = tid >> 6, c = tid & 63;
-    const float* prm = a.prm + (size_t)br * lay.size;
-    s.c.W2[br][0][c] = prm[lay.W2 + c];
-    s.c.W2[br][1][c] = (a.w == 2) ? prm[lay.W2 + F + c] : 0.f;
-    if (c < 2) s.c.b2[br][c] = (c < a.w) ? prm[lay.b2 + c] : 0.f;
-  }
-  float sacc[4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) sacc[i][0] = sacc[i][1] = 0.f;
-  umma::mbar_wait(&s.c.bar_load, 0);
-  __syncthreads();
-
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-  uint32_t phase = 0;
-  float xin[RES][3];
-  // ---------------- phase 1: h1 -> UMMA -> per-channel sum / sum of squares ----------------
-#pragma unroll
-  for (int ts = 0; ts < RES; ++ts) {
-    const int tile = blockIdx.x + ts * gridDim.x;
-    if (tile < a.n_tiles) {                      // uniform per CTA
-      const int b = tile / a.tiles_per_b;
-      const int n = (tile - b * a.tiles_per_b) * DPF_TILE + tid;
-      const bool valid = n < a.N;
-      const float* px = a.x + (size_t)b * 3 * a.N + n;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) xin[ts][ch] = valid ? px[(size_t)ch * a.N] : 0.f;
-      const float xk0 = pick3(xin[ts], a.keep0);
-      const float xk1 = (K == 2) ? pick3(xin[ts], a.keep1) : 0.f;
-#pragma unroll
-      for (int br = 0; br < 2; ++br) {
-        write_h1_row<K, SPLIT>(s.H, s.H + IMG_H, s.c.A0[br], xk0, xk1, tid);
-        umma::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-          umma::fence_after_sync();
-          issue_gemm1<SPLIT>(tmem + ts * 128 + br * F, s.H, s.H + IMG_H, wimg_at<false>(s.W, br, 0), wimg_at<false>(s.W, br, 1));
-          umma::mma_commit(&s.c.bar_mma);
-        }
-        umma::mbar_wait(&s.c.bar_mma, phase);
-        phase ^= 1;
-        umma::fence_after_sync();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          umma::tmem_ld32(lane_addr + ts * 128 + br * F + half * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] : 0.f;
-          float rs, rq;
-          colreduce32_sq(s.scratch, v, tid, rs, rq);
-          sacc[br * 2 + half][0] += rs;
-          sacc[br * 2 + half][1] += rq;
-        }
-        umma::fence_before_sync();
-        __syncthreads();                         // the activation tiles are free again (TMEM columns stay)
-      }
-    }
-  }
-  {
-    float* fin = &s.fin[0][0];
-    for (int i = tid; i < 4 * F; i += DPF_TILE) fin[i] = 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      atomicAdd(&s.fin[0][ch * 32 + (tid & 31)], sacc[ch][0]);
-      atomicAdd(&s.fin[1][ch * 32 + (tid & 31)], sacc[ch][1]);
-    }
-    __syncthreads();
-    if (blockIdx.x < a.n_tiles) {
-      atomicAdd(&a.bnb_sums[tid * 2 + 0], (double)s.fin[0][tid]);
-      atomicAdd(&a.bnb_sums[tid * 2 + 1], (double)s.fin[1][tid]);
-    }
-  }
-  // ---------------- grid-wide barrier: every CTA's statistics are in bnb_sums ----------------
-  grid_barrier(barrier_counter, gridDim.x);
-  // ---------------- phase 2: BN_b x FiLM fold, epilogue from the resident accumulators ----------------
-  {
-    const int br = tid >> 6, c = tid & 63;
-    const double M = (double)a.B * (double)a.N;
-    const double sm = __ldcg(&a.bnb_sums[(br * F + c) * 2 + 0]), sq = __ldcg(&a.bnb_sums[(br * F + c) * 2 + 1]);
-    const double dm = sm / M;
-    const double dv = fmax(sq / M - dm * dm, 0.0);
-    s.c.mb[br][c] = (float)dm;
-    s.c.ib[br][c] = 1.f / sqrtf((float)dv + DPF_BN_EPS);
-    if (writer) {
-      float* st = a.stat + (size_t)br * ST_COUNT * F;
-      st[ST_BNB_RM * F + c] = (1.f - DPF_BN_MOM) * st[ST_BNB_RM * F + c] + DPF_BN_MOM * (float)dm;
-      st[ST_BNB_RV * F + c] = (1.f - DPF_BN_MOM) * st[ST_BNB_RV * F + c] + DPF_BN_MOM * (float)(dv * (M / fmax(M - 1.0, 1.0)));
-    }
-  }
-  __syncthreads();
-  float macc[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) macc[i] = 0.f;
-  umma::fence_after_sync();
-#pragma unroll
-  for (int ts = 0; ts < RES; ++ts) {
-    const int tile = blockIdx.x + ts * gridDim.x;
-    if (tile < a.n_tiles) {
-      const int b = tile / a.tiles_per_b;
-      const int n = (tile - b * a.tiles_per_b) * DPF_TILE + tid;
-      const bool valid = n < a.N;
-      __syncthreads();                           // previous tile finished with the epi table
-      tc_tile_film(a, s.c, b);
-      __syncthreads();
-      float o[2][2];
-#pragma unroll
-      for (int br = 0; br < 2; ++br) {
-        float o0 = s.c.b2[br][0], o1 = s.c.b2[br][1];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          umma::tmem_ld32(lane_addr + ts * 128 + br * F + half * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float4 e = s.c.epi[br][half * 32 + i];
-            const float h3 = fmaxf(fmaf(e.x, v[i], e.y), 0.f);
-            o0 = fmaf(e.z, h3, o0);
-            o1 = fmaf(e.w, h3, o1);
-          }
-        }
-        o[br][0] = o0;
-        o[br][1] = o1;
-      }
-      float yv[3], muv[3] = {0.f, 0.f, 0.f}, lvv[3] = {0.f, 0.f, 0.f};
-      const float sig1 = sqrtf(a.eps + 1.0f);
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) yv[ch] = (MODE == 0) ? sig1 * xin[ts][ch] : xin[ts][ch] / sig1;
-#pragma unroll
-      for (int wi = 0; wi < 2; ++wi) {
-        if (wi < a.w) {
-          const int ch = wi == 0 ? a.warp0 : a.warp1;
-          const float l = softsign(o[1][wi]);
-          const float sig = sqrtf(a.eps + expf(l));
-          const float m = o[0][wi];
-          const float xv = pick3(xin[ts], ch);
-          const float r = (MODE == 0) ? fmaf(sig, xv, m) : (xv - m) / sig;
-#pragma unroll
-          for (int q = 0; q < 3; ++q)
-            if (q == ch) { yv[q] = r; muv[q] = m; lvv[q] = l; }
-        }
-      }
-      if (valid) {
-        const size_t base = (size_t)b * 3 * a.N + n;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          a.y[base + (size_t)ch * a.N] = yv[ch];
-          a.mu[base + (size_t)ch * a.N] = muv[ch];
-          a.lv[base + (size_t)ch * a.N] = lvv[ch];
-        }
-        macc[0] += yv[0]; macc[1] += yv[1]; macc[2] += yv[2];
-        macc[3] = fmaf(yv[0], yv[0], macc[3]); macc[4] = fmaf(yv[0], yv[1], macc[4]); macc[5] = fmaf(yv[0], yv[2], macc[5]);
-        macc[6] = fmaf(yv[1], yv[1], macc[6]); macc[7] = fmaf(yv[1], yv[2], macc[7]); macc[8] = fmaf(yv[2], yv[2], macc[8]);
-      }
-    }
-  }
-  if (a.mom_out) {
-    const int lane = tid & 31;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const double v = warp_sum_d((double)macc[i]);
-      if (lane == 0) s.mom[i][warp] = v;
-    }
-    __syncthreads();
-    if (tid < 9) atomicAdd(a.mom_out + tid, s.mom[tid][0] + s.mom[tid][1] + s.mom[tid][2] + s.mom[tid][3]);
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, RES * 128);
 }
 
 // =============================================================================================
@@ -712,8 +372,10 @@ coupling_bwd_p1_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
   TcP1Smem& s = *reinterpret_cast<TcP1Smem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
+  pdl_launch_dependents();
   const uint32_t tmem = tc_setup(s.c, 128);
   tc_load_weights<false>(s.c, s.W, wimg);
+  pdl_wait();          // the previous backward step's sums / gradients are read from here on
   tc_prologue_tables(a.f, lay, s.c, false, true);
   for (int i = tid; i < 4 * 2 * F; i += DPF_TILE) (&s.fin[0][0])[i] = 0.f;
   if (tid < 4) (&s.b2fin[0][0])[tid] = 0.f;
@@ -820,216 +482,6 @@ coupling_bwd_p1_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wi
   if (warp == 0) umma::tmem_dealloc(tmem, 128);
 }
 
-// =============================================================================================
-// Backward pass 2: BN_b backward, dgrad, wgrad (TMEM-resident across tiles), BN_a sums, dx.
-// Both branches' h1 (hi) and dh2pre tiles are live together: wgrad reads them as one MN-major
-// operand of width 128.  The h1 lo tiles alias the dh2pre tiles (dead once the recompute is done).
-// =============================================================================================
-struct TcP2Smem {
-  unsigned char W[2 * N_IMG * IMG_W];   // [br][W1 hi, W1 lo, W1^T hi]
-  unsigned char H[2 * IMG_H];           // h1 hi tiles (mu, logvar) - contiguous: MN-major N = 128 for wgrad
-  unsigned char D[2 * IMG_H];           // h1 lo tiles during the recompute, then dh2pre tiles (MN-major M = 128)
-  TcCommon c;
-  float m1[2][F], m2[2][F];
-  float scratch[2 * DPF_TILE * 33];
-  float fin[3][2 * F];
-};
-
-template <int K, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(DPF_TILE)
-coupling_bwd_p2_tc_kernel(const BwdArgs a, const unsigned short* __restrict__ wimg) {
-  extern __shared__ unsigned char smraw[];
-  TcP2Smem& s = *reinterpret_cast<TcP2Smem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
-  const uint32_t tmem = tc_setup(s.c, 512);
-  tc_load_weights<true>(s.c, s.W, wimg);
-  tc_prologue_tables(a.f, lay, s.c, false, true);
-  {
-    const int br = tid >> 6, c = tid & 63;
-    float m1 = 0.f, m2 = 0.f;
-    if (a.f.training) {
-      // sum_b s[b,c] * {dt, ds}[b,c]: 4 independent chains so the loads of 4 shapes are in flight together
-      double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
-      const float* fs = a.f.film + (size_t)(br * 2 + 0) * a.f.B * F + c;
-      const float* dsr = a.dfilm + (size_t)(br * 2 + 0) * a.f.B * F + c;
-      const float* dtr = a.dfilm + (size_t)(br * 2 + 1) * a.f.B * F + c;
-      int b = 0;
-      for (; b + 4 <= a.f.B; b += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const double sc = fs[(size_t)(b + u) * F];
-          s1[u] += sc * (double)dtr[(size_t)(b + u) * F];
-          s2[u] += sc * (double)dsr[(size_t)(b + u) * F];
-        }
-      }
-      for (; b < a.f.B; ++b) {
-        const double sc = fs[(size_t)b * F];
-        s1[0] += sc * (double)dtr[(size_t)b * F];
-        s2[0] += sc * (double)dsr[(size_t)b * F];
-      }
-      const double M = (double)a.f.B * (double)a.f.N;
-      m1 = (float)(((s1[0] + s1[1]) + (s1[2] + s1[3])) / M);
-      m2 = (float)(((s2[0] + s2[1]) + (s2[2] + s2[3])) / M);
-    }
-    s.m1[br][c] = m1;
-    s.m2[br][c] = m2;
-  }
-  for (int i = tid; i < 3 * 2 * F; i += DPF_TILE) (&s.fin[0][0])[i] = 0.f;
-  __syncthreads();
-  const Pending P = tc_compute_pending(a, false, s.c.pend);
-  const float sig1 = sqrtf(a.f.eps + 1.0f);
-  umma::mbar_wait(&s.c.bar_load, 0);
-  __syncthreads();
-
-  int t0, t1;
-  tile_range(a.f.n_tiles, t0, t1);
-  uint32_t phase = 0;
-  const uint32_t T_FWD = tmem, T_DG = tmem + 128, T_WG = tmem + 256;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-  for (int tile = t0; tile < t1; ++tile) {
-    const int b = tile / a.f.tiles_per_b;
-    const int n = (tile - b * a.f.tiles_per_b) * DPF_TILE + tid;
-    const bool valid = n < a.f.N;
-    tc_tile_film(a.f, s.c, b);
-    const TcPoint g = tc_load_point<MODE>(a, P, b, n, valid);
-    const float xk0 = pick3(g.x, a.f.keep0);
-    const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
-    write_h1_row<K, SPLIT>(s.H, s.D, s.c.A0[0], xk0, xk1, tid);
-    write_h1_row<K, SPLIT>(s.H + IMG_H, s.D + IMG_H, s.c.A0[1], xk0, xk1, tid);
-    umma::fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      issue_gemm1<SPLIT>(T_FWD, s.H, s.D, wimg_at<true>(s.W, 0, 0), wimg_at<true>(s.W, 0, 1));
-      issue_gemm1<SPLIT>(T_FWD + F, s.H + IMG_H, s.D + IMG_H, wimg_at<true>(s.W, 1, 0), wimg_at<true>(s.W, 1, 1));
-      umma::mma_commit(&s.c.bar_mma);
-    }
-    umma::mbar_wait(&s.c.bar_mma, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    // ---- epilogue A: dh2pre (bf16) -> D tiles (the lo tiles are dead now) ----
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      const int br = ch >> 1, half = ch & 1;
-      const float d0 = br == 0 ? g.do_mu[0] : g.do_lv[0];
-      const float d1 = br == 0 ? g.do_mu[1] : g.do_lv[1];
-      float v[32];
-      umma::tmem_ld32(T_FWD + lane_off + ch * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int c = half * 32 + i;
-        const float4 e = s.c.epi[br][c];
-        const float h2n = (v[i] - s.c.mb[br][c]) * s.c.ib[br][c];
-        const float av = fmaf(e.x, v[i], e.y);
-        const float da = av > 0.f ? fmaf(e.z, d0, e.w * d1) : 0.f;
-        const float dh = s.c.ib[br][c] * (da * s.c.sraw[br][c] - s.m1[br][c] - h2n * s.m2[br][c]);
-        v[i] = valid ? dh : 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                    umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-        *reinterpret_cast<uint4*>(s.D + br * IMG_H + umma::sw128_offset(tid, half * 4 + q)) = pk;
-      }
-    }
-    umma::fence_async_smem();
-    umma::fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      // dgrad: DH1[br] = DH2[br] (K-major, K = c) x W1^T image (rows j, K = c)
-#pragma unroll
-      for (int br = 0; br < 2; ++br)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma::mma_bf16(T_DG + br * F, umma::desc_at(DESC_K, umma::smem_u32(s.D + br * IMG_H) + 32 * k),
-                         umma::desc_at(DESC_K, umma::smem_u32(wimg_at<true>(s.W, br, 2)) + 32 * k), IDESC_GEMM, k > 0);
-      // wgrad: [c_mu | c_lv] x [j_mu | j_lv] += sum over the tile's 128 points (MN-major views, K = 16 rows per step)
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma::mma_bf16(T_WG, umma::desc_at(DESC_MN, umma::smem_u32(s.D) + 2048 * k), umma::desc_at(DESC_MN, umma::smem_u32(s.H) + 2048 * k),
-                       IDESC_WGRAD, (tile > t0 || k > 0) ? 1u : 0u);
-      umma::mma_commit(&s.c.bar_mma);
-    }
-    umma::mbar_wait(&s.c.bar_mma, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-    // ---- epilogue B: dz, T1, BN_a sums ----
-    float T1_0 = 0.f, T1_1 = 0.f;
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      const int br = ch >> 1, half = ch & 1;
-      float v[32], q1[32], q2[32];
-      umma::tmem_ld32(T_DG + lane_off + ch * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float4 A = s.c.A0[br][half * 32 + i];
-        float z = fmaf(A.x, xk0, A.z);
-        if (K == 2) z = fmaf(A.y, xk1, z);
-        const float dz = (z > 0.f && valid) ? v[i] : 0.f;
-        T1_0 = fmaf(A.x, dz, T1_0);
-        if (K == 2) T1_1 = fmaf(A.y, dz, T1_1);
-        v[i] = dz;
-        q1[i] = dz * xk0;
-        q2[i] = dz * xk1;
-      }
-      float ra, rb;
-      colreduce32x2(s.scratch, v, q1, tid, ra, rb);
-      atomicAdd(&s.fin[0][ch * 32 + lane], ra);
-      atomicAdd(&s.fin[1][ch * 32 + lane], rb);
-      if (K == 2) {
-        colreduce32x2(s.scratch, q2, q2, tid, ra, rb);
-        atomicAdd(&s.fin[2][ch * 32 + lane], ra);
-      }
-    }
-    if (valid) {
-      float dx[3];
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) dx[ch] = (MODE == 1) ? g.dy[ch] / sig1 : g.dy[ch] * sig1;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        if (ch == a.f.keep0) dx[ch] += T1_0;
-        if (K == 2 && ch == a.f.keep1) dx[ch] += T1_1;
-        if (ch == a.f.warp0) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[0] : g.dy[ch] * g.sig[0];
-        if (K == 1 && ch == a.f.warp1) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[1] : g.dy[ch] * g.sig[1];
-      }
-      const size_t base = (size_t)b * 3 * a.f.N + n;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) a.dx_out[base + (size_t)ch * a.f.N] = dx[ch];
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-  }
-  // ---- CTA epilogue: BN_a sums and the TMEM-resident wgrad accumulator ----
-  __syncthreads();
-  atomicAdd(&a.bna_sums[tid * 4 + 0], (double)s.fin[0][tid]);
-  atomicAdd(&a.bna_sums[tid * 4 + 1], (double)s.fin[1][tid]);
-  atomicAdd(&a.bna_sums[tid * 4 + 2], (double)s.fin[2][tid]);
-  {
-    // accumulator row = tid: rows 0..63 -> branch mu channel c = tid, its dW1 row lives in columns 0..63;
-    // rows 64..127 -> branch logvar channel c = tid-64, columns 64..127 (off-diagonal blocks are unused).
-    // Every CTA stores its partial (zeros if it had no tile); dw1_reduce_kernel sums them once per pass.
-    const int br = tid >> 6, c = tid & 63;
-    float4* d = reinterpret_cast<float4*>(a.dw1_partial + ((size_t)blockIdx.x * 2 + br) * (F * F) + c * F);
-    umma::fence_after_sync();
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float v[32];
-      if (t1 > t0) {
-        umma::tmem_ld32(T_WG + lane_off + br * F + half * 32, v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[half * 8 + i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    }
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, 512);
-}
 
 // =============================================================================================
 // Backward pass 2, two threads per point (256 threads per CTA): thread (row = tid & 127, part =
@@ -1072,8 +524,10 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & 127, part = tid >> 7, quarter = warp & 3;
   const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
+  pdl_launch_dependents();
   const uint32_t tmem = tc_setup(s.c, 512);
   tc_load_weights<true>(s.c, s.W, wimg);
+  pdl_wait();          // pass 1's FiLM sums are read from here on
   tc_prologue_tables(a.f, lay, s.c, false, true);
   if (tid < 128) {
     const int br = tid >> 6, c = tid & 63;
@@ -1318,6 +772,227 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
 }
 
 // =============================================================================================
+// Backward pass 1, two threads per point, reductions over points on the tensor cores.
+//
+// With mask m = [a > 0], a = s*h2n + t (FiLM scale s, shift t), h3 = m*a, da = m*(W2_0 d0 + W2_1 d1):
+//     S_w[c] = sum_p d_w[p] h3[p,c]      M_w[c] = sum_p d_w[p] m[p,c]          (w = 0, 1)
+//     dW2_w = S_w     dt = W2_0 M_0 + W2_1 M_1     ds = sum_p da*h2n = (W2_0 S_0 + W2_1 S_1 - t*dt) / s
+// so the four column sums per branch are all pass 1 needs.  They are UMMAs with K = the 128 points:
+//     D[channel, j] += sum_p A[p, channel] * X[p, j]
+// A = the h3 (bf16 hi | lo) tiles / the 0-1 mask tile read as MN-major M = 128 operands, X = the
+// per-point weights {d0 hi, d0 lo, d1 hi, d1 lo} of both branches (MN-major, N = 16), accumulated in
+// TMEM over the consecutive tiles of one shape and read back one channel per lane.
+// =============================================================================================
+constexpr uint32_t IDESC_RED = umma::make_idesc_bf16(128, 16, 1, 1);
+
+struct TcP1Smem2 {
+  unsigned char W[4 * IMG_W];           // [br][W1 hi, W1 lo]
+  unsigned char H[2 * IMG_H];           // h1 hi | lo, then h3 hi | lo of the branch in flight
+  unsigned char Mk[IMG_H];              // mask tile; the M = 128 operand's second block is X (ignored lanes)
+  unsigned char X[IMG_H];               // per-point weights, chunk 0 of every row (chunk 1 stays zero)
+  TcCommon c;
+  float shift[2][F];                    // FiLM shift of the current shape
+  float sbuf[2][2][DPF_TILE];           // S_w partials: lanes 0..63 = h3 hi part, 64..127 = h3 lo part
+  float mbuf[2][2][F];
+  float b2fin[2][2];
+};
+
+template <int K, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(NT2, 2)
+coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ wimg) {
+  extern __shared__ unsigned char smraw[];
+  TcP1Smem2& s = *reinterpret_cast<TcP1Smem2*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, part = tid >> 7, quarter = warp & 3;
+  const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
+  const uint32_t tmem = tc_setup(s.c, 256);
+  tc_load_weights<false>(s.c, s.W, wimg);
+  tc_prologue_tables(a.f, lay, s.c, false, true);
+  for (int i = tid; i < (int)(IMG_H / 16); i += NT2) reinterpret_cast<uint4*>(s.X)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 4) (&s.b2fin[0][0])[tid] = 0.f;
+  __syncthreads();
+  const Pending P = tc_compute_pending(a, blockIdx.x == 0, s.c.pend);
+  float b2acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float dW2acc[2] = {0.f, 0.f};        // threads < 128: (branch, channel) = (tid >> 6, tid & 63)
+  umma::mbar_wait(&s.c.bar_load, 0);
+  __syncthreads();
+
+  int t0, t1;
+  tile_range(a.f.n_tiles, t0, t1);
+  uint32_t phase = 0, phase_aux = 0;
+  const uint32_t T_FWD = tmem, T_RED = tmem + 128;   // T_RED + br*32: [0,16) h3 sums, [16,32) mask sums
+  const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+  int cur_b = -1;
+  bool run_start = true;
+
+  // sums of the finished run of tiles (all of shape b) -> FiLM gradients (global) and dW2 (registers)
+  auto flush_run = [&](int b) {
+    if (part == 0) {
+      umma::fence_after_sync();
+#pragma unroll
+      for (int br = 0; br < 2; ++br) {
+        uint32_t d1[4], d2[4];
+        umma::tmem_ld4(T_RED + lane_off + br * 32 + br * 4, d1);
+        umma::tmem_ld4(T_RED + lane_off + br * 32 + 16 + br * 4, d2);
+        umma::tmem_ld_wait4(d1);
+        umma::tmem_ld_wait4(d2);
+        s.sbuf[br][0][row] = __uint_as_float(d1[0]) + __uint_as_float(d1[1]);
+        s.sbuf[br][1][row] = __uint_as_float(d1[2]) + __uint_as_float(d1[3]);
+        if (row < F) {
+          s.mbuf[br][0][row] = __uint_as_float(d2[0]) + __uint_as_float(d2[1]);
+          s.mbuf[br][1][row] = __uint_as_float(d2[2]) + __uint_as_float(d2[3]);
+        }
+      }
+      umma::fence_before_sync();
+    }
+    __syncthreads();
+    if (tid < 2 * F) {
+      const int br = tid >> 6, c = tid & 63;
+      const float S0 = s.sbuf[br][0][c] + s.sbuf[br][0][F + c], S1 = s.sbuf[br][1][c] + s.sbuf[br][1][F + c];
+      const float M0 = s.mbuf[br][0][c], M1 = s.mbuf[br][1][c];
+      const float W20 = s.c.W2[br][0][c], W21 = s.c.W2[br][1][c];
+      const float dt = fmaf(W20, M0, W21 * M1);
+      const float ds = (fmaf(W20, S0, W21 * S1) - s.shift[br][c] * dt) / s.c.sraw[br][c];
+      atomicAdd(&a.dfilm[((size_t)(br * 2 + 0) * a.f.B + b) * F + c], ds);
+      atomicAdd(&a.dfilm[((size_t)(br * 2 + 1) * a.f.B + b) * F + c], dt);
+      dW2acc[0] += S0;
+      dW2acc[1] += S1;
+    }
+    __syncthreads();
+  };
+
+  for (int tile = t0; tile < t1; ++tile) {
+    const int b = tile / a.f.tiles_per_b;
+    const int n = (tile - b * a.f.tiles_per_b) * DPF_TILE + row;
+    const bool valid = n < a.f.N;
+    if (tile > t0) {   // the previous tile's reduction UMMAs read H / Mk / X and feed the accumulators
+      umma::mbar_wait(&s.c.bar_aux, phase_aux);
+      phase_aux ^= 1;
+    }
+    if (b != cur_b) {
+      if (cur_b >= 0) flush_run(cur_b);
+      cur_b = b;
+      run_start = true;
+      tc_tile_film(a.f, s.c, b);
+      if (tid < 2 * F) s.shift[tid >> 6][tid & 63] = a.f.film[((size_t)((tid >> 6) * 2 + 1) * a.f.B + b) * F + (tid & 63)];
+    }
+    const TcPoint g = tc_load_point<MODE>(a, P, b, n, valid);
+    const float xk0 = pick3(g.x, a.f.keep0);
+    const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
+    if (part == 0) {   // weights of both branches: {mu0 hi, mu0 lo, mu1 hi, mu1 lo, lv0 hi, lv0 lo, lv1 hi, lv1 lo}
+      uint32_t w[4];
+      const float dv[4] = {g.do_mu[0], g.do_mu[1], g.do_lv[0], g.do_lv[1]};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t hi = umma::pack_bf16(dv[i], 0.f) & 0xffffu;
+        const float lo = dv[i] - __uint_as_float(hi << 16);
+        w[i] = umma::pack_bf16(0.f, lo) | hi;
+      }
+      *reinterpret_cast<uint4*>(s.X + umma::sw128_offset(row, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+#pragma unroll 1
+    for (int br = 0; br < 2; ++br) {
+      if (br == 1) {   // branch 0's reductions still read the h3 tiles in H
+        umma::mbar_wait(&s.c.bar_aux, phase_aux);
+        phase_aux ^= 1;
+      }
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const int q = part * 4 + qq;
+        uint32_t w[4], wl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 Aa = s.c.A0[br][q * 8 + 2 * i], Ab = s.c.A0[br][q * 8 + 2 * i + 1];
+          float va = fmaf(Aa.x, xk0, Aa.z), vb = fmaf(Ab.x, xk0, Ab.z);
+          if (K == 2) { va = fmaf(Aa.y, xk1, va); vb = fmaf(Ab.y, xk1, vb); }
+          va = fmaxf(va, 0.f);
+          vb = fmaxf(vb, 0.f);
+          w[i] = umma::pack_bf16(va, vb);
+          if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
+        }
+        const uint32_t off = umma::sw128_offset(row, q);
+        *reinterpret_cast<uint4*>(s.H + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (SPLIT) *reinterpret_cast<uint4*>(s.H + IMG_H + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      }
+      umma::fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        issue_gemm1<SPLIT>(T_FWD + br * F, s.H, s.H + IMG_H, wimg_at<false>(s.W, br, 0), wimg_at<false>(s.W, br, 1));
+        umma::mma_commit(&s.c.bar_mma);
+      }
+      umma::mbar_wait(&s.c.bar_mma, phase);
+      phase ^= 1;
+      umma::fence_after_sync();
+      // h3 (hi | lo) and mask of this part's 32 channels -> tiles
+      {
+        float v[32];
+        umma::tmem_ld32(T_FWD + lane_off + br * F + part * 32, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t wh[4], wl[4], wm[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 ea = s.c.epi[br][part * 32 + q * 8 + 2 * i], eb = s.c.epi[br][part * 32 + q * 8 + 2 * i + 1];
+            const float ha = fmaxf(fmaf(ea.x, v[q * 8 + 2 * i], ea.y), 0.f);
+            const float hb = fmaxf(fmaf(eb.x, v[q * 8 + 2 * i + 1], eb.y), 0.f);
+            wh[i] = umma::pack_bf16(ha, hb);
+            wl[i] = umma::pack_bf16(ha - __uint_as_float(wh[i] << 16), hb - __uint_as_float(wh[i] & 0xffff0000u));
+            wm[i] = (ha > 0.f ? 0x3f80u : 0u) | (hb > 0.f ? 0x3f800000u : 0u);
+          }
+          const uint32_t off = umma::sw128_offset(row, part * 4 + q);
+          *reinterpret_cast<uint4*>(s.H + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+          *reinterpret_cast<uint4*>(s.H + IMG_H + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+          *reinterpret_cast<uint4*>(s.Mk + off) = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+        }
+      }
+      umma::fence_async_smem();
+      umma::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        umma::fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma::mma_bf16(T_RED + br * 32, umma::desc_at(DESC_MN, umma::smem_u32(s.H) + 2048 * k),
+                         umma::desc_at(DESC_MN, umma::smem_u32(s.X) + 2048 * k), IDESC_RED, (!run_start || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma::mma_bf16(T_RED + br * 32 + 16, umma::desc_at(DESC_MN, umma::smem_u32(s.Mk) + 2048 * k),
+                         umma::desc_at(DESC_MN, umma::smem_u32(s.X) + 2048 * k), IDESC_RED, (!run_start || k > 0) ? 1u : 0u);
+        umma::mma_commit(&s.c.bar_aux);
+      }
+    }
+    run_start = false;
+    b2acc[0][0] += g.do_mu[0]; b2acc[0][1] += g.do_mu[1];
+    b2acc[1][0] += g.do_lv[0]; b2acc[1][1] += g.do_lv[1];
+  }
+  if (t1 > t0) {
+    umma::mbar_wait(&s.c.bar_aux, phase_aux);
+    flush_run(cur_b);
+  }
+  if (part == 0) {
+#pragma unroll
+    for (int br = 0; br < 2; ++br)
+#pragma unroll
+      for (int wi = 0; wi < 2; ++wi) {
+        const float v = warp_sum(b2acc[br][wi]);
+        if (lane == 0) atomicAdd(&s.b2fin[br][wi], v);
+      }
+  }
+  __syncthreads();
+  if (tid < 2 * F) {
+    const int br = tid >> 6, c = tid & 63;
+    float* d = a.dprm + (size_t)br * lay.size;
+    atomicAdd(&d[lay.W2 + c], dW2acc[0]);
+    if (a.f.w == 2) atomicAdd(&d[lay.W2 + F + c], dW2acc[1]);
+    if (c < a.f.w) atomicAdd(&d[lay.b2 + c], s.b2fin[br][c]);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+
+// =============================================================================================
 // Forward kernels, two threads per point (256 threads per CTA, same shared memory as the 128-thread
 // form => 16 warps per SM): statistics pass, apply pass, and the merged train-mode launch.
 // =============================================================================================
@@ -1559,8 +1234,10 @@ coupling_fwd_train_tc2_kernel(const CouplingArgs a, const unsigned short* __rest
   const int row = tid & 127, part = tid >> 7, quarter = warp & 3;
   const BranchLayout lay = branch_layout(a.k, a.w, a.G);
   const bool writer = (blockIdx.x == 0) && a.update_stats && tid < 128;
+  pdl_launch_dependents();
   const uint32_t tmem = tc_setup(s.c, RES * 128);
   tc_load_weights<false>(s.c, s.W, wimg);
+  pdl_wait();          // everything above is independent of the previous layer's kernel
   tc_prologue_tables(a, lay, s.c, writer, false);
   if (tid < 128) {
     const int br = tid >> 6, c = tid & 63;
@@ -1665,16 +1342,21 @@ int launch_bwd_tc_t(const BwdArgs& a, const unsigned short* wimg, int pass, cuda
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(coupling_bwd_p1_tc_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP1Smem>());
+    cudaFuncSetAttribute(coupling_bwd_p1_tc2_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP1Smem2>());
     cudaFuncSetAttribute(coupling_bwd_p2_tc2_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP2Smem2>());
     attr = true;
   }
   if (pass == 1) {
     const int grid = min(a.f.n_tiles, dpf_num_sms() * 2);
-    coupling_bwd_p1_tc_kernel<K, MODE, SPLIT><<<grid, DPF_TILE, smem_for<TcP1Smem>(), st>>>(a, wimg);
+    if (g_dpf_p1_tensor_sums) {
+      dpf_launch_pdl(coupling_bwd_p1_tc2_kernel<K, MODE, SPLIT>, grid, NT2, smem_for<TcP1Smem2>(), st, a, wimg);
+      return dpf_check_launch("coupling_bwd_p1_tc2_kernel");
+    }
+    dpf_launch_pdl(coupling_bwd_p1_tc_kernel<K, MODE, SPLIT>, grid, DPF_TILE, smem_for<TcP1Smem>(), st, a, wimg);
     return dpf_check_launch("coupling_bwd_p1_tc_kernel");
   }
   const int grid = min(a.f.n_tiles, dpf_num_sms());
-  coupling_bwd_p2_tc2_kernel<K, MODE, SPLIT><<<grid, NT2, smem_for<TcP2Smem2>(), st>>>(a, wimg);
+  dpf_launch_pdl(coupling_bwd_p2_tc2_kernel<K, MODE, SPLIT>, grid, NT2, smem_for<TcP2Smem2>(), st, a, wimg);
   return dpf_check_launch("coupling_bwd_p2_tc2_kernel");
 }
 
@@ -1705,7 +1387,7 @@ int launch_fwd_train_t(const CouplingArgs& a, const unsigned short* wimg, unsign
   // kernel that allocates TMEM (occupancy query returns 1 at every shared-memory size), although two
   // CTAs with 256 columns each do share an SM.  grid <= 2 * SMs keeps every CTA resident.
   const int grid = min(a.n_tiles, max_grid);
-  kern<<<grid, NT2, smem_for<TcFwdSmem2>(), st>>>(a, wimg, counter);
+  dpf_launch_pdl(kern, grid, NT2, smem_for<TcFwdSmem2>(), st, a, wimg, counter);
   return dpf_check_launch("coupling_fwd_train_tc_kernel");
 }
 
@@ -1772,14 +1454,14 @@ int launch_coupling_fwd_train_tc(const CouplingArgs& a, const unsigned short* wi
 int tc_debug_occupancy(int which, int smem) {
   int n = -1;
   if (which == 0) {
-    auto k = coupling_fwd_train_tc_kernel<1, 1, true>;
+    auto k = coupling_fwd_train_tc2_kernel<1, 1, true>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, DPF_TILE, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NT2, smem);
   } else {
-    auto k = coupling_fwd_tc_kernel<1, 1, false, true>;
+    auto k = coupling_fwd_tc2_kernel<1, 1, false, true>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, DPF_TILE, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NT2, smem);
   }
   return n;
 }

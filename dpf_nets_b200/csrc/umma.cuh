@@ -86,6 +86,16 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t r[16]) {
                : "memory");
 }
 
+// 4 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t r[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait4(uint32_t r[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : : "memory");
+}
+
 // ---- MMA -------------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread on behalf of the CTA.
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
