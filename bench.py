@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="shapes per GPU")
     ap.add_argument("--points", type=int, default=2048)
     ap.add_argument("--no-extras", action="store_true", help="skip sampling / Chamfer / cpu_baseline legs")
+    ap.add_argument("--side-stream", action="store_true", help="run on a non-default CUDA stream (A/B tests)")
     ap.add_argument("--lib-option", action="append", default=[], metavar="K=V", help="dpf_set_option(K, V) before the run (A/B tests)")
     return ap.parse_args()
 
@@ -469,7 +470,13 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        if args.side_stream:      # A/B: everything on a non-default stream
+            import torch as _t
+            _t.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            with _t.cuda.stream(_t.cuda.Stream()):
+                run_ours(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":

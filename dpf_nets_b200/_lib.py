@@ -9,7 +9,7 @@ import re
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "_C", "libdpfnets_b200.so")
+LIB_PATH = os.environ.get("DPF_LIB_PATH") or os.path.join(_PKG, "_C", "libdpfnets_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "dpfnets_b200.h")
 
 _lib = None

@@ -10,13 +10,17 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-OUT_DIR = os.path.join(PKG_DIR, "_C")
+# DPF_STAMPS=1: development build with in-kernel phase timers (tools/stamp_probe.py), kept apart from
+# the product library (_C_stamps/, loaded only when DPF_LIB_PATH points at it)
+STAMPS = os.environ.get("DPF_STAMPS", "0") == "1"
+OUT_DIR = os.path.join(PKG_DIR, "_C_stamps" if STAMPS else "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libdpfnets_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + (["-DDPF_STAMPS"] if STAMPS else []) + (
+    ["-DDPF_EXP_NOATOMICS"] if os.environ.get("DPF_EXP_NOATOMICS") == "1" else [])
 
 
 def _sources():

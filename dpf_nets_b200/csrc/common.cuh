@@ -65,7 +65,7 @@ static inline int dpf_num_sms() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-extern int g_dpf_pdl;   // decoder.cu: dpf_set_option(2, v), default 1
+extern int g_dpf_pdl;   // decoder.cu: dpf_set_option(2, v)
 
 template <typename... KArgs, typename... Args>
 static inline void dpf_launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {

@@ -70,18 +70,12 @@ int launch_decoder_eval_tc(const float* arena, const float* stats, const LayerMe
                            const unsigned short* wimg, unsigned char* ltab, float* epi, const float* p, float* P, float* MU,
                            float* LV, int L, int G, int B, int N, int mode, int split, float eps, cudaStream_t s);
 // Option 2: programmatic dependent launch of the per-layer tensor-path kernels (common.cuh).
-// Measured on B200: no gain (7.50 vs 7.36 ms per step) - the kernels fill every SM's shared memory, so
-// a dependent CTA cannot become resident before its predecessor's CTAs exit.  Off by default.
-int g_dpf_pdl = 0;
-// Option 3: backward pass 1 with the per-channel sums on the tensor cores (1, default) or through
-// shared-memory column reductions (0).
-int g_dpf_p1_tensor_sums = 1;
+int g_dpf_pdl = 1;
 DPF_API int dpf_set_option(int option, int value) {
-  DPF_REQUIRE(option >= 0 && option <= 3, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
+  DPF_REQUIRE(option >= 0 && option <= 2, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
   if (option == 0) g_merged_forward = value != 0;
   else if (option == 1) g_fused_eval = value != 0;
-  else if (option == 2) g_dpf_pdl = value != 0;
-  else g_dpf_p1_tensor_sums = value != 0;
+  else g_dpf_pdl = value != 0;
   return DPF_OK;
 }
 

@@ -26,6 +26,48 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     p[i] = pi - (pi * wd + lr * ((mi / bc1) / denom));
   }
 }
+// Multi-tensor form: up to ADAM_CHUNK tensors per launch, pointers passed by value in the kernel
+// arguments; block -> (tensor, 4096-element slab) through a prefix table.
+constexpr int ADAM_CHUNK = 48;
+constexpr int ADAM_SLAB = 4096;
+struct AdamTensors {
+  float* p[ADAM_CHUNK];
+  const float* g[ADAM_CHUNK];
+  float* m[ADAM_CHUNK];
+  float* v[ADAM_CHUNK];
+  float* vmax[ADAM_CHUNK];
+  int numel[ADAM_CHUNK];
+  int block_start[ADAM_CHUNK + 1];
+  int count;
+};
+
+__global__ void __launch_bounds__(256)
+adam_step_multi_kernel(const __grid_constant__ AdamTensors t, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+  int k = 0;
+  while (k + 1 < t.count && (int)blockIdx.x >= t.block_start[k + 1]) ++k;
+  const int base = ((int)blockIdx.x - t.block_start[k]) * ADAM_SLAB;
+  const int end = min(t.numel[k], base + ADAM_SLAB);
+  float* __restrict__ p = t.p[k];
+  const float* __restrict__ g = t.g[k];
+  float* __restrict__ m = t.m[k];
+  float* __restrict__ v = t.v[k];
+  float* __restrict__ vmax = t.vmax[k];
+  for (int i = base + threadIdx.x; i < end; i += 256) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float vm = vi;
+    if (vmax) {
+      vm = fmaxf(vmax[i], vi);
+      vmax[i] = vm;
+    }
+    const float denom = sqrtf(vm) / bc2 + eps;
+    const float pi = p[i];
+    p[i] = pi - (pi * wd + lr * ((mi / bc1) / denom));
+  }
+}
 }  // namespace
 
 // vmax may be NULL (amsgrad off).  bc1 = 1 - beta1^t, bc2 = sqrt(1 - beta2^t).
@@ -37,4 +79,37 @@ DPF_API int dpf_adam_step(float* p, const float* g, float* m, float* v, float* v
   const int grid = (int)min((long long)dpf_num_sms() * 8, (n + 255) / 256);
   adam_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, vmax, n, lr, b1, b2, eps, wd, bc1, bc2);
   return dpf_check_launch("adam_step_kernel");
+}
+
+// The same update for n tensors in ceil(n / 48) launches (tensors < 2^31 elements; larger ones go through
+// dpf_adam_step).  p/g/m/v/vmax: host arrays of n device pointers (vmax may be NULL = amsgrad off);
+// numel: host array of n sizes.  All tensors share the hyper-parameters and the step count.
+DPF_API int dpf_adam_step_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                                float* const* vmax, const long long* numel, float lr, float b1, float b2, float eps,
+                                float wd, float bc1, float bc2, void* stream) {
+  DPF_REQUIRE(n >= 0, DPF_ERR_BAD_ARG, "dpf_adam_step_multi: negative count");
+  if (n == 0) return DPF_OK;
+  DPF_REQUIRE(p && g && m && v && numel, DPF_ERR_NULL_PTR, "dpf_adam_step_multi: null table");
+  for (int i0 = 0; i0 < n;) {
+    AdamTensors t{};
+    int blocks = 0, c = 0;
+    for (; i0 < n && c < ADAM_CHUNK; ++i0) {
+      if (numel[i0] == 0) continue;
+      DPF_REQUIRE(numel[i0] > 0 && numel[i0] < (1LL << 31) - ADAM_SLAB, DPF_ERR_BAD_ARG, "dpf_adam_step_multi: tensor %d has %lld elements", i0, numel[i0]);
+      DPF_REQUIRE(p[i0] && g[i0] && m[i0] && v[i0], DPF_ERR_NULL_PTR, "dpf_adam_step_multi: null pointer in tensor %d", i0);
+      t.p[c] = p[i0]; t.g[c] = g[i0]; t.m[c] = m[i0]; t.v[c] = v[i0];
+      t.vmax[c] = vmax ? vmax[i0] : nullptr;
+      t.numel[c] = (int)numel[i0];
+      t.block_start[c] = blocks;
+      blocks += (int)((numel[i0] + ADAM_SLAB - 1) / ADAM_SLAB);
+      ++c;
+    }
+    if (c == 0) break;
+    t.block_start[c] = blocks;
+    t.count = c;
+    adam_step_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t, lr, b1, b2, eps, wd, bc1, bc2);
+    int rc = dpf_check_launch("adam_step_multi_kernel");
+    if (rc) return rc;
+  }
+  return DPF_OK;
 }

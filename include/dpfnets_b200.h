@@ -116,6 +116,13 @@ int dpf_decoder_backward_scratch_bytes(int L, int B, int N, long long* bytes);
 int dpf_adam_step(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float b1,
                   float b2, float eps, float wd, float bc1, float bc2, void* stream);
 
+/* The same update for n tensors in ceil(n/48) launches instead of the reference's per-parameter
+ * Python loop (optimizers.py:20-74; ~170 parameter tensors in the generation model).  p/g/m/v/vmax:
+ * HOST arrays of n device pointers (vmax NULL = amsgrad off), numel: host array of n sizes. */
+int dpf_adam_step_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                        float* const* vmax, const long long* numel, float lr, float b1, float b2, float eps,
+                        float wd, float bc1, float bc2, void* stream);
+
 /* tcgen05 self-test (tests/test_umma_gpu.py): D[128,ncols] = sum_k A_k B_k from raw shared-memory
  * operand images and descriptor fields; validates the UMMA layouts the coupling kernels rely on. */
 int dpf_umma_selftest(const void* a_img, int a_bytes, const void* b_img, int b_bytes,

@@ -60,17 +60,23 @@ def test_train_step_checkpoint_and_generate(native_lib, cuda, tmp_path):
 
 
 def test_fused_adam_matches_host_formula(native_lib, cuda):
+    """Multi-tensor AMSGrad kernel (several launches: > 48 tensors, slabs of 4096, ragged sizes, one
+    parameter without gradient) vs the reference formula evaluated on the CPU by the same class."""
     from dpf_nets_b200.lib.networks.optimizers import Adam
     torch.manual_seed(0)
-    w0 = torch.randn(1000)
-    ws = [torch.nn.Parameter(w0.clone().to(d)) for d in ("cpu", cuda)]
-    opts = [Adam([w], lr=1e-2, weight_decay=1e-3, betas=(0.9, 0.99), amsgrad=True) for w in ws]
+    sizes = [1, 7, 4096, 4097, 10000, 64, 3, 12289] + [5 + 11 * i for i in range(55)]
+    w0 = [torch.randn(n) for n in sizes]
+    sets = [[torch.nn.Parameter(w.clone().to(d)) for w in w0] for d in ("cpu", cuda)]
+    opts = [Adam(ws, lr=1e-2, weight_decay=1e-3, betas=(0.9, 0.99), amsgrad=True) for ws in sets]
     for it in range(5):
-        for w, o in zip(ws, opts):
+        for ws, o in zip(sets, opts):
             o.zero_grad()
-            ((w ** 2).sum() * 0.5 + (w * (it + 1)).sum()).backward()
+            loss = sum((w ** 2).sum() * 0.5 + (w * (it + 1 + 0.1 * j)).sum() for j, w in enumerate(ws) if j != 5)
+            loss.backward()
             o.step()
-    assert torch.allclose(ws[0].detach(), ws[1].detach().cpu(), rtol=1e-5, atol=1e-6)
+    for a, b in zip(*sets):
+        assert torch.allclose(a.detach(), b.detach().cpu(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(sets[1][5].detach().cpu(), w0[5])
 
 
 def test_generation_sweep_metrics(native_lib, cuda):
