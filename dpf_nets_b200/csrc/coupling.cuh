@@ -18,6 +18,7 @@
 #define DPF_BN_EPS 1e-5f
 #define DPF_BN_MOM 0.1f
 #define DPF_TILE 128      // points per tile = threads per CTA (one TMEM lane / one thread per point)
+#define DPF_BNB_REP 16     // replicas of the BN_b sum accumulators in the merged train-mode forward
 #define DPF_EVAL_LTAB_BYTES 2112   // sizeof(EvalLayerTab), coupling_tc.cu
 
 struct LayerMeta {        // 8 x int64 per layer, identical on host (numpy int64) and device
@@ -60,6 +61,7 @@ struct DecoderWorkspace {
   float* film;        // [L][4][B][F]   s_mu, t_mu, s_lv, t_lv  (s already = eps + exp(.))
   double* moments;    // [L+1][16]      sum x_c (3), sum x_c x_c' (xx,xy,xz,yy,yz,zz) of each step's input
   double* bnb_sums;   // [L][2][F][2]   sum / sum of squares of h2pre (train)
+  double* bnb_rep;    // [L][DPF_BNB_REP][2][F][2] replicated accumulators of the merged forward (cuts same-address atomics)
   float* dfilm;       // [L][4][B][F]   backward: ds_raw_mu, dt_mu, ds_raw_lv, dt_lv
   double* bna_sums;   // [L][2][F][4]   backward: dbeta, E0, E1, pad
   float* dx[2];       // [B][3][N]      ping-pong stored input gradients
@@ -80,6 +82,7 @@ __host__ inline DecoderWorkspace carve_workspace(void* base, int L, int G, int B
   w.film = (float*)take(sizeof(float) * (size_t)L * 4 * B * DPF_F);
   w.moments = (double*)take(sizeof(double) * (size_t)(L + 1) * 16);
   w.bnb_sums = (double*)take(sizeof(double) * (size_t)L * 2 * DPF_F * 2);
+  w.bnb_rep = (double*)take(sizeof(double) * (size_t)L * DPF_BNB_REP * 2 * DPF_F * 2);
   w.dfilm = (float*)take(sizeof(float) * (size_t)L * 4 * B * DPF_F);
   w.bna_sums = (double*)take(sizeof(double) * (size_t)L * 2 * DPF_F * 4);
   w.dx[0] = (float*)take(sizeof(float) * (size_t)B * 3 * N);
@@ -105,6 +108,7 @@ struct CouplingArgs {
   const double* mom_in;  // [16] moments of x (train)
   double* mom_out;       // [16] accumulators for moments of y (train, next step) or null
   double* bnb_sums;      // [2][F][2]
+  double* bnb_rep;       // [DPF_BNB_REP][2][F][2] or null (merged forward only)
   int B, N, G;
   int k, w, keep0, keep1, warp0, warp1;
   int training, update_stats;

@@ -1009,8 +1009,10 @@ __device__ __forceinline__ void fwd2_flush_stats(const CouplingArgs& a, TcFwdSme
   }
   __syncthreads();
   if (tid < 128) {
-    DPF_GATOMIC(atomicAdd(&a.bnb_sums[tid * 2 + 0], (double)s.fin[0][tid]));   // tid == br*F + c
-    DPF_GATOMIC(atomicAdd(&a.bnb_sums[tid * 2 + 1], (double)s.fin[1][tid]));
+    // merged forward: DPF_BNB_REP replicas, so that ~300 CTAs do not serialise on 256 addresses right before the grid barrier
+    double* dst = a.bnb_rep ? a.bnb_rep + (size_t)(blockIdx.x & (DPF_BNB_REP - 1)) * (2 * F * 2) : a.bnb_sums;
+    DPF_GATOMIC(atomicAdd(&dst[tid * 2 + 0], (double)s.fin[0][tid]));   // tid == br*F + c
+    DPF_GATOMIC(atomicAdd(&dst[tid * 2 + 1], (double)s.fin[1][tid]));
   }
 }
 
@@ -1167,7 +1169,17 @@ coupling_fwd_train_tc2_kernel(const CouplingArgs a, const unsigned short* __rest
   if (tid < 128) {
     const int br = tid >> 6, c = tid & 63;
     const double M = (double)a.B * (double)a.N;
-    const double sm = __ldcg(&a.bnb_sums[(br * F + c) * 2 + 0]), sq = __ldcg(&a.bnb_sums[(br * F + c) * 2 + 1]);
+    double sm = 0.0, sq = 0.0;
+#pragma unroll
+    for (int r = 0; r < DPF_BNB_REP; ++r) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(a.bnb_rep + (size_t)r * (2 * F * 2) + (br * F + c) * 2));
+      sm += v.x;
+      sq += v.y;
+    }
+    if (blockIdx.x == 0) {   // canonical copy for the backward kernels (bn_b_stats)
+      a.bnb_sums[(br * F + c) * 2 + 0] = sm;
+      a.bnb_sums[(br * F + c) * 2 + 1] = sq;
+    }
     const double dm = sm / M;
     const double dv = fmax(sq / M - dm * dm, 0.0);
     s.c.mb[br][c] = (float)dm;

@@ -107,6 +107,7 @@ static CouplingArgs make_args(const LayerMeta& m, const float* arena, float* sta
   a.mom_in = ws.moments + (size_t)q * 16;
   a.mom_out = training ? ws.moments + (size_t)(q + 1) * 16 : nullptr;
   a.bnb_sums = ws.bnb_sums + (size_t)l * 2 * DPF_F * 2;
+  a.bnb_rep = nullptr;
   a.B = B; a.N = N; a.G = G;
   a.k = (int)m.k; a.w = (int)m.w;
   a.keep0 = (int)m.keep0; a.keep1 = (int)m.keep1; a.warp0 = (int)m.warp0; a.warp1 = (int)m.warp1;
@@ -147,6 +148,7 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
   if (training) {
     cudaMemsetAsync(ws.moments, 0, sizeof(double) * (size_t)(L + 1) * 16, s);
     cudaMemsetAsync(ws.bnb_sums, 0, sizeof(double) * (size_t)L * 2 * DPF_F * 2, s);
+    if (precision >= 1 && g_merged_forward) cudaMemsetAsync(ws.bnb_rep, 0, sizeof(double) * (size_t)L * DPF_BNB_REP * 2 * DPF_F * 2, s);
     ProfScope ps(CAT_MOMENTS, s);
     rc = launch_moments(p, B, N, ws.moments, s);
     if (rc) return rc;
@@ -171,7 +173,9 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
     if (training && precision >= 1 && merged_ok) {
       // one cooperative launch: statistics -> grid barrier -> apply from TMEM-resident accumulators
       ProfScope ps(CAT_FWD_APPLY, s);
+      a.bnb_rep = ws.bnb_rep + (size_t)l * DPF_BNB_REP * 2 * DPF_F * 2;
       rc = launch_coupling_fwd_train_tc(a, wimg, mode, precision == 2, ws.barriers + (size_t)l * 32, s);
+      a.bnb_rep = nullptr;
       if (rc == DPF_OK) { x = a.y; continue; }
       if (rc != DPF_ERR_UNSUPPORTED) return rc;
       merged_ok = false;                        // does not fit: two-launch form for this and later layers
