@@ -387,6 +387,7 @@ def extras(model, dev, B, N, pk, flush):
     out["sampling"] = {"value": samp, "unit": "points/s", "ms_per_pass": ms,
                        "tensor_frac": samp * FLOP_PER_POINT_LAYER_FWD * 3 * N_FLOWS / 1e12 / pk["bf16_tflops_sustained"]}
     model.train()
+    out["encoder_eval"] = encoder_eval(dev, B, N, flush)
     S = 256
     A = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
     Bc = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
@@ -407,6 +408,31 @@ def extras(model, dev, B, N, pk, flush):
                       "fp32_issue": {"achieved_dist_evals_per_s": 2 * pairs * N * N, "bound": fp32_issue_peak,
                                      "frac": 2 * pairs * N * N / fp32_issue_peak}}
     return out
+
+
+def encoder_eval(dev, B, N, flush):
+    """PointNet encoder + max-pool in eval mode: fused tcgen05 kernel vs the library path."""
+    from dpf_nets_b200.lib.networks.encoders import PointNetCloudEncoder
+    torch.manual_seed(0)
+    enc = PointNetCloudEncoder(3, 64, [128, 256, 512]).to(dev).eval()
+    x = (torch.rand((B, 3, N), generator=torch.Generator().manual_seed(3)) - 0.5).to(dev)
+    res = {}
+    with torch.no_grad():
+        for name, prec in (("fused", "auto"), ("library_path", "fp32")):
+            enc.precision = prec
+            for _ in range(3):
+                enc.global_features(x)
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); enc.global_features(x); b.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            res[name + "_ms"] = sum(ts) / len(ts)
+    ms = res["fused_ms"]
+    flop = 2.0 * (3 * 64 + 64 * 128 + 128 * 256 + 256 * 512) * B * N
+    res.update({"value": B * N / (ms * 1e-3), "unit": "points/s", "tflops": flop / (ms * 1e-3) / 1e12})
+    return res
 
 
 def full_model_step(dev, B, N, precision, flush, steps=5, warmup=3):

@@ -1,9 +1,13 @@
 """PointNet cloud encoder and latent feature heads with the reference's names / state_dict keys
-(lib/networks/encoders.py:9-83).  Round 1: the shared-MLP GEMMs of the encoder go through the
-library path (cuBLAS bmm + ATen batch-norm); the fused tcgen05 tiles are DESIGN.md section 7 item 3."""
+(lib/networks/encoders.py:9-83).  Eval mode: encoder + max-pool run as ONE fused tcgen05 kernel
+(dpf_pointnet_eval_forward, csrc/pointnet.cu).  Train mode (batch statistics, autograd): the shared-MLP
+GEMMs still go through the library path (cuBLAS bmm + ATen batch-norm) - DESIGN.md section 7."""
+import ctypes
+
 import torch
 import torch.nn as nn
 
+from ... import _lib
 from .layers import SharedDot, Swish
 
 
@@ -21,6 +25,38 @@ class PointNetCloudEncoder(nn.Module):
 
     def forward(self, input):
         return self.features(input)
+
+    precision = 'auto'      # 'fp32' keeps the library path in eval mode too
+
+    def _fused_ok(self, input):
+        return (not self.training and not torch.is_grad_enabled() and input.is_cuda and input.dtype == torch.float32
+                and self.precision != 'fp32' and self.init_n_channels == 3 and self.init_n_features == 64
+                and list(self.n_features) == [128, 256, 512] and input.dim() == 3 and input.shape[1] == 3)
+
+    def global_features(self, input):
+        """max over the points of forward(input): (B, 3, N) -> (B, n_features[-1]); what the models take
+        from the encoder (reference models.py:130-131).  Eval mode without autograd runs the fused kernel
+        (bf16 tensor cores, fp32 accumulation)."""
+        if not self._fused_ok(input):
+            return torch.max(self.forward(input), dim=2)[0]
+        x = input.contiguous()
+        B, _, N = x.shape
+        f = self.features
+        sds = [f.init_sd, f.sd0, f.sd1, f.sd2]
+        bns = [f.init_sd_bn, f.sd0_bn, f.sd1_bn, f.sd2_bn]
+        nbytes = ctypes.c_longlong(0)
+        _lib.check(_lib.lib().dpf_pointnet_workspace_bytes(ctypes.byref(nbytes)), "dpf_pointnet_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+        out = torch.empty((B, self.n_features[-1]), dtype=torch.float32, device=x.device)
+        weights = [sd.weight.detach().reshape(sd.weight.shape[-2], sd.weight.shape[-1]).contiguous() for sd in sds]
+        bn = []
+        for m in bns:
+            bn += [m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var]
+        wp = (ctypes.c_void_p * 4)(*[w.data_ptr() for w in weights])
+        bp = (ctypes.c_void_p * 16)(*[t.data_ptr() for t in bn])
+        with torch.cuda.device(x.device):
+            _lib.call("dpf_pointnet_eval_forward", x, int(B), int(N), wp, bp, float(bns[0].eps), ws, out, device=x.device)
+        return out
 
 
 class FeatureEncoder(nn.Module):

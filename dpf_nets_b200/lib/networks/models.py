@@ -72,7 +72,7 @@ class _DPFBase(nn.Module):
         return mu.expand(B, P, n_points), lv.expand(B, P, n_points)
 
     def _posterior(self, g_input, sample):
-        feats = torch.max(self.pc_encoder(g_input), dim=2)[0]
+        feats = self.pc_encoder.global_features(g_input)
         mus, logvars = self.g_posterior(feats)
         return mus, logvars, (_reparameterize(mus, logvars) if sample else mus)
 
@@ -120,7 +120,7 @@ class Local_Cond_RNVP_MC_Global_RNVP_VAE(_DPFBase):
         self._build_common(kwargs, with_base_var=True)
 
     def encode(self, g_input):
-        feats = torch.max(self.pc_encoder(g_input), dim=2)[0]
+        feats = self.pc_encoder.global_features(g_input)
         return {'g_posterior_mus': self.g_posterior(feats)[0]}
 
     def decode(self, g_sample, n_sampled_points=2048):

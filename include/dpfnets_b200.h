@@ -110,6 +110,18 @@ int dpf_decoder_status(const void* workspace, int L, int G, int B, int N, int* f
 /* bwd_scratch: per-CTA wgrad partials of the tensor path (may be NULL for precision 0). */
 int dpf_decoder_backward_scratch_bytes(int L, int B, int N, long long* bytes);
 
+/* ---- PointNet cloud encoder, eval mode ------------------------------------------------------
+ * Replaces PointNetCloudEncoder.forward in .eval() (lib/networks/encoders.py:9-28: SharedDot -> BatchNorm1d
+ * -> ReLU x 4, widths 3 -> 64 -> 128 -> 256 -> 512) together with the max over points the models apply to
+ * it (lib/networks/models.py:130-131): x (B,3,N) fp32 -> out (B,512) fp32, one fused kernel (BatchNorm
+ * running statistics folded into the weights, bf16 tensor cores with fp32 accumulation).
+ * weights: HOST array of 4 device pointers, SharedDot weights (out,in) row-major;
+ * bn: HOST array of 16 device pointers, {weight, bias, running_mean, running_var} per layer.
+ * workspace: dpf_pointnet_workspace_bytes() bytes, 256-byte aligned (folded tables + weight images). */
+int dpf_pointnet_workspace_bytes(long long* bytes);
+int dpf_pointnet_eval_forward(const float* x, int B, int N, const float* const* weights, const float* const* bn,
+                              float bn_eps, void* workspace, float* out, void* stream);
+
 /* Fused AMSGrad step with the reference's exact update (lib/networks/optimizers.py:53-74):
  * denom = sqrt(max_exp_avg_sq or exp_avg_sq)/bc2 + eps; p -= wd*p + lr*(exp_avg/bc1)/denom.
  * vmax may be NULL (amsgrad off); bc1 = 1-beta1^t, bc2 = sqrt(1-beta2^t). */
