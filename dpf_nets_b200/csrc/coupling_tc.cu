@@ -46,6 +46,7 @@ __device__ unsigned long long* g_stamps = nullptr;      // [3 classes][512 CTAs]
 #define DPF_STAMP(cls, i) do { } while (0)
 #define DPF_STAMP_NS(cls, i) do { } while (0)
 #endif
+extern int g_dpf_p2_two_tiles;   // decoder.cu: dpf_set_option(3, v)
 #ifdef DPF_EXP_NOATOMICS
 #define DPF_GATOMIC(stmt) do { } while (0)
 #else
@@ -626,6 +627,369 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
   DPF_STAMP_NS(2, 15);
 }
 
+constexpr uint32_t IDESC_RED = umma::make_idesc_bf16(128, 16, 1, 1);
+
+// =============================================================================================
+// Backward pass 2, TWO tiles in flight per SM: a 544-thread CTA = two 256-thread halves, each running
+// the two-threads-per-point tile pipeline above on its own tile (own H / D / X tiles, own 128 TMEM
+// columns for the recompute / dgrad accumulators), plus ONE MMA-issuer warp that serves both halves:
+// a half writes its operand tiles, arrives on its request mbarrier, the issuer's elected lane issues
+// that stage's UMMAs and commits to the half's completion mbarrier.  One issuing thread keeps every
+// accumulation into the shared wgrad / BN_a-sum accumulators in program order.  While one half waits
+// on a UMMA round trip or its global loads, the other half's CUDA-core phase runs.
+//   TMEM: [0,128) half 0 recompute -> dgrad, [128,256) half 1, [256,384) wgrad, [384,400) BN_a sums.
+// The BN_a sums use the operand roles of pass 1's reductions: A = dz tile (M = 128 channels of both
+// branches, MN-major), B = per-point weights {1, xk0 hi, xk0 lo, xk1 hi, xk1 lo} (N = 16), so lane m
+// = channel, columns 0..4 = the five sums.
+// The deferred correction P and the BN_b batch terms m1, m2 are not recomputed: pass 1 hands them over
+// (pend_store, m12_rep).
+// =============================================================================================
+constexpr int NT4 = 512 + 32;
+
+struct TcP2Half {
+  unsigned char H[2 * IMG_H];           // h1 hi tiles [br]
+  unsigned char D[2 * IMG_H];           // h1 lo tiles, then dh2pre tiles, then dz tiles
+  unsigned char X[IMG_H];               // per-point weights, chunk 0 of every row (the rest stays zero)
+};
+struct TcP2Smem4 {
+  unsigned char W[2 * N_IMG * IMG_W];   // [br][W1 hi, W1 lo, W1^T hi]
+  TcP2Half h[2];
+  float4 A0[2][F];                      // folded BN_a: {A00, A01, c0, -}
+  float4 epi[2][2][F];                  // [half][br][c]: {S, T, W2_0, W2_1},  a = S*acc + T
+  float sraw[2][2][F];                  // [half][br][c]: FiLM scale of the half's current shape
+  float mb[2][F], ib[2][F], W2[2][2][F], m1[2][F], m2[2][F];
+  float t1buf[2][DPF_TILE][2];
+  uint64_t bar_load, bar_req[2], bar_done[2];
+  uint32_t tmem_base;
+};
+
+template <int K, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(NT4, 1)   // 17 warps are allocated as 20: 96 registers per thread
+coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ wimg) {
+  extern __shared__ unsigned char smraw[];
+  TcP2Smem4& s = *reinterpret_cast<TcP2Smem4*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = tid >= 512;
+  const int half = (tid >> 8) & 1, row = tid & 127, part = (tid >> 7) & 1, quarter = warp & 3;
+  const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
+  const int n_workers = 2 * gridDim.x;
+  const int worker = 2 * blockIdx.x + half;
+  auto iters_of = [&](int w) { return w < a.f.n_tiles ? (a.f.n_tiles - w + n_workers - 1) / n_workers : 0; };
+  DPF_STAMP(2, 0);
+  DPF_STAMP_NS(2, 14);
+  pdl_launch_dependents();
+  if (tid == 0) {
+    umma::mbar_init(&s.bar_load, 1);
+    umma::mbar_init(&s.bar_req[0], 256);
+    umma::mbar_init(&s.bar_req[1], 256);
+    umma::mbar_init(&s.bar_done[0], 1);
+    umma::mbar_init(&s.bar_done[1], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&s.tmem_base, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  if (tid == 0) {
+    umma::mbar_expect_tx(&s.bar_load, 2 * N_IMG * IMG_W);
+    umma::bulk_g2s(s.W, wimg, 2 * N_IMG * IMG_W, &s.bar_load);
+  }
+  DPF_STAMP(2, 1);
+  pdl_wait();          // pass 1's sums / pending correction are read from here on
+  DPF_STAMP(2, 2);
+  const uint32_t T_WG = tmem + 256, T_BN = tmem + 384;
+
+  if (issuer) {
+    // ------------------------------ MMA issuer warp ------------------------------
+    if (lane == 0) {
+      umma::mbar_wait(&s.bar_load, 0);
+      int n_it[2] = {iters_of(2 * (int)blockIdx.x), iters_of(2 * (int)blockIdx.x + 1)};
+      int it[2] = {0, 0}, stage[2] = {0, 0};
+      uint32_t ph[2] = {0u, 0u};
+      uint32_t wg_acc = 0u, bn_acc = 0u;
+      int remaining = 3 * (n_it[0] + n_it[1]);
+      while (remaining > 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (it[h] < n_it[h] && umma::mbar_test(&s.bar_req[h], ph[h])) {
+            ph[h] ^= 1u;
+            umma::fence_after_sync();
+            TcP2Half& hb = s.h[h];
+            const uint32_t T_F = tmem + h * 128;
+            if (stage[h] == 0) {          // forward recompute, both branches
+              issue_gemm1<SPLIT>(T_F, hb.H, hb.D, wimg_at<true>(s.W, 0, 0), wimg_at<true>(s.W, 0, 1));
+              issue_gemm1<SPLIT>(T_F + F, hb.H + IMG_H, hb.D + IMG_H, wimg_at<true>(s.W, 1, 0), wimg_at<true>(s.W, 1, 1));
+            } else if (stage[h] == 1) {   // dgrad (overwrites the recompute accumulators) + wgrad
+#pragma unroll
+              for (int br = 0; br < 2; ++br)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma::mma_bf16(T_F + br * F, umma::desc_at(DESC_K, umma::smem_u32(hb.D + br * IMG_H) + 32 * k),
+                                 umma::desc_at(DESC_K, umma::smem_u32(wimg_at<true>(s.W, br, 2)) + 32 * k), IDESC_GEMM, k > 0);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                umma::mma_bf16(T_WG, umma::desc_at(DESC_MN, umma::smem_u32(hb.D) + 2048 * k), umma::desc_at(DESC_MN, umma::smem_u32(hb.H) + 2048 * k),
+                               IDESC_WGRAD, wg_acc);
+                wg_acc = 1u;
+              }
+            } else {                      // BN_a sums
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                umma::mma_bf16(T_BN, umma::desc_at(DESC_MN, umma::smem_u32(hb.D) + 2048 * k), umma::desc_at(DESC_MN, umma::smem_u32(hb.X) + 2048 * k),
+                               IDESC_RED, bn_acc);
+                bn_acc = 1u;
+              }
+            }
+            umma::mma_commit(&s.bar_done[h]);
+            if (++stage[h] == 3) { stage[h] = 0; ++it[h]; }
+            --remaining;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ the two tile pipelines ------------------------------
+    TcP2Half& hb = s.h[half];
+    const int n_it = iters_of(worker);
+    // first tile's global loads are issued before the table work
+    TcRaw raw0;
+    {
+      const int b0 = worker / a.f.tiles_per_b;
+      const int n0 = (worker - b0 * a.f.tiles_per_b) * DPF_TILE + row;
+      raw0 = tc_load_raw(a, b0, n0, n_it > 0 && n0 < a.f.N);
+    }
+    if (tid < 128) {
+      const int br = tid >> 6, c = tid & 63;
+      float A00, A01, c0;
+      fold_bn_a(a.f, lay, br, c, false, A00, A01, c0, nullptr, nullptr);
+      s.A0[br][c] = make_float4(A00, A01, c0, 0.f);
+      float mean, istd;
+      bn_b_stats(a.f, br, c, false, mean, istd);
+      s.mb[br][c] = mean;
+      s.ib[br][c] = istd;
+      const float* prm = a.f.prm + (size_t)br * lay.size;
+      s.W2[br][0][c] = prm[lay.W2 + c];
+      s.W2[br][1][c] = (a.f.w == 2) ? prm[lay.W2 + F + c] : 0.f;
+    } else if (tid < 256) {
+      const int br = (tid - 128) >> 6, c = tid & 63;
+      float m1 = 0.f, m2 = 0.f;
+      if (a.f.training) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < DPF_M12_REP; ++r) {
+          const double2 v = *reinterpret_cast<const double2*>(a.m12_rep + (size_t)r * (2 * F * 2) + (size_t)(br * F + c) * 2);
+          s1 += v.x;
+          s2 += v.y;
+        }
+        const double M = (double)a.f.B * (double)a.f.N;
+        m1 = (float)(s1 / M);
+        m2 = (float)(s2 / M);
+      }
+      s.m1[br][c] = m1;
+      s.m2[br][c] = m2;
+    }
+    for (int i = tid; i < (int)(IMG_H / 16); i += 512) {
+      reinterpret_cast<uint4*>(s.h[0].X)[i] = make_uint4(0u, 0u, 0u, 0u);
+      reinterpret_cast<uint4*>(s.h[1].X)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    Pending P{0.f, 0.f, 0.f, 0.f, 0.f};
+    if (a.has_pending) { P.c0 = a.pend_store[0]; P.c1 = a.pend_store[1]; P.q00 = a.pend_store[2]; P.q01 = a.pend_store[3]; P.q11 = a.pend_store[4]; }
+    const float sig1 = sqrtf(a.f.eps + 1.0f);
+    umma::named_bar_sync(3, 512);        // tables + zeroed X tiles visible to both halves
+    DPF_STAMP(2, 3);
+
+    uint32_t ph = 0;
+    const uint32_t T_F = tmem + half * 128;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    uint64_t* req = &s.bar_req[half];
+    uint64_t* done = &s.bar_done[half];
+    for (int it = 0; it < n_it; ++it) {
+      const int tile = worker + it * n_workers;
+      const int b = tile / a.f.tiles_per_b;
+      const int n = (tile - b * a.f.tiles_per_b) * DPF_TILE + row;
+      const bool valid = n < a.f.N;
+      if (part == 0) {   // FiLM fold of this tile's shape (read again only after the next request / completion round trip)
+        const int br = row >> 6, c = row & 63;
+        const float sc = a.f.film[((size_t)(br * 2 + 0) * a.f.B + b) * F + c];
+        const float sh = a.f.film[((size_t)(br * 2 + 1) * a.f.B + b) * F + c];
+        const float S = sc * s.ib[br][c];
+        s.sraw[half][br][c] = sc;
+        s.epi[half][br][c] = make_float4(S, fmaf(-S, s.mb[br][c], sh), s.W2[br][0][c], s.W2[br][1][c]);
+      }
+      const TcPoint g = tc_finish_point<MODE>(a, P, it == 0 ? raw0 : tc_load_raw(a, b, n, valid), valid);
+      const float xk0 = pick3(g.x, a.f.keep0);
+      const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
+      if (it == 0) DPF_STAMP(2, 4);
+      // ---- stage 0: h1 hi -> H, lo -> D (the previous tile's BN_a-sum UMMAs still read D / X: wait for them) ----
+      if (it > 0) {
+        umma::mbar_wait(done, ph);
+        ph ^= 1;
+      }
+#pragma unroll
+      for (int br = 0; br < 2; ++br) {
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int q = part * 4 + qq;
+          uint32_t w[4], wl[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 Aa = s.A0[br][q * 8 + 2 * i], Ab = s.A0[br][q * 8 + 2 * i + 1];
+            float va = fmaf(Aa.x, xk0, Aa.z), vb = fmaf(Ab.x, xk0, Ab.z);
+            if (K == 2) { va = fmaf(Aa.y, xk1, va); vb = fmaf(Ab.y, xk1, vb); }
+            va = fmaxf(va, 0.f);
+            vb = fmaxf(vb, 0.f);
+            w[i] = umma::pack_bf16(va, vb);
+            if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
+          }
+          const uint32_t off = umma::sw128_offset(row, q);
+          *reinterpret_cast<uint4*>(hb.H + br * IMG_H + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          if (SPLIT) *reinterpret_cast<uint4*>(hb.D + br * IMG_H + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        }
+      }
+      umma::fence_async_smem();
+      if (it == 0) DPF_STAMP(2, 5);
+      umma::mbar_arrive(req);
+      umma::mbar_wait(done, ph);
+      ph ^= 1;
+      umma::fence_after_sync();
+      if (it == 0) DPF_STAMP(2, 6);
+      // ---- stage 1: epilogue A: dh2pre (bf16) of this part's 32 channels of each branch -> D tiles ----
+#pragma unroll 1
+      for (int br = 0; br < 2; ++br) {
+        const float d0 = br == 0 ? g.do_mu[0] : g.do_lv[0];
+        const float d1 = br == 0 ? g.do_mu[1] : g.do_lv[1];
+        float v[32];
+        umma::tmem_ld32(T_F + lane_off + br * F + part * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = part * 32 + i;
+          const float4 e = s.epi[half][br][c];
+          const float h2n = (v[i] - s.mb[br][c]) * s.ib[br][c];
+          const float av = fmaf(e.x, v[i], e.y);
+          const float da = av > 0.f ? fmaf(e.z, d0, e.w * d1) : 0.f;
+          const float dh = s.ib[br][c] * (da * s.sraw[half][br][c] - s.m1[br][c] - h2n * s.m2[br][c]);
+          v[i] = valid ? dh : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                      umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+          *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + q)) = pk;
+        }
+      }
+      umma::fence_async_smem();
+      umma::fence_before_sync();
+      if (it == 0) DPF_STAMP(2, 7);
+      umma::mbar_arrive(req);
+      umma::mbar_wait(done, ph);
+      ph ^= 1;
+      umma::fence_after_sync();
+      if (it == 0) DPF_STAMP(2, 8);
+      // ---- stage 2: epilogue B: dz (bf16) -> D tiles, T1 = A0^T dz, per-point weight row -> X ----
+      float T1_0 = 0.f, T1_1 = 0.f;
+#pragma unroll 1
+      for (int br = 0; br < 2; ++br) {
+        float v[32];
+        umma::tmem_ld32(T_F + lane_off + br * F + part * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float4 A = s.A0[br][part * 32 + i];
+          float z = fmaf(A.x, xk0, A.z);
+          if (K == 2) z = fmaf(A.y, xk1, z);
+          const float dz = (z > 0.f && valid) ? v[i] : 0.f;
+          T1_0 = fmaf(A.x, dz, T1_0);
+          if (K == 2) T1_1 = fmaf(A.y, dz, T1_1);
+          v[i] = dz;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                      umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+          *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + q)) = pk;
+        }
+      }
+      if (part == 0) {
+        const float one = valid ? 1.f : 0.f;
+        const uint32_t w0 = umma::pack_bf16(one, xk0);                                   // {1, xk0 hi}
+        const float xk0_lo = xk0 - __uint_as_float(w0 & 0xffff0000u);
+        const uint32_t w1 = umma::pack_bf16(xk0_lo, xk1);                                // {xk0 lo, xk1 hi}
+        const float xk1_lo = xk1 - __uint_as_float(w1 & 0xffff0000u);
+        const uint32_t w2 = umma::pack_bf16(xk1_lo, 0.f);                                // {xk1 lo, 0}
+        *reinterpret_cast<uint4*>(hb.X + umma::sw128_offset(row, 0)) = make_uint4(w0, w1, w2, 0u);
+      } else {
+        s.t1buf[half][row][0] = T1_0;
+        s.t1buf[half][row][1] = T1_1;
+      }
+      umma::fence_async_smem();
+      umma::fence_before_sync();
+      if (it == 0) DPF_STAMP(2, 9);
+      umma::mbar_arrive(req);
+      umma::named_bar_sync(1 + half, 256);   // t1buf hand-over inside the half
+      if (part == 0 && valid) {
+        T1_0 += s.t1buf[half][row][0];
+        T1_1 += s.t1buf[half][row][1];
+        float dx[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) dx[ch] = (MODE == 1) ? g.dy[ch] / sig1 : g.dy[ch] * sig1;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          if (ch == a.f.keep0) dx[ch] += T1_0;
+          if (K == 2 && ch == a.f.keep1) dx[ch] += T1_1;
+          if (ch == a.f.warp0) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[0] : g.dy[ch] * g.sig[0];
+          if (K == 1 && ch == a.f.warp1) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[1] : g.dy[ch] * g.sig[1];
+        }
+        const size_t base = (size_t)b * 3 * a.f.N + n;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) a.dx_out[base + (size_t)ch * a.f.N] = dx[ch];
+      }
+    }
+    if (n_it > 0) DPF_STAMP(2, 10);
+    if (n_it > 0) {     // the last tile's BN_a-sum UMMAs
+      umma::mbar_wait(done, ph);
+      ph ^= 1;
+    }
+    umma::fence_before_sync();
+  }
+  // ---- CTA epilogue (every UMMA of both halves has completed) ----
+  __syncthreads();
+  DPF_STAMP(2, 11);
+  umma::fence_after_sync();
+  const bool had_work = 2 * (int)blockIdx.x < a.f.n_tiles;
+  if (tid < 128 && had_work) {     // lane = channel m = br*64 + c; columns {dbeta, E0 hi, E0 lo, E1 hi, E1 lo}
+    uint32_t r0[4], r1[4];
+    umma::tmem_ld4(T_BN + ((uint32_t)(quarter * 32) << 16), r0);
+    umma::tmem_ld4(T_BN + ((uint32_t)(quarter * 32) << 16) + 4, r1);
+    umma::tmem_ld_wait4(r0);
+    umma::tmem_ld_wait4(r1);
+    DPF_GATOMIC(atomicAdd(&a.bna_sums[tid * 4 + 0], (double)__uint_as_float(r0[0])));
+    DPF_GATOMIC(atomicAdd(&a.bna_sums[tid * 4 + 1], (double)__uint_as_float(r0[1]) + (double)__uint_as_float(r0[2])));
+    DPF_GATOMIC(atomicAdd(&a.bna_sums[tid * 4 + 2], (double)__uint_as_float(r0[3]) + (double)__uint_as_float(r1[0])));
+  }
+  if (!issuer) {
+    // accumulator row = branch*64 + channel; this thread stores 16 columns of its branch's 64x64 block
+    const int br = row >> 6, c = row & 63, cg = half * 2 + part;
+    float4* d = reinterpret_cast<float4*>(a.dw1_partial + ((size_t)blockIdx.x * 2 + br) * (F * F) + c * F + cg * 16);
+    uint32_t r[16];
+    if (had_work) {
+      umma::tmem_ld16_issue(T_WG + ((uint32_t)(quarter * 32) << 16) + br * F + cg * 16, r);
+      umma::tmem_ld_wait16(r);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      d[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+  DPF_STAMP(2, 12);
+  DPF_STAMP_NS(2, 15);
+}
+
 // =============================================================================================
 // Backward pass 1, two threads per point, reductions over points on the tensor cores.
 //
@@ -638,8 +1002,6 @@ coupling_bwd_p2_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
 // per-point weights {d0 hi, d0 lo, d1 hi, d1 lo} of both branches (MN-major, N = 16), accumulated in
 // TMEM over the consecutive tiles of one shape and read back one channel per lane.
 // =============================================================================================
-constexpr uint32_t IDESC_RED = umma::make_idesc_bf16(128, 16, 1, 1);
-
 struct TcP1Smem2 {
   unsigned char W[4 * IMG_W];           // [br][W1 hi, W1 lo]
   unsigned char H[2 * IMG_H];           // h1 hi | lo, then h3 hi | lo of the branch in flight
@@ -674,7 +1036,17 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
   for (int i = tid; i < (int)(IMG_H / 16); i += NT2) reinterpret_cast<uint4*>(s.X)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 4) (&s.b2fin[0][0])[tid] = 0.f;
   __syncthreads();
+  // the first tile's global loads are issued before the (latency-bound) pending computation
+  TcRaw raw0;
+  {
+    const int b0 = t0 / a.f.tiles_per_b;
+    const int n0 = (t0 - b0 * a.f.tiles_per_b) * DPF_TILE + row;
+    raw0 = tc_load_raw(a, b0, n0, t0 < t1 && n0 < a.f.N);
+  }
   const Pending P = tc_compute_pending(a, blockIdx.x == 0, s.c.pend);
+  if (blockIdx.x == 0 && tid == 0 && a.pend_store) {   // pass 2 of this layer reads it instead of recomputing
+    a.pend_store[0] = P.c0; a.pend_store[1] = P.c1; a.pend_store[2] = P.q00; a.pend_store[3] = P.q01; a.pend_store[4] = P.q11;
+  }
   DPF_STAMP(1, 3);
   float b2acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   float dW2acc[2] = {0.f, 0.f};        // threads < 128: (branch, channel) = (tid >> 6, tid & 63)
@@ -718,6 +1090,12 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
       const float ds = (fmaf(W20, S0, W21 * S1) - s.shift[br][c] * dt) / s.c.sraw[br][c];
       atomicAdd(&a.dfilm[((size_t)(br * 2 + 0) * a.f.B + b) * F + c], ds);
       atomicAdd(&a.dfilm[((size_t)(br * 2 + 1) * a.f.B + b) * F + c], dt);
+      if (a.m12_rep && a.f.training) {   // BN_b batch terms for pass 2: m1 = sum_b s*dt / M, m2 = sum_b s*ds / M
+        double* rep = a.m12_rep + (size_t)(blockIdx.x & (DPF_M12_REP - 1)) * (2 * F * 2) + (size_t)tid * 2;
+        const double sc = (double)s.c.sraw[br][c];
+        DPF_GATOMIC(atomicAdd(rep + 0, sc * (double)dt));
+        DPF_GATOMIC(atomicAdd(rep + 1, sc * (double)ds));
+      }
       dW2acc[0] += S0;
       dW2acc[1] += S1;
     }
@@ -739,7 +1117,7 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
       tc_tile_film(a.f, s.c, b);
       if (tid < 2 * F) s.shift[tid >> 6][tid & 63] = a.f.film[((size_t)((tid >> 6) * 2 + 1) * a.f.B + b) * F + (tid & 63)];
     }
-    const TcPoint g = tc_finish_point<MODE>(a, P, tc_load_raw(a, b, n, valid), valid);
+    const TcPoint g = tc_finish_point<MODE>(a, P, tile == t0 ? raw0 : tc_load_raw(a, b, n, valid), valid);
     if (tile == t0) DPF_STAMP(1, 5);
     const float xk0 = pick3(g.x, a.f.keep0);
     const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
@@ -1247,6 +1625,15 @@ int launch_bwd_tc_t(const BwdArgs& a, const unsigned short* wimg, int pass, cuda
     return dpf_check_launch("coupling_bwd_p1_tc2_kernel");
   }
   const int grid = min(a.f.n_tiles, dpf_num_sms());
+  if (g_dpf_p2_two_tiles && a.pend_store && a.m12_rep) {   // two tiles in flight per SM (dpf_set_option(3, 0) = one)
+    static bool attr4 = false;
+    if (!attr4) {
+      cudaFuncSetAttribute(coupling_bwd_p2_tc4_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP2Smem4>());
+      attr4 = true;
+    }
+    dpf_launch_pdl(coupling_bwd_p2_tc4_kernel<K, MODE, SPLIT>, grid, NT4, smem_for<TcP2Smem4>(), st, a, wimg);
+    return dpf_check_launch("coupling_bwd_p2_tc4_kernel");
+  }
   dpf_launch_pdl(coupling_bwd_p2_tc2_kernel<K, MODE, SPLIT>, grid, NT2, smem_for<TcP2Smem2>(), st, a, wimg);
   return dpf_check_launch("coupling_bwd_p2_tc2_kernel");
 }

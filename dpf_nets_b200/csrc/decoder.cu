@@ -71,11 +71,15 @@ int launch_decoder_eval_tc(const float* arena, const float* stats, const LayerMe
                            float* LV, int L, int G, int B, int N, int mode, int split, float eps, cudaStream_t s);
 // Option 2: programmatic dependent launch of the per-layer tensor-path kernels (common.cuh).
 int g_dpf_pdl = 1;
+// Option 3: backward pass 2 with two tiles in flight per SM (544-thread CTAs, MMA issuer warp); 0 = the
+// one-tile-per-SM form (tests compare both).
+int g_dpf_p2_two_tiles = 1;
 DPF_API int dpf_set_option(int option, int value) {
-  DPF_REQUIRE(option >= 0 && option <= 2, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
+  DPF_REQUIRE(option >= 0 && option <= 3, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
   if (option == 0) g_merged_forward = value != 0;
   else if (option == 1) g_fused_eval = value != 0;
-  else g_dpf_pdl = value != 0;
+  else if (option == 2) g_dpf_pdl = value != 0;
+  else g_dpf_p2_two_tiles = value != 0;
   return DPF_OK;
 }
 
@@ -257,6 +261,7 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
   cudaMemsetAsync(dg, 0, sizeof(float) * (size_t)B * G, s);
   cudaMemsetAsync(ws.dfilm, 0, sizeof(float) * (size_t)L * 4 * B * DPF_F, s);
   cudaMemsetAsync(ws.bna_sums, 0, sizeof(double) * (size_t)L * 2 * DPF_F * 4, s);
+  if (precision >= 1) cudaMemsetAsync(ws.m12_rep, 0, sizeof(double) * (size_t)L * DPF_M12_REP * 2 * DPF_F * 2, s);
 
   auto layer_of = [&](int q) { return mode == 0 ? q : L - 1 - q; };
   auto set_pending = [&](BwdArgs& a, int qn) {   // correction owed by the layer of step qn
@@ -285,6 +290,8 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     a.dfilm = ws.dfilm + (size_t)l * 4 * B * DPF_F;
     a.dprm = darena + meta[l].param_off;
     a.bna_sums = ws.bna_sums + (size_t)l * 2 * DPF_F * 4;
+    a.pend_store = precision >= 1 ? ws.pend + (size_t)l * 8 : nullptr;
+    a.m12_rep = precision >= 1 ? ws.m12_rep + (size_t)l * DPF_M12_REP * 2 * DPF_F * 2 : nullptr;
     a.dw1_partial = precision >= 1 ? (float*)bwd_scratch + (size_t)l * p2_ctas * 2 * DPF_F * DPF_F : nullptr;
     if (q < L - 1) set_pending(a, q + 1);
     const unsigned short* wimg = ws.w1_bf16 + (size_t)l * tc_weight_image_elems_per_layer();

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_decoder_gpu.py -x -q -m gpu -k "two_tile" -s 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_decoder_gpu.py tests/test_model_gpu.py -x -q -m gpu 2>&1 | tail -5
+for opt in "3=1" "3=0"; do
+  timeout 300 python bench.py --steps 20 --warmup 3 --no-extras --lib-option $opt > gpurun_out/bench_ab.json 2> gpurun_out/bench_ab.err; echo "bench rc=$? ($opt)"
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_ab.json"))
+kc=d["roofline"]["kernel_classes"]
+print("   ms=%.3f pts/s=%.3e e2e=%.3e loss=%s"%(d["ms_per_step"], d["value"], d["e2e"]["value"], d["e2e"]["loss"]), {k: (round(v["us_per_launch"],1) if v["us_per_launch"] else None) for k,v in kc.items()})
+PY
+done

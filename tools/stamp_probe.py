@@ -19,10 +19,10 @@ NAMES = {
         "apply_phase(tiles)", "flush_moments", "end"],
     1: ["start", "tmem_alloc", "tables", "pending", "weights_ready", "t0:load_point", "t0:h1+gemm(br0)", "t0:epilogue(br0)",
         "t0:rest(br1)", "other_tiles", "final_flush", "end"],
-    2: ["start", "tmem_alloc", "tables", "m1m2+pending", "weights_ready", "t0:load_point", "t0:h1_write", "t0:gemm_wait",
-        "t0:epilogue_A", "t0:dgrad_wgrad_wait", "t0:epilogue_B", "t0:dx+sync", "other_tiles", "cta_epilogue"],
+    2: ["start", "setup+tmem_alloc", "pdl_wait", "tables+m1m2", "t0:load_point+finish", "t0:h1_write", "t0:gemm_wait",
+        "t0:epilogue_A", "t0:dgrad_wgrad_wait", "t0:epilogue_B", "t0:dx + other tiles", "last BN wait + cta sync", "cta_epilogue"],
 }
-KERNEL = {0: "coupling_fwd_train_tc2_kernel", 1: "coupling_bwd_p1_tc2_kernel", 2: "coupling_bwd_p2_tc2_kernel"}
+KERNEL = {0: "coupling_fwd_train_tc2_kernel", 1: "coupling_bwd_p1_tc2_kernel", 2: "coupling_bwd_p2_tc4_kernel"}
 
 
 def main():
