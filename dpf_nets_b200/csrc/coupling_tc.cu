@@ -117,6 +117,19 @@ __device__ __forceinline__ void tc_prologue_tables(const CouplingArgs& a, const 
   }
 }
 
+// backward kernels: the same tables loaded from the per-pass table (bwd_tables_kernel)
+__device__ __forceinline__ void tc_prologue_tables_ltab(const float* __restrict__ ltab, TcCommon& s) {
+  const int tid = threadIdx.x & 127, br = tid >> 6, c = tid & 63;
+  const float4 t0 = reinterpret_cast<const float4*>(ltab)[tid * 2 + 0];
+  const float4 t1 = reinterpret_cast<const float4*>(ltab)[tid * 2 + 1];
+  s.A0[br][c] = make_float4(t0.x, t0.y, t0.z, 0.f);
+  s.mb[br][c] = t0.w;
+  s.ib[br][c] = t1.x;
+  s.W2[br][0][c] = t1.y;
+  s.W2[br][1][c] = t1.z;
+  if (c < 2) s.b2[br][c] = t1.w;
+}
+
 __device__ __forceinline__ void tc_tile_film(const CouplingArgs& a, TcCommon& s, int b) {
   const int tid = threadIdx.x & 127, br = tid >> 6, c = tid & 63;
   const float sc = a.film[((size_t)(br * 2 + 0) * a.B + b) * F + c];
@@ -656,8 +669,10 @@ struct TcP2Smem4 {
   TcP2Half h[2];
   float4 A0[2][F];                      // folded BN_a: {A00, A01, c0, -}
   float4 epi[2][2][F];                  // [half][br][c]: {S, T, W2_0, W2_1},  a = S*acc + T
-  float sraw[2][2][F];                  // [half][br][c]: FiLM scale of the half's current shape
-  float mb[2][F], ib[2][F], W2[2][2][F], m1[2][F], m2[2][F];
+  float4 epi2[2][2][F];                 // [half][br][c]: {c1, c2, c3, -},  dh2pre = c1*da - c2 - c3*acc
+  float4 lt0[2][F];                     // per channel: {bnB istd, bnB mean, c2, c3}
+  float2 lt1[2][F];                     // per channel: {W2_0, W2_1}
+  float pend[8];
   float t1buf[2][DPF_TILE][2];
   uint64_t bar_load, bar_req[2], bar_done[2];
   uint32_t tmem_base;
@@ -694,6 +709,12 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
   if (tid == 0) {
     umma::mbar_expect_tx(&s.bar_load, 2 * N_IMG * IMG_W);
     umma::bulk_g2s(s.W, wimg, 2 * N_IMG * IMG_W, &s.bar_load);
+  }
+  if (!issuer) {       // independent of the previous kernels: zero the per-point weight tiles
+    for (int i = tid; i < (int)(IMG_H / 16); i += 512) {
+      reinterpret_cast<uint4*>(s.h[0].X)[i] = make_uint4(0u, 0u, 0u, 0u);
+      reinterpret_cast<uint4*>(s.h[1].X)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   DPF_STAMP(2, 1);
   pdl_wait();          // pass 1's sums / pending correction are read from here on
@@ -760,42 +781,31 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
       const int n0 = (worker - b0 * a.f.tiles_per_b) * DPF_TILE + row;
       raw0 = tc_load_raw(a, b0, n0, n_it > 0 && n0 < a.f.N);
     }
+    // per-channel constants.  BN_b backward of a channel:
+    //   dh2pre = ib*(da*s - m1 - h2n*m2),  h2n = (acc - mb)*ib   =>   dh2pre = (ib*s)*da - c2 - c3*acc
     if (tid < 128) {
-      const int br = tid >> 6, c = tid & 63;
-      float A00, A01, c0;
-      fold_bn_a(a.f, lay, br, c, false, A00, A01, c0, nullptr, nullptr);
-      s.A0[br][c] = make_float4(A00, A01, c0, 0.f);
-      float mean, istd;
-      bn_b_stats(a.f, br, c, false, mean, istd);
-      s.mb[br][c] = mean;
-      s.ib[br][c] = istd;
-      const float* prm = a.f.prm + (size_t)br * lay.size;
-      s.W2[br][0][c] = prm[lay.W2 + c];
-      s.W2[br][1][c] = (a.f.w == 2) ? prm[lay.W2 + F + c] : 0.f;
-    } else if (tid < 256) {
-      const int br = (tid - 128) >> 6, c = tid & 63;
-      float m1 = 0.f, m2 = 0.f;
+      const float4 t0 = reinterpret_cast<const float4*>(a.ltab)[tid * 2 + 0];
+      const float4 t1 = reinterpret_cast<const float4*>(a.ltab)[tid * 2 + 1];
+      float c2 = 0.f, c3 = 0.f;
       if (a.f.training) {
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int r = 0; r < DPF_M12_REP; ++r) {
-          const double2 v = *reinterpret_cast<const double2*>(a.m12_rep + (size_t)r * (2 * F * 2) + (size_t)(br * F + c) * 2);
+          const double2 v = *reinterpret_cast<const double2*>(a.m12_rep + (size_t)r * (2 * F * 2) + (size_t)tid * 2);
           s1 += v.x;
           s2 += v.y;
         }
-        const double M = (double)a.f.B * (double)a.f.N;
-        m1 = (float)(s1 / M);
-        m2 = (float)(s2 / M);
+        const float rM = 1.f / ((float)a.f.B * (float)a.f.N);
+        const float m1 = (float)s1 * rM, m2 = (float)s2 * rM;
+        c3 = t1.x * t1.x * m2;
+        c2 = t1.x * m1 - c3 * t0.w;
       }
-      s.m1[br][c] = m1;
-      s.m2[br][c] = m2;
+      s.A0[tid >> 6][tid & 63] = make_float4(t0.x, t0.y, t0.z, 0.f);
+      s.lt0[tid >> 6][tid & 63] = make_float4(t1.x, t0.w, c2, c3);
+      s.lt1[tid >> 6][tid & 63] = make_float2(t1.y, t1.z);
+    } else if (tid < 128 + 5) {
+      s.pend[tid - 128] = a.has_pending ? a.pend_store[tid - 128] : 0.f;
     }
-    for (int i = tid; i < (int)(IMG_H / 16); i += 512) {
-      reinterpret_cast<uint4*>(s.h[0].X)[i] = make_uint4(0u, 0u, 0u, 0u);
-      reinterpret_cast<uint4*>(s.h[1].X)[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    Pending P{0.f, 0.f, 0.f, 0.f, 0.f};
-    if (a.has_pending) { P.c0 = a.pend_store[0]; P.c1 = a.pend_store[1]; P.q00 = a.pend_store[2]; P.q01 = a.pend_store[3]; P.q11 = a.pend_store[4]; }
     const float sig1 = sqrtf(a.f.eps + 1.0f);
     umma::named_bar_sync(3, 512);        // tables + zeroed X tiles visible to both halves
     DPF_STAMP(2, 3);
@@ -814,10 +824,13 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
         const int br = row >> 6, c = row & 63;
         const float sc = a.f.film[((size_t)(br * 2 + 0) * a.f.B + b) * F + c];
         const float sh = a.f.film[((size_t)(br * 2 + 1) * a.f.B + b) * F + c];
-        const float S = sc * s.ib[br][c];
-        s.sraw[half][br][c] = sc;
-        s.epi[half][br][c] = make_float4(S, fmaf(-S, s.mb[br][c], sh), s.W2[br][0][c], s.W2[br][1][c]);
+        const float4 l0 = s.lt0[br][c];
+        const float2 l1 = s.lt1[br][c];
+        const float S = sc * l0.x;
+        s.epi[half][br][c] = make_float4(S, fmaf(-S, l0.y, sh), l1.x, l1.y);
+        s.epi2[half][br][c] = make_float4(S, l0.z, l0.w, 0.f);
       }
+      const Pending P{s.pend[0], s.pend[1], s.pend[2], s.pend[3], s.pend[4]};
       const TcPoint g = tc_finish_point<MODE>(a, P, it == 0 ? raw0 : tc_load_raw(a, b, n, valid), valid);
       const float xk0 = pick3(g.x, a.f.keep0);
       const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
@@ -860,23 +873,29 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
       for (int br = 0; br < 2; ++br) {
         const float d0 = br == 0 ? g.do_mu[0] : g.do_lv[0];
         const float d1 = br == 0 ? g.do_mu[1] : g.do_lv[1];
-        float v[32];
-        umma::tmem_ld32(T_F + lane_off + br * F + part * 32, v);
+#pragma unroll 1
+        for (int hc = 0; hc < 2; ++hc) {     // 16 columns at a time (register pressure: 96 per thread)
+          uint32_t r[16];
+          umma::tmem_ld16_issue(T_F + lane_off + br * F + part * 32 + hc * 16, r);
+          umma::tmem_ld_wait16(r);
+          float v[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = part * 32 + i;
-          const float4 e = s.epi[half][br][c];
-          const float h2n = (v[i] - s.mb[br][c]) * s.ib[br][c];
-          const float av = fmaf(e.x, v[i], e.y);
-          const float da = av > 0.f ? fmaf(e.z, d0, e.w * d1) : 0.f;
-          const float dh = s.ib[br][c] * (da * s.sraw[half][br][c] - s.m1[br][c] - h2n * s.m2[br][c]);
-          v[i] = valid ? dh : 0.f;
-        }
+          for (int i = 0; i < 16; ++i) {
+            const int c = part * 32 + hc * 16 + i;
+            const float acc = __uint_as_float(r[i]);
+            const float4 e = s.epi[half][br][c];
+            const float4 e2 = s.epi2[half][br][c];
+            const float av = fmaf(e.x, acc, e.y);
+            const float da = av > 0.f ? fmaf(e.z, d0, e.w * d1) : 0.f;
+            const float dh = fmaf(e2.x, da, -fmaf(e2.z, acc, e2.y));
+            v[i] = valid ? dh : 0.f;
+          }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                      umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-          *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + q)) = pk;
+          for (int q = 0; q < 2; ++q) {
+            const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                        umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+            *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + hc * 2 + q)) = pk;
+          }
         }
       }
       umma::fence_async_smem();
@@ -891,23 +910,28 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
       float T1_0 = 0.f, T1_1 = 0.f;
 #pragma unroll 1
       for (int br = 0; br < 2; ++br) {
-        float v[32];
-        umma::tmem_ld32(T_F + lane_off + br * F + part * 32, v);
+#pragma unroll 1
+        for (int hc = 0; hc < 2; ++hc) {
+          uint32_t r[16];
+          umma::tmem_ld16_issue(T_F + lane_off + br * F + part * 32 + hc * 16, r);
+          umma::tmem_ld_wait16(r);
+          float v[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float4 A = s.A0[br][part * 32 + i];
-          float z = fmaf(A.x, xk0, A.z);
-          if (K == 2) z = fmaf(A.y, xk1, z);
-          const float dz = (z > 0.f && valid) ? v[i] : 0.f;
-          T1_0 = fmaf(A.x, dz, T1_0);
-          if (K == 2) T1_1 = fmaf(A.y, dz, T1_1);
-          v[i] = dz;
-        }
+          for (int i = 0; i < 16; ++i) {
+            const float4 A = s.A0[br][part * 32 + hc * 16 + i];
+            float z = fmaf(A.x, xk0, A.z);
+            if (K == 2) z = fmaf(A.y, xk1, z);
+            const float dz = (z > 0.f && valid) ? __uint_as_float(r[i]) : 0.f;
+            T1_0 = fmaf(A.x, dz, T1_0);
+            if (K == 2) T1_1 = fmaf(A.y, dz, T1_1);
+            v[i] = dz;
+          }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                      umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-          *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + q)) = pk;
+          for (int q = 0; q < 2; ++q) {
+            const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                        umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+            *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + hc * 2 + q)) = pk;
+          }
         }
       }
       if (part == 0) {
@@ -1031,7 +1055,8 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
   DPF_STAMP(1, 1);
   tc_load_weights<false>(s.c, s.W, wimg);
   pdl_wait();          // the previous backward kernel's sums / gradients are read from here on
-  tc_prologue_tables(a.f, lay, s.c, false, true);
+  if (a.ltab) tc_prologue_tables_ltab(a.ltab, s.c);
+  else tc_prologue_tables(a.f, lay, s.c, false, true);
   DPF_STAMP(1, 2);
   for (int i = tid; i < (int)(IMG_H / 16); i += NT2) reinterpret_cast<uint4*>(s.X)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 4) (&s.b2fin[0][0])[tid] = 0.f;
@@ -1625,7 +1650,7 @@ int launch_bwd_tc_t(const BwdArgs& a, const unsigned short* wimg, int pass, cuda
     return dpf_check_launch("coupling_bwd_p1_tc2_kernel");
   }
   const int grid = min(a.f.n_tiles, dpf_num_sms());
-  if (g_dpf_p2_two_tiles && a.pend_store && a.m12_rep) {   // two tiles in flight per SM (dpf_set_option(3, 0) = one)
+  if (g_dpf_p2_two_tiles && a.pend_store && a.m12_rep && a.ltab) {   // two tiles in flight per SM (dpf_set_option(3, 0) = one)
     static bool attr4 = false;
     if (!attr4) {
       cudaFuncSetAttribute(coupling_bwd_p2_tc4_kernel<K, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcP2Smem4>());
@@ -1676,6 +1701,41 @@ int launch_fwd_tc_k(const CouplingArgs& a, const unsigned short* wimg, int mode,
 }
 
 }  // namespace
+
+// Folded per-(branch, channel) tables of every layer for the backward kernels, once per pass:
+// {A00, A01, c0} (BN_a folded into the first SharedDot), BN_b mean / istd, last SharedDot weights and bias.
+__global__ void __launch_bounds__(2 * DPF_F)
+bwd_tables_kernel(const float* __restrict__ arena, float* stats, const LayerMeta* __restrict__ meta, const double* __restrict__ moments,
+                  double* bnb_sums, float* __restrict__ ltab, int L, int G, int B, int N, int mode, int training) {
+  const int l = blockIdx.x, q = mode == 0 ? l : L - 1 - l;
+  const LayerMeta m = meta[l];
+  CouplingArgs a{};
+  a.prm = arena + m.param_off;
+  a.stat = stats + m.stat_off;
+  a.mom_in = moments + (size_t)q * 16;
+  a.bnb_sums = bnb_sums + (size_t)l * 2 * DPF_F * 2;
+  a.B = B; a.N = N; a.G = G;
+  a.k = (int)m.k; a.w = (int)m.w; a.keep0 = (int)m.keep0; a.keep1 = (int)m.keep1;
+  a.training = training;
+  const BranchLayout lay = branch_layout(a.k, a.w, G);
+  const int br = threadIdx.x >> 6, c = threadIdx.x & 63;
+  float A00, A01, c0, mean, istd;
+  fold_bn_a(a, lay, br, c, false, A00, A01, c0, nullptr, nullptr);
+  bn_b_stats(a, br, c, false, mean, istd);
+  const float* prm = a.prm + (size_t)br * lay.size;
+  const float w20 = prm[lay.W2 + c];
+  const float w21 = (a.w == 2) ? prm[lay.W2 + DPF_F + c] : 0.f;
+  const float b2 = (c < a.w) ? prm[lay.b2 + c] : 0.f;
+  float4* d = reinterpret_cast<float4*>(ltab + ((size_t)l * 2 * DPF_F + threadIdx.x) * 8);
+  d[0] = make_float4(A00, A01, c0, mean);
+  d[1] = make_float4(istd, w20, w21, b2);
+}
+
+int launch_bwd_tables(const float* arena, float* stats, const LayerMeta* meta_dev, const double* moments, const double* bnb_sums,
+                      float* ltab, int L, int G, int B, int N, int mode, int training, cudaStream_t s) {
+  bwd_tables_kernel<<<L, 2 * DPF_F, 0, s>>>(arena, stats, meta_dev, moments, const_cast<double*>(bnb_sums), ltab, L, G, B, N, mode, training);
+  return dpf_check_launch("bwd_tables_kernel");
+}
 
 // dW1 of every layer = sum over the pass-2 CTAs' partials (deterministic, no global atomics).
 // grid = (L*2, 16): blockIdx.x = layer*2 + branch, each thread owns one of the 64x64 entries.

@@ -221,6 +221,8 @@ int launch_coupling_bwd_fp32(const BwdArgs& a, int mode, int pass, cudaStream_t 
 int launch_coupling_bwd_tc(const BwdArgs& a, const unsigned short* wimg, int mode, int pass, int split, cudaStream_t s);
 int launch_dw1_reduce(const float* partial, int n_cta, float* darena, const LayerMeta* meta_dev, int L, int G, cudaStream_t s);
 int tc_bwd_p2_max_ctas();
+int launch_bwd_tables(const float* arena, float* stats, const LayerMeta* meta_dev, const double* moments, const double* bnb_sums,
+                      float* ltab, int L, int G, int B, int N, int mode, int training, cudaStream_t s);
 
 // Scratch of the tensor-core backward: per-CTA wgrad partials [L][ctas][2][64*64] fp32.
 DPF_API int dpf_decoder_backward_scratch_bytes(int L, int B, int N, long long* bytes) {
@@ -263,6 +265,11 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
   cudaMemsetAsync(ws.bna_sums, 0, sizeof(double) * (size_t)L * 2 * DPF_F * 4, s);
   if (precision >= 1) cudaMemsetAsync(ws.m12_rep, 0, sizeof(double) * (size_t)L * DPF_M12_REP * 2 * DPF_F * 2, s);
 
+  if (precision >= 1) {   // folded BN_a / BN_b tables of every layer, once per pass (the per-layer kernels only load them)
+    rc = launch_bwd_tables(arena, stats, reinterpret_cast<const LayerMeta*>(meta_dev), ws.moments, ws.bnb_sums, ws.ltab, L, G, B, N,
+                           mode, training, s);
+    if (rc) return rc;
+  }
   auto layer_of = [&](int q) { return mode == 0 ? q : L - 1 - q; };
   auto set_pending = [&](BwdArgs& a, int qn) {   // correction owed by the layer of step qn
     const int ln = layer_of(qn);
@@ -290,6 +297,7 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     a.dfilm = ws.dfilm + (size_t)l * 4 * B * DPF_F;
     a.dprm = darena + meta[l].param_off;
     a.bna_sums = ws.bna_sums + (size_t)l * 2 * DPF_F * 4;
+    a.ltab = precision >= 1 ? ws.ltab + (size_t)l * 2 * DPF_F * 8 : nullptr;
     a.pend_store = precision >= 1 ? ws.pend + (size_t)l * 8 : nullptr;
     a.m12_rep = precision >= 1 ? ws.m12_rep + (size_t)l * DPF_M12_REP * 2 * DPF_F * 2 : nullptr;
     a.dw1_partial = precision >= 1 ? (float*)bwd_scratch + (size_t)l * p2_ctas * 2 * DPF_F * DPF_F : nullptr;
