@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="shapes per GPU")
     ap.add_argument("--points", type=int, default=2048)
     ap.add_argument("--no-extras", action="store_true", help="skip sampling / Chamfer / cpu_baseline legs")
+    ap.add_argument("--sweep-clouds", type=int, default=1000,
+                    help="clouds per set of the row-sharded evaluation sweep in the extras (BASELINE config 5: 1000; 0 = skip)")
     ap.add_argument("--side-stream", action="store_true", help="run on a non-default CUDA stream (A/B tests)")
     ap.add_argument("--lib-option", action="append", default=[], metavar="K=V", help="dpf_set_option(K, V) before the run (A/B tests)")
     return ap.parse_args()
@@ -347,8 +349,13 @@ def run_ours(args):
         "gpu_launches": l1 - l0, "clocks": clocks, "roofline": roofline,
     }
 
+    sweep = None
+    if not args.no_extras and args.sweep_clouds > 0:     # every rank takes part in the sharded sweep
+        sweep = eval_sweep(dev, args.sweep_clouds, N, world, rank, flush)
     if rank == 0 and not args.no_extras:
         line["extra"] = extras(model, dev, B, N, pk, flush)
+        if sweep is not None:
+            line["extra"]["eval_sweep"] = sweep
         line["extra"]["full_model_step"] = full_model_step(dev, B, N, precision, flush)
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -362,6 +369,7 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()          # rank 0's single-GPU extras / cpu_baseline legs run while the others wait here
         dist.destroy_process_group()
 
 
@@ -408,6 +416,45 @@ def extras(model, dev, B, N, pk, flush):
                       "fp32_issue": {"achieved_dist_evals_per_s": 2 * pairs * N * N, "bound": fp32_issue_peak,
                                      "frac": 2 * pairs * N * N / fp32_issue_peak}}
     return out
+
+
+def eval_sweep(dev, S, N, world, rank, flush):
+    """BASELINE config 5: gg, tt, gt Chamfer matrices of S generated vs S reference clouds of N points, rows
+    sharded across the ranks (interleaved; gg / tt upper triangle only), ONE collective per matrix, then
+    COV / MMD / 1-NNA on every rank (lib/networks/evaluating.py:245-253 -> utils.pairwise_CD / COV / MMD / KNN).
+    Timed on the device, max over ranks; all ranks take part."""
+    import torch.distributed as dist
+    from dpf_nets_b200.lib.networks.utils import COV, KNN, MMD, pairwise_CD
+    gen = torch.Generator().manual_seed(4321)          # every rank holds both sets (24.6 MB each at 1000 x 2048)
+    G = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
+    R = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
+    small = G[:8].contiguous()
+    pairwise_CD(small, small)                          # warm-up (kernel attributes, NCCL channels)
+    pairwise_CD(small, R[:8].contiguous())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    flush.zero_()
+    a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    a.record()
+    gg = pairwise_CD(G, G)
+    tt = pairwise_CD(R, R)
+    gt = pairwise_CD(G, R)
+    b.record()
+    cov, mmd, nna = COV(gt), MMD(gt), KNN(gg, gt, tt, 1)
+    c.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b), a.elapsed_time(c)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_mat, ms_all = float(t[0]), float(t[1])
+    evaluated = S * (S + 1) + S * S                    # cloud pairs actually evaluated (two triangles + one full matrix)
+    return {"clouds": "%d generated x %d reference of %d points" % (S, S, N), "n_gpus": world,
+            "ms_matrices": ms_mat, "ms_with_cov_mmd_1nna": ms_all,
+            "value": evaluated / (ms_mat * 1e-3), "unit": "cloud-pair CD evals/s (pairs evaluated; symmetric halves of gg/tt skipped)",
+            "matrix_entries_per_s": 3.0 * S * S / (ms_mat * 1e-3),
+            "point_pair_evals_per_s": evaluated / (ms_mat * 1e-3) * N * N,
+            "scores": {"COV": cov, "MMD": mmd, "1-NNA": nna}, "sharding": "interleaved rows, one all-reduce(sum) of disjoint row blocks per matrix"}
 
 
 def encoder_eval(dev, B, N, flush):
@@ -463,19 +510,34 @@ def full_model_step(dev, B, N, precision, flush, steps=5, warmup=3):
         opt.step()
         return loss
 
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    ts, loss = [], None
-    for _ in range(steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); loss = step(); b.record(); torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ms = sum(ts) / len(ts)
-    return {"value": B * N / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "loss": float(loss),
-            "model": "generation/chair VAE, %d params" % sum(p.numel() for p in model.parameters()),
-            "includes": "H2D of both clouds, encoder, latent flows, priors, decoder, loss, backward, AMSGrad step"}
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        ts, loss = [], None
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); loss = fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sum(ts) / len(ts), float(loss.detach())
+
+    ms, loss = timed(step)
+    res = {"value": B * N / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "loss": loss,
+           "model": "generation/chair VAE, %d params" % sum(p.numel() for p in model.parameters()),
+           "includes": "H2D of both clouds, encoder, latent flows, priors, decoder, loss, backward, AMSGrad step"}
+    # the same step as two CUDA graphs (config key cuda_graph: forward+loss+backward | optimizer), _graphstep.py
+    try:
+        from dpf_nets_b200.lib.networks._graphstep import GraphedTrainStep
+        gstep = GraphedTrainStep(model, crit, opt, eager_steps=0)
+
+        def graphed():
+            return gstep(clouds[0].to(dev, non_blocking=True), clouds[1].to(dev, non_blocking=True))[0]
+        gms, gloss = timed(graphed)
+        res["cuda_graph"] = {"value": B * N / (gms * 1e-3), "unit": "points/s", "ms_per_step": gms, "loss": gloss}
+    except Exception as e:      # reported, never fatal for the headline line
+        res["cuda_graph"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return res
 
 
 def main():

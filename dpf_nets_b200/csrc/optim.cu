@@ -41,8 +41,14 @@ struct AdamTensors {
   int count;
 };
 
+// hyper (nullable): device array {lr, b1, b2, eps, wd, bc1, bc2} that overrides the by-value scalars, so that a
+// CUDA graph holding this launch can be replayed with a new learning rate / step count (dpf_adam_step_multi_dev)
 __global__ void __launch_bounds__(256)
-adam_step_multi_kernel(const __grid_constant__ AdamTensors t, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+adam_step_multi_kernel(const __grid_constant__ AdamTensors t, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
+                       const float* __restrict__ hyper) {
+  if (hyper) {
+    lr = hyper[0]; b1 = hyper[1]; b2 = hyper[2]; eps = hyper[3]; wd = hyper[4]; bc1 = hyper[5]; bc2 = hyper[6];
+  }
   int k = 0;
   while (k + 1 < t.count && (int)blockIdx.x >= t.block_start[k + 1]) ++k;
   const int base = ((int)blockIdx.x - t.block_start[k]) * ADAM_SLAB;
@@ -84,9 +90,9 @@ DPF_API int dpf_adam_step(float* p, const float* g, float* m, float* v, float* v
 // The same update for n tensors in ceil(n / 48) launches (tensors < 2^31 elements; larger ones go through
 // dpf_adam_step).  p/g/m/v/vmax: host arrays of n device pointers (vmax may be NULL = amsgrad off);
 // numel: host array of n sizes.  All tensors share the hyper-parameters and the step count.
-DPF_API int dpf_adam_step_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
-                                float* const* vmax, const long long* numel, float lr, float b1, float b2, float eps,
-                                float wd, float bc1, float bc2, void* stream) {
+static int adam_multi_impl(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                           float* const* vmax, const long long* numel, float lr, float b1, float b2, float eps,
+                           float wd, float bc1, float bc2, const float* hyper, void* stream) {
   DPF_REQUIRE(n >= 0, DPF_ERR_BAD_ARG, "dpf_adam_step_multi: negative count");
   if (n == 0) return DPF_OK;
   DPF_REQUIRE(p && g && m && v && numel, DPF_ERR_NULL_PTR, "dpf_adam_step_multi: null table");
@@ -107,9 +113,22 @@ DPF_API int dpf_adam_step_multi(int n, float* const* p, const float* const* g, f
     if (c == 0) break;
     t.block_start[c] = blocks;
     t.count = c;
-    adam_step_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t, lr, b1, b2, eps, wd, bc1, bc2);
+    adam_step_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t, lr, b1, b2, eps, wd, bc1, bc2, hyper);
     int rc = dpf_check_launch("adam_step_multi_kernel");
     if (rc) return rc;
   }
   return DPF_OK;
+}
+
+DPF_API int dpf_adam_step_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                                float* const* vmax, const long long* numel, float lr, float b1, float b2, float eps,
+                                float wd, float bc1, float bc2, void* stream) {
+  return adam_multi_impl(n, p, g, m, v, vmax, numel, lr, b1, b2, eps, wd, bc1, bc2, nullptr, stream);
+}
+
+// Graph-replayable form: the hyper-parameters {lr, b1, b2, eps, wd, bc1, bc2} are read from DEVICE memory at run time.
+DPF_API int dpf_adam_step_multi_dev(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                                    float* const* vmax, const long long* numel, const float* hyper_dev, void* stream) {
+  DPF_REQUIRE(hyper_dev, DPF_ERR_NULL_PTR, "dpf_adam_step_multi_dev: null hyper-parameter pointer");
+  return adam_multi_impl(n, p, g, m, v, vmax, numel, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1.f, hyper_dev, stream);
 }

@@ -65,8 +65,12 @@ def train_main(svr=False, argv=None):
     ap.add_argument('--precision', default='auto')
     ap.add_argument('--batch_size', type=int, default=None)
     ap.add_argument('--path2save', default=None)
+    ap.add_argument('--cuda_graph', action='store_true',
+                    help='run the training step as two CUDA graphs (forward+loss+backward | optimizer); static batch shapes')
     args = ap.parse_args(argv)
     config = _configs.load(args.config)
+    if args.cuda_graph:
+        config['cuda_graph'] = True
     config.update(model_name='{0}.pkl'.format(args.modelname), n_epochs=args.n_epochs, min_lr=args.lr, max_lr=args.lr,
                   resume=bool(args.resume), resume_optimizer=bool(args.resume_optimizer))
     if args.batch_size:

@@ -64,6 +64,10 @@ class RealNVPFlow(_nn.Module):
         self.warp_inds = [int(i) for i in warp_inds]
         self.keep_inds = [i for i in range(g_n_features) if i not in set(self.warp_inds)]
         self.register_buffer('eps', _torch.tensor([eps], dtype=_torch.float32))
+        # device-resident index vectors (not in the state_dict): indexing with Python lists would build a CPU
+        # index tensor and copy it to the GPU on every call - a sync per layer, and illegal under graph capture
+        self.register_buffer('_keep_idx', _torch.tensor(self.keep_inds, dtype=_torch.long), persistent=False)
+        self.register_buffer('_warp_idx', _torch.tensor(self.warp_inds, dtype=_torch.long), persistent=False)
         for br in ('mu', 'logvar'):
             net = _nn.Sequential()
             net.add_module(br + '_mlp0', _nn.Linear(len(self.keep_inds), n_features, bias=False))
@@ -76,11 +80,9 @@ class RealNVPFlow(_nn.Module):
             setattr(self, 'T_%s_0' % br, net)
 
     def forward(self, g, mode='direct'):
-        kept = g[:, self.keep_inds].contiguous()
-        logvar = _torch.zeros_like(g)
-        mu = _torch.zeros_like(g)
-        logvar[:, self.warp_inds] = _torch.log(self.eps + _torch.exp(self.T_logvar_0(kept)))
-        mu[:, self.warp_inds] = self.T_mu_0(kept)
+        kept = g.index_select(1, self._keep_idx)
+        logvar = _torch.zeros_like(g).index_copy(1, self._warp_idx, _torch.log(self.eps + _torch.exp(self.T_logvar_0(kept))))
+        mu = _torch.zeros_like(g).index_copy(1, self._warp_idx, self.T_mu_0(kept))
         if mode == 'direct':
             g_out = _torch.exp(0.5 * logvar) * g + mu
         elif mode == 'inverse':

@@ -16,6 +16,39 @@ from ... import _lib
 class Adam(Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad))
+        # capturable: the fused launches read {lr, betas, eps, wd, bias corrections} from device memory that a
+        # captured H2D copy refreshes from a pinned host table, so step() can live in a CUDA graph (_graphstep.py)
+        self.capturable = False
+        self._hyper_host = None
+        self._hyper_dev = None
+
+    def _hyper_row(self, group, step):
+        beta1, beta2 = group['betas']
+        return [float(group['lr']), float(beta1), float(beta2), float(group['eps']), float(group['weight_decay']),
+                float(1 - beta1 ** step), float(math.sqrt(1 - beta2 ** step)), 0.0]
+
+    def _group_step(self, group):
+        steps = {self.state[p]['step'] for p in group['params'] if p.grad is not None and len(self.state[p])}
+        if len(steps) != 1:
+            raise RuntimeError('capturable Adam needs one shared step count per parameter group, got %s' % sorted(steps))
+        return steps.pop()
+
+    def enable_capture(self, device):
+        """Allocate the hyper tables (pinned host + device) OUTSIDE any stream capture and switch step() to the
+        graph-replayable launches."""
+        if self._hyper_host is None:
+            self._hyper_host = torch.zeros((len(self.param_groups), 8), dtype=torch.float32).pin_memory()
+            self._hyper_dev = torch.zeros((len(self.param_groups), 8), dtype=torch.float32, device=device)
+        self.capturable = True
+
+    def prepare_replay(self):
+        """Host side of one replayed step: advance the step counters and refresh the pinned hyper table (the
+        captured graph copies it to the device before the update kernels run)."""
+        for gi, group in enumerate(self.param_groups):
+            for p in group['params']:
+                if p.grad is not None and len(self.state[p]):
+                    self.state[p]['step'] += 1
+            self._hyper_host[gi] = torch.tensor(self._hyper_row(group, self._group_step(group)))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -54,11 +87,22 @@ class Adam(Optimizer):
                 if group['weight_decay'] != 0:
                     upd = upd + p * group['weight_decay']
                 p.sub_(upd)
+            if self.capturable and fused:
+                if len(fused) != 1:
+                    raise RuntimeError('capturable Adam: parameters of a group must share device and step')
+                gi = self.param_groups.index(group)
+                if self._hyper_host is None:
+                    raise RuntimeError('capturable Adam: call enable_capture(device) before the first captured step')
+                (device, step), ps = next(iter(fused.items()))
+                self._hyper_host[gi] = torch.tensor(self._hyper_row(group, step))
+                self._hyper_dev[gi].copy_(self._hyper_host[gi], non_blocking=True)
+                self._fused_step(group, device, step, ps, hyper_dev=self._hyper_dev[gi])
+                continue
             for (device, step), ps in fused.items():
                 self._fused_step(group, device, step, ps)
         return loss
 
-    def _fused_step(self, group, device, step, ps):
+    def _fused_step(self, group, device, step, ps, hyper_dev=None):
         """All CUDA fp32 parameters of one group that share a step count: dpf_adam_step_multi
         (48 tensors per launch) instead of one launch - or ~10 ATen kernels - per parameter."""
         ct = _lib.ctypes
@@ -67,6 +111,12 @@ class Adam(Optimizer):
         arr = ct.c_void_p * n
         states = [self.state[p] for p in ps]
         vmax = arr(*[s['max_exp_avg_sq'].data_ptr() for s in states]) if group['amsgrad'] else None
+        if hyper_dev is not None:
+            with torch.cuda.device(device):
+                _lib.call("dpf_adam_step_multi_dev", n, arr(*[p.data_ptr() for p in ps]), arr(*[p.grad.data_ptr() for p in ps]),
+                          arr(*[s['exp_avg'].data_ptr() for s in states]), arr(*[s['exp_avg_sq'].data_ptr() for s in states]),
+                          vmax, (ct.c_longlong * n)(*[p.numel() for p in ps]), hyper_dev, device=device)
+            return
         with torch.cuda.device(device):
             _lib.call("dpf_adam_step_multi", n, arr(*[p.data_ptr() for p in ps]), arr(*[p.grad.data_ptr() for p in ps]),
                       arr(*[s['exp_avg'].data_ptr() for s in states]), arr(*[s['exp_avg_sq'].data_ptr() for s in states]),

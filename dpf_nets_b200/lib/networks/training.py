@@ -28,6 +28,20 @@ def train(iterator, model, loss_func, optimizer, scheduler, epoch, iter, **kwarg
             save_model({'epoch': ep, 'iter': it, 'model_state': model.state_dict(),
                         'optimizer_state': optimizer.state_dict()}, model_name)
 
+    def nan_guard(loss):
+        if torch.isnan(loss.detach()):
+            print('Loss is NaN! Stopping without updating the net...')
+            raise SystemExit(1)
+
+    graphed = None
+    if kwargs.get('cuda_graph'):     # opt-in (not a reference key): the step as two CUDA graphs, _graphstep.py
+        from ._graphstep import GraphedTrainStep
+        graphed = getattr(model, '_dpf_graphed_step', None)      # one capture per model, reused across epochs
+        if graphed is None or graphed.optimizer is not optimizer:
+            graphed = GraphedTrainStep(model, loss_func, optimizer, allreduce=lambda: _dist.allreduce_arena_grads(model))
+            graphed.nan_guard = nan_guard
+            object.__setattr__(model, '_dpf_graphed_step', graphed)
+
     end = time()
     for i, batch in enumerate(iterator):
         if iter + i >= len(iterator):
@@ -35,23 +49,26 @@ def train(iterator, model, loss_func, optimizer, scheduler, epoch, iter, **kwarg
         scheduler(optimizer, epoch, iter + i)
         g_clouds = batch['cloud'].to(dev, non_blocking=True)
         p_clouds = batch['eval_cloud'].to(dev, non_blocking=True)
-        if train_mode == 'p_rnvp_mc_g_rnvp_vae_ic':
-            outputs = model(g_clouds, p_clouds, batch['image'].to(dev, non_blocking=True))
-        else:
-            outputs = model(g_clouds, p_clouds)
-        loss, pnll, gnll, gent = loss_func(g_clouds, p_clouds, outputs)
-        if torch.isnan(loss.detach()):
-            print('Loss is NaN! Stopping without updating the net...')
-            raise SystemExit(1)
         n = g_clouds.shape[0]
+        if graphed is not None:
+            inputs = (g_clouds, p_clouds) + ((batch['image'].to(dev, non_blocking=True),) if train_mode == 'p_rnvp_mc_g_rnvp_vae_ic' else ())
+            loss, pnll, gnll, gent = graphed(*inputs)
+        else:
+            if train_mode == 'p_rnvp_mc_g_rnvp_vae_ic':
+                outputs = model(g_clouds, p_clouds, batch['image'].to(dev, non_blocking=True))
+            else:
+                outputs = model(g_clouds, p_clouds)
+            loss, pnll, gnll, gent = loss_func(g_clouds, p_clouds, outputs)
+            nan_guard(loss)
         meters['PNLL'].update(pnll.item(), n)
         meters['GNLL'].update(gnll.item(), n)
         meters['GENT'].update(gent.item(), n)
         meters['LB'].update((pnll + gnll - gent).item(), n)
-        optimizer.zero_grad()
-        loss.backward()
-        _dist.allreduce_arena_grads(model)
-        optimizer.step()
+        if graphed is None:
+            optimizer.zero_grad()
+            loss.backward()
+            _dist.allreduce_arena_grads(model)
+            optimizer.step()
         meters['time'].update(time() - end)
         if rank == 0 and (iter + i + 1) % num_workers == 0:
             stdout.write('Epoch: [{0}][{1}/{2}]\tTime {t.val:.3f} ({t.avg:.3f})\tLB {lb.val:.2f} ({lb.avg:.2f})'

@@ -30,7 +30,9 @@ int dpf_launch_count(long long* count);
  * classes: 0 film_fwd, 1 moments, 2 fwd_stats, 3 fwd_apply, 4 bwd_p1, 5 bwd_p2, 6 bwd_final, 7 film_bwd */
 /* option 0: merged train-mode forward (1 = on, default; 0 = two launches per layer).
  * option 1: fused all-layer eval-mode decoder, one launch for the whole stack (1 = on, default;
- *           0 = one launch per layer).  Both exist so that tests can compare the two forms. */
+ *           0 = one launch per layer).  Both exist so that tests can compare the two forms.
+ * option 2: programmatic dependent launch of the per-layer kernels (1 = on, default).
+ * option 3: backward pass 2 with two tiles in flight per SM (1 = on, default; 0 = one tile per SM). */
 int dpf_set_option(int option, int value);
 int dpf_profile_enable(int on);
 int dpf_profile_collect(double* ms, long long* counts, int n);
@@ -134,6 +136,12 @@ int dpf_adam_step(float* p, const float* g, float* m, float* v, float* vmax, lon
 int dpf_adam_step_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
                         float* const* vmax, const long long* numel, float lr, float b1, float b2, float eps,
                         float wd, float bc1, float bc2, void* stream);
+
+/* dpf_adam_step_multi with the hyper-parameters {lr, b1, b2, eps, wd, bc1, bc2} read from DEVICE memory when the
+ * kernel runs, so that a CUDA graph holding the launch can be replayed with a new learning rate and step
+ * count (the reference recomputes them on the host every step, optimizers.py:53-66, 89-97). */
+int dpf_adam_step_multi_dev(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                            float* const* vmax, const long long* numel, const float* hyper_dev, void* stream);
 
 /* tcgen05 self-test (tests/test_umma_gpu.py): D[128,ncols] = sum_k A_k B_k from raw shared-memory
  * operand images and descriptor fields; validates the UMMA layouts the coupling kernels rely on. */
