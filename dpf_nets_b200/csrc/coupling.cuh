@@ -19,6 +19,7 @@
 #define DPF_BN_MOM 0.1f
 #define DPF_TILE 128      // points per tile = threads per CTA (one TMEM lane / one thread per point)
 #define DPF_BNB_REP 16     // replicas of the BN_b sum accumulators in the merged train-mode forward
+#define DPF_LTAB_ROW 16     // floats per (branch, channel) row of the backward tables
 #define DPF_M12_REP 8      // replicas of the BN_b backward mean accumulators (pass 1 -> pass 2)
 #define DPF_EVAL_LTAB_BYTES 2112   // sizeof(EvalLayerTab), coupling_tc.cu
 
@@ -69,7 +70,8 @@ struct DecoderWorkspace {
   unsigned short* w1_bf16;  // [L][2][3][F*F] bf16 images {W1 hi, W1^T hi, W1 lo} in UMMA smem layout (tensor path)
   unsigned char* eval_ltab; // [L] EvalLayerTab (fused eval decoder)
   float* eval_epi;          // [L][B][2][F] float4 {S, T, W2_0, W2_1} (fused eval decoder)
-  float* ltab;              // [L][2*F][8] backward: per-(branch, channel) {A00, A01, c0, bnB mean, bnB istd, W2_0, W2_1, b2} (bwd_tables_kernel)
+  float* ltab;              // [L][2*F][DPF_LTAB_ROW] backward: per-(branch, channel) {A00, A01, c0, bnB mean | bnB istd, W2_0, W2_1, b2 |
+                            //   W0_0, W0_1, bnA gamma, bnA mean | bnA istd, -, -, -} (bwd_tables_kernel)
   float* pend;              // [L][8]  backward: deferred BN_a correction {c0, c1, q00, q01, q11} pass 1 hands to pass 2
   double* m12_rep;          // [L][DPF_M12_REP][2][F][2] backward: replicated sum_b s*dt, sum_b s*ds (BN_b batch terms m1, m2)
   unsigned int* barriers;   // [L][32] grid-barrier counters of the merged train-mode forward (one 128-B line per layer)
@@ -93,7 +95,7 @@ __host__ inline DecoderWorkspace carve_workspace(void* base, int L, int G, int B
   w.dx[1] = (float*)take(sizeof(float) * (size_t)B * 3 * N);
   w.w1_bf16 = (unsigned short*)take(sizeof(unsigned short) * (size_t)L * 6 * DPF_F * DPF_F);
   w.barriers = (unsigned int*)take(sizeof(unsigned int) * (size_t)L * 32);
-  w.ltab = (float*)take(sizeof(float) * (size_t)L * 2 * DPF_F * 8);
+  w.ltab = (float*)take(sizeof(float) * (size_t)L * 2 * DPF_F * DPF_LTAB_ROW);
   w.pend = (float*)take(sizeof(float) * (size_t)L * 8);
   w.m12_rep = (double*)take(sizeof(double) * (size_t)L * DPF_M12_REP * 2 * DPF_F * 2);
   w.eval_ltab = (unsigned char*)take((size_t)L * DPF_EVAL_LTAB_BYTES);
@@ -240,7 +242,8 @@ struct BwdArgs {
   float* dfilm;            // [4][B][F]   ds_raw_mu, dt_mu, ds_raw_lv, dt_lv (accumulated)
   float* dprm;             // this layer's slice of the gradient arena
   double* bna_sums;        // [2][F][4]   dbeta, E0, E1 (accumulated in pass 2)
-  const float* ltab;       // tensor path: [2*F][8] this layer's folded tables (bwd_tables_kernel), nullable
+  const float* ltab;       // tensor path: [2*F][DPF_LTAB_ROW] this layer's folded tables (bwd_tables_kernel), nullable
+  const float* n_ltab;     // the same table of the layer that owes the pending correction (nullable)
   float* pend_store;       // tensor path: [8] pass 1 (CTA 0) stores this step's Pending, pass 2 loads it (nullable)
   double* m12_rep;         // tensor path: [DPF_M12_REP][2][F][2] pass 1 accumulates, pass 2 sums (nullable)
   float* dw1_partial;      // tensor path: per-CTA wgrad partials [grid][2][F*F] of this layer (reduced once per pass)

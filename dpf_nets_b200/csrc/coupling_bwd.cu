@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(FB_THREADS)
 film_backward_kernel(const float* __restrict__ arena, const float* __restrict__ stats, float* __restrict__ darena,
                      const LayerMeta* __restrict__ meta, const float* __restrict__ g, const float* __restrict__ film,
                      const float* __restrict__ dfilm, float* __restrict__ dg, int B, int G, int training, float eps) {
-  extern __shared__ float sm[];
+  extern __shared__ float sm[];        // tiles sized for B rows (launch_film_backward)
   const int l = blockIdx.x >> 2, net = blockIdx.x & 3, br = net >> 1, kind = net & 1;
   const LayerMeta m = meta[l];
   const BranchLayout lay = branch_layout((int)m.k, (int)m.w, G);
@@ -518,11 +518,11 @@ film_backward_kernel(const float* __restrict__ arena, const float* __restrict__ 
   const float* rv = st + (kind ? ST_FB_RV : ST_FW_RV) * F;
 
   float* XH = sm;                       // [B][F]  u, then xhat
-  float* DO = XH + (size_t)FB_MAXB * F; // [B][F]  cotangent of the net output
-  float* DU = DO + (size_t)FB_MAXB * F; // [B][F]  v (swish output), then dxhat, then du
-  float* Ws = DU + (size_t)FB_MAXB * F; // [F][F+1] / [32][F+1]
+  float* DO = XH + (size_t)B * F;       // [B][F]  cotangent of the net output
+  float* DU = DO + (size_t)B * F;       // [B][F]  v (swish output), then dxhat, then du
+  float* Ws = DU + (size_t)B * F;       // [F][F+1] / [32][F+1]
   float* gs = Ws + F * (F + 1);         // [B][33]
-  float* vec = gs + (size_t)FB_MAXB * 33;  // mean, istd, m1, m2, dgam[4][F], dbet[4][F]
+  float* vec = gs + (size_t)B * 33;     // mean, istd, m1, m2, dgam[4][F], dbet[4][F]
   float* mean_s = vec, *istd_s = vec + F, *m1_s = vec + 2 * F, *m2_s = vec + 3 * F;
   float* dgam_s = vec + 4 * F, *dbet_s = vec + 8 * F;
   const int tid = threadIdx.x, c = tid & 63, bq = tid >> 6;
@@ -710,10 +710,13 @@ int launch_film_backward(const float* arena, const float* stats, float* darena, 
                          const float* g, const float* film, const float* dfilm, float* dg, int L, int B, int G,
                          int training, float eps, cudaStream_t s) {
   DPF_REQUIRE(B <= FB_MAXB, DPF_ERR_UNSUPPORTED, "film backward supports B <= %d (got %d)", FB_MAXB, B);
-  const size_t smem = sizeof(float) * ((size_t)3 * FB_MAXB * F + F * (F + 1) + (size_t)FB_MAXB * 33 + 12 * F);
+  // shared memory sized for the actual batch: 48 KB at B = 32 -> 4 CTAs per SM, all L*4 CTAs in one wave
+  // (at the FB_MAXB cap, 137 KB, it is one CTA per SM and 252 CTAs take two waves)
+  const size_t smem = sizeof(float) * ((size_t)3 * B * F + F * (F + 1) + (size_t)B * 33 + 12 * F);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(film_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem_max = sizeof(float) * ((size_t)3 * FB_MAXB * F + F * (F + 1) + (size_t)FB_MAXB * 33 + 12 * F);
+    cudaFuncSetAttribute(film_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     attr = true;
   }
   film_backward_kernel<<<L * 4, FB_THREADS, smem, s>>>(arena, stats, darena, meta_dev, g, film, dfilm, dg, B, G, training, eps);

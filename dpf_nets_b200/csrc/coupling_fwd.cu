@@ -25,7 +25,7 @@ constexpr int FILM_BCHUNK = 256;
 __global__ void __launch_bounds__(FILM_THREADS)
 film_forward_kernel(const float* __restrict__ arena, float* __restrict__ stats, const LayerMeta* __restrict__ meta,
                     const float* __restrict__ g, float* __restrict__ film, int B, int G, int training,
-                    int update_stats, float eps) {
+                    int update_stats, float eps, int cap /* rows the shared-memory tiles are sized for */) {
   extern __shared__ float sm[];
   const int l = blockIdx.x >> 2, net = blockIdx.x & 3, br = net >> 1, kind = net & 1;
   const int b0 = blockIdx.y * FILM_BCHUNK;
@@ -43,9 +43,9 @@ film_forward_kernel(const float* __restrict__ arena, float* __restrict__ stats, 
   float* rv = st + (kind ? ST_FB_RV : ST_FW_RV) * F;
 
   float* u = sm;                         // [nb][F]
-  float* Ws = u + (size_t)FILM_BCHUNK * F;  // [32][F+1]  (later reused as W1s [F][F+1])
+  float* Ws = u + (size_t)cap * F;       // [32][F+1]  (later reused as W1s [F][F+1])
   float* gs = Ws + F * (F + 1);          // [nb][33]
-  float* mean_s = gs + (size_t)FILM_BCHUNK * 33;
+  float* mean_s = gs + (size_t)cap * 33;
   float* istd_s = mean_s + F;
   const int tid = threadIdx.x;
   const int c = tid & 63, bq = tid >> 6;
@@ -325,14 +325,18 @@ coupling_fwd_fp32_kernel(const CouplingArgs a) {
 // ---- launchers used by decoder.cu ----------------------------------------------------------
 int launch_film_forward(const float* arena, float* stats, const LayerMeta* meta_dev, const float* g, float* film,
                         int L, int B, int G, int training, int update_stats, float eps, cudaStream_t s) {
-  const size_t smem = sizeof(float) * ((size_t)FILM_BCHUNK * F + F * (F + 1) + (size_t)FILM_BCHUNK * 33 + 2 * F);
+  // shared memory sized for the actual batch: 30 KB at B = 32 -> all L*4 CTAs resident in one wave
+  // (at the FILM_BCHUNK cap, 116 KB, it is one CTA per SM and 252 CTAs take two waves)
+  const int cap = B < FILM_BCHUNK ? B : FILM_BCHUNK;
+  const size_t smem = sizeof(float) * ((size_t)cap * F + F * (F + 1) + (size_t)cap * 33 + 2 * F);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(film_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem_max = sizeof(float) * ((size_t)FILM_BCHUNK * F + F * (F + 1) + (size_t)FILM_BCHUNK * 33 + 2 * F);
+    cudaFuncSetAttribute(film_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     attr = true;
   }
   dim3 grid(L * 4, (B + FILM_BCHUNK - 1) / FILM_BCHUNK);
-  film_forward_kernel<<<grid, FILM_THREADS, smem, s>>>(arena, stats, meta_dev, g, film, B, G, training, update_stats, eps);
+  film_forward_kernel<<<grid, FILM_THREADS, smem, s>>>(arena, stats, meta_dev, g, film, B, G, training, update_stats, eps, cap);
   return dpf_check_launch("film_forward_kernel");
 }
 

@@ -120,8 +120,8 @@ __device__ __forceinline__ void tc_prologue_tables(const CouplingArgs& a, const 
 // backward kernels: the same tables loaded from the per-pass table (bwd_tables_kernel)
 __device__ __forceinline__ void tc_prologue_tables_ltab(const float* __restrict__ ltab, TcCommon& s) {
   const int tid = threadIdx.x & 127, br = tid >> 6, c = tid & 63;
-  const float4 t0 = reinterpret_cast<const float4*>(ltab)[tid * 2 + 0];
-  const float4 t1 = reinterpret_cast<const float4*>(ltab)[tid * 2 + 1];
+  const float4 t0 = reinterpret_cast<const float4*>(ltab)[tid * (DPF_LTAB_ROW / 4) + 0];
+  const float4 t1 = reinterpret_cast<const float4*>(ltab)[tid * (DPF_LTAB_ROW / 4) + 1];
   s.A0[br][c] = make_float4(t0.x, t0.y, t0.z, 0.f);
   s.mb[br][c] = t0.w;
   s.ib[br][c] = t1.x;
@@ -219,14 +219,22 @@ __device__ Pending tc_compute_pending(const BwdArgs& a, bool writer, double* red
   writer = writer && threadIdx.x < 128;
   const BranchLayout nlay = branch_layout(a.nk, a.nw, a.f.G);
   const double M = (double)a.f.B * (double)a.f.N;
-  const BnA bn = bn_a_of(a.nprm, a.nstat, nlay, a.n_mom, M, a.nk, a.nkeep0, a.nkeep1, a.f.training, br, c);
+  BnA bn;
+  if (a.n_ltab) {   // bn_a_of() of that layer, precomputed by bwd_tables_kernel
+    const float4 t2 = reinterpret_cast<const float4*>(a.n_ltab)[tid * (DPF_LTAB_ROW / 4) + 2];
+    const float4 t3 = reinterpret_cast<const float4*>(a.n_ltab)[tid * (DPF_LTAB_ROW / 4) + 3];
+    bn.w0 = t2.x; bn.w1 = t2.y; bn.gamma = t2.z; bn.mean = t2.w; bn.istd = t3.x;
+  } else {
+    bn = bn_a_of(a.nprm, a.nstat, nlay, a.n_mom, M, a.nk, a.nkeep0, a.nkeep1, a.f.training, br, c);
+  }
   const double dbeta = a.n_bna_sums[(br * F + c) * 4 + 0];
   const double E0 = a.n_bna_sums[(br * F + c) * 4 + 1];
   const double E1 = a.n_bna_sums[(br * F + c) * 4 + 2];
   const double istd = bn.istd, mean = bn.mean, w0 = bn.w0, w1 = bn.w1, gam = bn.gamma;
   const double dgamma = istd * (w0 * E0 + w1 * E1 - mean * dbeta);
-  const double n1 = a.f.training ? gam * dbeta / M : 0.0;
-  const double n2 = a.f.training ? gam * dgamma / M : 0.0;
+  const double rM = 1.0 / M;
+  const double n1 = a.f.training ? gam * dbeta * rM : 0.0;
+  const double n2 = a.f.training ? gam * dgamma * rM : 0.0;
   const double i2n2 = istd * istd * n2;
   double v[5] = {w0 * istd * n1 - i2n2 * mean * w0, w1 * istd * n1 - i2n2 * mean * w1, i2n2 * w0 * w0, i2n2 * w0 * w1, i2n2 * w1 * w1};
   if (writer) {
@@ -784,8 +792,8 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
     // per-channel constants.  BN_b backward of a channel:
     //   dh2pre = ib*(da*s - m1 - h2n*m2),  h2n = (acc - mb)*ib   =>   dh2pre = (ib*s)*da - c2 - c3*acc
     if (tid < 128) {
-      const float4 t0 = reinterpret_cast<const float4*>(a.ltab)[tid * 2 + 0];
-      const float4 t1 = reinterpret_cast<const float4*>(a.ltab)[tid * 2 + 1];
+      const float4 t0 = reinterpret_cast<const float4*>(a.ltab)[tid * (DPF_LTAB_ROW / 4) + 0];
+      const float4 t1 = reinterpret_cast<const float4*>(a.ltab)[tid * (DPF_LTAB_ROW / 4) + 1];
       float c2 = 0.f, c3 = 0.f;
       if (a.f.training) {
         double s1 = 0.0, s2 = 0.0;
@@ -1719,16 +1727,18 @@ bwd_tables_kernel(const float* __restrict__ arena, float* stats, const LayerMeta
   a.training = training;
   const BranchLayout lay = branch_layout(a.k, a.w, G);
   const int br = threadIdx.x >> 6, c = threadIdx.x & 63;
-  float A00, A01, c0, mean, istd;
-  fold_bn_a(a, lay, br, c, false, A00, A01, c0, nullptr, nullptr);
+  float A00, A01, c0, mean, istd, meanA, istdA;
+  fold_bn_a(a, lay, br, c, false, A00, A01, c0, &meanA, &istdA);
   bn_b_stats(a, br, c, false, mean, istd);
   const float* prm = a.prm + (size_t)br * lay.size;
   const float w20 = prm[lay.W2 + c];
   const float w21 = (a.w == 2) ? prm[lay.W2 + DPF_F + c] : 0.f;
   const float b2 = (c < a.w) ? prm[lay.b2 + c] : 0.f;
-  float4* d = reinterpret_cast<float4*>(ltab + ((size_t)l * 2 * DPF_F + threadIdx.x) * 8);
+  float4* d = reinterpret_cast<float4*>(ltab + ((size_t)l * 2 * DPF_F + threadIdx.x) * DPF_LTAB_ROW);
   d[0] = make_float4(A00, A01, c0, mean);
   d[1] = make_float4(istd, w20, w21, b2);
+  d[2] = make_float4(prm[lay.W0 + c * a.k], (a.k == 2) ? prm[lay.W0 + c * a.k + 1] : 0.f, prm[lay.bnA_w + c], meanA);   // = bn_a_of()
+  d[3] = make_float4(istdA, 0.f, 0.f, 0.f);
 }
 
 int launch_bwd_tables(const float* arena, float* stats, const LayerMeta* meta_dev, const double* moments, const double* bnb_sums,

@@ -280,6 +280,7 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     a.ndprm = darena + mn.param_off;
     a.n_bna_sums = ws.bna_sums + (size_t)ln * 2 * DPF_F * 4;
     a.n_mom = ws.moments + (size_t)qn * 16;
+    a.n_ltab = precision >= 1 ? ws.ltab + (size_t)ln * 2 * DPF_F * DPF_LTAB_ROW : nullptr;
     a.nk = (int)mn.k; a.nw = (int)mn.w; a.nkeep0 = (int)mn.keep0; a.nkeep1 = (int)mn.keep1;
   };
   for (int q = L - 1; q >= 0; --q) {
@@ -297,7 +298,7 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     a.dfilm = ws.dfilm + (size_t)l * 4 * B * DPF_F;
     a.dprm = darena + meta[l].param_off;
     a.bna_sums = ws.bna_sums + (size_t)l * 2 * DPF_F * 4;
-    a.ltab = precision >= 1 ? ws.ltab + (size_t)l * 2 * DPF_F * 8 : nullptr;
+    a.ltab = precision >= 1 ? ws.ltab + (size_t)l * 2 * DPF_F * DPF_LTAB_ROW : nullptr;
     a.pend_store = precision >= 1 ? ws.pend + (size_t)l * 8 : nullptr;
     a.m12_rep = precision >= 1 ? ws.m12_rep + (size_t)l * DPF_M12_REP * 2 * DPF_F * 2 : nullptr;
     a.dw1_partial = precision >= 1 ? (float*)bwd_scratch + (size_t)l * p2_ctas * 2 * DPF_F * DPF_F : nullptr;
