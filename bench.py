@@ -32,6 +32,9 @@ BASE_LOGVAR = -3.6990                    # configs/generation/chair.yaml:51 p_de
 FLOP_PER_POINT_LAYER_FWD = 17152         # 2 branches x (2k64 + 2*64*64 + 2*64w), k+w=3
 KERNEL_CLASSES = ["film_fwd", "moments", "fwd_stats", "fwd_apply", "bwd_p1", "bwd_p2", "bwd_final", "film_bwd"]
 # algorithmic (non-recompute) GEMM FLOP per point per layer each kernel class is responsible for
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each per-layer kernel, from the `ncu --set full` captures
+# of this workload kept under profiles/ (r01_ncu_coupling_*_summary.txt); inputs of a layer mostly hit in the 126 MB L2
+NCU_DRAM_BYTES_PER_LAUNCH = {"fwd_apply": 968704, "bwd_p1": 4921088, "bwd_p2": 5227008 + 5120}
 ALGO_FLOP = {"fwd_stats": 0, "fwd_apply": FLOP_PER_POINT_LAYER_FWD, "bwd_p1": 2 * 2 * 64 * 3,
              "bwd_p2": 2 * FLOP_PER_POINT_LAYER_FWD - 2 * 2 * 64 * 3}
 
@@ -333,7 +336,10 @@ def run_ours(args):
     achieved = ALGO_FLOP[dom] * B * N / (dom_us * 1e-6) / 1e12
     whole = 3 * FLOP_PER_POINT_LAYER_FWD * 3 * N_FLOWS * B * N / (ms_per_step * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+                "frac": achieved / tensor_peak,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if (B, N) == (32, 2048) else None,
+                "traffic_source": "ncu --set full capture of this kernel on this workload, profiles/r01_ncu_coupling_*_summary.txt",
+                "peak_source": pk["source"] + " (sustained bf16)",
                 "algorithmic_flop_per_launch": ALGO_FLOP[dom] * B * N,
                 "whole_step": {"achieved": whole, "frac": whole / tensor_peak,
                                "flop_per_point": 3 * FLOP_PER_POINT_LAYER_FWD * 3 * N_FLOWS},
