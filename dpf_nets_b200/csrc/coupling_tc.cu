@@ -727,6 +727,7 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
   DPF_STAMP(2, 1);
   pdl_wait();          // pass 1's sums / pending correction are read from here on
   DPF_STAMP(2, 2);
+  DPF_STAMP_NS(2, 13);
   const uint32_t T_WG = tmem + 256, T_BN = tmem + 384;
 
   if (issuer) {
@@ -1076,10 +1077,10 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
     const int n0 = (t0 - b0 * a.f.tiles_per_b) * DPF_TILE + row;
     raw0 = tc_load_raw(a, b0, n0, t0 < t1 && n0 < a.f.N);
   }
-  const Pending P = tc_compute_pending(a, blockIdx.x == 0, s.c.pend);
-  if (blockIdx.x == 0 && tid == 0 && a.pend_store) {   // pass 2 of this layer reads it instead of recomputing
-    a.pend_store[0] = P.c0; a.pend_store[1] = P.c1; a.pend_store[2] = P.q00; a.pend_store[3] = P.q01; a.pend_store[4] = P.q11;
-  }
+  // The deferred correction P needs the previous backward kernel's BN_a sums (a latency-bound double-precision
+  // chain); the first tile's h1 tiles and forward UMMA need only x and the tables, so P is computed while that
+  // UMMA is in flight (inside the tile loop, first tile / first branch).
+  Pending P{0.f, 0.f, 0.f, 0.f, 0.f};
   DPF_STAMP(1, 3);
   float b2acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   float dW2acc[2] = {0.f, 0.f};        // threads < 128: (branch, channel) = (tid >> 6, tid & 63)
@@ -1150,21 +1151,11 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
       tc_tile_film(a.f, s.c, b);
       if (tid < 2 * F) s.shift[tid >> 6][tid & 63] = a.f.film[((size_t)((tid >> 6) * 2 + 1) * a.f.B + b) * F + (tid & 63)];
     }
-    const TcPoint g = tc_finish_point<MODE>(a, P, tile == t0 ? raw0 : tc_load_raw(a, b, n, valid), valid);
+    const TcRaw raw = tile == t0 ? raw0 : tc_load_raw(a, b, n, valid);
     if (tile == t0) DPF_STAMP(1, 5);
-    const float xk0 = pick3(g.x, a.f.keep0);
-    const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
-    if (part == 0) {   // weights of both branches: {mu0 hi, mu0 lo, mu1 hi, mu1 lo, lv0 hi, lv0 lo, lv1 hi, lv1 lo}
-      uint32_t w[4];
-      const float dv[4] = {g.do_mu[0], g.do_mu[1], g.do_lv[0], g.do_lv[1]};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t hi = umma::pack_bf16(dv[i], 0.f) & 0xffffu;
-        const float lo = dv[i] - __uint_as_float(hi << 16);
-        w[i] = umma::pack_bf16(0.f, lo) | hi;
-      }
-      *reinterpret_cast<uint4*>(s.X + umma::sw128_offset(row, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    const float xk0 = pick3(raw.x, a.f.keep0);
+    const float xk1 = (K == 2) ? pick3(raw.x, a.f.keep1) : 0.f;
+    TcPoint g;
 #pragma unroll 1
     for (int br = 0; br < 2; ++br) {
       if (br == 1) {   // branch 0's reductions still read the h3 tiles in H
@@ -1195,6 +1186,26 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
         umma::fence_after_sync();
         issue_gemm1<SPLIT>(T_FWD + br * F, s.H, s.H + IMG_H, wimg_at<false>(s.W, br, 0), wimg_at<false>(s.W, br, 1));
         umma::mma_commit(&s.c.bar_mma);
+      }
+      if (br == 0) {   // while the forward UMMA runs: pending correction (once), this point's cotangents, weight row
+        if (tile == t0) {
+          P = tc_compute_pending(a, blockIdx.x == 0, s.c.pend);
+          if (blockIdx.x == 0 && tid == 0 && a.pend_store) {   // pass 2 of this layer reads it instead of recomputing
+            a.pend_store[0] = P.c0; a.pend_store[1] = P.c1; a.pend_store[2] = P.q00; a.pend_store[3] = P.q01; a.pend_store[4] = P.q11;
+          }
+        }
+        g = tc_finish_point<MODE>(a, P, raw, valid);
+        if (part == 0) {   // weights of both branches: {mu0 hi, mu0 lo, mu1 hi, mu1 lo, lv0 hi, lv0 lo, lv1 hi, lv1 lo}
+          uint32_t w[4];
+          const float dv[4] = {g.do_mu[0], g.do_mu[1], g.do_lv[0], g.do_lv[1]};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t hi = umma::pack_bf16(dv[i], 0.f) & 0xffffu;
+            const float lo = dv[i] - __uint_as_float(hi << 16);
+            w[i] = umma::pack_bf16(0.f, lo) | hi;
+          }
+          *reinterpret_cast<uint4*>(s.X + umma::sw128_offset(row, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
       umma::mbar_wait(&s.c.bar_mma, phase);
       phase ^= 1;

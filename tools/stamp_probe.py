@@ -47,6 +47,14 @@ def main():
     print("order check (ns, relative): fwd last start %.0f; P1 last start %.0f end %.0f; P2 last start %.0f end %.0f" % (
         0.0, g[1][g[1][:, 0] > 0][:, 0].min() - g[0][g[0][:, 0] > 0][:, 0].min(), g[1][:, 1].max() - g[0][g[0][:, 0] > 0][:, 0].min(),
         g[2][g[2][:, 0] > 0][:, 0].min() - g[0][g[0][:, 0] > 0][:, 0].min(), g[2][:, 1].max() - g[0][g[0][:, 0] > 0][:, 0].min()))
+    # launch-boundary latency: pass 1's last CTA end (globaltimer) -> pass 2's CTAs leaving griddepcontrol.wait
+    p1_end = st[1][:, 15][st[1][:, 15] > 0].double().max()
+    w = st[2][:, 13][st[2][:, 13] > 0].double()
+    p2_end = st[2][:, 15][st[2][:, 15] > 0].double()
+    print("boundary P1 -> P2: last P1 CTA end -> pdl_wait return in P2 CTAs: min %.2f us mean %.2f us max %.2f us; "
+          "pdl_wait return -> CTA end: mean %.2f us max %.2f us; last P1 end -> last P2 end %.2f us" % (
+              (w.min() - p1_end) / 1e3, (w.mean() - p1_end) / 1e3, (w.max() - p1_end) / 1e3,
+              (p2_end - w).mean() / 1e3, (p2_end - w).max() / 1e3, (p2_end.max() - p1_end) / 1e3))
     for cls in range(3):
         names = NAMES[cls]
         s = st[cls]
