@@ -533,3 +533,38 @@ def test_backward_pass2_two_tile_form_equals_one_tile_form(mods, cuda, native_li
         tol, tol_prm = (2e-2, 5e-2) if precision == "bf16" else (5e-3, 3e-2)
         assert rel(a[0], b[0]) < tol and rel(a[1], b[1]) < tol and rel(a[2], b[2]) < 0.15, (B, N)
         assert errs[0][0] < tol_prm, errs[:4]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16x3", 1e-4), ("bf16", 2e-2)])
+def test_full_size_round_trip_and_logdet_consistency(mods, cuda, precision, tol):
+    """BASELINE size (chair config: 63 layers, G = 128, 32 x 2048 points), eval mode, properties that need no
+    oracle: sampling followed by the inverse pass returns the input (every layer is an invertible affine map
+    conditioned on coordinates it leaves untouched up to the sqrt(1+eps) scale), both passes report the same
+    per-layer mu / logvar, kept channels carry exactly zero mu / logvar, and the per-point log-det is finite and
+    bounded by the softsign range (|logvar| < 1 per warped channel)."""
+    _, decoders = mods
+    torch.manual_seed(4)
+    m = decoders.LocalCondRNVPDecoder(21, 64, 128).to(cuda)
+    with torch.no_grad():                       # move the flow away from its near-identity initialisation
+        for k, v in m.named_views().items():
+            if k.endswith("sd2.weight"):
+                v.normal_(std=0.2)
+    m.precision = precision
+    m.eval()
+    gen = torch.Generator().manual_seed(5)
+    z = torch.randn((32, 3, 2048), generator=gen).to(cuda)
+    g = torch.randn((32, 128), generator=gen).to(cuda)
+    with torch.no_grad():
+        ys, mus_d, lvs_d = m(z, g, mode="direct")
+        xs, mus_i, lvs_i = m(ys[-1], g, mode="inverse")
+    assert torch.isfinite(ys.stacked).all() and torch.isfinite(xs.stacked).all()
+    assert rel(xs[0], z) < tol, rel(xs[0], z)                                  # round trip through 63 layers
+    assert rel(lvs_i.stacked, lvs_d.stacked) < max(tol, 1e-4) and rel(mus_i.stacked, mus_d.stacked) < max(tol, 1e-4)
+    # intermediate states agree too: inverse output of layer l+1 == direct output of layer l
+    assert rel(xs.stacked[1:], ys.stacked[:-1]) < tol
+    lv = lvs_d.stacked
+    assert (lv.abs() < 1.0).all()
+    zero_rows = (lv == 0).all(dim=3).all(dim=1)                                 # (L, 3): kept channels of each layer
+    from oracle import flow_oracle as fo
+    assert int(zero_rows.sum()) == sum(3 - len(warp) for _, warp in fo.decoder_layer_names(21))   # 96 kept rows
+    assert float(lv.sum(dim=(0, 2)).abs().max()) < 63 * 2
