@@ -421,6 +421,22 @@ def extras(model, dev, B, N, pk, flush):
                               "frac": pairs * (2 * N * 12 + 4) / 1e9 / pk["hbm_gbs"]},
                       "fp32_issue": {"achieved_dist_evals_per_s": 2 * pairs * N * N, "bound": fp32_issue_peak,
                                      "frac": 2 * pairs * N * N / fp32_issue_peak}}
+    # approximate EMD, fused all-pairs cost (match never materialised): MUFU(ex2)-bound, 27 sweeps x N^2 exps per pair
+    from dpf_nets_b200.ops import pairwise_emd
+    Se = 64
+    pairwise_emd(A[:8].contiguous(), Bc[:8].contiguous())
+    ts = []
+    for _ in range(2):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); pairwise_emd(A[:Se].contiguous(), Bc[:Se].contiguous()); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    sec = sum(ts) / len(ts) * 1e-3
+    epairs = Se * Se / sec
+    mufu_peak = 148 * 16 * 1.965e9                          # ex2 results/s, assuming 16 MUFU lanes per SM (4 per sub-partition)
+    out["emd"] = {"value": epairs, "unit": "cloud-pair approximate-EMD evals/s", "clouds": "%dx%d of %d points" % (Se, Se, N),
+                  "exp_per_pair": 27 * N * N, "mufu": {"achieved_ex2_per_s": epairs * 27 * N * N, "bound_assumed": mufu_peak,
+                                                        "frac": epairs * 27 * N * N / mufu_peak}}
     return out
 
 
