@@ -436,7 +436,9 @@ def extras(model, dev, B, N, pk, flush):
     mufu_peak = 148 * 16 * 1.965e9                          # ex2 results/s, assuming 16 MUFU lanes per SM (4 per sub-partition)
     out["emd"] = {"value": epairs, "unit": "cloud-pair approximate-EMD evals/s", "clouds": "%dx%d of %d points" % (Se, Se, N),
                   "exp_per_pair": 27 * N * N, "mufu": {"achieved_ex2_per_s": epairs * 27 * N * N, "bound_assumed": mufu_peak,
-                                                        "frac": epairs * 27 * N * N / mufu_peak}}
+                                                        "frac": epairs * 27 * N * N / mufu_peak,
+                                                        "executed_mufu_per_pair": 36 * N * N,   # + 9 N^2 rsqrt of the fused cost
+                                                        "frac_executed": epairs * 36 * N * N / mufu_peak}}
     return out
 
 

@@ -18,8 +18,14 @@ namespace {
 constexpr int EMD_THREADS = 512;
 constexpr int EMD_TILE = 1024;   // points staged per shared-memory tile (float4: x, y, z, weight)
 
-__device__ __forceinline__ float emd_w(float level, float x1, float y1, float z1, float x2, float y2, float z2) {
-  return __expf(level * ((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1)));
+// exp(level * d) as ONE multiply + MUFU.EX2: `level2` = level * log2(e) is folded on the caller's side (the reference's
+// __expf(level * d) is ex2.approx((level * d) * log2e): one more multiply, argument rounded once more - the two differ
+// by <= 1 ulp of an argument of magnitude < ~100 wherever the weight is not negligible, far inside the 1e-4 gate)
+__device__ __forceinline__ float emd_w(float level2, float x1, float y1, float z1, float x2, float y2, float z2) {
+  const float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
+  float w;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(d * level2));
+  return w;
 }
 
 // One soft-assignment run for the cloud pair (p1[n], p2[m]).  remainL/ratioL [n], remainR/ratioR [m]
@@ -39,7 +45,7 @@ __device__ void approxmatch_pair(int n, int m, const float* __restrict__ p1, con
   for (int j = tid; j < m; j += EMD_THREADS) remainR[j] = multiR;
   __syncthreads();
   for (int j = 7; j > -2; j--) {
-    const float level = -powf(4.0f, j);
+    const float level = -powf(4.0f, j) * 1.4426950408889634f;   // level * log2(e), see emd_w
     // (1) ratioL[k] = remainL[k] / (1e-9 + sum_l exp(level d_kl) remainR[l])
     for (int k0 = 0; k0 < n; k0 += EMD_THREADS) {
       const int k = k0 + tid;
@@ -106,7 +112,8 @@ __device__ void approxmatch_pair(int n, int m, const float* __restrict__ p1, con
             if (MATCH) match[(size_t)(l0 + l) * n + k] += w;
             if (COST) {
               const float dx = q.x - x1, dy = q.y - y1, dz = q.z - z1;
-              cost = fmaf(w, sqrtf(dx * dx + dy * dy + dz * dz), cost);
+              const float d2 = dx * dx + dy * dy + dz * dz;
+              cost = fmaf(w, d2 * rsqrtf(fmaxf(d2, 1e-30f)), cost);   // |x1 - x2| without the IEEE sqrt sequence
             }
             suml += w;
           }
