@@ -1,4 +1,4 @@
-"""Quick GPU probe: time our Chamfer kernels against the reference CUDA kernel (oracle/_ref)."""
+"""Quick GPU probe: timing of our Chamfer kernels (the comparison with the reference kernel lives in tests/test_chamfer_gpu.py)."""
 import json
 import os
 import sys
@@ -40,15 +40,6 @@ def main():
     t = ev_time(lambda: B.NNDistance(A, Bc))
     res["nndistance_b%d_s" % S] = t
     res["nndistance_pairs_per_s"] = S / t
-    if "--ref" in sys.argv:
-        from oracle.structural import RefCuda
-        ref = RefCuda()
-        t = ev_time(lambda: ref.nndistance(A, Bc))
-        res["ref_nndistance_b%d_s" % S] = t
-        Sr = min(S, 64)
-        t = ev_time(lambda: ref.pairwise_cd(A[:Sr], Bc[:Sr]), reps=2)
-        res["ref_pairwise_loop_S%d_s" % Sr] = t
-        res["ref_pairs_per_s"] = Sr * Sr / t
     print(json.dumps(res))
 
 
