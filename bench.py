@@ -126,19 +126,20 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port (CPU restatement of the reference algorithm)
 # --------------------------------------------------------------------------------------------
-def oracle_train_step_factory(B, N, rank=0):
+def oracle_train_step_factory(B, N, rank=0, device="cpu"):
     """Builds the oracle decoder (reference init through our module's reference-faithful
-    initialiser, same state_dict layout) and returns step() -> loss running fwd+bwd on CPU."""
+    initialiser, same state_dict layout) and returns step() -> loss running fwd+bwd on `device`
+    (bench.py itself only uses the CPU; tests/test_decoder_gpu.py also times the port on the GPU)."""
     from oracle import flow_oracle as fo
     from dpf_nets_b200.lib.networks._arena import ArenaLayout, init_arena, init_stats
     specs = fo.decoder_layer_names(N_FLOWS)
     lay = ArenaLayout(specs, G_LATENT)
     torch.manual_seed(0)
-    arena, stats = init_arena(lay, 0.01), init_stats(lay)
+    arena, stats = init_arena(lay, 0.01).to(device), init_stats(lay).to(device)
     arena.requires_grad_(True)
     layers = []
     for pre, warp in specs:
-        P = {"eps": torch.tensor([1e-6])}
+        P = {"eps": torch.tensor([1e-6], device=device)}
         for key, (off, shape) in lay.param_index.items():
             if key.startswith(pre):
                 n = 1
@@ -150,6 +151,7 @@ def oracle_train_step_factory(B, N, rank=0):
                 P[key[len(pre):]] = stats[off:off + 64]
         layers.append((P, warp))
     p, g = synth_inputs(B, N, G_LATENT, rank)
+    p, g = p.to(device), g.to(device)
     g.requires_grad_(True)
     base_mu, base_lv = torch.zeros_like(p), torch.full_like(p, BASE_LOGVAR)
 
