@@ -153,7 +153,7 @@ def test_graphed_train_step_matches_eager(native_lib, cuda, monkeypatch):
     print("losses eager", le, "graphed", lg, "update cosine: eager-eager2 %.4f, eager-graphed %.4f" % (floor, got))
     for a, b, c in zip(le, lg, l2):
         assert abs(a - b) <= 2e-3 * abs(a) + 3 * abs(a - c)
-    assert got > floor - 0.03 and got > 0.9
+    assert got > floor - 0.06 and got > 0.9
     assert abs(float(runs["eager"][1].norm()) - float(runs["graphed"][1].norm())) < 0.03 * float(runs["eager"][1].norm())
     for k, v in runs["eager"][2].items():
         assert torch.equal(v, runs["graphed"][2][k]), k
