@@ -143,13 +143,14 @@ __device__ inline void fold_bn_a(const CouplingArgs& a, const BranchLayout& lay,
   float mean, var;
   if (a.training) {
     const double M = (double)a.B * (double)a.N;
-    const double m0 = a.mom_in[a.keep0] / M;
-    const double v00 = a.mom_in[mom2_index(a.keep0, a.keep0)] / M - m0 * m0;
+    const double rM = 1.0 / M;        // one double-precision division instead of five (this runs in every CTA's prologue)
+    const double m0 = a.mom_in[a.keep0] * rM;
+    const double v00 = a.mom_in[mom2_index(a.keep0, a.keep0)] * rM - m0 * m0;
     double dm = (double)w0 * m0, dv = (double)w0 * w0 * v00;
     if (a.k == 2) {
-      const double m1 = a.mom_in[a.keep1] / M;
-      const double v11 = a.mom_in[mom2_index(a.keep1, a.keep1)] / M - m1 * m1;
-      const double v01 = a.mom_in[mom2_index(a.keep0, a.keep1)] / M - m0 * m1;
+      const double m1 = a.mom_in[a.keep1] * rM;
+      const double v11 = a.mom_in[mom2_index(a.keep1, a.keep1)] * rM - m1 * m1;
+      const double v01 = a.mom_in[mom2_index(a.keep0, a.keep1)] * rM - m0 * m1;
       dm += (double)w1 * m1;
       dv += (double)w1 * w1 * v11 + 2.0 * (double)w0 * w1 * v01;
     }
@@ -209,13 +210,14 @@ __device__ inline BnA bn_a_of(const float* prm_layer, const float* stat_layer, c
   o.gamma = prm[lay.bnA_w + c];
   float var;
   if (training) {
-    const double m0 = mom[keep0] / M;
-    const double v00 = mom[mom2_index(keep0, keep0)] / M - m0 * m0;
+    const double rM = 1.0 / M;        // same arithmetic as fold_bn_a (identical mean / istd)
+    const double m0 = mom[keep0] * rM;
+    const double v00 = mom[mom2_index(keep0, keep0)] * rM - m0 * m0;
     double dm = (double)o.w0 * m0, dv = (double)o.w0 * o.w0 * v00;
     if (k == 2) {
-      const double m1 = mom[keep1] / M;
-      const double v11 = mom[mom2_index(keep1, keep1)] / M - m1 * m1;
-      const double v01 = mom[mom2_index(keep0, keep1)] / M - m0 * m1;
+      const double m1 = mom[keep1] * rM;
+      const double v11 = mom[mom2_index(keep1, keep1)] * rM - m1 * m1;
+      const double v01 = mom[mom2_index(keep0, keep1)] * rM - m0 * m1;
       dm += (double)o.w1 * m1;
       dv += (double)o.w1 * o.w1 * v11 + 2.0 * (double)o.w0 * o.w1 * v01;
     }
