@@ -11,7 +11,8 @@
 //
 // Layout: clouds are (batch, points, 3) fp32 contiguous.  Targets are staged in shared
 // memory as float4 so that one broadcast LDS.128 feeds R register-resident queries; the
-// kernels are FP32-issue-bound (7-9 issue slots per point pair), not HBM-bound.
+// kernels are FP32-issue-bound, not HBM-bound; pairs of queries are evaluated with packed fp32x2 instructions
+// (FADD2 / FMUL2 / FFMA2 + FMNMX: ~4 issue slots per point pair instead of 7).
 #include "common.cuh"
 #include <math_constants.h>
 
@@ -24,6 +25,39 @@ __device__ __forceinline__ float sqdist(float4 t, float qx, float qy, float qz) 
   const float dy = __fsub_rn(t.y, qy);
   const float dz = __fsub_rn(t.z, qz);
   return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// Packed fp32x2 form (sm_100a FADD2 / FMUL2 / FFMA2: two IEEE fp32 lanes per instruction, each rounded exactly like
+// the scalar instruction, so the arithmetic contract above is unchanged): one target against TWO register-resident
+// queries in 6 issue slots instead of 12.  The target coordinate enters as the scalar-broadcast operand.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// d(t, q0), d(t, q1) for the packed query pair (qx2, qy2, qz2)
+__device__ __forceinline__ void sqdist2(float4 t, f32x2 qx2, f32x2 qy2, f32x2 qz2, float& d0, float& d1) {
+  const f32x2 dx = sub2(pack2(t.x, t.x), qx2);
+  const f32x2 dy = sub2(pack2(t.y, t.y), qy2);
+  const f32x2 dz = sub2(pack2(t.z, t.z), qz2);
+  unpack2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), d0, d1);
 }
 
 // Cooperative AoS(xyz) -> float4 tile load; reads are fully coalesced over the flat float array.
@@ -70,15 +104,42 @@ nn_search_kernel(int nq, const float* __restrict__ Q, int nt, const float* __res
     __syncthreads();
     load_tile<THREADS>(tile, t + (size_t)t0 * 3, cnt);
     __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < cnt; ++k) {
-      const float4 p = tile[k];
+    if (R % 2 == 0) {      // packed pairs of queries
+      f32x2 qx2[(R + 1) / 2], qy2[(R + 1) / 2], qz2[(R + 1) / 2];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float d = sqdist(p, qx[r], qy[r], qz[r]);
-        if (d < best[r]) {
-          best[r] = d;
-          besti[r] = t0 + k;
+      for (int r = 0; r + 1 < R; r += 2) {
+        qx2[r / 2] = pack2(qx[r], qx[r + 1]);
+        qy2[r / 2] = pack2(qy[r], qy[r + 1]);
+        qz2[r / 2] = pack2(qz[r], qz[r + 1]);
+      }
+#pragma unroll 4
+      for (int k = 0; k < cnt; ++k) {
+        const float4 p = tile[k];
+#pragma unroll
+        for (int r = 0; r + 1 < R; r += 2) {
+          float d0, d1;
+          sqdist2(p, qx2[r / 2], qy2[r / 2], qz2[r / 2], d0, d1);
+          if (d0 < best[r]) {
+            best[r] = d0;
+            besti[r] = t0 + k;
+          }
+          if (d1 < best[r + 1]) {
+            best[r + 1] = d1;
+            besti[r + 1] = t0 + k;
+          }
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int k = 0; k < cnt; ++k) {
+        const float4 p = tile[k];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float d = sqdist(p, qx[r], qy[r], qz[r]);
+          if (d < best[r]) {
+            best[r] = d;
+            besti[r] = t0 + k;
+          }
         }
       }
     }
@@ -119,11 +180,32 @@ __device__ __forceinline__ float one_direction_sum(float4* tile, const float* __
       __syncthreads();
       load_tile<THREADS>(tile, t + (size_t)t0 * 3, cnt);
       __syncthreads();
-#pragma unroll 4
-      for (int k = 0; k < cnt; ++k) {
-        const float4 p = tile[k];
+      if (R % 2 == 0) {    // packed pairs of queries
+        f32x2 qx2[(R + 1) / 2], qy2[(R + 1) / 2], qz2[(R + 1) / 2];
 #pragma unroll
-        for (int r = 0; r < R; ++r) best[r] = fminf(best[r], sqdist(p, qx[r], qy[r], qz[r]));
+        for (int r = 0; r + 1 < R; r += 2) {
+          qx2[r / 2] = pack2(qx[r], qx[r + 1]);
+          qy2[r / 2] = pack2(qy[r], qy[r + 1]);
+          qz2[r / 2] = pack2(qz[r], qz[r + 1]);
+        }
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+          const float4 p = tile[k];
+#pragma unroll
+          for (int r = 0; r + 1 < R; r += 2) {
+            float d0, d1;
+            sqdist2(p, qx2[r / 2], qy2[r / 2], qz2[r / 2], d0, d1);
+            best[r] = fminf(best[r], d0);
+            best[r + 1] = fminf(best[r + 1], d1);
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+          const float4 p = tile[k];
+#pragma unroll
+          for (int r = 0; r < R; ++r) best[r] = fminf(best[r], sqdist(p, qx[r], qy[r], qz[r]));
+        }
       }
     }
 #pragma unroll
