@@ -28,6 +28,65 @@ __device__ __forceinline__ float emd_w(float level2, float x1, float y1, float z
   return w;
 }
 
+// Packed fp32x2 evaluation (FADD2 / FMUL2 / FFMA2 of sm_100a, per-lane IEEE rounding): one register-resident point
+// against TWO staged points per instruction.  The staged tile holds point pairs as
+//   buf[2i] = {x_a, x_b, y_a, y_b},  buf[2i+1] = {z_a, z_b, w_a, w_b}      (a = point 2i, b = point 2i+1 of the tile)
+// so that every packed operand is an aligned register pair of one LDS.128.  An odd tail is padded with a zero-weight
+// point.  The sums over staged points stay sequential in ascending index (a, then b) like the reference's loops.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 emd_pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void emd_unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 emd_sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 emd_mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 emd_fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float emd_ex2(float x) {
+  float w;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(x));
+  return w;
+}
+// squared distances of the staged pair (A, B) to the point (x1, y1, z1), and exp(level * d) of both
+__device__ __forceinline__ void emd_pair(float4 A, float4 B, float x1, float y1, float z1, float level2, float& d_a, float& d_b,
+                                         float& e_a, float& e_b) {
+  const f32x2 dx = emd_sub2(emd_pack2(A.x, A.y), emd_pack2(x1, x1));
+  const f32x2 dy = emd_sub2(emd_pack2(A.z, A.w), emd_pack2(y1, y1));
+  const f32x2 dz = emd_sub2(emd_pack2(B.x, B.y), emd_pack2(z1, z1));
+  const f32x2 d = emd_fma2(dz, dz, emd_fma2(dy, dy, emd_mul2(dx, dx)));
+  float a0, a1;
+  emd_unpack2(emd_mul2(d, emd_pack2(level2, level2)), a0, a1);
+  emd_unpack2(d, d_a, d_b);
+  e_a = emd_ex2(a0);
+  e_b = emd_ex2(a1);
+}
+// stage `cnt` points (xyz of src + weight) in the pair layout, zero-weight padding up to an even count
+__device__ __forceinline__ void emd_stage(float4* buf, const float* __restrict__ src, const float* wsrc, int cnt) {
+  float* fb = reinterpret_cast<float*>(buf);
+  const int padded = (cnt + 1) & ~1;
+  for (int l = threadIdx.x; l < padded; l += EMD_THREADS) {
+    const bool ok = l < cnt;
+    const int base = (l >> 1) * 8 + (l & 1);
+    fb[base + 0] = ok ? src[l * 3 + 0] : 0.f;
+    fb[base + 2] = ok ? src[l * 3 + 1] : 0.f;
+    fb[base + 4] = ok ? src[l * 3 + 2] : 0.f;
+    fb[base + 6] = ok ? wsrc[l] : 0.f;
+  }
+}
+
 // One soft-assignment run for the cloud pair (p1[n], p2[m]).  remainL/ratioL [n], remainR/ratioR [m]
 // live in shared memory.  MATCH: accumulate into match (m, n) like the reference.  COST: accumulate
 // sum w * dist into the per-thread `cost`.
@@ -54,13 +113,14 @@ __device__ void approxmatch_pair(int n, int m, const float* __restrict__ p1, con
       float suml = 1e-9f;
       for (int l0 = 0; l0 < m; l0 += EMD_TILE) {
         const int lend = min(m, l0 + EMD_TILE) - l0;
-        for (int l = tid; l < lend; l += EMD_THREADS)
-          buf[l] = make_float4(p2[(l0 + l) * 3 + 0], p2[(l0 + l) * 3 + 1], p2[(l0 + l) * 3 + 2], remainR[l0 + l]);
+        emd_stage(buf, p2 + (size_t)l0 * 3, remainR + l0, lend);
         __syncthreads();
-        for (int l = 0; l < lend; l++) {
-          const float4 q = buf[l];
-          const float w = emd_w(level, x1, y1, z1, q.x, q.y, q.z) * q.w;
-          suml += w;
+        for (int pi = 0; pi < (lend + 1) / 2; pi++) {
+          const float4 A = buf[2 * pi], Bq = buf[2 * pi + 1];
+          float da, db, ea, eb;
+          emd_pair(A, Bq, x1, y1, z1, level, da, db, ea, eb);
+          suml += ea * Bq.z;
+          suml += eb * Bq.w;
         }
         __syncthreads();
       }
@@ -75,13 +135,14 @@ __device__ void approxmatch_pair(int n, int m, const float* __restrict__ p1, con
       float sumr = 0;
       for (int k0 = 0; k0 < n; k0 += EMD_TILE) {
         const int kend = min(n, k0 + EMD_TILE) - k0;
-        for (int k = tid; k < kend; k += EMD_THREADS)
-          buf[k] = make_float4(p1[(k0 + k) * 3 + 0], p1[(k0 + k) * 3 + 1], p1[(k0 + k) * 3 + 2], ratioL[k0 + k]);
+        emd_stage(buf, p1 + (size_t)k0 * 3, ratioL + k0, kend);
         __syncthreads();
-        for (int k = 0; k < kend; k++) {
-          const float4 q = buf[k];
-          const float w = emd_w(level, q.x, q.y, q.z, x2, y2, z2) * q.w;
-          sumr += w;
+        for (int pi = 0; pi < (kend + 1) / 2; pi++) {
+          const float4 A = buf[2 * pi], Bq = buf[2 * pi + 1];
+          float da, db, ea, eb;
+          emd_pair(A, Bq, x2, y2, z2, level, da, db, ea, eb);
+          sumr += ea * Bq.z;
+          sumr += eb * Bq.w;
         }
         __syncthreads();
       }
@@ -102,20 +163,24 @@ __device__ void approxmatch_pair(int n, int m, const float* __restrict__ p1, con
       const float rl = (k < n) ? ratioL[k] : 0.f;
       for (int l0 = 0; l0 < m; l0 += EMD_TILE) {
         const int lend = min(m, l0 + EMD_TILE) - l0;
-        for (int l = tid; l < lend; l += EMD_THREADS)
-          buf[l] = make_float4(p2[(l0 + l) * 3 + 0], p2[(l0 + l) * 3 + 1], p2[(l0 + l) * 3 + 2], ratioR[l0 + l]);
+        emd_stage(buf, p2 + (size_t)l0 * 3, ratioR + l0, lend);
         __syncthreads();
         if (k < n) {
-          for (int l = 0; l < lend; l++) {
-            const float4 q = buf[l];
-            const float w = emd_w(level, x1, y1, z1, q.x, q.y, q.z) * rl * q.w;
-            if (MATCH) match[(size_t)(l0 + l) * n + k] += w;
-            if (COST) {
-              const float dx = q.x - x1, dy = q.y - y1, dz = q.z - z1;
-              const float d2 = dx * dx + dy * dy + dz * dz;
-              cost = fmaf(w, d2 * rsqrtf(fmaxf(d2, 1e-30f)), cost);   // |x1 - x2| without the IEEE sqrt sequence
+          for (int pi = 0; pi < (lend + 1) / 2; pi++) {
+            const float4 A = buf[2 * pi], Bq = buf[2 * pi + 1];
+            float da, db, ea, eb;
+            emd_pair(A, Bq, x1, y1, z1, level, da, db, ea, eb);
+            const float wa = ea * rl * Bq.z, wb = eb * rl * Bq.w;
+            if (MATCH) {
+              match[(size_t)(l0 + 2 * pi) * n + k] += wa;
+              if (2 * pi + 1 < lend) match[(size_t)(l0 + 2 * pi + 1) * n + k] += wb;
             }
-            suml += w;
+            if (COST) {   // |x1 - x2| = d * rsqrt(d) without the IEEE sqrt sequence
+              cost = fmaf(wa, da * rsqrtf(fmaxf(da, 1e-30f)), cost);
+              cost = fmaf(wb, db * rsqrtf(fmaxf(db, 1e-30f)), cost);
+            }
+            suml += wa;
+            suml += wb;
           }
         }
         __syncthreads();
