@@ -675,9 +675,10 @@ struct TcP2Half {
 struct TcP2Smem4 {
   unsigned char W[2 * N_IMG * IMG_W];   // [br][W1 hi, W1 lo, W1^T hi]
   TcP2Half h[2];
-  float4 A0[2][F];                      // folded BN_a: {A00, A01, c0, -}
-  float4 epi[2][2][F];                  // [half][br][c]: {S, T, W2_0, W2_1},  a = S*acc + T
-  float4 epi2[2][2][F];                 // [half][br][c]: {c1, c2, c3, -},  dh2pre = c1*da - c2 - c3*acc
+  // tables in CHANNEL-PAIR layout (a = channel 2j, b = channel 2j+1) for the packed fp32x2 epilogue math
+  float4 PA[2][F / 2][2];               // [br][j]: {A00_a, A00_b, c0_a, c0_b}, {A01_a, A01_b, -, -}   (folded BN_a)
+  float4 PE[2][2][F / 2][3];            // [half][br][j]: {S_a, S_b, T_a, T_b}, {W20_a, W20_b, W21_a, W21_b}, {-c3_a, -c3_b, -c2_a, -c2_b}
+                                        //   a = S*acc + T ;  dh2pre = S*da - c2 - c3*acc
   float4 lt0[2][F];                     // per channel: {bnB istd, bnB mean, c2, c3}
   float2 lt1[2][F];                     // per channel: {W2_0, W2_1}
   float pend[8];
@@ -809,7 +810,14 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
         c3 = t1.x * t1.x * m2;
         c2 = t1.x * m1 - c3 * t0.w;
       }
-      s.A0[tid >> 6][tid & 63] = make_float4(t0.x, t0.y, t0.z, 0.f);
+      {
+        float* pa = reinterpret_cast<float*>(&s.PA[tid >> 6][(tid & 63) >> 1][0]);
+        const int ln = tid & 1;
+        pa[ln] = t0.x;        // A00
+        pa[2 + ln] = t0.z;    // c0
+        pa[4 + ln] = t0.y;    // A01
+        pa[6 + ln] = 0.f;
+      }
       s.lt0[tid >> 6][tid & 63] = make_float4(t1.x, t0.w, c2, c3);
       s.lt1[tid >> 6][tid & 63] = make_float2(t1.y, t1.z);
     } else if (tid < 128 + 5) {
@@ -836,13 +844,20 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
         const float4 l0 = s.lt0[br][c];
         const float2 l1 = s.lt1[br][c];
         const float S = sc * l0.x;
-        s.epi[half][br][c] = make_float4(S, fmaf(-S, l0.y, sh), l1.x, l1.y);
-        s.epi2[half][br][c] = make_float4(S, l0.z, l0.w, 0.f);
+        float* pe = reinterpret_cast<float*>(&s.PE[half][br][c >> 1][0]);
+        const int ln = c & 1;
+        pe[ln] = S;
+        pe[2 + ln] = fmaf(-S, l0.y, sh);
+        pe[4 + ln] = l1.x;
+        pe[6 + ln] = l1.y;
+        pe[8 + ln] = -l0.w;     // -c3
+        pe[10 + ln] = -l0.z;    // -c2
       }
       const Pending P{s.pend[0], s.pend[1], s.pend[2], s.pend[3], s.pend[4]};
       const TcPoint g = tc_finish_point<MODE>(a, P, it == 0 ? raw0 : tc_load_raw(a, b, n, valid), valid);
       const float xk0 = pick3(g.x, a.f.keep0);
       const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
+      const f32x2 xk0_2 = f2_pack(xk0, xk0), xk1_2 = f2_pack(xk1, xk1);
       if (it == 0) DPF_STAMP(2, 4);
       // ---- stage 0: h1 hi -> H, lo -> D (the previous tile's BN_a-sum UMMAs still read D / X: wait for them) ----
       if (it > 0) {
@@ -857,9 +872,14 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
           uint32_t w[4], wl[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 Aa = s.A0[br][q * 8 + 2 * i], Ab = s.A0[br][q * 8 + 2 * i + 1];
-            float va = fmaf(Aa.x, xk0, Aa.z), vb = fmaf(Ab.x, xk0, Ab.z);
-            if (K == 2) { va = fmaf(Aa.y, xk1, va); vb = fmaf(Ab.y, xk1, vb); }
+            const float4 P0 = s.PA[br][q * 4 + i][0];
+            f32x2 v2 = f2_fma(f2_pack(P0.x, P0.y), xk0_2, f2_pack(P0.z, P0.w));
+            if (K == 2) {
+              const float4 P1 = s.PA[br][q * 4 + i][1];
+              v2 = f2_fma(f2_pack(P1.x, P1.y), xk1_2, v2);
+            }
+            float va, vb;
+            f2_unpack(v2, va, vb);
             va = fmaxf(va, 0.f);
             vb = fmaxf(vb, 0.f);
             w[i] = umma::pack_bf16(va, vb);
@@ -882,29 +902,34 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
       for (int br = 0; br < 2; ++br) {
         const float d0 = br == 0 ? g.do_mu[0] : g.do_lv[0];
         const float d1 = br == 0 ? g.do_mu[1] : g.do_lv[1];
+        const f32x2 d0_2 = f2_pack(d0, d0), d1_2 = f2_pack(d1, d1);
 #pragma unroll 1
         for (int hc = 0; hc < 2; ++hc) {     // 16 columns at a time (register pressure: 96 per thread)
           uint32_t r[16];
           umma::tmem_ld16_issue(T_F + lane_off + br * F + part * 32 + hc * 16, r);
           umma::tmem_ld_wait16(r);
-          float v[16];
+          uint32_t wv[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = part * 32 + hc * 16 + i;
-            const float acc = __uint_as_float(r[i]);
-            const float4 e = s.epi[half][br][c];
-            const float4 e2 = s.epi2[half][br][c];
-            const float av = fmaf(e.x, acc, e.y);
-            const float da = av > 0.f ? fmaf(e.z, d0, e.w * d1) : 0.f;
-            const float dh = fmaf(e2.x, da, -fmaf(e2.z, acc, e2.y));
-            v[i] = valid ? dh : 0.f;
+          for (int j = 0; j < 8; ++j) {      // channel pair (2j, 2j+1) of this chunk, packed fp32x2 math
+            const float4* pe = s.PE[half][br][part * 16 + hc * 8 + j];
+            const float4 E0 = pe[0], E1 = pe[1], E2 = pe[2];
+            const f32x2 S2 = f2_pack(E0.x, E0.y);
+            const f32x2 v2 = f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            const f32x2 av2 = f2_fma(S2, v2, f2_pack(E0.z, E0.w));
+            const f32x2 g2 = f2_fma(f2_pack(E1.x, E1.y), d0_2, f2_mul(f2_pack(E1.z, E1.w), d1_2));
+            float av0, av1, g0, g1;
+            f2_unpack(av2, av0, av1);
+            f2_unpack(g2, g0, g1);
+            const f32x2 da2 = f2_pack(av0 > 0.f ? g0 : 0.f, av1 > 0.f ? g1 : 0.f);
+            const f32x2 dh2 = f2_fma(S2, da2, f2_fma(f2_pack(E2.x, E2.y), v2, f2_pack(E2.z, E2.w)));
+            float h0, h1;
+            f2_unpack(dh2, h0, h1);
+            wv[j] = valid ? umma::pack_bf16(h0, h1) : 0u;
           }
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                        umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-            *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + hc * 2 + q)) = pk;
-          }
+          for (int q = 0; q < 2; ++q)
+            *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + hc * 2 + q)) =
+                make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
         }
       }
       umma::fence_async_smem();
@@ -916,7 +941,7 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
       umma::fence_after_sync();
       if (it == 0) DPF_STAMP(2, 8);
       // ---- stage 2: epilogue B: dz (bf16) -> D tiles, T1 = A0^T dz, per-point weight row -> X ----
-      float T1_0 = 0.f, T1_1 = 0.f;
+      f32x2 T1_0_2 = f2_pack(0.f, 0.f), T1_1_2 = f2_pack(0.f, 0.f);     // even / odd channel partial sums
 #pragma unroll 1
       for (int br = 0; br < 2; ++br) {
 #pragma unroll 1
@@ -924,24 +949,41 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
           uint32_t r[16];
           umma::tmem_ld16_issue(T_F + lane_off + br * F + part * 32 + hc * 16, r);
           umma::tmem_ld_wait16(r);
-          float v[16];
+          uint32_t wv[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 A = s.A0[br][part * 32 + hc * 16 + i];
-            float z = fmaf(A.x, xk0, A.z);
-            if (K == 2) z = fmaf(A.y, xk1, z);
-            const float dz = (z > 0.f && valid) ? __uint_as_float(r[i]) : 0.f;
-            T1_0 = fmaf(A.x, dz, T1_0);
-            if (K == 2) T1_1 = fmaf(A.y, dz, T1_1);
-            v[i] = dz;
+          for (int j = 0; j < 8; ++j) {
+            const float4* pa = s.PA[br][part * 16 + hc * 8 + j];
+            const float4 P0 = pa[0];
+            const f32x2 A00_2 = f2_pack(P0.x, P0.y);
+            f32x2 z2 = f2_fma(A00_2, xk0_2, f2_pack(P0.z, P0.w));
+            f32x2 A01_2 = 0;
+            if (K == 2) {
+              const float4 P1 = pa[1];
+              A01_2 = f2_pack(P1.x, P1.y);
+              z2 = f2_fma(A01_2, xk1_2, z2);
+            }
+            float z0, z1;
+            f2_unpack(z2, z0, z1);
+            const float dz0 = (z0 > 0.f && valid) ? __uint_as_float(r[2 * j]) : 0.f;
+            const float dz1 = (z1 > 0.f && valid) ? __uint_as_float(r[2 * j + 1]) : 0.f;
+            const f32x2 dz2 = f2_pack(dz0, dz1);
+            T1_0_2 = f2_fma(A00_2, dz2, T1_0_2);
+            if (K == 2) T1_1_2 = f2_fma(A01_2, dz2, T1_1_2);
+            wv[j] = umma::pack_bf16(dz0, dz1);
           }
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const uint4 pk = make_uint4(umma::pack_bf16(v[8 * q + 0], v[8 * q + 1]), umma::pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                        umma::pack_bf16(v[8 * q + 4], v[8 * q + 5]), umma::pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-            *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + hc * 2 + q)) = pk;
-          }
+          for (int q = 0; q < 2; ++q)
+            *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + hc * 2 + q)) =
+                make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
         }
+      }
+      float T1_0, T1_1;
+      {
+        float lo, hi;
+        f2_unpack(T1_0_2, lo, hi);
+        T1_0 = lo + hi;
+        f2_unpack(T1_1_2, lo, hi);
+        T1_1 = lo + hi;
       }
       if (part == 0) {
         const float one = valid ? 1.f : 0.f;

@@ -17,6 +17,26 @@ constexpr uint32_t IDESC_WGRAD = umma::make_idesc_bf16(128, 128, 1, 1);
 
 __device__ __forceinline__ float pick3(const float v[3], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }
 
+// packed fp32x2 arithmetic of sm_100a (SASS FMUL2 / FFMA2): two IEEE fp32 lanes per instruction, each rounded like the
+// scalar instruction - used for the per-channel-pair epilogue math
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // forward UMMA chain of ONE branch into TMEM columns [tcol, tcol+64): K = 64 in 4 steps,
 // SPLIT: hi*hi + lo*hi + hi*lo
 template <bool SPLIT>
