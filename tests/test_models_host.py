@@ -89,3 +89,26 @@ def test_custom_adam_and_lr_updater_vs_reference():
     assert opt.param_groups[0]["lr"] == pytest.approx(fx["lr"])
     assert list(opt.param_groups[0]["betas"]) == pytest.approx(fx["betas"])
     assert set(opt.state[w].keys()) == {"step", "exp_avg", "exp_avg_sq", "max_exp_avg_sq"}
+
+
+def test_capturable_adam_hyper_table_matches_eager_formulas():
+    """Host side of the graph-replayable Adam (optimizers.Adam.prepare_replay / _hyper_row): the row written to the pinned
+    table for step t must hold exactly the scalars the eager path passes by value - lr, betas, eps, wd, 1 - beta1^t and
+    sqrt(1 - beta2^t) (reference optimizers.py:53-66) - also after a learning-rate / beta2 change by LRUpdater."""
+    import math
+    from dpf_nets_b200.lib.networks.optimizers import Adam, LRUpdater
+    p = torch.nn.Parameter(torch.randn(5))
+    opt = Adam([p], lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-6, amsgrad=True)
+    for _ in range(3):                       # eager CPU steps create the state and advance the counter
+        p.grad = torch.randn(5)
+        opt.step()
+    assert opt.state[p]['step'] == 3
+    sched = LRUpdater(10, cycle_length=2, min_lr=1e-4, max_lr=1e-3, beta1=0.9, min_beta2=0.9, max_beta2=0.99)
+    sched(opt, 0, 7)
+    group = opt.param_groups[0]
+    opt._hyper_host = torch.zeros((1, 8))    # what enable_capture() allocates (pinned on a CUDA box)
+    opt.prepare_replay()                     # the host work of one replayed step
+    assert opt.state[p]['step'] == 4
+    b1, b2 = group['betas']
+    want = [group['lr'], b1, b2, 1e-8, 1e-6, 1 - b1 ** 4, math.sqrt(1 - b2 ** 4)]
+    assert torch.allclose(opt._hyper_host[0, :7], torch.tensor(want, dtype=torch.float32), rtol=1e-6, atol=0)
