@@ -35,8 +35,12 @@ def _dataset(config, part, svr, n_synth):
 def _loader(ds, config, train):
     rank, world = _dist.world()
     sampler = None
-    if world > 1:
-        sampler = torch.utils.data.distributed.DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=train and config['shuffle'])
+    if world > 1 and train:
+        sampler = torch.utils.data.distributed.DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=config['shuffle'])
+    elif world > 1:
+        # evaluation: contiguous un-padded shards (DistributedSampler pads with duplicates, which would enter the
+        # all-pairs metrics); evaluating.evaluate gathers the per-rank clouds back in dataset order
+        sampler = _dist.ShardSampler(len(ds), rank, world)
     return DataLoader(ds, batch_size=config['batch_size'], shuffle=(train and config['shuffle'] and sampler is None),
                       sampler=sampler, num_workers=0 if getattr(ds, 'n_shapes', None) else config['num_workers'],
                       pin_memory=True, drop_last=train)
@@ -135,4 +139,9 @@ def evaluate_main(argv=None):
         model.load_state_dict(torch.load(path, map_location=dev, weights_only=False)['model_state'])
         print('Model {} loaded.'.format(path))
     criterion = Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss(**config).to(dev)
+    rank, world = _dist.world()
+    if world > 1:
+        # 'generating' draws every cloud from the prior: ranks must not share a noise stream, or each of them
+        # would generate the same clouds and the gathered set would hold R copies of everything
+        torch.manual_seed(torch.initial_seed() + 7919 * rank)
     return evaluate(it, model, criterion, **config)

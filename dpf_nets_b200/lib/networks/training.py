@@ -1,7 +1,9 @@
 """Training epoch loop with the reference's signature and behaviour (lib/networks/training.py:10-87):
 NaN guard, stdout meters every `num_workers` iterations, checkpoint dict
 {'epoch','iter','model_state','optimizer_state'} every 100*num_workers iterations and at epoch end.
-Added: gradient averaging across ranks when torch.distributed is initialised (batch sharding)."""
+Added: gradient averaging across ranks when torch.distributed is initialised (batch sharding; the decoder
+arena's all-reduce overlaps the rest of the backward, dist.GradSync), a NaN guard that all ranks agree on, and
+rank-averaged BatchNorm buffers at every checkpoint."""
 import os
 from sys import stdout
 from time import time
@@ -23,22 +25,30 @@ def train(iterator, model, loss_func, optimizer, scheduler, epoch, iter, **kwarg
     dev = next(model.parameters()).device
 
     def checkpoint(ep, it):
+        _dist.average_buffers(model)      # per-rank BatchNorm running statistics -> their mean (all ranks call this)
         if rank == 0:
             os.makedirs(os.path.dirname(model_name), exist_ok=True)
             save_model({'epoch': ep, 'iter': it, 'model_state': model.state_dict(),
                         'optimizer_state': optimizer.state_dict()}, model_name)
 
     def nan_guard(loss):
-        if torch.isnan(loss.detach()):
+        # every rank takes the same decision (a rank that stopped alone would leave the others blocked in the
+        # next collective): one MAX all-reduce of the NaN flag when distributed
+        if _dist.any_rank(torch.isnan(loss.detach()), dev):
             print('Loss is NaN! Stopping without updating the net...')
             raise SystemExit(1)
+
+    sync = getattr(model, '_dpf_grad_sync', None)      # one set of hooks per model, reused across epochs
+    if sync is None:
+        sync = _dist.GradSync(model)
+        object.__setattr__(model, '_dpf_grad_sync', sync)
 
     graphed = None
     if kwargs.get('cuda_graph'):     # opt-in (not a reference key): the step as two CUDA graphs, _graphstep.py
         from ._graphstep import GraphedTrainStep
         graphed = getattr(model, '_dpf_graphed_step', None)      # one capture per model, reused across epochs
         if graphed is None or graphed.optimizer is not optimizer:
-            graphed = GraphedTrainStep(model, loss_func, optimizer, allreduce=lambda: _dist.allreduce_arena_grads(model))
+            graphed = GraphedTrainStep(model, loss_func, optimizer, allreduce=sync.finish)
             graphed.nan_guard = nan_guard
             object.__setattr__(model, '_dpf_graphed_step', graphed)
 
@@ -67,7 +77,7 @@ def train(iterator, model, loss_func, optimizer, scheduler, epoch, iter, **kwarg
         if graphed is None:
             optimizer.zero_grad()
             loss.backward()
-            _dist.allreduce_arena_grads(model)
+            sync.finish()
             optimizer.step()
         meters['time'].update(time() - end)
         if rank == 0 and (iter + i + 1) % num_workers == 0:

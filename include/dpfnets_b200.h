@@ -61,6 +61,23 @@ int dpf_pairwise_cd(int S1, int S2, int n, int m, const float* A, const float* B
 /* Mirrors the upper triangle of an (S,S) matrix into the lower one (after dpf_pairwise_cd symmetric). */
 int dpf_symmetrize_upper(float* M, int S, void* stream);
 
+/* Generation scores on the device-resident all-pairs matrices, one launch + a 3-number result instead of the
+ * reference's torch ops with host syncs — lib/networks/utils.py:120-121 (COV), :124-125 (MMD), :128-144 (KNN, k=1):
+ * gg (S1,S1), gt (S1,S2), tt (S2,S2) fp32 row-major, gg / tt full symmetric matrices.
+ * out[0] = COV(gt) = #distinct argmin_j gt[i,j] / S2;  out[1] = MMD(gt) = mean_j min_i gt[i,j];
+ * out[2] = leave-one-out 1-NN accuracy on [[gg, gt], [gt^T, tt]] (exact ties: lowest index).
+ * scratch: dpf_cd_scores_scratch_bytes() bytes of device memory. */
+int dpf_cd_scores_scratch_bytes(int S1, int S2, long long* bytes);
+int dpf_cd_scores(const float* gg, const float* gt, const float* tt, int S1, int S2, void* scratch, float* out,
+                  void* stream);
+
+/* Voxel-occupancy counts of get_voxel_occ_dist — lib/networks/utils.py:45-79 (the histogram behind JSD, :82-87):
+ * pts (n_points,3) fp32; edges: res+1 DEVICE doubles (the reference's -0.5 + arange(res+1)/res); a point is
+ * counted in cell (i,j,k) when edges[i] <= x < edges[i+1] holds for each coordinate, otherwise dropped.
+ * hist: res^3 uint64 counts, overwritten. */
+int dpf_voxel_hist(const float* pts, long long n_points, int res, const double* edges, unsigned long long* hist,
+                   void* stream);
+
 /* ---- Approximate EMD (soft auction, 9 levels) -----------------------------------------------
  * dpf_approxmatch replaces approxmatch() — src/approxmatch.cuh:6 (kernel approxmatch.cu:3-182, shim
  * structural_loss.cpp:22-37): xyz1 (b,n,3), xyz2 (b,m,3) -> match (b,m,n).  `temp` (b,2(n+m)) of the
