@@ -126,7 +126,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port (CPU restatement of the reference algorithm)
 # --------------------------------------------------------------------------------------------
-def oracle_train_step_factory(B, N, rank=0, device="cpu"):
+def oracle_train_step_factory(B, N, rank=0, device="cpu", return_state=False):
     """Builds the oracle decoder (reference init through our module's reference-faithful
     initialiser, same state_dict layout) and returns step() -> loss running fwd+bwd on `device`
     (bench.py itself only uses the CPU; tests/test_decoder_gpu.py also times the port on the GPU)."""
@@ -161,6 +161,9 @@ def oracle_train_step_factory(B, N, rank=0, device="cpu"):
         ps, mus, lvs = fo.decoder_forward(layers, p, g, "inverse", training=True)
         nll = fo.point_flow_nll(ps + [p], [base_mu] + mus, [base_lv] + lvs)
         nll.backward()
+        if return_state:     # tests/test_decoder_gpu.py: full-size outputs and gradients of the port
+            return float(nll.detach()), {"arena": arena.detach(), "z": ps[0].detach(), "sum_logvar": sum(lvs).detach(),
+                                         "darena": arena.grad.detach(), "dg": g.grad.detach()}
         return float(nll.detach())
     return step
 

@@ -11,6 +11,7 @@
 #define DPF_ERR_NULL_PTR (-2)
 #define DPF_ERR_UNSUPPORTED (-3)
 #define DPF_ERR_ALIGN (-4)
+#define DPF_ERR_BARRIER (-5)   /* a grid barrier of an earlier decoder pass timed out; that pass was aborted */
 
 void dpf_set_error(const char* fmt, ...);
 

@@ -108,9 +108,11 @@ __host__ inline DecoderWorkspace carve_workspace(void* base, int L, int G, int B
 // Per-launch arguments of the per-layer kernels (passed by value).
 struct CouplingArgs {
   const float* x;        // layer input (B,3,N)
-  float* y;              // outputs (B,3,N): transformed points, mu, logvar
+  float* y;              // outputs (B,3,N): transformed points, mu (nullable: not written), logvar
   float* mu;
   float* lv;
+  float* slv;            // nullable: running sum over the processed layers of logvar (B,3,N) - the per-point log-det the
+  int slv_init;          //   flow NLL consumes (losses.py:12-13); slv_init != 0 = first processed layer (store, not add)
   const float* prm;      // this layer's parameters (arena + param_off)
   float* stat;           // this layer's stats block (2 branches x 8 x F)
   const float* film;     // [4][B][F] of this layer
@@ -126,6 +128,22 @@ struct CouplingArgs {
 };
 
 __device__ __forceinline__ float softsign(float o) { return o / (1.f + fabsf(o)); }
+
+// outputs of one point of one layer: y, logvar always; mu and the running log-det sum when requested
+__device__ __forceinline__ void store_point_outputs(const CouplingArgs& a, size_t base, const float yv[3], const float muv[3],
+                                                    const float lvv[3]) {
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const size_t o = base + (size_t)ch * a.N;
+    a.y[o] = yv[ch];
+    if (a.mu) a.mu[o] = muv[ch];
+    a.lv[o] = lvv[ch];
+    if (a.slv) {
+      if (a.slv_init) a.slv[o] = lvv[ch];
+      else if (ch == a.warp0 || ch == a.warp1) a.slv[o] += lvv[ch];     // kept channels contribute exactly 0
+    }
+  }
+}
 
 // second-moment index of (i,j), i<=j, in the 9-vector layout [s0 s1 s2 xx xy xz yy yz zz]
 __device__ __forceinline__ int mom2_index(int i, int j) {

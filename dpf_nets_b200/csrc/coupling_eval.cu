@@ -69,7 +69,8 @@ eval_tables_kernel(const float* __restrict__ arena, const float* __restrict__ st
 
 struct EvalArgs {
   const float* p;                  // (B,3,N) input of the first processed layer
-  float* P; float* MU; float* LV;  // (L,B,3,N) list outputs, indexed by layer
+  float* P; float* MU; float* LV;  // (L,B,3,N) list outputs, indexed by layer (MU nullable: not written)
+  float* SLV;                      // nullable (B,3,N): sum over all layers of logvar, accumulated in registers
   const unsigned char* ltab;       // [L] EvalLayerTab
   const float4* epi;               // [L][B][2][F]
   const unsigned short* wimg;      // [L][2][N_IMG] weight images (pack_w1_kernel)
@@ -159,6 +160,7 @@ decoder_eval_tc_kernel(const EvalArgs a) {
     float xin[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) xin[ch] = valid ? a.p[pbase + (size_t)ch * a.N] : 0.f;
+    float slv[3] = {0.f, 0.f, 0.f};
 
     for (int q = 0; q < a.L; ++q, ++it) {
       const int l = MODE == 0 ? q : a.L - 1 - q;
@@ -245,7 +247,7 @@ decoder_eval_tc_kernel(const EvalArgs a) {
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
             a.P[obase + (size_t)ch * a.N] = yv[ch];
-            a.MU[obase + (size_t)ch * a.N] = muv[ch];
+            if (a.MU) a.MU[obase + (size_t)ch * a.N] = muv[ch];
           }
         } else {
 #pragma unroll
@@ -253,7 +255,14 @@ decoder_eval_tc_kernel(const EvalArgs a) {
         }
       }
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) xin[ch] = yv[ch];
+      for (int ch = 0; ch < 3; ++ch) {
+        xin[ch] = yv[ch];
+        slv[ch] += lvv[ch];
+      }
+    }
+    if (a.SLV && valid && part == 1) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) a.SLV[pbase + (size_t)ch * a.N] = slv[ch];
     }
   }
   umma::fence_before_sync();
@@ -281,12 +290,12 @@ int launch_eval_t(const EvalArgs& a, cudaStream_t st) {
 // [L][4][B][F] (film_forward_kernel), wimg = packed W1 images (pack_w1_kernel).
 int launch_decoder_eval_tc(const float* arena, const float* stats, const LayerMeta* meta_dev, const float* film,
                            const unsigned short* wimg, unsigned char* ltab, float* epi, const float* p, float* P, float* MU,
-                           float* LV, int L, int G, int B, int N, int mode, int split, float eps, cudaStream_t s) {
+                           float* LV, float* SLV, int L, int G, int B, int N, int mode, int split, float eps, cudaStream_t s) {
   eval_tables_kernel<<<dim3(L, B), 128, 0, s>>>(arena, stats, meta_dev, film, ltab, reinterpret_cast<float4*>(epi), B, G);
   int rc = dpf_check_launch("eval_tables_kernel");
   if (rc) return rc;
   EvalArgs a{};
-  a.p = p; a.P = P; a.MU = MU; a.LV = LV;
+  a.p = p; a.P = P; a.MU = MU; a.LV = LV; a.SLV = SLV;
   a.ltab = ltab; a.epi = reinterpret_cast<const float4*>(epi); a.wimg = wimg;
   a.L = L; a.B = B; a.N = N;
   a.tiles_per_b = (N + DPF_TILE - 1) / DPF_TILE;

@@ -290,13 +290,7 @@ coupling_fwd_fp32_kernel(const CouplingArgs a) {
         }
       }
       if (valid) {
-        const size_t base = (size_t)b * 3 * a.N + n;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          a.y[base + (size_t)ch * a.N] = yv[ch];
-          a.mu[base + (size_t)ch * a.N] = muv[ch];
-          a.lv[base + (size_t)ch * a.N] = lvv[ch];
-        }
+        store_point_outputs(a, (size_t)b * 3 * a.N + n, yv, muv, lvv);
         macc[0] += yv[0]; macc[1] += yv[1]; macc[2] += yv[2];
         macc[3] = fmaf(yv[0], yv[0], macc[3]); macc[4] = fmaf(yv[0], yv[1], macc[4]); macc[5] = fmaf(yv[0], yv[2], macc[5]);
         macc[6] = fmaf(yv[1], yv[1], macc[6]); macc[7] = fmaf(yv[1], yv[2], macc[7]); macc[8] = fmaf(yv[2], yv[2], macc[8]);

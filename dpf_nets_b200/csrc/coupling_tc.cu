@@ -184,10 +184,13 @@ __device__ __forceinline__ void tile_range(int n_tiles, int& t0, int& t1) {   //
 // across the grid barrier (RES * 128 columns; two CTAs per SM use all 512).
 constexpr int RES = 2;
 
-// Software grid barrier.  The launch puts exactly as many CTAs on the chip as fit (2 per SM by shared
-// memory and TMEM), so all of them are resident and the barrier completes; should that ever not hold
-// (another tenant on the SMs) the spin gives up after ~2 s and raises counter[1] instead of hanging
-// the GPU - the host side checks it (dpf_decoder_status).
+// Software grid barrier.  Every CTA of the launch must be resident for it to complete: the launcher sizes the grid to
+// what fits (2 CTAs per SM by shared memory, registers and TMEM) and VERIFIES that co-residency once per process with
+// a probe launch of the same footprint (tc_verify_coresidency).  Should a CTA nevertheless wait longer than ~2 s
+// (another tenant on the SMs), the barrier does not continue with partial sums: it raises the host-visible failure
+// flag and traps, so the pass ends with a CUDA error and every later decoder call reports the timeout.
+__device__ int* g_barrier_fail_dev = nullptr;      // device alias of a pinned, mapped host int (tc_barrier_setup)
+
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -201,12 +204,48 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
         __nanosleep(64);
         if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
           atomicExch(counter + 1, 1u);
-          break;
+          if (g_barrier_fail_dev) {
+            *reinterpret_cast<volatile int*>(g_barrier_fail_dev) = 1;
+            __threadfence_system();
+          }
+          __trap();
         }
       }
     } while (v < expected);
   }
   __syncthreads();
+}
+
+// Probe with the resource footprint of the cooperative kernels (threads, dynamic shared memory, TMEM columns,
+// <= 128 registers): all CTAs meet at a barrier with a short timeout; counter[1] != 0 afterwards = they were NOT all
+// resident at the same time.
+__global__ void __launch_bounds__(256, 2)
+coresidency_probe_kernel(unsigned int* counter, int tmem_cols) {
+  extern __shared__ unsigned char smraw[];
+  __shared__ uint32_t tmem_base;
+  if (threadIdx.x == 0) smraw[0] = 0;
+  if ((threadIdx.x >> 5) == 0) umma::tmem_alloc(&tmem_base, tmem_cols);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v < gridDim.x) {
+        __nanosleep(64);
+        if (clock64() - t0 > 100000000LL) {   // ~50 ms
+          atomicExch(counter + 1, 1u);
+          break;
+        }
+      }
+    } while (v < gridDim.x);
+  }
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) umma::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // =============================================================================================
@@ -1429,13 +1468,7 @@ __device__ __forceinline__ void fwd2_finish(const CouplingArgs& a, const float x
     }
   }
   if (valid) {
-    const size_t base = (size_t)b * 3 * a.N + n;
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      a.y[base + (size_t)ch * a.N] = yv[ch];
-      a.mu[base + (size_t)ch * a.N] = muv[ch];
-      a.lv[base + (size_t)ch * a.N] = lvv[ch];
-    }
+    store_point_outputs(a, (size_t)b * 3 * a.N + n, yv, muv, lvv);
     macc[0] += yv[0]; macc[1] += yv[1]; macc[2] += yv[2];
     macc[3] = fmaf(yv[0], yv[0], macc[3]); macc[4] = fmaf(yv[0], yv[1], macc[4]); macc[5] = fmaf(yv[0], yv[2], macc[5]);
     macc[6] = fmaf(yv[1], yv[1], macc[6]); macc[7] = fmaf(yv[1], yv[2], macc[7]); macc[8] = fmaf(yv[2], yv[2], macc[8]);
@@ -1725,6 +1758,46 @@ int launch_bwd_tc_t(const BwdArgs& a, const unsigned short* wimg, int pass, cuda
 }
 
 static int g_coop_occupancy = -1;
+static int* g_barrier_fail_host = nullptr;     // pinned + mapped; written by a timed-out grid barrier
+static int g_coresident_ok = -1;               // -1 not probed yet, 0 probe failed, 1 verified
+
+static int tc_barrier_setup() {
+  if (g_barrier_fail_host) return DPF_OK;
+  int* h = nullptr;
+  cudaError_t e = cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped);
+  if (e != cudaSuccess) { dpf_set_error("grid barrier flag: %s", cudaGetErrorString(e)); return (int)e; }
+  *h = 0;
+  int* d = nullptr;
+  e = cudaHostGetDevicePointer(&d, h, 0);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_barrier_fail_dev, &d, sizeof(d));
+  if (e != cudaSuccess) { cudaFreeHost(h); dpf_set_error("grid barrier flag: %s", cudaGetErrorString(e)); return (int)e; }
+  g_barrier_fail_host = h;
+  return DPF_OK;
+}
+
+// One synchronous probe launch per process: `grid` CTAs of 256 threads with `smem` dynamic bytes and `tmem_cols`
+// TMEM columns each must all be resident at once.  Cannot run during stream capture (returns -1 = unknown).
+static int tc_verify_coresidency(int grid, size_t smem, int tmem_cols, cudaStream_t st) {
+  if (g_coresident_ok >= 0) return g_coresident_ok;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (cap != cudaStreamCaptureStatusNone) return -1;
+  if (tc_barrier_setup() != DPF_OK) return -1;
+  unsigned int* counter = nullptr;
+  if (cudaMalloc(&counter, 2 * sizeof(unsigned int)) != cudaSuccess) return -1;
+  cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st);
+  cudaFuncSetAttribute(coresidency_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(coresidency_probe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  coresidency_probe_kernel<<<grid, 256, smem, st>>>(counter, tmem_cols);
+  ++g_dpf_launches;
+  unsigned int host[2] = {0u, 1u};
+  cudaError_t e = cudaMemcpyAsync(host, counter, sizeof(host), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(counter);
+  if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+  g_coresident_ok = (host[0] == (unsigned int)grid && host[1] == 0u) ? 1 : 0;
+  return g_coresident_ok;
+}
 
 // cooperative (all CTAs co-resident) launch of the merged train-mode forward; DPF_ERR_UNSUPPORTED when
 // the problem does not fit RES tiles per resident CTA - the caller then uses the two-launch form
@@ -1749,7 +1822,14 @@ int launch_fwd_train_t(const CouplingArgs& a, const unsigned short* wimg, unsign
   }
   // Not cudaLaunchCooperativeKernel: the runtime's co-residency check assumes ONE CTA per SM for any
   // kernel that allocates TMEM (occupancy query returns 1 at every shared-memory size), although two
-  // CTAs with 256 columns each do share an SM.  grid <= 2 * SMs keeps every CTA resident.
+  // CTAs with 256 columns each do share an SM.  Instead the full-size grid's co-residency is verified
+  // once per process with a probe launch of the same footprint; until / unless that succeeds the caller
+  // uses the two-launch form (no grid barrier).
+  const int ok = tc_verify_coresidency(max_grid, smem_for<TcFwdSmem2>(), RES * 128, st);
+  if (ok != 1) {
+    dpf_set_error("merged forward not used: co-residency of %d CTAs %s", max_grid, ok == 0 ? "could not be established" : "not verified yet (stream capture)");
+    return DPF_ERR_UNSUPPORTED;
+  }
   const int grid = min(a.n_tiles, max_grid);
   dpf_launch_pdl(kern, grid, NT2, smem_for<TcFwdSmem2>(), st, a, wimg, counter);
   return dpf_check_launch("coupling_fwd_train_tc_kernel");
@@ -1825,6 +1905,10 @@ int launch_dw1_reduce(const float* partial, int n_cta, float* darena, const Laye
 }
 
 int tc_bwd_p2_max_ctas() { return dpf_num_sms(); }
+
+// 1 when a grid barrier of this process has timed out (the pass that hit it trapped; outputs are invalid)
+int tc_barrier_failed() { return g_barrier_fail_host && *reinterpret_cast<volatile int*>(g_barrier_fail_host) != 0; }
+int tc_coresidency_state() { return g_coresident_ok; }
 
 size_t tc_weight_image_elems_per_layer() { return (size_t)2 * N_IMG * F * F; }
 

@@ -68,7 +68,7 @@ static bool g_merged_forward = true;
 static bool g_fused_eval = true;
 int launch_decoder_eval_tc(const float* arena, const float* stats, const LayerMeta* meta_dev, const float* film,
                            const unsigned short* wimg, unsigned char* ltab, float* epi, const float* p, float* P, float* MU,
-                           float* LV, int L, int G, int B, int N, int mode, int split, float eps, cudaStream_t s);
+                           float* LV, float* SLV, int L, int G, int B, int N, int mode, int split, float eps, cudaStream_t s);
 // Option 2: programmatic dependent launch of the per-layer tensor-path kernels (common.cuh).
 int g_dpf_pdl = 1;
 // Option 3: backward pass 2 with two tiles in flight per SM (544-thread CTAs, MMA issuer warp); 0 = the
@@ -83,7 +83,13 @@ DPF_API int dpf_set_option(int option, int value) {
   return DPF_OK;
 }
 
+int tc_barrier_failed();
+int tc_coresidency_state();
+
 static int validate_common(const long long* meta_host, int L, int G, int B, int N, int mode, int precision) {
+  DPF_REQUIRE(!tc_barrier_failed(), DPF_ERR_BARRIER,
+              "decoder: a grid barrier of an earlier pass timed out (its CTAs were not co-resident: another tenant on the GPU?); "
+              "that pass was aborted and its outputs are invalid");
   DPF_REQUIRE(meta_host, DPF_ERR_NULL_PTR, "decoder: layer table is null");
   DPF_REQUIRE(L > 0 && G > 0 && B > 0 && N > 0, DPF_ERR_BAD_ARG, "decoder: L, G, B, N must be positive");
   DPF_REQUIRE(mode == 0 || mode == 1, DPF_ERR_BAD_ARG, "decoder: mode must be 0 (direct) or 1 (inverse)");
@@ -124,13 +130,16 @@ static CouplingArgs make_args(const LayerMeta& m, const float* arena, float* sta
 // Forward of the whole stack: LocalCondRNVPDecoder.forward (decoders.py:54-72) over
 // CondRealNVPFlow3D.forward (flows.py:95-117).  mode 0 = 'direct' (layer 0 first), 1 = 'inverse'
 // (layer L-1 first); outputs are indexed by LAYER, like the reference's lists.
-DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* meta_dev, const float* arena,
-                                float* stats, const float* p, const float* g, float* P_out, float* MU, float* LV,
-                                void* workspace, int L, int G, int B, int N, int mode, int training,
-                                int update_stats, int precision, float eps, void* stream) {
+// MU may be NULL (the per-layer mu outputs are not written: nothing on the training path reads them, losses.py:7-15,
+// and the backward does not need them); SLV (B,3,N), nullable, receives sum_l LV[l] - the per-point log-det sum
+// of PointFlowNLL, accumulated in the kernels' epilogues instead of a separate reduction over the 63 planes.
+DPF_API int dpf_decoder_forward_ex(const long long* meta_host, const long long* meta_dev, const float* arena,
+                                   float* stats, const float* p, const float* g, float* P_out, float* MU, float* LV,
+                                   float* SLV, void* workspace, int L, int G, int B, int N, int mode, int training,
+                                   int update_stats, int precision, float eps, void* stream) {
   int rc = validate_common(meta_host, L, G, B, N, mode, precision);
   if (rc) return rc;
-  DPF_REQUIRE(meta_dev && arena && stats && p && g && P_out && MU && LV && workspace, DPF_ERR_NULL_PTR,
+  DPF_REQUIRE(meta_dev && arena && stats && p && g && P_out && LV && workspace, DPF_ERR_NULL_PTR,
               "dpf_decoder_forward: null pointer");
   DPF_REQUIRE(!training || B <= 256, DPF_ERR_UNSUPPORTED, "dpf_decoder_forward: train-mode FiLM BatchNorm supports B <= 256 (got %d)", B);
   DPF_REQUIRE(!training || ((long long)B * N > 1 && B > 1), DPF_ERR_BAD_ARG, "dpf_decoder_forward: BatchNorm in training mode needs more than 1 value per channel");
@@ -161,7 +170,7 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
     // eval mode has no cross-point reduction: the whole stack is one launch (+ one for its tables)
     ProfScope ps(CAT_FWD_APPLY, s);
     return launch_decoder_eval_tc(arena, stats, reinterpret_cast<const LayerMeta*>(meta_dev), ws.film, ws.w1_bf16, ws.eval_ltab,
-                                  ws.eval_epi, p, P_out, MU, LV, L, G, B, N, mode, precision == 2, eps, s);
+                                  ws.eval_epi, p, P_out, MU, LV, SLV, L, G, B, N, mode, precision == 2, eps, s);
   }
   const float* x = p;
   bool merged_ok = g_merged_forward;
@@ -171,8 +180,10 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
     CouplingArgs a = make_args(meta[l], arena, stats, ws, l, q, G, B, N, training, update_stats, eps);
     a.x = x;
     a.y = P_out + (size_t)l * plane;
-    a.mu = MU + (size_t)l * plane;
+    a.mu = MU ? MU + (size_t)l * plane : nullptr;
     a.lv = LV + (size_t)l * plane;
+    a.slv = SLV;
+    a.slv_init = q == 0;
     const unsigned short* wimg = ws.w1_bf16 + (size_t)l * tc_weight_image_elems_per_layer();
     if (training && precision >= 1 && merged_ok) {
       // one cooperative launch: statistics -> grid barrier -> apply from TMEM-resident accumulators
@@ -199,6 +210,15 @@ DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* met
   return DPF_OK;
 }
 
+DPF_API int dpf_decoder_forward(const long long* meta_host, const long long* meta_dev, const float* arena,
+                                float* stats, const float* p, const float* g, float* P_out, float* MU, float* LV,
+                                void* workspace, int L, int G, int B, int N, int mode, int training,
+                                int update_stats, int precision, float eps, void* stream) {
+  DPF_REQUIRE(MU, DPF_ERR_NULL_PTR, "dpf_decoder_forward: null pointer (MU); dpf_decoder_forward_ex accepts MU == NULL");
+  return dpf_decoder_forward_ex(meta_host, meta_dev, arena, stats, p, g, P_out, MU, LV, nullptr, workspace, L, G, B, N, mode,
+                                training, update_stats, precision, eps, stream);
+}
+
 // Synchronous health check of a forward workspace: *flag = number of layers whose grid barrier gave up
 // (must be 0; a non-zero value means the merged forward's CTAs were not co-resident and the outputs
 // of that pass are invalid).
@@ -211,9 +231,19 @@ DPF_API int dpf_decoder_status(const void* workspace, int L, int G, int B, int N
     dpf_set_error("dpf_decoder_status: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  int bad = 0;
+  int bad = tc_barrier_failed() ? 1 : 0;
   for (int l = 0; l < L; ++l) bad += host[(size_t)l * 32 + 1] != 0;
   *flag = bad;
+  return DPF_OK;
+}
+
+// Non-blocking: *failed = 1 when a grid barrier of this process has timed out (reads a pinned host flag, no
+// device synchronisation); *coresident = 1 verified by the probe launch, 0 probe failed (the merged forward is
+// then not used), -1 not probed yet.
+DPF_API int dpf_decoder_barrier_state(int* failed, int* coresident) {
+  DPF_REQUIRE(failed && coresident, DPF_ERR_NULL_PTR, "dpf_decoder_barrier_state: null pointer");
+  *failed = tc_barrier_failed();
+  *coresident = tc_coresidency_state();
   return DPF_OK;
 }
 
@@ -291,7 +321,7 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     a.yv = P_out + (size_t)l * plane;
     a.lvv = LV + (size_t)l * plane;
     a.dy_chain = q == L - 1 ? nullptr : ws.dx[(q + 1) & 1];
-    a.dP = dP ? dP + (size_t)l * dP_stride : nullptr;
+    a.dP = dP ? (dP_stride < 0 ? (l == 0 ? dP : nullptr) : dP + (size_t)l * dP_stride) : nullptr;
     a.dMU = dMU ? dMU + (size_t)l * dMU_stride : nullptr;
     a.dLV = dLV ? dLV + (size_t)l * dLV_stride : nullptr;
     a.dx_out = ws.dx[q & 1];

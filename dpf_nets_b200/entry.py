@@ -28,7 +28,8 @@ def _dataset(config, part, svr, n_synth):
     if n_synth:
         from .lib.datasets.synthetic import SyntheticCloudDataset
         return SyntheticCloudDataset(n_synth, cloud_size=config['cloud_size'], part=part, with_image=svr,
-                                     return_original_scale=config.get('cloud_rescale2orig', False))
+                                     # evaluate_ae.py:49 / train_ae.py: the datasets hand out orig_c / orig_s when either flag asks for them
+                                     return_original_scale=bool(config.get('cloud_rescale2orig') or config.get('orig_scale_evaluation')))
     raise SystemExit('real ShapeNet loading is out of scope here (no h5py / data in this image): pass --synthetic N')
 
 
@@ -55,7 +56,7 @@ def _model(config, svr, dev, precision):
 
 def train_main(svr=False, argv=None):
     from .lib.networks.losses import Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss
-    from .lib.networks.optimizers import Adam, LRUpdater
+    from .lib.networks.optimizers import Adam, LRUpdater, optimizer_state_from_reference
     from .lib.networks.training import train
     from .lib.networks.utils import cnt_params
     ap = argparse.ArgumentParser(description='Model training script. Provide a suitable config.')
@@ -97,7 +98,8 @@ def train_main(svr=False, argv=None):
         cur_epoch, cur_iter = ck['epoch'], ck['iter']
         model.load_state_dict(ck['model_state'])
         if config['resume_optimizer']:
-            optimizer.load_state_dict(ck['optimizer_state'])
+            # stored in the reference's per-tensor layout (also what a reference checkpoint holds)
+            optimizer.load_state_dict(optimizer_state_from_reference(model, ck['optimizer_state']))
         print('Model {} loaded.'.format(path))
     for epoch in range(cur_epoch, config['n_epochs']):
         if hasattr(it.sampler, 'set_epoch'):

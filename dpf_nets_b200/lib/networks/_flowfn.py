@@ -21,11 +21,15 @@ def _meta_host_ptr(stack):
 
 
 class CouplingStackFunction(torch.autograd.Function):
-    """(p, g, arena) -> stacked (P, MU, LV) of shape (L, B, 3, N), indexed by layer like the
-    reference's output lists."""
+    """(p, g, arena) -> stacked (P, MU, LV) of shape (L, B, 3, N), indexed by layer like the reference's
+    output lists, plus the two tensors the flow NLL consumes (losses.py:7-15) as SEPARATE outputs:
+    Z = P[0] (samples[0]) and SLV = sum_l LV[l] (accumulated in the kernels' epilogues).  A loss that
+    touches only Z and SLV - the reference's - back-propagates through two (B,3,N) cotangents: no dense
+    (L,B,3,N) zero-filled gradients, no 63-way reduction.  Every stacked output stays differentiable, so
+    any other use of the lists is still correct (and costs what it used to)."""
 
     @staticmethod
-    def forward(ctx, p, g, arena, stack, mode, training, precision):
+    def forward(ctx, p, g, arena, stack, mode, training, precision, want_mu):
         _lib.require_cuda(p, g, arena)
         L, G = stack.layout.L, stack.g_n_features
         B, C, N = p.shape
@@ -33,25 +37,32 @@ class CouplingStackFunction(torch.autograd.Function):
             raise _lib.DpfNativeError("coupling stack expects p (B,3,N) and g (B,%d) float32; got %s, %s"
                                       % (G, tuple(p.shape), tuple(g.shape)))
         dev = p.device
-        out = torch.empty((3, L, B, 3, N), dtype=torch.float32, device=dev)
+        P = torch.empty((L, B, 3, N), dtype=torch.float32, device=dev)
+        LV = torch.empty((L, B, 3, N), dtype=torch.float32, device=dev)
+        MU = torch.empty((L, B, 3, N), dtype=torch.float32, device=dev) if want_mu else None
+        SLV = torch.empty((B, 3, N), dtype=torch.float32, device=dev)
         ws = _workspace(L, G, B, N, dev)
         update = bool(training)
         with torch.cuda.device(dev):
-            _lib.call("dpf_decoder_forward", _meta_host_ptr(stack), stack.layer_meta, arena, stack.stats, p, g,
-                      out[0], out[1], out[2], ws, L, G, B, N, MODES[mode], bool(training), update,
+            _lib.call("dpf_decoder_forward_ex", _meta_host_ptr(stack), stack.layer_meta, arena, stack.stats, p, g,
+                      P, MU, LV, SLV, ws, L, G, B, N, MODES[mode], bool(training), update,
                       PRECISIONS[precision], ctypes.c_float(stack.eps_value), device=dev)
         if training:
             stack.num_batches_tracked += 1
         ctx.stack, ctx.mode, ctx.training, ctx.ws, ctx.precision = stack, mode, bool(training), ws, precision
         stack._last_pass = (ws, L, G, B, N)
-        ctx.save_for_backward(p, g, arena, out)
+        ctx.save_for_backward(p, g, arena, P, LV)
         ctx.set_materialize_grads(False)
-        return out[0], out[1], out[2]
+        Z = P[0].clone()
+        if MU is None:
+            MU = P.new_empty(0)
+            ctx.mark_non_differentiable(MU)
+        return P, MU, LV, Z, SLV
 
     @staticmethod
-    def backward(ctx, dP, dMU, dLV):
+    def backward(ctx, dP, dMU, dLV, dZ, dSLV):
         from ._flowbwd import run_backward
-        return run_backward(ctx, dP, dMU, dLV)
+        return run_backward(ctx, dP, dMU, dLV, dZ, dSLV)
 
 
 def resolve_precision(stack):
@@ -65,12 +76,13 @@ def resolve_precision(stack):
     return prec
 
 
-def run_stack(stack, p, g, mode):
+def run_stack(stack, p, g, mode, want_mu=True):
+    """-> (P, MU, LV, Z, SLV); MU is an empty tensor when want_mu is False."""
     if mode not in MODES:
         raise ValueError("mode must be 'direct' or 'inverse', got %r" % (mode,))
     p = p.contiguous()
     g = g.contiguous()
-    return CouplingStackFunction.apply(p, g, stack.arena, stack, mode, stack.training, resolve_precision(stack))
+    return CouplingStackFunction.apply(p, g, stack.arena, stack, mode, stack.training, resolve_precision(stack), want_mu)
 
 
 def last_pass_status(stack):

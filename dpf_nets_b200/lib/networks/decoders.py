@@ -8,13 +8,20 @@ from .flows import _triple_warps
 
 class FlowOutputs(list):
     """A plain list of per-layer tensors that also carries the stacked (L,B,3,N) tensor it was
-    unbound from, so that losses can reduce over layers in one op."""
+    unbound from and, for the logvar list, `total` = the sum over layers the kernels accumulated
+    (what PointFlowNLL needs, losses.py:12-13) as its own autograd output."""
     stacked = None
+    total = None
 
 
-def _as_list(stacked):
+def _as_list(stacked, first=None, total=None):
     out = FlowOutputs(stacked.unbind(0))
     out.stacked = stacked
+    if first is not None:
+        # element 0 (samples[0] of the flow NLL) is the kernel's separate output Z == stacked[0]: its cotangent is one
+        # (B,3,N) block instead of a zero-filled dense (L,B,3,N) gradient through unbind's backward
+        out[0] = first
+    out.total = total
     return out
 
 
@@ -28,18 +35,26 @@ class LocalCondRNVPDecoder(CouplingStack):
         self.n_flows = n_flows
 
     def forward(self, p, g, mode="direct"):
-        P, MU, LV = run_stack(self, p, g, mode)
-        return _as_list(P), _as_list(MU), _as_list(LV)
+        P, MU, LV, Z, SLV = run_stack(self, p, g, mode)
+        return _as_list(P, first=Z), _as_list(MU), _as_list(LV, total=SLV)
+
+    def nll_terms(self, p, g, mode="inverse"):
+        """-> (samples[0], sum over layers of logvar), each (B,3,N): everything PointFlowNLL reads from the
+        decoder (losses.py:7-15), without materialising the per-layer mu outputs."""
+        _, _, _, Z, SLV = run_stack(self, p, g, mode, want_mu=False)
+        return Z, SLV
 
 
 class TailedList(list):
-    """[base] + decoder list: keeps a handle on the decoder's stacked tensor for fused reductions."""
+    """[base] + decoder list: keeps a handle on the decoder's stacked tensor / layer total for fused reductions."""
     tail_stacked = None
+    tail_total = None
 
 
 def prepend(base, flow_list):
     out = TailedList([base] + list(flow_list))
     out.tail_stacked = getattr(flow_list, "stacked", None)
+    out.tail_total = getattr(flow_list, "total", None)
     return out
 
 

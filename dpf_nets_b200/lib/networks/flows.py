@@ -28,7 +28,7 @@ class CondRealNVPFlow3D(CouplingStack):
         self.centered_translation = centered_translation  # accepted and ignored, like the reference
 
     def forward(self, p, g, mode="direct"):
-        P, MU, LV = run_stack(self, p, g, mode)
+        P, MU, LV, _, _ = run_stack(self, p, g, mode)
         return P[0], MU[0], LV[0]
 
 
@@ -42,7 +42,7 @@ class CondRealNVPFlow3DTriple(CouplingStack):
         self.centered_translation = centered_translation
 
     def forward(self, p, g, mode="direct"):
-        P, MU, LV = run_stack(self, p, g, mode)
+        P, MU, LV, _, _ = run_stack(self, p, g, mode)
         return list(P.unbind(0)), list(MU.unbind(0)), list(LV.unbind(0))
 
 

@@ -1,6 +1,7 @@
 """Flow NLL / entropy losses with the reference's class names and formulas
 (lib/networks/losses.py:7-51).  The sum over the per-layer log-dets uses the stacked tensor
-carried by the decoder's output lists when present (one reduction instead of 63 adds)."""
+carried by the decoder's output lists when present: the kernels' own per-point sum over layers (`total`),
+else one reduction over the stacked tensor, instead of 63 full-tensor adds."""
 import math
 
 import torch
@@ -12,6 +13,9 @@ def _sum_over_layers(logvars):
     if len(logvars) > 1:
         tail = logvars[1:] if isinstance(logvars, list) else list(logvars)[1:]
         stacked = getattr(tail, "stacked", None)
+        total = getattr(logvars, "tail_total", None)
+        if total is not None:            # accumulated per point in the decoder kernels' epilogues
+            return logvars[0] + total
         src = getattr(logvars, "tail_stacked", None)
         if src is not None:
             return logvars[0] + src.sum(0)

@@ -139,3 +139,82 @@ class LRUpdater(object):
         for group in optimizer.param_groups:
             group['lr'] = self.min_lr + (self.max_lr - self.min_lr) * c
             group['betas'] = (self.beta1, self.min_beta2 + (self.max_beta2 - self.min_beta2) * c)
+
+
+# ---- checkpoint boundary of the optimizer state --------------------------------------------------
+# The reference's checkpoints hold one optimizer-state entry per nn.Parameter of ITS modules
+# (training.py:75-80, optimizers.py:32-40); here every coupling stack owns ONE arena parameter.  The
+# arena's field order equals the reference's parameter registration order (flows.py:25-93), so the two
+# layouts convert into each other by slicing / concatenating the per-tensor moments.
+def _plan(model):
+    """[(parameter, None | [(offset, shape), ...])] in model.parameters() order; a list = arena fields."""
+    from ._arena import CouplingStack
+    arenas = {id(m.arena): m for m in model.modules() if isinstance(m, CouplingStack)}
+    plan = []
+    for p in model.parameters():
+        m = arenas.get(id(p))
+        plan.append((p, None if m is None else [(off, shape) for off, shape in m.layout.param_index.values()]))
+    return plan
+
+
+def optimizer_state_to_reference(model, opt_state):
+    """This package's Adam.state_dict() (one group) -> the reference's per-tensor layout."""
+    if len(opt_state['param_groups']) != 1:
+        raise ValueError('optimizer state conversion supports a single parameter group')
+    state, out, idx = opt_state['state'], {}, 0
+    for i, (p, fields) in enumerate(_plan(model)):
+        st = state.get(i)
+        if fields is None:
+            if st is not None:
+                out[idx] = st
+            idx += 1
+            continue
+        for off, shape in fields:
+            if st is not None:
+                n = int(np.prod(shape))
+                out[idx] = {k: (v.reshape(-1)[off:off + n].view(shape).clone() if torch.is_tensor(v) and v.numel() == p.numel() else v)
+                            for k, v in st.items()}
+            idx += 1
+    group = dict(opt_state['param_groups'][0])
+    group['params'] = list(range(idx))
+    return {'state': out, 'param_groups': [group]}
+
+
+def optimizer_state_from_reference(model, ref_state):
+    """The reference's per-tensor optimizer state -> this package's layout (arena moments concatenated).
+    Returns `ref_state` unchanged when it already has this model's parameter count."""
+    plan = _plan(model)
+    n_ref = sum(1 if f is None else len(f) for _, f in plan)
+    if len(ref_state['param_groups']) != 1:
+        raise ValueError('optimizer state conversion supports a single parameter group')
+    n_have = len(ref_state['param_groups'][0]['params'])
+    if n_have == len(plan) and n_have != n_ref:
+        return ref_state
+    if n_have != n_ref:
+        raise ValueError('optimizer_state has %d parameters; this model has %d (%d in the reference layout): '
+                         'the checkpoint belongs to a different architecture' % (n_have, len(plan), n_ref))
+    state, out, idx = ref_state['state'], {}, 0
+    for i, (p, fields) in enumerate(plan):
+        if fields is None:
+            if idx in state:
+                out[i] = state[idx]
+            idx += 1
+            continue
+        parts = [state.get(idx + j) for j in range(len(fields))]
+        idx += len(fields)
+        have = [s for s in parts if s is not None]
+        if not have:
+            continue
+        if len(have) != len(parts):
+            raise ValueError('optimizer_state covers only part of a coupling stack')
+        steps = {int(s['step']) for s in parts}
+        if len(steps) != 1:
+            raise ValueError('coupling-stack parameters carry different step counts: %s' % sorted(steps))
+        merged = {'step': steps.pop()}
+        for k in parts[0]:
+            if torch.is_tensor(parts[0][k]):
+                merged[k] = torch.cat([s[k].reshape(-1) for s in parts]).to(p.device)
+        out[i] = merged
+    group = dict(ref_state['param_groups'][0])
+    group['params'] = list(range(len(plan)))
+    return {'state': out, 'param_groups': [group]}

@@ -11,6 +11,7 @@ from time import time
 import torch
 
 from ... import dist as _dist
+from .optimizers import optimizer_state_to_reference
 from .utils import AverageMeter, save_model
 
 
@@ -29,7 +30,7 @@ def train(iterator, model, loss_func, optimizer, scheduler, epoch, iter, **kwarg
         if rank == 0:
             os.makedirs(os.path.dirname(model_name), exist_ok=True)
             save_model({'epoch': ep, 'iter': it, 'model_state': model.state_dict(),
-                        'optimizer_state': optimizer.state_dict()}, model_name)
+                        'optimizer_state': optimizer_state_to_reference(model, optimizer.state_dict())}, model_name)
 
     def nan_guard(loss):
         # every rank takes the same decision (a rank that stopped alone would leave the others blocked in the

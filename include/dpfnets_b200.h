@@ -20,6 +20,7 @@ extern "C" {
 #define DPF_ERR_NULL_PTR (-2)
 #define DPF_ERR_UNSUPPORTED (-3)
 #define DPF_ERR_ALIGN (-4)
+#define DPF_ERR_BARRIER (-5)   /* a grid barrier of an earlier decoder pass timed out; that pass was aborted */
 
 const char* dpf_last_error(void);
 int dpf_version(void);
@@ -112,10 +113,19 @@ int dpf_decoder_forward(const long long* meta_host, const long long* meta_dev, c
                         void* workspace, int L, int G, int B, int N, int mode, int training,
                         int update_stats, int precision, float eps, void* stream);
 
+/* dpf_decoder_forward with the outputs the flow NLL actually consumes (PointFlowNLL, lib/networks/losses.py:7-15:
+ * samples[0], sum_l logvars[l]): MU may be NULL (per-layer mu not written); SLV (B,3,N), nullable, receives
+ * sum_l LV[l] accumulated in the kernels' epilogues (the reference adds 63 full tensors with Python sum()). */
+int dpf_decoder_forward_ex(const long long* meta_host, const long long* meta_dev, const float* arena,
+                           float* stats, const float* p, const float* g, float* P_out, float* MU, float* LV,
+                           float* SLV, void* workspace, int L, int G, int B, int N, int mode, int training,
+                           int update_stats, int precision, float eps, void* stream);
+
 /* Backward of dpf_decoder_forward = what torch.autograd derives for flows.py:95-117 (the reference
  * has no hand-written backward; formulas: SURVEY.md Appendix F).  `workspace` must be the buffer
  * the forward call used.  dP/dMU/dLV: cotangents of the stacked outputs (nullable), *_stride =
- * elements between layers (0 = one (B,3,N) block shared by all layers).  darena (n_params, arena
+ * elements between layers (0 = one (B,3,N) block shared by all layers; dP_stride < 0 = dP is ONE (B,3,N) block
+ * that belongs to layer 0 only - the cotangent of samples[0], all the flow NLL produces).  darena (n_params, arena
  * layout) and dg (B,G) are overwritten; dp (B,3,N) is optional (NULL = not needed). */
 int dpf_decoder_backward(const long long* meta_host, const long long* meta_dev, const float* arena,
                          float* stats, const float* p, const float* g, const float* P_out, const float* LV,
@@ -126,6 +136,11 @@ int dpf_decoder_backward(const long long* meta_host, const long long* meta_dev, 
 /* Synchronous health check of a forward workspace: *flag = layers whose merged-forward grid barrier
  * timed out (must be 0). */
 int dpf_decoder_status(const void* workspace, int L, int G, int B, int N, int* flag);
+/* Non-blocking (reads a pinned host flag): *failed = 1 when a grid barrier of this process has timed out - the
+ * kernel that hit it trapped, and every later dpf_decoder_forward / dpf_decoder_backward returns DPF_ERR_BARRIER;
+ * *coresident = 1 the merged forward's full grid was verified co-resident by a probe launch, 0 the probe failed
+ * (the two-launch form is used instead), -1 not probed yet. */
+int dpf_decoder_barrier_state(int* failed, int* coresident);
 /* bwd_scratch: per-CTA wgrad partials of the tensor path (may be NULL for precision 0). */
 int dpf_decoder_backward_scratch_bytes(int L, int B, int N, long long* bytes);
 

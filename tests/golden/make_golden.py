@@ -118,6 +118,37 @@ def decoder_fixture(n_flows, G, B, N, seed):
     return fx
 
 
+def decoder_g512_fixture(n_flows, B, N, seed):
+    """BASELINE configs 3 / 4 (AE all_original, SVR): G = 512 FiLM nets, N = 2500 points per cloud
+    (configs/svr/all.yaml:6 - ragged last tile).  Stores only what the gates need: eval outputs of both
+    modes (P, logvars), train-mode outputs, NLL, autograd gradients, updated running statistics."""
+    G = 512
+    torch.manual_seed(seed)
+    m = LocalCondRNVPDecoder(n_flows, 64, G, weight_std=0.01)
+    perturb(m, seed + 1)
+    warm_stats(m, G, 300, seed, "inverse")
+    p, lat = inputs(B, N, G, seed + 2)
+    fx = {"n_flows": n_flows, "G": G, "state": clone_sd(m), "p": p, "g": lat}
+    m.eval()
+    with torch.no_grad():
+        for mode in ("direct", "inverse"):
+            ps, mus, lvs = m(p, lat, mode=mode)
+            fx["eval_" + mode] = {"ps": torch.stack(ps), "logvars": torch.stack(lvs)}
+    m.train()
+    m.zero_grad()
+    lr = lat.clone().requires_grad_(True)
+    ps, mus, lvs = m(p, lr, mode="inverse")
+    nll = PointFlowNLL()(ps + [p], [torch.zeros_like(p)] + mus, [torch.full_like(p, -0.5)] + lvs)
+    nll.backward()
+    fx["train_inverse"] = {
+        "ps": torch.stack([t.detach() for t in ps]), "logvars": torch.stack([t.detach() for t in lvs]),
+        "nll": nll.detach().clone(), "dg": lr.grad.clone(),
+        "grads": {k: v.grad.clone() for k, v in m.named_parameters()},
+        "running_after": {k: v.clone() for k, v in m.state_dict().items() if "running" in k}, "base_logvar": -0.5,
+    }
+    return fx
+
+
 def perturb_survey(module, seed):
     """SURVEY.md 8d recipe: only the last SharedDot of each branch gets std 0.3."""
     g = torch.Generator().manual_seed(seed)
@@ -157,6 +188,9 @@ def main():
     torch.save(coupling_fixture((1,), 128, 4, 128, 13), os.path.join(HERE, "coupling_w1_g128.pt"))
     torch.save(decoder_fixture(2, 16, 3, 200, 21), os.path.join(HERE, "decoder_f2.pt"))
     torch.save(decoder_survey_fixture(6, 16, 6, 384, 31), os.path.join(HERE, "decoder_f6_survey.pt"))
+    if "--g512" in sys.argv or not os.path.exists(os.path.join(HERE, "decoder_f1_g512.pt")):
+        torch.save(coupling_fixture((1, 2), 512, 4, 160, 14), os.path.join(HERE, "coupling_w12_g512.pt"))
+        torch.save(decoder_g512_fixture(1, 3, 2500, 22), os.path.join(HERE, "decoder_f1_g512.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

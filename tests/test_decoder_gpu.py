@@ -629,3 +629,172 @@ def test_speed_vs_eager_torch_port_on_this_gpu(mods, cuda):
         pass
     assert abs(res["loss_fused"] - res["loss_eager"]) < 5e-3 * abs(res["loss_eager"])     # same model, same inputs: NLL within 0.5 %
     assert res["speedup"] > 1.0
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs 3 / 4: G = 512 FiLM nets, N = 2500 (ragged tiles); the flow-NLL outputs Z / SLV
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["inverse", "direct"])
+def test_coupling_layer_g512_vs_reference(mods, cuda, mode):
+    """One coupling layer with the AE / SVR latent width (G = 512, warp [1,2]): eval + train outputs and
+    autograd gradients vs the reference (golden generated by importing it)."""
+    flows, _ = mods
+    fx = load("coupling_w12_g512.pt")
+    t = fx["train_" + mode]
+    m = flows.CondRealNVPFlow3D(64, 512, warp_inds=fx["warp"]).to(cuda)
+    m.precision = "fp32"
+    m.load_state_dict(fx["state"])
+    p0, g0 = fx["p"].to(cuda), fx["g"].to(cuda)
+    m.eval()
+    with torch.no_grad():
+        for a, b in zip(m(p0, g0, mode=mode), fx["eval_" + mode]):
+            assert rel(a, b) < TOL32
+    m.train()
+    p = p0.clone().requires_grad_(True)
+    g = g0.clone().requires_grad_(True)
+    p_out, mu, lv = m(p, g, mode=mode)
+    for a, b in zip((p_out, mu, lv), t["out"]):
+        assert rel(a, b) < TOL32
+    cy, cm, cl = [c.to(cuda) for c in t["cot"]]
+    ((p_out * cy).sum() + (mu * cm).sum() + (lv * cl).sum()).backward()
+    assert rel(p.grad, t["dp"]) < TOLG and rel(g.grad, t["dg"]) < TOLG
+    gv = m.named_views(grad=True)
+    worst = max((rel(gv[k], v), k) for k, v in t["grads"].items())
+    assert worst[0] < TOLG, worst
+
+
+@pytest.mark.parametrize("precision,tol,tolg", [("fp32", 1e-4, 5e-3), ("bf16x3", 5e-3, 2e-2)])
+def test_decoder_g512_n2500_vs_reference(mods, cuda, precision, tol, tolg):
+    """3-layer decoder at G = 512, N = 2500 points (configs/svr/all.yaml:6; 2500 = 19 full tiles + 68 points):
+    eval both modes, train-mode outputs, NLL (0.5 %), gradients and running statistics vs the reference."""
+    _, decoders = mods
+    from dpf_nets_b200.lib.networks.losses import PointFlowNLL
+    fx = load("decoder_f1_g512.pt")
+    t = fx["train_inverse"]
+    m = decoders.LocalCondRNVPDecoder(fx["n_flows"], 64, 512).to(cuda)
+    m.precision = precision
+    m.load_state_dict(fx["state"])
+    p = fx["p"].to(cuda)
+    m.eval()
+    with torch.no_grad():
+        for mode in ("direct", "inverse"):
+            ps, mus, lvs = m(p, fx["g"].to(cuda), mode=mode)
+            assert rel(ps.stacked, fx["eval_" + mode]["ps"]) < max(tol, 2e-2 if precision != "fp32" else 0)
+            assert rel(lvs.stacked, fx["eval_" + mode]["logvars"]) < max(tol, 2e-2 if precision != "fp32" else 0)
+    m.load_state_dict(fx["state"])
+    m.train()
+    g = fx["g"].to(cuda).requires_grad_(True)
+    ps, mus, lvs = m(p, g, mode="inverse")
+    assert rel(ps.stacked, t["ps"]) < tol and rel(lvs.stacked, t["logvars"]) < tol
+    assert rel(lvs.total, t["logvars"].sum(0)) < tol                      # epilogue-accumulated log-det sum
+    base_mu, base_lv = torch.zeros_like(p), torch.full_like(p, t["base_logvar"])
+    nll = PointFlowNLL()(decoders.prepend(None, ps)[1:] + [p], decoders.prepend(base_mu, mus), decoders.prepend(base_lv, lvs))
+    assert abs(nll.item() - t["nll"].item()) < 5e-3 * abs(t["nll"].item())
+    nll.backward()
+    gv = m.named_views(grad=True)
+    errs = sorted(((rel(gv[k], v), k) for k, v in t["grads"].items()), reverse=True)
+    assert errs[0][0] < tolg, errs[:5]
+    assert rel(g.grad, t["dg"]) < tolg
+    sd = m.state_dict()
+    for k, v in t["running_after"].items():
+        assert rel(sd[k], v) < 2e-4, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_nll_outputs_equal_list_path(mods, cuda, precision):
+    """The separate flow-NLL outputs (Z = samples[0], SLV = sum_l logvar_l accumulated in the epilogues) and their
+    two-block backward (dP for layer 0 only, dLV shared by all layers) against the dense list path of the SAME
+    kernels: loss through the 63-adds plain lists (the reference's Python sum(), losses.py:12), through the stacked
+    tensor, through PointFlowNLL's fused route and through decoder.nll_terms()."""
+    _, decoders = mods
+    from dpf_nets_b200.lib.networks.losses import PointFlowNLL
+    torch.manual_seed(3)
+    m = decoders.LocalCondRNVPDecoder(3, 64, 24).to(cuda)
+    m.precision = precision
+    with torch.no_grad():
+        m.arena.add_(0.05 * torch.randn_like(m.arena))
+    m.train()
+    gen = torch.Generator().manual_seed(4)
+    p = (torch.rand((5, 3, 333), generator=gen) - 0.5).to(cuda)
+    g0 = torch.randn((5, 24), generator=gen).to(cuda)
+    base_mu, base_lv = torch.zeros_like(p), torch.full_like(p, -0.7)
+    crit = PointFlowNLL()
+    res = {}
+    for how in ("plain_lists", "stacked", "fused", "nll_terms"):
+        m.zero_grad()
+        g = g0.clone().requires_grad_(True)
+        pp = p.clone().requires_grad_(True)
+        if how == "nll_terms":
+            z, slv = m.nll_terms(pp, g)
+            nll = 0.5 * (torch.sum(base_lv + slv + (z - base_mu) ** 2 / torch.exp(base_lv)) / p.shape[0]
+                         + torch.log(torch.tensor(2.0 * torch.pi)) * 3 * p.shape[2])
+        else:
+            ps, mus, lvs = m(pp, g, mode="inverse")
+            if how == "plain_lists":
+                nll = crit([ps.stacked[i] for i in range(9)] + [pp], [base_mu] + list(mus), [base_lv] + [lvs.stacked[i] for i in range(9)])
+            elif how == "stacked":
+                nll = 0.5 * (torch.sum(base_lv + lvs.stacked.sum(0) + (ps.stacked[0] - base_mu) ** 2 / torch.exp(base_lv)) / p.shape[0]
+                             + torch.log(torch.tensor(2.0 * torch.pi)) * 3 * p.shape[2])
+            else:
+                assert torch.equal(ps[0], ps.stacked[0]) and rel(lvs.total, lvs.stacked.sum(0)) < 1e-6
+                nll = crit(decoders.prepend(None, ps)[1:] + [pp], decoders.prepend(base_mu, mus), decoders.prepend(base_lv, lvs))
+        nll.backward()
+        res[how] = (nll.item(), m.arena.grad.clone(), g.grad.clone(), pp.grad.clone())
+    ref = res["plain_lists"]
+    for how in ("stacked", "fused", "nll_terms"):
+        got = res[how]
+        assert abs(got[0] - ref[0]) < 1e-5 * abs(ref[0]), how
+        assert rel(got[1], ref[1]) < 2e-3 and rel(got[2], ref[2]) < 2e-3 and rel(got[3], ref[3]) < 2e-3, how
+    # a loss that touches an inner layer's P as well as Z still gets the full gradient (dense dP + dZ are merged)
+    m.zero_grad()
+    g = g0.clone().requires_grad_(True)
+    ps, mus, lvs = m(p, g, mode="inverse")
+    ((ps[0] ** 2).sum() + (ps[4] * 0.3).sum() + lvs.total.sum() + lvs[2].sum()).backward()
+    ga = m.arena.grad.clone()
+    m.zero_grad()
+    g2 = g0.clone().requires_grad_(True)
+    ps, mus, lvs = m(p, g2, mode="inverse")
+    P, LV = ps.stacked, lvs.stacked
+    ((P[0] ** 2).sum() + (P[4] * 0.3).sum() + LV.sum() + LV[2].sum()).backward()
+    assert rel(ga, m.arena.grad) < 2e-3 and rel(g.grad, g2.grad) < 2e-3
+
+
+def test_full_size_train_outputs_and_gradients_vs_port(mods, cuda):
+    """BASELINE size (63 layers x 32 x 2048 points, chair config, default bf16x3 training path): z = samples[0],
+    the per-point log-det sum, the NLL AND the gradients (darena per parameter tensor, dg) against the oracle port
+    (oracle/flow_oracle.py, pinned to the reference by tests/test_oracle_flow.py) executed in fp32 on the same GPU.
+    Tolerances: outputs 1e-3 (max-abs relative; both sides are fp32-class, 63 layers of batch-stat BN amplify
+    re-association noise), NLL 1e-5, gradients 2e-2 per tensor for tensors holding at least 1e-3 of the largest
+    gradient norm (tiny-norm tensors are compared in absolute terms against that scale)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    _, decoders = mods
+    from dpf_nets_b200.lib.networks.losses import PointFlowNLL
+    B, N, G = 32, 2048, 128
+    step_ref = bench.oracle_train_step_factory(B, N, device=cuda, return_state=True)
+    loss_ref, st = step_ref()
+    torch.manual_seed(0)
+    m = decoders.LocalCondRNVPDecoder(21, 64, G).to(cuda).train()
+    with torch.no_grad():
+        m.arena.copy_(st["arena"])
+    p, g = bench.synth_inputs(B, N, G, 0)
+    p, g = p.to(cuda), g.to(cuda).requires_grad_(True)
+    ps, mus, lvs = m(p, g, mode="inverse")
+    base_mu, base_lv = torch.zeros_like(p), torch.full_like(p, bench.BASE_LOGVAR)
+    nll = PointFlowNLL()(decoders.prepend(None, ps)[1:] + [p], decoders.prepend(base_mu, mus), decoders.prepend(base_lv, lvs))
+    nll.backward()
+    assert rel(ps[0], st["z"]) < 1e-3, rel(ps[0], st["z"])
+    assert rel(lvs.total, st["sum_logvar"]) < 1e-3, rel(lvs.total, st["sum_logvar"])
+    assert abs(nll.item() - loss_ref) < 1e-5 * abs(loss_ref)
+    assert rel(g.grad, st["dg"]) < 2e-2, rel(g.grad, st["dg"])
+    lay = m.layout
+    scale = max(float(st["darena"][off:off + int(torch.tensor(shape).prod())].norm()) for off, shape in lay.param_index.values())
+    worst = []
+    for key, (off, shape) in lay.param_index.items():
+        n = int(torch.tensor(shape).prod())
+        a, b = m.arena.grad[off:off + n], st["darena"][off:off + n]
+        err = float((a - b).norm() / max(float(b.norm()), 1e-3 * scale))
+        worst.append((err, key))
+    worst.sort(reverse=True)
+    assert worst[0][0] < 2e-2, worst[:5]

@@ -157,3 +157,89 @@ def test_graphed_train_step_matches_eager(native_lib, cuda, monkeypatch):
     assert abs(float(runs["eager"][1].norm()) - float(runs["graphed"][1].norm())) < 0.03 * float(runs["eager"][1].norm())
     for k, v in runs["eager"][2].items():
         assert torch.equal(v, runs["graphed"][2][k]), k
+
+
+# ---- whole-model parity against the reference (BASELINE configs 2, 3, 4) -------------------------------------
+@pytest.mark.parametrize("name,cls,ic", [("generation_chair", "Local_Cond_RNVP_MC_Global_RNVP_VAE", False),
+                                         ("autoencoding_all_original", "Local_Cond_RNVP_MC_Global_RNVP_VAE", False),
+                                         ("svr_all", "Local_Cond_RNVP_MC_Global_RNVP_VAE_IC", True)])
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_wholemodel_training_loss_and_gradients_vs_reference(native_lib, cuda, name, cls, ic, precision):
+    """Whole-model training-mode forward + VAE loss + backward of the generation (G=128), AE all_original (G=512) and
+    SVR all (image encoder + G=512) models against the UNMODIFIED reference (tests/golden/make_golden_wholemodel.py:
+    weights regenerated from key names, torch.randn_like replaced by the same seeded stream on both sides).
+    Tolerances: (loss, pnll, gnll, gent) 1e-4 relative in fp32 mode / 0.5 % on the tensor path (north star: total
+    NLL within 0.5 %), z and sum-logvar 1e-3 / 2e-2, gradients of parameters of every sub-module 2e-2 / 5e-2."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _detstate import DetRandn, GRAD_KEYS, det_state, whole_model_inputs
+    from dpf_nets_b200 import configs
+    from dpf_nets_b200.lib.networks import models
+    from dpf_nets_b200.lib.networks.losses import Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "wholemodel.pt"), weights_only=False)[name]
+    c = configs.get(fx["config_path"][len("configs/"):-len(".yaml")])
+    c["util_mode"] = "training"
+    m = getattr(models, cls)(**c)
+    m.load_state_dict(det_state({k: list(v.shape) for k, v in m.state_dict().items()}))
+    m = m.to(cuda).train()
+    m.pc_decoder.precision = precision
+    crit = Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss(**c)
+    inp = {k: v.to(cuda) for k, v in whole_model_inputs(fx["B"], fx["N"], 77, ic).items()}
+    with DetRandn(5):
+        out = m(inp["cloud"], inp["eval_cloud"], inp["image"]) if ic else m(inp["cloud"], inp["eval_cloud"])
+    losses = crit(inp["cloud"], inp["eval_cloud"], out)
+    losses[0].backward()
+    fp32 = precision == "fp32"
+    got = torch.stack([l.detach().double().cpu() for l in losses])
+    tol_loss = 1e-4 if fp32 else 5e-3
+    assert ((got - fx["losses"]).abs() <= tol_loss * fx["losses"].abs()).all(), (got, fx["losses"])
+    rel = lambda a, b: float((a.detach().cpu() - b).abs().max() / b.abs().max())
+    assert rel(out["g_posterior_mus"], fx["g_posterior_mus"]) < 1e-4
+    assert rel(out["p_prior_samples"][0], fx["z"]) < (1e-3 if fp32 else 2e-2)
+    assert rel(out["p_prior_logvars"].tail_total, fx["sum_logvar"]) < (1e-3 if fp32 else 2e-2)
+    named = dict(m.named_parameters())
+    dec = m.pc_decoder.named_views(grad=True)
+    for k in GRAD_KEYS[ic]:
+        gk = dec[k[len("pc_decoder."):]] if k.startswith("pc_decoder.") else named[k].grad
+        assert rel(gk, fx["grads"][k]) < (2e-2 if fp32 else 5e-2), (k, rel(gk, fx["grads"][k]))
+
+
+def test_entry_points_svr_and_predicting(native_lib, cuda, tmp_path):
+    """train_svr.py on synthetic image + cloud pairs (BASELINE config 4 model: ResNet-18 image encoder, G = 512,
+    2500-point clouds), then evaluate_ae.py in 'predicting' mode (per-batch CD + F1, evaluating.py:144-205) and
+    'evaluating' mode with --orig_scale_evaluation."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    save = str(tmp_path)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "train_svr.py"), "svr/all", "svr_smoke", "1", "0.000256",
+                        "--synthetic", "8", "--batch_size", "4", "--path2save", save], capture_output=True, text=True,
+                       timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert os.path.exists(os.path.join(save, "models", "DPFNets", "svr_smoke.pkl"))
+    ck = torch.load(os.path.join(save, "models", "DPFNets", "svr_smoke.pkl"), weights_only=False)
+    n_ref_params = 25203197          # SURVEY App. E: svr/all.yaml model
+    assert sum(v['exp_avg'].numel() for v in ck['optimizer_state']['state'].values()) == n_ref_params
+    assert len(ck['optimizer_state']['state']) > 2000       # the reference's per-tensor layout, not one arena entry
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "evaluate_ae.py"), "svr/all", "svr_smoke", "test", "2500",
+                        "2500", "predicting", "--synthetic", "6", "--path2save", save], capture_output=True, text=True,
+                       timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "CD:" in r.stdout and "F1:" in r.stdout
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "evaluate_ae.py"), "svr/all", "svr_smoke", "test", "2500",
+                        "1024", "evaluating", "--orig_scale_evaluation", "--synthetic", "6", "--path2save", save],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "CD:" in r.stdout
+
+
+def test_f_score_vs_oracle(native_lib, cuda):
+    """f_score (utils.py:38-42) through the native NN search against the numpy oracle."""
+    import numpy as np
+    from oracle import metrics_oracle as mo
+    from oracle import structural as so
+    from dpf_nets_b200.lib.networks.utils import f_score
+    g = torch.Generator().manual_seed(9)
+    a = (torch.rand((5, 700, 3), generator=g) - 0.5) * 0.2
+    b = a + 0.02 * torch.randn((5, 700, 3), generator=g)
+    got = f_score(a.to(cuda), b.to(cuda)).cpu().numpy()
+    d1, _, d2, _ = so.nndistance(a.numpy(), b.numpy())
+    want = mo.f_score(d1, d2)
+    assert np.allclose(got, want, rtol=1e-5) and (got > 0).all() and (got < 100).all()

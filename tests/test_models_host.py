@@ -112,3 +112,72 @@ def test_capturable_adam_hyper_table_matches_eager_formulas():
     b1, b2 = group['betas']
     want = [group['lr'], b1, b2, 1e-8, 1e-6, 1 - b1 ** 4, math.sqrt(1 - b2 ** 4)]
     assert torch.allclose(opt._hyper_host[0, :7], torch.tensor(want, dtype=torch.float32), rtol=1e-6, atol=0)
+
+
+def test_optimizer_state_round_trips_through_the_reference_layout():
+    """Checkpoint boundary of the optimizer state (reference: training.py:75-80, optimizers.py:32-40): one entry per
+    reference parameter on disk, one arena entry per coupling stack in memory; the conversion is lossless both ways
+    and the on-disk layout has exactly the reference model's parameter count and tensor shapes."""
+    from dpf_nets_b200.lib.networks import models
+    from dpf_nets_b200.lib.networks.optimizers import Adam, optimizer_state_from_reference, optimizer_state_to_reference
+    from dpf_nets_b200 import configs
+    c = configs.get('generation/chair')
+    c.update(p_decoder_n_flows=2, g_latent_space_size=16, g_prior_n_flows=2, g_prior_n_features=16)
+    torch.manual_seed(0)
+    m = models.Local_Cond_RNVP_MC_Global_RNVP_VAE(**c)
+    opt = Adam(m.parameters(), lr=1e-3, weight_decay=1e-6, betas=(0.9, 0.99), amsgrad=True)
+    g = torch.Generator().manual_seed(1)
+    for p in m.parameters():                      # a fake step: state without running the (GPU-only) decoder
+        opt.state[p] = {'step': 7, 'exp_avg': torch.randn(p.shape, generator=g), 'exp_avg_sq': torch.rand(p.shape, generator=g),
+                        'max_exp_avg_sq': torch.rand(p.shape, generator=g)}
+    ours = opt.state_dict()
+    ref = optimizer_state_to_reference(m, ours)
+    # the reference model has one nn.Parameter per state_dict entry that is not a buffer
+    sd = m.state_dict()
+    ref_params = [k for k in sd if not (k.endswith('running_mean') or k.endswith('running_var') or k.endswith('num_batches_tracked')
+                                        or k.endswith('.eps') or k.endswith('p_prior_mus') or k.endswith('p_prior_logvar'))]
+    assert len(ref['param_groups'][0]['params']) == len(ref_params) == len(ref['state'])
+    assert len(ref['param_groups'][0]['params']) > len(ours['param_groups'][0]['params'])
+    n_dec = len(m.pc_decoder.layout.param_index)
+    views = list(m.pc_decoder.layout.param_index.values())
+    names = [n for n, _ in m.named_parameters()]
+    first = names.index('pc_decoder.arena')     # reference entries first .. first + n_dec - 1 belong to the decoder
+    for j, (off, shape) in enumerate(views[:5] + views[-3:]):
+        jj = j if j < 5 else n_dec - 3 + (j - 5)
+        assert tuple(ref['state'][first + jj]['exp_avg'].shape) == tuple(shape)
+    back = optimizer_state_from_reference(m, ref)
+    assert back['param_groups'][0]['params'] == ours['param_groups'][0]['params']
+    for i, st in ours['state'].items():
+        assert back['state'][i]['step'] == st['step']
+        for k in ('exp_avg', 'exp_avg_sq', 'max_exp_avg_sq'):
+            assert torch.equal(back['state'][i][k].reshape(-1), st[k].reshape(-1)), (i, k)
+    opt2 = Adam(m.parameters(), lr=1e-3, amsgrad=True)
+    opt2.load_state_dict(back)                   # loads into a fresh optimizer
+    assert optimizer_state_from_reference(m, ours) is ours       # already in this package's layout: untouched
+    bad = {'state': {}, 'param_groups': [dict(ref['param_groups'][0], params=list(range(5)))]}
+    with pytest.raises(ValueError):
+        optimizer_state_from_reference(m, bad)
+
+
+@pytest.mark.parametrize("name,cls,ic", [("generation_chair", "Local_Cond_RNVP_MC_Global_RNVP_VAE", False),
+                                         ("autoencoding_all_original", "Local_Cond_RNVP_MC_Global_RNVP_VAE", False),
+                                         ("svr_all", "Local_Cond_RNVP_MC_Global_RNVP_VAE_IC", True)])
+def test_wholemodel_encoder_side_vs_reference(name, cls, ic):
+    """CPU half of the whole-model parity (the decoder half needs the GPU: tests/test_model_gpu.py): with the
+    key-derived deterministic weights, the train-mode PointNet encoder -> g_posterior head reproduces the
+    reference's g_posterior_mus (golden: tests/golden/make_golden_wholemodel.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _detstate import det_state, whole_model_inputs
+    from dpf_nets_b200 import configs
+    from dpf_nets_b200.lib.networks import models
+    fx = torch.load(os.path.join(GOLD, "wholemodel.pt"), weights_only=False)[name]
+    c = configs.get(fx["config_path"][len("configs/"):-len(".yaml")])
+    c["util_mode"] = "training"
+    m = getattr(models, cls)(**c)
+    m.load_state_dict(det_state({k: list(v.shape) for k, v in m.state_dict().items()}))
+    m.train()
+    inp = whole_model_inputs(fx["B"], fx["N"], 77, ic)
+    with torch.no_grad():
+        mus, logvars, _ = m._posterior(inp["cloud"], sample=False)
+    assert rel(mus, fx["g_posterior_mus"]) < 1e-5
