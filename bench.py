@@ -455,7 +455,8 @@ def eval_sweep(dev, S, N, world, rank, flush):
     COV / MMD / 1-NNA on every rank (lib/networks/evaluating.py:245-253 -> utils.pairwise_CD / COV / MMD / KNN).
     Timed on the device, max over ranks; all ranks take part."""
     import torch.distributed as dist
-    from dpf_nets_b200.lib.networks.utils import COV, KNN, MMD, pairwise_CD
+    from dpf_nets_b200.lib.networks.utils import pairwise_CD
+    from dpf_nets_b200.ops.metrics import cd_scores
     gen = torch.Generator().manual_seed(4321)          # every rank holds both sets (24.6 MB each at 1000 x 2048)
     G = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
     R = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
@@ -472,9 +473,10 @@ def eval_sweep(dev, S, N, world, rank, flush):
     tt = pairwise_CD(R, R)
     gt = pairwise_CD(G, R)
     b.record()
-    cov, mmd, nna = COV(gt), MMD(gt), KNN(gg, gt, tt, 1)
+    scores = cd_scores(gg, gt, tt)                     # one reduction launch on the device-resident matrices
     c.record()
     torch.cuda.synchronize()
+    cov, mmd, nna = scores.tolist()
     t = torch.tensor([a.elapsed_time(b), a.elapsed_time(c)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -65,6 +65,16 @@ def _to_eval_scale(r_clouds, p_clouds, batch, dev, kwargs, util_mode):
 
 
 def evaluate(iterator, model, loss_func, **kwargs):
+    """Reference signature (evaluating.py:13).  Gradient recording is switched off for the evaluation like in the
+    reference (:59) and - unlike it - switched back to its previous state on return."""
+    grad_was = torch.is_grad_enabled()
+    try:
+        return _evaluate(iterator, model, loss_func, **kwargs)
+    finally:
+        torch.set_grad_enabled(grad_was)
+
+
+def _evaluate(iterator, model, loss_func, **kwargs):
     train_mode, util_mode = kwargs.get('train_mode'), kwargs.get('util_mode')
     if kwargs.get('saving'):
         try:
