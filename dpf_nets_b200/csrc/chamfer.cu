@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include <math_constants.h>
 
+extern int g_fused_pairwise;
+
 namespace {
 
 constexpr int kTile = 2048;  // targets per shared-memory tile (32 KB as float4)
@@ -253,6 +255,136 @@ pairwise_cd_kernel(int S2, int n, int m, const float* __restrict__ A, const floa
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused all-pairs Chamfer matrix, BOTH directions from ONE distance evaluation per point pair
+// (the reference launches NmDistanceKernel twice, nndistance.cu:125-128, i.e. 2 n m evaluations per cloud pair).
+//
+// A thread keeps R query points of the row cloud A_i in registers (two per packed fp32x2 lane pair) and streams
+// the targets of B_j through shared memory, two per iteration.  For every distance d(q_r, t_k):
+//   * row direction  : best[r] = min(best[r], d(q_r,t_k), d(q_r,t_k+1))            one 3-input FMNMX3 per 2 evaluations
+//   * column direction: c_k = min_r d(q_r, t_k) in registers (FMNMX3 tree), then ONE warp-wide CREDUX.MIN on the fp32
+//     bit pattern (distances are >= +0, so unsigned order == float order) and a one-lane store into the warp's
+//     row of a [warps][targets] shared-memory table; the 8 warp rows are min-combined once per cloud pair.
+// Minima are exact, so per-point distances stay bit-identical with the reference kernel; the two sums run over
+// shared-memory arrays of per-point minima with ONE canonical summation order, which keeps out[i,j] == out[j,i]
+// bit-exact for A == B.  Requires n <= THREADS * R (one register-resident pass over the row cloud); larger row clouds
+// use the two-direction kernel above.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }   // -> FMNMX3
+
+__device__ __forceinline__ float warp_min_nonneg(float v) {
+  unsigned r;
+  asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(__float_as_uint(v)));
+  return __uint_as_float(r);
+}
+
+// canonical sum of arr[0..len): strided per-thread partials in ascending order, xor-tree per warp, warps in order
+template <int THREADS>
+__device__ __forceinline__ float canonical_sum(const float* __restrict__ arr, int len, float* red) {
+  float s = 0.f;
+  for (int e = threadIdx.x; e < len; e += THREADS) s += arr[e];
+  s = warp_sum(s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) t += red[w];
+  return t;
+}
+
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
+pairwise_cd_fused_kernel(int S2, int n, int m, const float* __restrict__ A, const float* __restrict__ B,
+                         float* __restrict__ out, int row_start, int row_step, int jblocks, int JB, int symmetric) {
+  static_assert(R % 2 == 0, "queries are processed in packed pairs");
+  constexpr int WARPS = THREADS / 32;
+  extern __shared__ float4 dyn_smem[];
+  float4* tile = dyn_smem;                                        // [kTile] targets of the chunk
+  float* colw = reinterpret_cast<float*>(tile + kTile);           // [WARPS][kTile] per-warp column minima
+  float* rowm = colw + WARPS * kTile;                             // [THREADS * R] row minima of the pair
+  __shared__ float red[WARPS];
+  const int rt = blockIdx.x / jblocks;
+  const int jb = blockIdx.x - rt * jblocks;
+  const int i = row_start + rt * row_step;
+  int j0 = jb * JB;
+  const int j1 = min(S2, j0 + JB);
+  if (symmetric) j0 = max(j0, i);
+  const float* a = A + (size_t)i * n * 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // the row cloud's queries: registers for the whole CTA lifetime; slots beyond n sit at +inf (d = +inf: never a minimum)
+  f32x2 qx2[R / 2], qy2[R / 2], qz2[R / 2];
+#pragma unroll
+  for (int r = 0; r < R; r += 2) {
+    float c[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int sidx = (r + h) * THREADS + threadIdx.x;
+      const bool ok = sidx < n;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) c[h][d] = ok ? __ldg(a + (size_t)sidx * 3 + d) : CUDART_INF_F;
+    }
+    qx2[r / 2] = pack2(c[0][0], c[1][0]);
+    qy2[r / 2] = pack2(c[0][1], c[1][1]);
+    qz2[r / 2] = pack2(c[0][2], c[1][2]);
+  }
+
+  for (int j = j0; j < j1; ++j) {
+    const float* b = B + (size_t)j * m * 3;
+    float best[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) best[r] = CUDART_INF_F;
+    float s2 = 0.f;
+    for (int t0 = 0; t0 < m; t0 += kTile) {
+      const int cnt = min(kTile, m - t0);
+      __syncthreads();                                            // previous chunk / pair fully consumed
+      load_tile<THREADS>(tile, b + (size_t)t0 * 3, cnt);
+      if ((cnt & 1) && threadIdx.x == 0) tile[cnt] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);   // pad to a pair
+      __syncthreads();
+      float* cw = colw + warp * kTile;
+#pragma unroll 2
+      for (int k = 0; k < cnt; k += 2) {
+        const float4 p0 = tile[k], p1 = tile[k + 1];
+        float d0[R], d1[R];
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+          sqdist2(p0, qx2[r / 2], qy2[r / 2], qz2[r / 2], d0[r], d0[r + 1]);
+          sqdist2(p1, qx2[r / 2], qy2[r / 2], qz2[r / 2], d1[r], d1[r + 1]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) best[r] = min3f(best[r], d0[r], d1[r]);
+        float c0 = d0[0], c1 = d1[0];
+#pragma unroll
+        for (int r = 1; r + 1 < R; r += 2) {
+          c0 = min3f(c0, d0[r], d0[r + 1]);
+          c1 = min3f(c1, d1[r], d1[r + 1]);
+        }
+        c0 = fminf(c0, d0[R - 1]);
+        c1 = fminf(c1, d1[R - 1]);
+        c0 = warp_min_nonneg(c0);
+        c1 = warp_min_nonneg(c1);
+        if (lane == 0) *reinterpret_cast<float2*>(cw + k) = make_float2(c0, c1);
+      }
+      __syncthreads();
+      // combine the warps' rows of this chunk (in place into row 0), then the canonical sum over the chunk
+      for (int e = threadIdx.x; e < cnt; e += THREADS) {
+        float v = colw[e];
+#pragma unroll
+        for (int w = 1; w < WARPS; ++w) v = fminf(v, colw[w * kTile + e]);
+        colw[e] = v;
+      }
+      __syncthreads();
+      s2 += canonical_sum<THREADS>(colw, cnt, red);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) rowm[r * THREADS + threadIdx.x] = best[r];
+    __syncthreads();
+    const float s1 = canonical_sum<THREADS>(rowm, n, red);
+    if (threadIdx.x == 0) out[(size_t)i * S2 + j] = s1 / (float)n + s2 / (float)m;
+  }
+}
+
 __global__ void symmetrize_upper_kernel(float* __restrict__ M, int S) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
@@ -302,6 +434,9 @@ int nn_one_direction(int b, int nq, const float* Q, int nt, const float* T, floa
 }
 
 }  // namespace
+
+// dpf_set_option(4, v): 1 (default) = the one-evaluation all-pairs kernel, 0 = the two-direction kernel (tests compare both)
+int g_fused_pairwise = 1;
 
 // Replaces nndistance() (nndistance.cuh:1, nndistance.cu:125-128).
 DPF_API int dpf_nndistance(int b, int n, const float* xyz, int m, const float* xyz2, float* result,
@@ -356,8 +491,20 @@ DPF_API int dpf_pairwise_cd(int S1, int S2, int n, int m, const float* A, const 
   const int jblocks = (S2 + JB - 1) / JB;
   const long long grid = (long long)n_rows * jblocks;
   DPF_REQUIRE(grid < 2147483647LL, DPF_ERR_BAD_ARG, "dpf_pairwise_cd: grid too large");
-  pairwise_cd_kernel<8, 256><<<(int)grid, 256, 0, (cudaStream_t)stream>>>(S2, n, m, A, B, out, row_start, row_step,
-                                                                  jblocks, JB, symmetric);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 2048 && g_fused_pairwise) {        // one distance evaluation per point pair for both directions
+    constexpr int T = 256;
+    auto launch = [&](auto kern, int R) {
+      const size_t smem = sizeof(float4) * kTile + sizeof(float) * ((size_t)(T / 32) * kTile + (size_t)T * R);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<(int)grid, T, smem, st>>>(S2, n, m, A, B, out, row_start, row_step, jblocks, JB, symmetric);
+    };
+    if (n <= 512) launch(pairwise_cd_fused_kernel<2, T>, 2);
+    else if (n <= 1024) launch(pairwise_cd_fused_kernel<4, T>, 4);
+    else launch(pairwise_cd_fused_kernel<8, T>, 8);
+    return dpf_check_launch("pairwise_cd_fused_kernel");
+  }
+  pairwise_cd_kernel<8, 256><<<(int)grid, 256, 0, st>>>(S2, n, m, A, B, out, row_start, row_step, jblocks, JB, symmetric);
   return dpf_check_launch("pairwise_cd_kernel");
 }
 

@@ -74,12 +74,14 @@ int g_dpf_pdl = 1;
 // Option 3: backward pass 2 with two tiles in flight per SM (544-thread CTAs, MMA issuer warp); 0 = the
 // one-tile-per-SM form (tests compare both).
 int g_dpf_p2_two_tiles = 1;
+extern int g_fused_pairwise;   // chamfer.cu
 DPF_API int dpf_set_option(int option, int value) {
-  DPF_REQUIRE(option >= 0 && option <= 3, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
+  DPF_REQUIRE(option >= 0 && option <= 4, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
   if (option == 0) g_merged_forward = value != 0;
   else if (option == 1) g_fused_eval = value != 0;
   else if (option == 2) g_dpf_pdl = value != 0;
-  else g_dpf_p2_two_tiles = value != 0;
+  else if (option == 3) g_dpf_p2_two_tiles = value != 0;
+  else g_fused_pairwise = value != 0;
   return DPF_OK;
 }
 

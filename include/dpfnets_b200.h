@@ -33,7 +33,9 @@ int dpf_launch_count(long long* count);
  * option 1: fused all-layer eval-mode decoder, one launch for the whole stack (1 = on, default;
  *           0 = one launch per layer).  Both exist so that tests can compare the two forms.
  * option 2: programmatic dependent launch of the per-layer kernels (1 = on, default).
- * option 3: backward pass 2 with two tiles in flight per SM (1 = on, default; 0 = one tile per SM). */
+ * option 3: backward pass 2 with two tiles in flight per SM (1 = on, default; 0 = one tile per SM).
+ * option 4: all-pairs Chamfer with both directions from one distance evaluation per point pair (1 = on, default;
+ *           0 = one pass per direction like the reference's two launches). */
 int dpf_set_option(int option, int value);
 int dpf_profile_enable(int on);
 int dpf_profile_collect(double* ms, long long* counts, int n);

@@ -153,3 +153,24 @@ def test_speed_vs_reference_kernels_on_this_gpu(backend, ref, cuda):
     assert torch.allclose(pairwise_cd(A[:4].contiguous(), Bc[:4].contiguous()), ref.pairwise_cd(A[:4].contiguous(), Bc[:4].contiguous()),
                           rtol=1e-5, atol=0.0)
     assert res["speedup_nndistance"] > 1.0 and res["speedup_pairwise"] > 1.0
+
+
+@pytest.mark.parametrize("S1,S2,n,m", [(3, 4, 2048, 2048), (4, 3, 2047, 2049), (5, 5, 300, 513), (2, 3, 1000, 4100), (3, 2, 1, 7),
+                                       (2, 2, 600, 1), (3, 3, 1025, 333)])
+def test_pairwise_cd_one_evaluation_equals_two_direction_kernel(native_lib, cuda, S1, S2, n, m):
+    """The all-pairs kernel that takes both Chamfer directions from ONE distance evaluation per point pair
+    (row minima in registers, column minima through CREDUX.MIN + a per-warp shared-memory table) against the
+    two-direction kernel (one pass per direction like the reference's two launches, nndistance.cu:125-128) and the
+    C oracle: per-point minima are exact in both, only the order of the two sums over points differs."""
+    from dpf_nets_b200 import _lib
+    from dpf_nets_b200.ops import pairwise_cd
+    A, B = _clouds(S1, n, 21, cuda), _clouds(S2, m, 22, cuda)
+    fused = pairwise_cd(A, B)
+    _lib.check(native_lib.dpf_set_option(4, 0), "dpf_set_option")
+    try:
+        two = pairwise_cd(A, B)
+    finally:
+        _lib.check(native_lib.dpf_set_option(4, 1), "dpf_set_option")
+    assert ((fused - two).abs() <= 2e-6 * two.abs()).all(), ((fused - two).abs() / two.abs()).max()
+    o = so.pairwise_cd(A.cpu().numpy(), B.cpu().numpy())
+    np.testing.assert_allclose(fused.cpu().numpy(), o, rtol=1e-5)
