@@ -43,22 +43,30 @@ def main():
         torch.manual_seed(0)
         model = (Local_Cond_RNVP_MC_Global_RNVP_VAE_IC if ic else Local_Cond_RNVP_MC_Global_RNVP_VAE)(**config)
         shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
-        model.load_state_dict(det_state(shapes))
-        model.train()
-        crit = Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss(**config)
+        state = det_state(shapes)
         inp = whole_model_inputs(B, N, 77, ic)
-        with DetRandn(5):
-            out = model(inp["cloud"], inp["eval_cloud"], inp["image"]) if ic else model(inp["cloud"], inp["eval_cloud"])
-        loss, pnll, gnll, gent = crit(inp["cloud"], inp["eval_cloud"], out)
-        loss.backward()
-        named = dict(model.named_parameters())
-        fx[name] = {"config_path": path, "B": B, "N": N, "shapes": shapes,
-                    "losses": torch.stack([loss.detach(), pnll.detach(), gnll.detach(), gent.detach()]).double(),
-                    "z": out["p_prior_samples"][0].detach().clone(),
-                    "sum_logvar": sum(out["p_prior_logvars"][1:]).detach().clone(),
-                    "g_posterior_mus": out["g_posterior_mus"].detach().clone(),
-                    "grads": {k: named[k].grad.clone() for k in GRAD_KEYS[ic]}}
-        print(name, [float(x) for x in fx[name]["losses"]], float(fx[name]["z"].abs().max()))
+        res = {}
+        for prec in ("f32", "f64"):      # f64 = the same reference modules in double: the truth both fp32 results are measured against
+            model.load_state_dict(state)
+            model = model.double() if prec == "f64" else model.float()
+            model.train()
+            model.zero_grad()
+            crit = Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss(**config)
+            x = {k: (v.double() if prec == "f64" else v) for k, v in inp.items()}
+            with DetRandn(5):
+                out = model(x["cloud"], x["eval_cloud"], x["image"]) if ic else model(x["cloud"], x["eval_cloud"])
+            loss, pnll, gnll, gent = crit(x["cloud"], x["eval_cloud"], out)
+            loss.backward()
+            named = dict(model.named_parameters())
+            res[prec] = {"losses": torch.stack([loss.detach(), pnll.detach(), gnll.detach(), gent.detach()]).double(),
+                         "z": out["p_prior_samples"][0].detach().clone(),
+                         "sum_logvar": sum(out["p_prior_logvars"][1:]).detach().clone(),
+                         "g_posterior_mus": out["g_posterior_mus"].detach().clone(),
+                         "grads": {k: named[k].grad.clone() for k in GRAD_KEYS[ic]}}
+        fx[name] = dict(res["f32"], config_path=path, B=B, N=N, shapes=shapes,
+                        truth64={"losses": res["f64"]["losses"], "z": res["f64"]["z"].float(), "sum_logvar": res["f64"]["sum_logvar"].float(),
+                                 "grads": {k: v.float() for k, v in res["f64"]["grads"].items()}})
+        print(name, [float(v) for v in fx[name]["losses"]], [float(v) for v in fx[name]["truth64"]["losses"]])
     # the key -> shape listing is regenerated on the test side from this package's own model (it is checked against
     # the reference's in tests/test_models_host.py), so it is not stored
     for v in fx.values():

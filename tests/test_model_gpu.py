@@ -164,7 +164,7 @@ def test_graphed_train_step_matches_eager(native_lib, cuda, monkeypatch):
                                          ("autoencoding_all_original", "Local_Cond_RNVP_MC_Global_RNVP_VAE", False),
                                          ("svr_all", "Local_Cond_RNVP_MC_Global_RNVP_VAE_IC", True)])
 @pytest.mark.parametrize("precision", ["fp32", "auto"])
-def test_wholemodel_training_loss_and_gradients_vs_reference(native_lib, cuda, name, cls, ic, precision):
+def test_wholemodel_training_loss_and_gradients_vs_reference(native_lib, cuda, monkeypatch, name, cls, ic, precision):
     """Whole-model training-mode forward + VAE loss + backward of the generation (G=128), AE all_original (G=512) and
     SVR all (image encoder + G=512) models against the UNMODIFIED reference (tests/golden/make_golden_wholemodel.py:
     weights regenerated from key names, torch.randn_like replaced by the same seeded stream on both sides).
@@ -178,6 +178,8 @@ def test_wholemodel_training_loss_and_gradients_vs_reference(native_lib, cuda, n
     fx = torch.load(os.path.join(ROOT, "tests", "golden", "wholemodel.pt"), weights_only=False)[name]
     c = configs.get(fx["config_path"][len("configs/"):-len(".yaml")])
     c["util_mode"] = "training"
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)      # the ResNet-18 convolutions in true fp32, like the CPU reference
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
     m = getattr(models, cls)(**c)
     m.load_state_dict(det_state({k: list(v.shape) for k, v in m.state_dict().items()}))
     m = m.to(cuda).train()
@@ -189,18 +191,29 @@ def test_wholemodel_training_loss_and_gradients_vs_reference(native_lib, cuda, n
     losses = crit(inp["cloud"], inp["eval_cloud"], out)
     losses[0].backward()
     fp32 = precision == "fp32"
+    t64 = fx["truth64"]
+
+    def rel(a, b):
+        return float((a.detach().cpu().double() - b.double()).abs().max() / b.double().abs().max())
+
+    def gate(a, ref32, truth, tol, what):
+        """within `tol` of the reference's fp32 result, or no further from the fp64 truth (the same reference modules run
+        in double) than twice the reference's own fp32 result is: batch-statistics BatchNorm over B = 3..4 shapes
+        (FiLM nets, latent flows, ResNet) makes some gradients ill-conditioned in fp32 on BOTH sides."""
+        e = rel(a, ref32)
+        assert e < tol or rel(a, truth) < 2 * rel(ref32, truth) + 1e-6, (what, e, rel(a, truth), rel(ref32, truth))
+
     got = torch.stack([l.detach().double().cpu() for l in losses])
     tol_loss = 1e-4 if fp32 else 5e-3
     assert ((got - fx["losses"]).abs() <= tol_loss * fx["losses"].abs()).all(), (got, fx["losses"])
-    rel = lambda a, b: float((a.detach().cpu() - b).abs().max() / b.abs().max())
     assert rel(out["g_posterior_mus"], fx["g_posterior_mus"]) < 1e-4
-    assert rel(out["p_prior_samples"][0], fx["z"]) < (1e-3 if fp32 else 2e-2)
-    assert rel(out["p_prior_logvars"].tail_total, fx["sum_logvar"]) < (1e-3 if fp32 else 2e-2)
+    gate(out["p_prior_samples"][0], fx["z"], t64["z"], 1e-3 if fp32 else 2e-2, "z")
+    gate(out["p_prior_logvars"].tail_total, fx["sum_logvar"], t64["sum_logvar"], 1e-3 if fp32 else 2e-2, "sum_logvar")
     named = dict(m.named_parameters())
     dec = m.pc_decoder.named_views(grad=True)
     for k in GRAD_KEYS[ic]:
         gk = dec[k[len("pc_decoder."):]] if k.startswith("pc_decoder.") else named[k].grad
-        assert rel(gk, fx["grads"][k]) < (2e-2 if fp32 else 5e-2), (k, rel(gk, fx["grads"][k]))
+        gate(gk, fx["grads"][k], t64["grads"][k], 2e-2 if fp32 else 5e-2, k)
 
 
 def test_entry_points_svr_and_predicting(native_lib, cuda, tmp_path):
