@@ -717,14 +717,18 @@ def test_nll_outputs_equal_list_path(mods, cuda, precision):
     _, decoders = mods
     from dpf_nets_b200.lib.networks.losses import PointFlowNLL
     torch.manual_seed(3)
-    m = decoders.LocalCondRNVPDecoder(3, 64, 24).to(cuda)
+    m = decoders.LocalCondRNVPDecoder(3, 64, 24)
+    with torch.no_grad():                      # SURVEY 8d recipe: default init + non-trivial last SharedDots (well-conditioned BN)
+        g5 = torch.Generator().manual_seed(5)
+        for k, t in m.named_views().items():
+            if k.endswith("sd2.weight"):
+                t.copy_(torch.randn(t.shape, generator=g5) * 0.3)
+    m = m.to(cuda)
     m.precision = precision
-    with torch.no_grad():
-        m.arena.add_(0.05 * torch.randn_like(m.arena))
     m.train()
     gen = torch.Generator().manual_seed(4)
-    p = (torch.rand((5, 3, 333), generator=gen) - 0.5).to(cuda)
-    g0 = torch.randn((5, 24), generator=gen).to(cuda)
+    p = (torch.rand((6, 3, 333), generator=gen) - 0.5).to(cuda)
+    g0 = torch.randn((6, 24), generator=gen).to(cuda)
     base_mu, base_lv = torch.zeros_like(p), torch.full_like(p, -0.7)
     crit = PointFlowNLL()
     res = {}
