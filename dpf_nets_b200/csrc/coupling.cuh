@@ -75,6 +75,7 @@ struct DecoderWorkspace {
   float* pend;              // [L][8]  backward: deferred BN_a correction {c0, c1, q00, q01, q11} pass 1 hands to pass 2
   double* m12_rep;          // [L][DPF_M12_REP][2][F][2] backward: replicated sum_b s*dt, sum_b s*ds (BN_b batch terms m1, m2)
   unsigned int* barriers;   // [L][32] grid-barrier counters of the merged train-mode forward (one 128-B line per layer)
+  unsigned int* barriers_bwd;   // [L][32] the same for the merged backward launch
   size_t bytes;
 };
 
@@ -95,6 +96,7 @@ __host__ inline DecoderWorkspace carve_workspace(void* base, int L, int G, int B
   w.dx[1] = (float*)take(sizeof(float) * (size_t)B * 3 * N);
   w.w1_bf16 = (unsigned short*)take(sizeof(unsigned short) * (size_t)L * 6 * DPF_F * DPF_F);
   w.barriers = (unsigned int*)take(sizeof(unsigned int) * (size_t)L * 32);
+  w.barriers_bwd = (unsigned int*)take(sizeof(unsigned int) * (size_t)L * 32);
   w.ltab = (float*)take(sizeof(float) * (size_t)L * 2 * DPF_F * DPF_LTAB_ROW);
   w.pend = (float*)take(sizeof(float) * (size_t)L * 8);
   w.m12_rep = (double*)take(sizeof(double) * (size_t)L * DPF_M12_REP * 2 * DPF_F * 2);

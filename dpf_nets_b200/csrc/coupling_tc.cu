@@ -219,7 +219,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // Probe with the resource footprint of the cooperative kernels (threads, dynamic shared memory, TMEM columns,
 // <= 128 registers): all CTAs meet at a barrier with a short timeout; counter[1] != 0 afterwards = they were NOT all
 // resident at the same time.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(576)
 coresidency_probe_kernel(unsigned int* counter, int tmem_cols) {
   extern __shared__ unsigned char smraw[];
   __shared__ uint32_t tmem_base;
@@ -1105,6 +1105,655 @@ coupling_bwd_p2_tc4_kernel(const BwdArgs a, const unsigned short* __restrict__ w
 }
 
 // =============================================================================================
+// MERGED backward launch of one layer: pass 1 -> software grid barrier -> pass 2 in ONE kernel (one CTA per SM,
+// the two-pipelines + MMA-issuer-warp organisation of coupling_bwd_p2_tc4_kernel for BOTH phases).  What it removes
+// per layer: one launch transition (the pass-2 CTAs own a whole SM, so PDL cannot overlap pass 1 <-> pass 2), one
+// set of per-CTA prologues (barrier init, TMEM allocation, 48 KB weight stage, tables), the pend / m12 hand-over
+// through global memory.  Phase 1 (the per-shape FiLM / last-SharedDot reductions on the tensor cores, see the
+// pass-1 kernel below) reuses phase 2's buffers: h3 hi | lo tiles in H[0] | H[1], the 0/1 mask tile in D[1] (its
+// ignored second M block is X), the per-point weight rows in X, its accumulators in the wgrad TMEM columns.
+//   TMEM: [0,128) / [128,256) the halves' recompute -> dgrad accumulators; phase 1: [256,320) / [320,384) the halves'
+//   reduction accumulators {br: h3 sums [0,16), mask sums [16,32)}; phase 2: [256,384) wgrad, [384,400) BN_a sums.
+// Tiles: phase 1 gives every pipeline a CONTIGUOUS run of tiles (mostly one shape: one accumulator flush per run),
+// phase 2 the strided assignment of the tc4 kernel.
+// =============================================================================================
+struct TcBwdMSmem {
+  unsigned char W[2 * N_IMG * IMG_W];   // [br][W1 hi, W1 lo, W1^T hi]
+  TcP2Half h[2];
+  float4 PA[2][F / 2][2];               // folded BN_a, channel-pair layout (see TcP2Smem4)
+  float4 PE[2][2][F / 2][3];            // [half][br][j]: {S_a, S_b, T_a, T_b}, {W20_a, W20_b, W21_a, W21_b}, phase 2: {-c3_a, -c3_b, -c2_a, -c2_b};
+                                        //   phase 1: slot [2] = {s_raw_a, s_raw_b, shift_a, shift_b} of the tile's shape
+  float4 lt0[2][F];                     // per channel: {bnB istd, bnB mean, c2, c3}
+  float2 lt1[2][F];                     // per channel: {W2_0, W2_1}
+  float t1buf[2][DPF_TILE][2];          // phase 2: T1 hand-over inside a half; phase 1: lo-part sums of the flush [half][br][w][64]
+  double pend_red[20];
+  float b2fin[2][2];
+  uint64_t bar_load, bar_req[2], bar_done[2];
+  uint32_t tmem_base;
+};
+
+static_assert(sizeof(TcBwdMSmem) + 1024 <= 232448, "merged backward: shared memory exceeds the 227 KB per-CTA limit");
+
+template <int K, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(NT4, 1)
+coupling_bwd_merged_kernel(const BwdArgs a, const unsigned short* __restrict__ wimg, unsigned int* __restrict__ barrier_counter) {
+  extern __shared__ unsigned char smraw[];
+  TcBwdMSmem& s = *reinterpret_cast<TcBwdMSmem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = tid >= 512;
+  const int half = (tid >> 8) & 1, row = tid & 127, part = (tid >> 7) & 1, quarter = warp & 3;
+  const BranchLayout lay = branch_layout(a.f.k, a.f.w, a.f.G);
+  const int n_workers = 2 * gridDim.x;
+  const int worker = 2 * blockIdx.x + half;
+  // phase 1: contiguous tiles [p1_lo(w), p1_lo(w+1)); phase 2: tiles w, w + n_workers, ...
+  const int p1_per = (a.f.n_tiles + n_workers - 1) / n_workers;
+  auto p1_lo = [&](int w) { return min(a.f.n_tiles, w * p1_per); };
+  auto iters_of = [&](int w) { return w < a.f.n_tiles ? (a.f.n_tiles - w + n_workers - 1) / n_workers : 0; };
+  pdl_launch_dependents();
+  if (tid == 0) {
+    umma::mbar_init(&s.bar_load, 1);
+    umma::mbar_init(&s.bar_req[0], 256);
+    umma::mbar_init(&s.bar_req[1], 256);
+    umma::mbar_init(&s.bar_done[0], 1);
+    umma::mbar_init(&s.bar_done[1], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&s.tmem_base, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  if (tid == 0) {
+    umma::mbar_expect_tx(&s.bar_load, 2 * N_IMG * IMG_W);
+    umma::bulk_g2s(s.W, wimg, 2 * N_IMG * IMG_W, &s.bar_load);
+  }
+  if (!issuer) {       // independent of the previous kernels: zero the per-point weight tiles
+    for (int i = tid; i < (int)(IMG_H / 16); i += 512) {
+      reinterpret_cast<uint4*>(s.h[0].X)[i] = make_uint4(0u, 0u, 0u, 0u);
+      reinterpret_cast<uint4*>(s.h[1].X)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  if (tid < 4) (&s.b2fin[0][0])[tid] = 0.f;
+  pdl_wait();          // the previous backward kernel's sums / gradients are read from here on
+  // static tables of this layer (bwd_tables_kernel) + the deferred BN_a correction owed by the previous step
+  if (tid < 128) {
+    const float4 t0 = reinterpret_cast<const float4*>(a.ltab)[tid * (DPF_LTAB_ROW / 4) + 0];
+    const float4 t1 = reinterpret_cast<const float4*>(a.ltab)[tid * (DPF_LTAB_ROW / 4) + 1];
+    float* pa = reinterpret_cast<float*>(&s.PA[tid >> 6][(tid & 63) >> 1][0]);
+    const int ln = tid & 1;
+    pa[ln] = t0.x;        // A00
+    pa[2 + ln] = t0.z;    // c0
+    pa[4 + ln] = t0.y;    // A01
+    pa[6 + ln] = 0.f;
+    s.lt0[tid >> 6][tid & 63] = make_float4(t1.x, t0.w, 0.f, 0.f);
+    s.lt1[tid >> 6][tid & 63] = make_float2(t1.y, t1.z);
+  }
+  const Pending P = tc_compute_pending(a, blockIdx.x == 0, s.pend_red);     // all threads (contains __syncthreads)
+  const float sig1 = sqrtf(a.f.eps + 1.0f);
+  const uint32_t T_WG = tmem + 256, T_BN = tmem + 384;
+  const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+
+  // =========================================== phase 1 ===========================================
+  if (issuer) {
+    if (lane == 0) {
+      umma::mbar_wait(&s.bar_load, 0);
+      int t_lo[2] = {p1_lo(2 * (int)blockIdx.x), p1_lo(2 * (int)blockIdx.x + 1)};
+      int n_it[2] = {p1_lo(2 * (int)blockIdx.x + 1) - t_lo[0], p1_lo(2 * (int)blockIdx.x + 2) - t_lo[1]};
+      int it[2] = {0, 0}, stage[2] = {0, 0}, cur_b[2] = {-1, -1};
+      uint32_t ph[2] = {0u, 0u}, acc[2] = {0u, 0u};
+      int remaining = 3 * (n_it[0] + n_it[1]);
+      while (remaining > 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (it[h] < n_it[h] && umma::mbar_test(&s.bar_req[h], ph[h])) {
+            ph[h] ^= 1u;
+            umma::fence_after_sync();
+            TcP2Half& hb = s.h[h];
+            const uint32_t T_F = tmem + h * 128, T_R = tmem + 256 + h * 64;
+            if (stage[h] == 0) {          // forward recompute, both branches
+              const int b = (t_lo[h] + it[h]) / a.f.tiles_per_b;
+              acc[h] = (b == cur_b[h]) ? 1u : 0u;       // a new shape starts a new accumulation run
+              cur_b[h] = b;
+              issue_gemm1<SPLIT>(T_F, hb.H, hb.D, wimg_at<true>(s.W, 0, 0), wimg_at<true>(s.W, 0, 1));
+              issue_gemm1<SPLIT>(T_F + F, hb.H + IMG_H, hb.D + IMG_H, wimg_at<true>(s.W, 1, 0), wimg_at<true>(s.W, 1, 1));
+            } else {                      // reductions of branch stage - 1: h3 (hi | lo) and mask tiles against the weight rows
+              const int br = stage[h] - 1;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma::mma_bf16(T_R + br * 32, umma::desc_at(DESC_MN, umma::smem_u32(hb.H) + 2048 * k),
+                               umma::desc_at(DESC_MN, umma::smem_u32(hb.X) + 2048 * k), IDESC_RED, (acc[h] || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma::mma_bf16(T_R + br * 32 + 16, umma::desc_at(DESC_MN, umma::smem_u32(hb.D + IMG_H) + 2048 * k),
+                               umma::desc_at(DESC_MN, umma::smem_u32(hb.X) + 2048 * k), IDESC_RED, (acc[h] || k > 0) ? 1u : 0u);
+            }
+            umma::mma_commit(&s.bar_done[h]);
+            if (++stage[h] == 3) { stage[h] = 0; ++it[h]; }
+            --remaining;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    TcP2Half& hb = s.h[half];
+    const int t_lo = p1_lo(worker), n_it = p1_lo(worker + 1) - t_lo;
+    const uint32_t T_F = tmem + half * 128, T_R = tmem + 256 + half * 64;
+    uint64_t* req = &s.bar_req[half];
+    uint64_t* done = &s.bar_done[half];
+    uint32_t ph = 0;
+    float dW2acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};      // part 0, row < 64: channel row of branch [br], output [w]
+    float b2acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    int cur_b = -1;
+    umma::named_bar_sync(3, 512);        // tables + zeroed X tiles visible to both halves
+
+    // sums of the finished run (all tiles of shape b) -> FiLM gradients, BN_b batch terms, dW2 (registers)
+    auto flush_run = [&](int b) {
+      umma::fence_after_sync();
+      if (part == 0) {
+        if (row >= F) {                    // lanes 64..127 hold the h3-lo part of channel row - 64
+#pragma unroll
+          for (int br = 0; br < 2; ++br) {
+            uint32_t d1[4];
+            umma::tmem_ld4(T_R + lane_off + br * 32 + br * 4, d1);
+            umma::tmem_ld_wait4(d1);
+            s.t1buf[half][(br * 2 + 0) * F / 2 + (row - F) / 2][(row - F) & 1] = __uint_as_float(d1[0]) + __uint_as_float(d1[1]);
+            s.t1buf[half][(br * 2 + 1) * F / 2 + (row - F) / 2][(row - F) & 1] = __uint_as_float(d1[2]) + __uint_as_float(d1[3]);
+          }
+        }
+      }
+      umma::named_bar_sync(1 + half, 256);
+      if (part == 0 && row < F) {
+        const int c = row;
+#pragma unroll
+        for (int br = 0; br < 2; ++br) {
+          uint32_t d1[4], d2[4];
+          umma::tmem_ld4(T_R + lane_off + br * 32 + br * 4, d1);
+          umma::tmem_ld4(T_R + lane_off + br * 32 + 16 + br * 4, d2);
+          umma::tmem_ld_wait4(d1);
+          umma::tmem_ld_wait4(d2);
+          const float S0 = __uint_as_float(d1[0]) + __uint_as_float(d1[1]) + s.t1buf[half][(br * 2 + 0) * F / 2 + c / 2][c & 1];
+          const float S1 = __uint_as_float(d1[2]) + __uint_as_float(d1[3]) + s.t1buf[half][(br * 2 + 1) * F / 2 + c / 2][c & 1];
+          const float M0 = __uint_as_float(d2[0]) + __uint_as_float(d2[1]);
+          const float M1 = __uint_as_float(d2[2]) + __uint_as_float(d2[3]);
+          const float2 w2 = s.lt1[br][c];
+          const float* pe2 = reinterpret_cast<const float*>(&s.PE[half][br][c >> 1][2]);
+          const float sraw = pe2[c & 1], shift = pe2[2 + (c & 1)];
+          const float dt = fmaf(w2.x, M0, w2.y * M1);
+          const float ds = (fmaf(w2.x, S0, w2.y * S1) - shift * dt) / sraw;
+          atomicAdd(&a.dfilm[((size_t)(br * 2 + 0) * a.f.B + b) * F + c], ds);
+          atomicAdd(&a.dfilm[((size_t)(br * 2 + 1) * a.f.B + b) * F + c], dt);
+          if (a.f.training) {              // BN_b batch terms for phase 2: m1 = sum_b s*dt / M, m2 = sum_b s*ds / M
+            double* rep = a.m12_rep + (size_t)(worker & (DPF_M12_REP - 1)) * (2 * F * 2) + (size_t)(br * F + c) * 2;
+            DPF_GATOMIC(atomicAdd(rep + 0, (double)sraw * (double)dt));
+            DPF_GATOMIC(atomicAdd(rep + 1, (double)sraw * (double)ds));
+          }
+          dW2acc[br][0] += S0;
+          dW2acc[br][1] += S1;
+        }
+      }
+      umma::fence_before_sync();
+      umma::named_bar_sync(1 + half, 256);   // t1buf / accumulators are free again
+    };
+
+    for (int it = 0; it < n_it; ++it) {
+      const int tile = t_lo + it;
+      const int b = tile / a.f.tiles_per_b;
+      const int n = (tile - b * a.f.tiles_per_b) * DPF_TILE + row;
+      const bool valid = n < a.f.N;
+      const TcRaw raw = tc_load_raw(a, b, n, valid);
+      if (it > 0) {      // the previous tile's branch-1 reductions read H / D[1] / X and feed the accumulators
+        umma::mbar_wait(done, ph);
+        ph ^= 1;
+      }
+      if (b != cur_b) {
+        if (cur_b >= 0) flush_run(cur_b);
+        cur_b = b;
+      }
+      if (part == 0) {   // FiLM fold of this tile's shape
+        const int br = row >> 6, c = row & 63;
+        const float sc = a.f.film[((size_t)(br * 2 + 0) * a.f.B + b) * F + c];
+        const float sh = a.f.film[((size_t)(br * 2 + 1) * a.f.B + b) * F + c];
+        const float4 l0 = s.lt0[br][c];
+        const float S = sc * l0.x;
+        float* pe = reinterpret_cast<float*>(&s.PE[half][br][c >> 1][0]);
+        const int ln = c & 1;
+        pe[ln] = S;
+        pe[2 + ln] = fmaf(-S, l0.y, sh);
+        pe[8 + ln] = sc;
+        pe[10 + ln] = sh;
+      }
+      const TcPoint g = tc_finish_point<MODE>(a, P, raw, valid);
+      const float xk0 = pick3(g.x, a.f.keep0);
+      const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
+      const f32x2 xk0_2 = f2_pack(xk0, xk0), xk1_2 = f2_pack(xk1, xk1);
+      // ---- stage 0: h1 hi -> H, lo -> D (both branches), per-point weight row -> X ----
+#pragma unroll
+      for (int br = 0; br < 2; ++br) {
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int q = part * 4 + qq;
+          uint32_t w[4], wl[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 P0 = s.PA[br][q * 4 + i][0];
+            f32x2 v2 = f2_fma(f2_pack(P0.x, P0.y), xk0_2, f2_pack(P0.z, P0.w));
+            if (K == 2) {
+              const float4 P1 = s.PA[br][q * 4 + i][1];
+              v2 = f2_fma(f2_pack(P1.x, P1.y), xk1_2, v2);
+            }
+            float va, vb;
+            f2_unpack(v2, va, vb);
+            va = fmaxf(va, 0.f);
+            vb = fmaxf(vb, 0.f);
+            w[i] = umma::pack_bf16(va, vb);
+            if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
+          }
+          const uint32_t off = umma::sw128_offset(row, q);
+          *reinterpret_cast<uint4*>(hb.H + br * IMG_H + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          if (SPLIT) *reinterpret_cast<uint4*>(hb.D + br * IMG_H + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        }
+      }
+      if (part == 0) {   // weights of both branches: {mu0 hi, mu0 lo, mu1 hi, mu1 lo, lv0 hi, lv0 lo, lv1 hi, lv1 lo}
+        uint32_t w[4];
+        const float dv[4] = {g.do_mu[0], g.do_mu[1], g.do_lv[0], g.do_lv[1]};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t hi = umma::pack_bf16(dv[i], 0.f) & 0xffffu;
+          const float lo = dv[i] - __uint_as_float(hi << 16);
+          w[i] = umma::pack_bf16(0.f, lo) | hi;
+        }
+        *reinterpret_cast<uint4*>(hb.X + umma::sw128_offset(row, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+        b2acc[0][0] += g.do_mu[0]; b2acc[0][1] += g.do_mu[1];
+        b2acc[1][0] += g.do_lv[0]; b2acc[1][1] += g.do_lv[1];
+      }
+      umma::fence_async_smem();
+      umma::mbar_arrive(req);
+      umma::mbar_wait(done, ph);
+      ph ^= 1;
+      umma::fence_after_sync();
+      // ---- stages 1, 2: h3 (hi | lo) and mask of one branch -> H[0] | H[1], D[1]; reductions on the tensor cores ----
+#pragma unroll 1
+      for (int br = 0; br < 2; ++br) {
+        if (br == 1) {   // branch 0's reductions still read the tiles
+          umma::mbar_wait(done, ph);
+          ph ^= 1;
+          umma::fence_after_sync();
+        }
+#pragma unroll 1
+        for (int hc = 0; hc < 2; ++hc) {
+          uint32_t r[16];
+          umma::tmem_ld16_issue(T_F + lane_off + br * F + part * 32 + hc * 16, r);
+          umma::tmem_ld_wait16(r);
+          uint32_t wh[8], wl[8], wm[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 E0 = s.PE[half][br][part * 16 + hc * 8 + j][0];
+            const f32x2 a2 = f2_fma(f2_pack(E0.x, E0.y), f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), f2_pack(E0.z, E0.w));
+            float ha, hbv;
+            f2_unpack(a2, ha, hbv);
+            ha = fmaxf(ha, 0.f);
+            hbv = fmaxf(hbv, 0.f);
+            wh[j] = umma::pack_bf16(ha, hbv);
+            wl[j] = umma::pack_bf16(ha - __uint_as_float(wh[j] << 16), hbv - __uint_as_float(wh[j] & 0xffff0000u));
+            wm[j] = (ha > 0.f ? 0x3f80u : 0u) | (hbv > 0.f ? 0x3f800000u : 0u);
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t off = umma::sw128_offset(row, part * 4 + hc * 2 + q);
+            *reinterpret_cast<uint4*>(hb.H + off) = make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3]);
+            *reinterpret_cast<uint4*>(hb.H + IMG_H + off) = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+            *reinterpret_cast<uint4*>(hb.D + IMG_H + off) = make_uint4(wm[4 * q], wm[4 * q + 1], wm[4 * q + 2], wm[4 * q + 3]);
+          }
+        }
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        umma::mbar_arrive(req);
+      }
+    }
+    if (n_it > 0) {
+      umma::mbar_wait(done, ph);
+      ph ^= 1;
+      flush_run(cur_b);
+    }
+    // last-SharedDot gradients of this pipeline
+    if (part == 0) {
+#pragma unroll
+      for (int br = 0; br < 2; ++br)
+#pragma unroll
+        for (int wi = 0; wi < 2; ++wi) {
+          const float v = warp_sum(b2acc[br][wi]);
+          if (lane == 0 && n_it > 0) atomicAdd(&s.b2fin[br][wi], v);
+        }
+      if (row < F && n_it > 0) {
+#pragma unroll
+        for (int br = 0; br < 2; ++br) {
+          float* d = a.dprm + (size_t)br * lay.size;
+          DPF_GATOMIC(atomicAdd(&d[lay.W2 + row], dW2acc[br][0]));
+          if (a.f.w == 2) DPF_GATOMIC(atomicAdd(&d[lay.W2 + F + row], dW2acc[br][1]));
+        }
+      }
+    }
+    umma::fence_before_sync();
+  }
+  __syncthreads();
+  if (tid < 4) {
+    const int br = tid >> 1, c = tid & 1;
+    if (c < a.f.w) DPF_GATOMIC(atomicAdd(&a.dprm[(size_t)br * lay.size + lay.b2 + c], s.b2fin[br][c]));
+  }
+  // every CTA's FiLM / BN_b sums are complete and visible after this barrier
+  grid_barrier(barrier_counter, gridDim.x);
+  umma::fence_after_sync();
+
+  // =========================================== phase 2 ===========================================
+  // (the body of coupling_bwd_p2_tc4_kernel; the mbarrier phases continue from phase 1)
+  if (issuer) {
+    if (lane == 0) {
+      int n_it[2] = {iters_of(2 * (int)blockIdx.x), iters_of(2 * (int)blockIdx.x + 1)};
+      int p1n[2] = {p1_lo(2 * (int)blockIdx.x + 1) - p1_lo(2 * (int)blockIdx.x), p1_lo(2 * (int)blockIdx.x + 2) - p1_lo(2 * (int)blockIdx.x + 1)};
+      int it[2] = {0, 0}, stage[2] = {0, 0};
+      uint32_t ph[2] = {(uint32_t)(3 * p1n[0]) & 1u, (uint32_t)(3 * p1n[1]) & 1u};
+      uint32_t wg_acc = 0u, bn_acc = 0u;
+      int remaining = 3 * (n_it[0] + n_it[1]);
+      while (remaining > 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (it[h] < n_it[h] && umma::mbar_test(&s.bar_req[h], ph[h])) {
+            ph[h] ^= 1u;
+            umma::fence_after_sync();
+            TcP2Half& hb = s.h[h];
+            const uint32_t T_F = tmem + h * 128;
+            if (stage[h] == 0) {          // forward recompute, both branches
+              issue_gemm1<SPLIT>(T_F, hb.H, hb.D, wimg_at<true>(s.W, 0, 0), wimg_at<true>(s.W, 0, 1));
+              issue_gemm1<SPLIT>(T_F + F, hb.H + IMG_H, hb.D + IMG_H, wimg_at<true>(s.W, 1, 0), wimg_at<true>(s.W, 1, 1));
+            } else if (stage[h] == 1) {   // dgrad (overwrites the recompute accumulators) + wgrad
+#pragma unroll
+              for (int br = 0; br < 2; ++br)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma::mma_bf16(T_F + br * F, umma::desc_at(DESC_K, umma::smem_u32(hb.D + br * IMG_H) + 32 * k),
+                                 umma::desc_at(DESC_K, umma::smem_u32(wimg_at<true>(s.W, br, 2)) + 32 * k), IDESC_GEMM, k > 0);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                umma::mma_bf16(T_WG, umma::desc_at(DESC_MN, umma::smem_u32(hb.D) + 2048 * k), umma::desc_at(DESC_MN, umma::smem_u32(hb.H) + 2048 * k),
+                               IDESC_WGRAD, wg_acc);
+                wg_acc = 1u;
+              }
+            } else {                      // BN_a sums
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                umma::mma_bf16(T_BN, umma::desc_at(DESC_MN, umma::smem_u32(hb.D) + 2048 * k), umma::desc_at(DESC_MN, umma::smem_u32(hb.X) + 2048 * k),
+                               IDESC_RED, bn_acc);
+                bn_acc = 1u;
+              }
+            }
+            umma::mma_commit(&s.bar_done[h]);
+            if (++stage[h] == 3) { stage[h] = 0; ++it[h]; }
+            --remaining;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    TcP2Half& hb = s.h[half];
+    const int n_it = iters_of(worker);
+    const int p1n = p1_lo(worker + 1) - p1_lo(worker);
+    TcRaw raw0;
+    {
+      const int b0 = worker / a.f.tiles_per_b;
+      const int n0 = (worker - b0 * a.f.tiles_per_b) * DPF_TILE + row;
+      raw0 = tc_load_raw(a, b0, n0, n_it > 0 && n0 < a.f.N);
+    }
+    // BN_b backward of a channel: dh2pre = ib*(da*s - m1 - h2n*m2), h2n = (acc - mb)*ib  =>  dh2pre = (ib*s)*da - c2 - c3*acc
+    if (tid < 128) {
+      float c2 = 0.f, c3 = 0.f;
+      const float4 l0 = s.lt0[tid >> 6][tid & 63];
+      if (a.f.training) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < DPF_M12_REP; ++r) {
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(a.m12_rep + (size_t)r * (2 * F * 2) + (size_t)tid * 2));
+          s1 += v.x;
+          s2 += v.y;
+        }
+        const float rM = 1.f / ((float)a.f.B * (float)a.f.N);
+        const float m1 = (float)s1 * rM, m2 = (float)s2 * rM;
+        c3 = l0.x * l0.x * m2;
+        c2 = l0.x * m1 - c3 * l0.y;
+      }
+      s.lt0[tid >> 6][tid & 63] = make_float4(l0.x, l0.y, c2, c3);
+    }
+    // the X tiles hold phase 1's weight rows in chunk 0 of every row: phase 2 overwrites chunk 0 of every row of its tiles
+    // (rows of invalid points get {0, ...}), nothing else of X was touched
+    umma::named_bar_sync(3, 512);
+
+    uint32_t ph = (uint32_t)(3 * p1n) & 1u;
+    const uint32_t T_F = tmem + half * 128;
+    uint64_t* req = &s.bar_req[half];
+    uint64_t* done = &s.bar_done[half];
+    for (int it = 0; it < n_it; ++it) {
+      const int tile = worker + it * n_workers;
+      const int b = tile / a.f.tiles_per_b;
+      const int n = (tile - b * a.f.tiles_per_b) * DPF_TILE + row;
+      const bool valid = n < a.f.N;
+      if (part == 0) {   // FiLM fold of this tile's shape (read again only after the next request / completion round trip)
+        const int br = row >> 6, c = row & 63;
+        const float sc = a.f.film[((size_t)(br * 2 + 0) * a.f.B + b) * F + c];
+        const float sh = a.f.film[((size_t)(br * 2 + 1) * a.f.B + b) * F + c];
+        const float4 l0 = s.lt0[br][c];
+        const float2 l1 = s.lt1[br][c];
+        const float S = sc * l0.x;
+        float* pe = reinterpret_cast<float*>(&s.PE[half][br][c >> 1][0]);
+        const int ln = c & 1;
+        pe[ln] = S;
+        pe[2 + ln] = fmaf(-S, l0.y, sh);
+        pe[4 + ln] = l1.x;
+        pe[6 + ln] = l1.y;
+        pe[8 + ln] = -l0.w;     // -c3
+        pe[10 + ln] = -l0.z;    // -c2
+      }
+      const TcPoint g = tc_finish_point<MODE>(a, P, it == 0 ? raw0 : tc_load_raw(a, b, n, valid), valid);
+      const float xk0 = pick3(g.x, a.f.keep0);
+      const float xk1 = (K == 2) ? pick3(g.x, a.f.keep1) : 0.f;
+      const f32x2 xk0_2 = f2_pack(xk0, xk0), xk1_2 = f2_pack(xk1, xk1);
+      // ---- stage 0: h1 hi -> H, lo -> D (the previous tile's BN_a-sum UMMAs still read D / X: wait for them) ----
+      if (it > 0) {
+        umma::mbar_wait(done, ph);
+        ph ^= 1;
+      }
+#pragma unroll
+      for (int br = 0; br < 2; ++br) {
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int q = part * 4 + qq;
+          uint32_t w[4], wl[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 P0 = s.PA[br][q * 4 + i][0];
+            f32x2 v2 = f2_fma(f2_pack(P0.x, P0.y), xk0_2, f2_pack(P0.z, P0.w));
+            if (K == 2) {
+              const float4 P1 = s.PA[br][q * 4 + i][1];
+              v2 = f2_fma(f2_pack(P1.x, P1.y), xk1_2, v2);
+            }
+            float va, vb;
+            f2_unpack(v2, va, vb);
+            va = fmaxf(va, 0.f);
+            vb = fmaxf(vb, 0.f);
+            w[i] = umma::pack_bf16(va, vb);
+            if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
+          }
+          const uint32_t off = umma::sw128_offset(row, q);
+          *reinterpret_cast<uint4*>(hb.H + br * IMG_H + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          if (SPLIT) *reinterpret_cast<uint4*>(hb.D + br * IMG_H + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        }
+      }
+      umma::fence_async_smem();
+      umma::mbar_arrive(req);
+      umma::mbar_wait(done, ph);
+      ph ^= 1;
+      umma::fence_after_sync();
+      // ---- stage 1: epilogue A: dh2pre (bf16) of this part's 32 channels of each branch -> D tiles ----
+#pragma unroll 1
+      for (int br = 0; br < 2; ++br) {
+        const float d0 = br == 0 ? g.do_mu[0] : g.do_lv[0];
+        const float d1 = br == 0 ? g.do_mu[1] : g.do_lv[1];
+        const f32x2 d0_2 = f2_pack(d0, d0), d1_2 = f2_pack(d1, d1);
+#pragma unroll 1
+        for (int hc = 0; hc < 2; ++hc) {
+          uint32_t r[16];
+          umma::tmem_ld16_issue(T_F + lane_off + br * F + part * 32 + hc * 16, r);
+          umma::tmem_ld_wait16(r);
+          uint32_t wv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4* pe = s.PE[half][br][part * 16 + hc * 8 + j];
+            const float4 E0 = pe[0], E1 = pe[1], E2 = pe[2];
+            const f32x2 S2 = f2_pack(E0.x, E0.y);
+            const f32x2 v2 = f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            const f32x2 av2 = f2_fma(S2, v2, f2_pack(E0.z, E0.w));
+            const f32x2 g2 = f2_fma(f2_pack(E1.x, E1.y), d0_2, f2_mul(f2_pack(E1.z, E1.w), d1_2));
+            float av0, av1, g0, g1;
+            f2_unpack(av2, av0, av1);
+            f2_unpack(g2, g0, g1);
+            const f32x2 da2 = f2_pack(av0 > 0.f ? g0 : 0.f, av1 > 0.f ? g1 : 0.f);
+            const f32x2 dh2 = f2_fma(S2, da2, f2_fma(f2_pack(E2.x, E2.y), v2, f2_pack(E2.z, E2.w)));
+            float h0, h1;
+            f2_unpack(dh2, h0, h1);
+            wv[j] = valid ? umma::pack_bf16(h0, h1) : 0u;
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + hc * 2 + q)) =
+                make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
+        }
+      }
+      umma::fence_async_smem();
+      umma::fence_before_sync();
+      umma::mbar_arrive(req);
+      umma::mbar_wait(done, ph);
+      ph ^= 1;
+      umma::fence_after_sync();
+      // ---- stage 2: epilogue B: dz (bf16) -> D tiles, T1 = A0^T dz, per-point weight row -> X ----
+      f32x2 T1_0_2 = f2_pack(0.f, 0.f), T1_1_2 = f2_pack(0.f, 0.f);     // even / odd channel partial sums
+#pragma unroll 1
+      for (int br = 0; br < 2; ++br) {
+#pragma unroll 1
+        for (int hc = 0; hc < 2; ++hc) {
+          uint32_t r[16];
+          umma::tmem_ld16_issue(T_F + lane_off + br * F + part * 32 + hc * 16, r);
+          umma::tmem_ld_wait16(r);
+          uint32_t wv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4* pa = s.PA[br][part * 16 + hc * 8 + j];
+            const float4 P0 = pa[0];
+            const f32x2 A00_2 = f2_pack(P0.x, P0.y);
+            f32x2 z2 = f2_fma(A00_2, xk0_2, f2_pack(P0.z, P0.w));
+            f32x2 A01_2 = 0;
+            if (K == 2) {
+              const float4 P1 = pa[1];
+              A01_2 = f2_pack(P1.x, P1.y);
+              z2 = f2_fma(A01_2, xk1_2, z2);
+            }
+            float z0, z1;
+            f2_unpack(z2, z0, z1);
+            const float dz0 = (z0 > 0.f && valid) ? __uint_as_float(r[2 * j]) : 0.f;
+            const float dz1 = (z1 > 0.f && valid) ? __uint_as_float(r[2 * j + 1]) : 0.f;
+            const f32x2 dz2 = f2_pack(dz0, dz1);
+            T1_0_2 = f2_fma(A00_2, dz2, T1_0_2);
+            if (K == 2) T1_1_2 = f2_fma(A01_2, dz2, T1_1_2);
+            wv[j] = umma::pack_bf16(dz0, dz1);
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            *reinterpret_cast<uint4*>(hb.D + br * IMG_H + umma::sw128_offset(row, part * 4 + hc * 2 + q)) =
+                make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
+        }
+      }
+      float T1_0, T1_1;
+      {
+        float lo, hi;
+        f2_unpack(T1_0_2, lo, hi);
+        T1_0 = lo + hi;
+        f2_unpack(T1_1_2, lo, hi);
+        T1_1 = lo + hi;
+      }
+      if (part == 0) {
+        const float one = valid ? 1.f : 0.f;
+        const uint32_t w0 = umma::pack_bf16(one, xk0);                                   // {1, xk0 hi}
+        const float xk0_lo = xk0 - __uint_as_float(w0 & 0xffff0000u);
+        const uint32_t w1 = umma::pack_bf16(xk0_lo, xk1);                                // {xk0 lo, xk1 hi}
+        const float xk1_lo = xk1 - __uint_as_float(w1 & 0xffff0000u);
+        const uint32_t w2 = umma::pack_bf16(xk1_lo, 0.f);                                // {xk1 lo, 0}
+        *reinterpret_cast<uint4*>(hb.X + umma::sw128_offset(row, 0)) = make_uint4(w0, w1, w2, 0u);
+      } else {
+        s.t1buf[half][row][0] = T1_0;
+        s.t1buf[half][row][1] = T1_1;
+      }
+      umma::fence_async_smem();
+      umma::fence_before_sync();
+      umma::mbar_arrive(req);
+      umma::named_bar_sync(1 + half, 256);   // t1buf hand-over inside the half
+      if (part == 0 && valid) {
+        T1_0 += s.t1buf[half][row][0];
+        T1_1 += s.t1buf[half][row][1];
+        float dx[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) dx[ch] = (MODE == 1) ? g.dy[ch] / sig1 : g.dy[ch] * sig1;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          if (ch == a.f.keep0) dx[ch] += T1_0;
+          if (K == 2 && ch == a.f.keep1) dx[ch] += T1_1;
+          if (ch == a.f.warp0) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[0] : g.dy[ch] * g.sig[0];
+          if (K == 1 && ch == a.f.warp1) dx[ch] = (MODE == 1) ? g.dy[ch] / g.sig[1] : g.dy[ch] * g.sig[1];
+        }
+        const size_t base = (size_t)b * 3 * a.f.N + n;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) a.dx_out[base + (size_t)ch * a.f.N] = dx[ch];
+      }
+    }
+    if (n_it > 0) {     // the last tile's BN_a-sum UMMAs
+      umma::mbar_wait(done, ph);
+      ph ^= 1;
+    }
+    umma::fence_before_sync();
+  }
+  // ---- CTA epilogue (every UMMA of both halves has completed) ----
+  __syncthreads();
+  umma::fence_after_sync();
+  const bool had_work = 2 * (int)blockIdx.x < a.f.n_tiles;
+  if (tid < 128 && had_work) {     // lane = channel m = br*64 + c; columns {dbeta, E0 hi, E0 lo, E1 hi, E1 lo}
+    uint32_t r0[4], r1[4];
+    umma::tmem_ld4(T_BN + ((uint32_t)(quarter * 32) << 16), r0);
+    umma::tmem_ld4(T_BN + ((uint32_t)(quarter * 32) << 16) + 4, r1);
+    umma::tmem_ld_wait4(r0);
+    umma::tmem_ld_wait4(r1);
+    DPF_GATOMIC(atomicAdd(&a.bna_sums[tid * 4 + 0], (double)__uint_as_float(r0[0])));
+    DPF_GATOMIC(atomicAdd(&a.bna_sums[tid * 4 + 1], (double)__uint_as_float(r0[1]) + (double)__uint_as_float(r0[2])));
+    DPF_GATOMIC(atomicAdd(&a.bna_sums[tid * 4 + 2], (double)__uint_as_float(r0[3]) + (double)__uint_as_float(r1[0])));
+  }
+  if (!issuer) {
+    const int br = row >> 6, c = row & 63, cg = half * 2 + part;
+    float4* d = reinterpret_cast<float4*>(a.dw1_partial + ((size_t)blockIdx.x * 2 + br) * (F * F) + c * F + cg * 16);
+    uint32_t r[16];
+    if (had_work) {
+      umma::tmem_ld16_issue(T_WG + ((uint32_t)(quarter * 32) << 16) + br * F + cg * 16, r);
+      umma::tmem_ld_wait16(r);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      d[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
 // Backward pass 1, two threads per point, reductions over points on the tensor cores.
 //
 // With mask m = [a > 0], a = s*h2n + t (FiLM scale s, shift t), h3 = m*a, da = m*(W2_0 d0 + W2_1 d1):
@@ -1759,7 +2408,7 @@ int launch_bwd_tc_t(const BwdArgs& a, const unsigned short* wimg, int pass, cuda
 
 static int g_coop_occupancy = -1;
 static int* g_barrier_fail_host = nullptr;     // pinned + mapped; written by a timed-out grid barrier
-static int g_coresident_ok = -1;               // -1 not probed yet, 0 probe failed, 1 verified
+static int g_coresident_ok[2] = {-1, -1};     // per kernel footprint (0 merged forward, 1 merged backward): -1 not probed, 0 failed, 1 verified
 
 static int tc_barrier_setup() {
   if (g_barrier_fail_host) return DPF_OK;
@@ -1775,10 +2424,11 @@ static int tc_barrier_setup() {
   return DPF_OK;
 }
 
-// One synchronous probe launch per process: `grid` CTAs of 256 threads with `smem` dynamic bytes and `tmem_cols`
-// TMEM columns each must all be resident at once.  Cannot run during stream capture (returns -1 = unknown).
-static int tc_verify_coresidency(int grid, size_t smem, int tmem_cols, cudaStream_t st) {
-  if (g_coresident_ok >= 0) return g_coresident_ok;
+// One synchronous probe launch per process and footprint: `grid` CTAs of `threads` threads with `smem` dynamic bytes
+// and `tmem_cols` TMEM columns each must all be resident at once (the probe uses fewer registers than any kernel it
+// stands for, whose own __launch_bounds__ guarantee the register fit).  Cannot run during stream capture (-1).
+static int tc_verify_coresidency(int which, int grid, int threads, size_t smem, int tmem_cols, cudaStream_t st) {
+  if (g_coresident_ok[which] >= 0) return g_coresident_ok[which];
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cap);
   if (cap != cudaStreamCaptureStatusNone) return -1;
@@ -1788,19 +2438,36 @@ static int tc_verify_coresidency(int grid, size_t smem, int tmem_cols, cudaStrea
   cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st);
   cudaFuncSetAttribute(coresidency_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(coresidency_probe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  coresidency_probe_kernel<<<grid, 256, smem, st>>>(counter, tmem_cols);
+  coresidency_probe_kernel<<<grid, threads, smem, st>>>(counter, tmem_cols);
   ++g_dpf_launches;
   unsigned int host[2] = {0u, 1u};
   cudaError_t e = cudaMemcpyAsync(host, counter, sizeof(host), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(counter);
   if (e != cudaSuccess) { cudaGetLastError(); return -1; }
-  g_coresident_ok = (host[0] == (unsigned int)grid && host[1] == 0u) ? 1 : 0;
-  return g_coresident_ok;
+  g_coresident_ok[which] = (host[0] == (unsigned int)grid && host[1] == 0u) ? 1 : 0;
+  return g_coresident_ok[which];
 }
 
-// cooperative (all CTAs co-resident) launch of the merged train-mode forward; DPF_ERR_UNSUPPORTED when
-// the problem does not fit RES tiles per resident CTA - the caller then uses the two-launch form
+// merged backward launch of one layer (pass 1 -> grid barrier -> pass 2); DPF_ERR_UNSUPPORTED = use the two launches
+template <int K, int MODE, bool SPLIT>
+int launch_bwd_merged_t(const BwdArgs& a, const unsigned short* wimg, unsigned int* counter, cudaStream_t st) {
+  auto kern = coupling_bwd_merged_kernel<K, MODE, SPLIT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for<TcBwdMSmem>());
+    attr = true;
+  }
+  const int ok = tc_verify_coresidency(1, dpf_num_sms(), NT4, smem_for<TcBwdMSmem>(), 512, st);
+  if (ok != 1) {
+    dpf_set_error("merged backward not used: co-residency of %d CTAs %s", dpf_num_sms(), ok == 0 ? "could not be established" : "not verified yet (stream capture)");
+    return DPF_ERR_UNSUPPORTED;
+  }
+  const int grid = min((a.f.n_tiles + 1) / 2, dpf_num_sms());
+  dpf_launch_pdl(kern, grid, NT4, smem_for<TcBwdMSmem>(), st, a, wimg, counter);
+  return dpf_check_launch("coupling_bwd_merged_kernel");
+}
+
 template <int K, int MODE, bool SPLIT>
 int launch_fwd_train_t(const CouplingArgs& a, const unsigned short* wimg, unsigned int* counter, cudaStream_t st) {
   static int max_grid = -1;
@@ -1825,7 +2492,7 @@ int launch_fwd_train_t(const CouplingArgs& a, const unsigned short* wimg, unsign
   // CTAs with 256 columns each do share an SM.  Instead the full-size grid's co-residency is verified
   // once per process with a probe launch of the same footprint; until / unless that succeeds the caller
   // uses the two-launch form (no grid barrier).
-  const int ok = tc_verify_coresidency(max_grid, smem_for<TcFwdSmem2>(), RES * 128, st);
+  const int ok = tc_verify_coresidency(0, max_grid, NT2, smem_for<TcFwdSmem2>(), RES * 128, st);
   if (ok != 1) {
     dpf_set_error("merged forward not used: co-residency of %d CTAs %s", max_grid, ok == 0 ? "could not be established" : "not verified yet (stream capture)");
     return DPF_ERR_UNSUPPORTED;
@@ -1908,7 +2575,7 @@ int tc_bwd_p2_max_ctas() { return dpf_num_sms(); }
 
 // 1 when a grid barrier of this process has timed out (the pass that hit it trapped; outputs are invalid)
 int tc_barrier_failed() { return g_barrier_fail_host && *reinterpret_cast<volatile int*>(g_barrier_fail_host) != 0; }
-int tc_coresidency_state() { return g_coresident_ok; }
+int tc_coresidency_state() { return g_coresident_ok[0] < g_coresident_ok[1] ? g_coresident_ok[0] : g_coresident_ok[1]; }
 
 size_t tc_weight_image_elems_per_layer() { return (size_t)2 * N_IMG * F * F; }
 
@@ -1958,6 +2625,16 @@ int launch_coupling_bwd_tc(const BwdArgs& a, const unsigned short* wimg, int mod
   }
   if (split) return mode == 0 ? launch_bwd_tc_t<1, 0, true>(a, wimg, pass, s) : launch_bwd_tc_t<1, 1, true>(a, wimg, pass, s);
   return mode == 0 ? launch_bwd_tc_t<1, 0, false>(a, wimg, pass, s) : launch_bwd_tc_t<1, 1, false>(a, wimg, pass, s);
+}
+
+int launch_coupling_bwd_merged_tc(const BwdArgs& a, const unsigned short* wimg, int mode, int split, unsigned int* counter, cudaStream_t s) {
+  if (!(a.ltab && a.m12_rep)) return DPF_ERR_UNSUPPORTED;
+  if (a.f.k == 2) {
+    if (split) return mode == 0 ? launch_bwd_merged_t<2, 0, true>(a, wimg, counter, s) : launch_bwd_merged_t<2, 1, true>(a, wimg, counter, s);
+    return mode == 0 ? launch_bwd_merged_t<2, 0, false>(a, wimg, counter, s) : launch_bwd_merged_t<2, 1, false>(a, wimg, counter, s);
+  }
+  if (split) return mode == 0 ? launch_bwd_merged_t<1, 0, true>(a, wimg, counter, s) : launch_bwd_merged_t<1, 1, true>(a, wimg, counter, s);
+  return mode == 0 ? launch_bwd_merged_t<1, 0, false>(a, wimg, counter, s) : launch_bwd_merged_t<1, 1, false>(a, wimg, counter, s);
 }
 
 #ifdef DPF_STAMPS

@@ -75,8 +75,12 @@ int g_dpf_pdl = 1;
 // one-tile-per-SM form (tests compare both).
 int g_dpf_p2_two_tiles = 1;
 extern int g_fused_pairwise;   // chamfer.cu
+// Option 5: backward of a layer as ONE launch (pass 1 -> grid barrier -> pass 2); 0 = two launches (tests compare both).
+static bool g_merged_backward = true;
+int launch_coupling_bwd_merged_tc(const BwdArgs& a, const unsigned short* wimg, int mode, int split, unsigned int* counter, cudaStream_t s);
 DPF_API int dpf_set_option(int option, int value) {
-  DPF_REQUIRE(option >= 0 && option <= 4, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
+  DPF_REQUIRE(option >= 0 && option <= 5, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);
+  if (option == 5) { g_merged_backward = value != 0; return DPF_OK; }
   if (option == 0) g_merged_forward = value != 0;
   else if (option == 1) g_fused_eval = value != 0;
   else if (option == 2) g_dpf_pdl = value != 0;
@@ -296,6 +300,8 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
   cudaMemsetAsync(ws.dfilm, 0, sizeof(float) * (size_t)L * 4 * B * DPF_F, s);
   cudaMemsetAsync(ws.bna_sums, 0, sizeof(double) * (size_t)L * 2 * DPF_F * 4, s);
   if (precision >= 1) cudaMemsetAsync(ws.m12_rep, 0, sizeof(double) * (size_t)L * DPF_M12_REP * 2 * DPF_F * 2, s);
+  if (precision >= 1) cudaMemsetAsync(ws.barriers_bwd, 0, sizeof(unsigned int) * (size_t)L * 32, s);
+  bool merged_bwd = precision >= 1 && g_merged_backward;
 
   if (precision >= 1) {   // folded BN_a / BN_b tables of every layer, once per pass (the per-layer kernels only load them)
     rc = launch_bwd_tables(arena, stats, reinterpret_cast<const LayerMeta*>(meta_dev), ws.moments, ws.bnb_sums, ws.ltab, L, G, B, N,
@@ -336,6 +342,13 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     a.dw1_partial = precision >= 1 ? (float*)bwd_scratch + (size_t)l * p2_ctas * 2 * DPF_F * DPF_F : nullptr;
     if (q < L - 1) set_pending(a, q + 1);
     const unsigned short* wimg = ws.w1_bf16 + (size_t)l * tc_weight_image_elems_per_layer();
+    if (merged_bwd) {
+      ProfScope ps(CAT_BWD_P2, s);
+      rc = launch_coupling_bwd_merged_tc(a, wimg, mode, precision == 2, ws.barriers_bwd + (size_t)l * 32, s);
+      if (rc == DPF_OK) continue;
+      if (rc != DPF_ERR_UNSUPPORTED) return rc;
+      merged_bwd = false;                       // not available (stream capture before the probe ran): two launches
+    }
     {
       ProfScope ps(CAT_BWD_P1, s);
       rc = precision >= 1 ? launch_coupling_bwd_tc(a, wimg, mode, 1, precision == 2, s) : launch_coupling_bwd_fp32(a, mode, 1, s);

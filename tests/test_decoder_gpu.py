@@ -813,3 +813,45 @@ def test_full_size_train_outputs_and_gradients_vs_port(mods, cuda):
         worst.append((err, key))
     worst.sort(reverse=True)
     assert worst[0][0] < 2e-2, worst[:5]
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("B,N", [(4, 300), (32, 2048), (3, 1000), (64, 2048)])
+def test_merged_backward_equals_two_launch_backward(mods, native_lib, cuda, precision, B, N):
+    """The one-launch backward of a layer (pass 1 -> grid barrier -> pass 2 in one kernel, dpf_set_option(5, 1), default)
+    against the two-launch form (option 5 = 0) on the same forward: same arithmetic per point, only the order of the
+    float atomics differs -> agreement at the run-to-run noise level of the two-launch form itself."""
+    from dpf_nets_b200 import _lib
+    _, decoders = mods
+    torch.manual_seed(1)
+    m = decoders.LocalCondRNVPDecoder(2, 64, 32)
+    with torch.no_grad():
+        g5 = torch.Generator().manual_seed(6)
+        for k, t in m.named_views().items():
+            if k.endswith("sd2.weight"):
+                t.copy_(torch.randn(t.shape, generator=g5) * 0.3)
+    m = m.to(cuda).train()
+    m.precision = precision
+    gen = torch.Generator().manual_seed(2)
+    p = (torch.rand((B, 3, N), generator=gen) - 0.5).to(cuda)
+    g0 = torch.randn((B, 32), generator=gen).to(cuda)
+
+    def run(opt):
+        _lib.check(native_lib.dpf_set_option(5, opt), "dpf_set_option")
+        try:
+            m.zero_grad()
+            g = g0.clone().requires_grad_(True)
+            pp = p.clone().requires_grad_(True)
+            ps, mus, lvs = m(pp, g, mode="inverse")
+            (0.5 * (lvs.total.sum() + (ps[0] ** 2).sum()) / B + 0.01 * (mus.stacked * ps.stacked).sum()).backward()
+            return m.arena.grad.clone(), g.grad.clone(), pp.grad.clone()
+        finally:
+            _lib.check(native_lib.dpf_set_option(5, 1), "dpf_set_option")
+    two_a, two_b, merged = run(0), run(0), run(1)
+    for a, b, c, what in zip(two_a, two_b, merged, ("darena", "dg", "dp")):
+        floor = rel(b, a)
+        assert torch.isfinite(c).all()
+        assert rel(c, a) < max(2e-3, 4 * floor), (what, rel(c, a), floor)
+    fail, cores = __import__("ctypes").c_int(-1), __import__("ctypes").c_int(-2)
+    _lib.check(native_lib.dpf_decoder_barrier_state(__import__("ctypes").byref(fail), __import__("ctypes").byref(cores)), "dpf_decoder_barrier_state")
+    assert fail.value == 0 and cores.value == 1      # no barrier timed out; both cooperative footprints were verified co-resident
