@@ -2463,7 +2463,7 @@ int launch_bwd_merged_t(const BwdArgs& a, const unsigned short* wimg, unsigned i
     dpf_set_error("merged backward not used: co-residency of %d CTAs %s", dpf_num_sms(), ok == 0 ? "could not be established" : "not verified yet (stream capture)");
     return DPF_ERR_UNSUPPORTED;
   }
-  const int grid = min((a.f.n_tiles + 1) / 2, dpf_num_sms());
+  const int grid = min(a.f.n_tiles, dpf_num_sms());      // = the CTA count dpf_decoder_backward sized the wgrad partials for
   dpf_launch_pdl(kern, grid, NT4, smem_for<TcBwdMSmem>(), st, a, wimg, counter);
   return dpf_check_launch("coupling_bwd_merged_kernel");
 }
