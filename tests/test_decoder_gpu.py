@@ -771,7 +771,7 @@ def test_nll_outputs_equal_list_path(mods, cuda, precision):
     ps, mus, lvs = m(p, g2, mode="inverse")
     P, LV = ps.stacked, lvs.stacked
     ((P[0] ** 2).sum() + (P[4] * 0.3).sum() + LV.sum() + LV[2].sum()).backward()
-    assert rel(ga, m.arena.grad) < 5e-3 and rel(g.grad, g2.grad) < 5e-3      # run-to-run noise of the float atomics: ~2e-3
+    assert rel(ga, m.arena.grad) < 2e-2 and rel(g.grad, g2.grad) < 2e-2      # run-to-run noise of the float atomics: 2e-3 .. 8e-3 measured
 
 
 def test_full_size_train_outputs_and_gradients_vs_port(mods, cuda):
