@@ -75,8 +75,11 @@ int g_dpf_pdl = 1;
 // one-tile-per-SM form (tests compare both).
 int g_dpf_p2_two_tiles = 1;
 extern int g_fused_pairwise;   // chamfer.cu
-// Option 5: backward of a layer as ONE launch (pass 1 -> grid barrier -> pass 2); 0 = two launches (tests compare both).
-static bool g_merged_backward = true;
+// Option 5: backward of a layer as ONE launch (pass 1 -> grid barrier -> pass 2).  Measured r02 (32 x 2048, bf16x3, 20 timed
+// steps, A/B/A/B on one B200): 4.813 ms per step merged vs 4.765 ms with two PDL-chained launches - programmatic dependent
+// launch already hides the launch boundary, and the in-kernel grid barrier costs what the boundary did.  Default = two
+// launches; the merged form stays available (dpf_set_option(5, 1)) and is compared against it in the tests.
+static bool g_merged_backward = false;
 int launch_coupling_bwd_merged_tc(const BwdArgs& a, const unsigned short* wimg, int mode, int split, unsigned int* counter, cudaStream_t s);
 DPF_API int dpf_set_option(int option, int value) {
   DPF_REQUIRE(option >= 0 && option <= 5, DPF_ERR_BAD_ARG, "dpf_set_option: unknown option %d", option);

@@ -818,8 +818,8 @@ def test_full_size_train_outputs_and_gradients_vs_port(mods, cuda):
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 @pytest.mark.parametrize("B,N", [(4, 300), (32, 2048), (3, 1000), (64, 2048)])
 def test_merged_backward_equals_two_launch_backward(mods, native_lib, cuda, precision, B, N):
-    """The one-launch backward of a layer (pass 1 -> grid barrier -> pass 2 in one kernel, dpf_set_option(5, 1), default)
-    against the two-launch form (option 5 = 0) on the same forward: same arithmetic per point, only the order of the
+    """The one-launch backward of a layer (pass 1 -> grid barrier -> pass 2 in one kernel, dpf_set_option(5, 1))
+    against the default two-launch form (option 5 = 0) on the same forward: same arithmetic per point, only the order of the
     float atomics differs -> agreement at the run-to-run noise level of the two-launch form itself."""
     from dpf_nets_b200 import _lib
     _, decoders = mods
@@ -846,7 +846,7 @@ def test_merged_backward_equals_two_launch_backward(mods, native_lib, cuda, prec
             (0.5 * (lvs.total.sum() + (ps[0] ** 2).sum()) / B + 0.01 * (mus.stacked * ps.stacked).sum()).backward()
             return m.arena.grad.clone(), g.grad.clone(), pp.grad.clone()
         finally:
-            _lib.check(native_lib.dpf_set_option(5, 1), "dpf_set_option")
+            _lib.check(native_lib.dpf_set_option(5, 0), "dpf_set_option")
     two_a, two_b, merged = run(0), run(0), run(1)
     prec = m.precision
     m.precision = "fp32"                 # the exact CUDA-core path as the common yardstick
