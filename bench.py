@@ -25,6 +25,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs (reference arm, cpu_baseline) run on rank 0 only and
+# must see all host cores, and the thread pools are sized when torch is imported - so this comes first.
+if int(os.environ.get("RANK", "0")) == 0:
+    for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import torch  # noqa: E402
 
 N_FLOWS, F_WIDTH, G_LATENT = 21, 64, 128
@@ -34,7 +40,18 @@ KERNEL_CLASSES = ["film_fwd", "moments", "fwd_stats", "fwd_apply", "bwd_p1", "bw
 # algorithmic (non-recompute) GEMM FLOP per point per layer each kernel class is responsible for
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each per-layer kernel, from the `ncu --set full` captures
 # of this workload kept under profiles/ (r01_ncu_coupling_*_summary.txt); inputs of a layer mostly hit in the 126 MB L2
-NCU_DRAM_BYTES_PER_LAUNCH = {"fwd_apply": 968704, "bwd_p1": 4921088, "bwd_p2": 5227008 + 5120}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each per-layer kernel class, from the newest
+    profiles/r*_ncu_traffic.json (written by tools/ncu_summary.py from an `ncu --set full` capture of THIS workload;
+    inputs of a layer mostly hit in the 126 MB L2)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return {}, None
+    with open(files[-1]) as f:
+        return json.load(f), os.path.relpath(files[-1], ROOT)
 ALGO_FLOP = {"fwd_stats": 0, "fwd_apply": FLOP_PER_POINT_LAYER_FWD, "bwd_p1": 2 * 2 * 64 * 3,
              "bwd_p2": 2 * FLOP_PER_POINT_LAYER_FWD - 2 * 2 * 64 * 3}
 
@@ -126,44 +143,23 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port (CPU restatement of the reference algorithm)
 # --------------------------------------------------------------------------------------------
-def oracle_train_step_factory(B, N, rank=0, device="cpu", return_state=False):
-    """Builds the oracle decoder (reference init through our module's reference-faithful
-    initialiser, same state_dict layout) and returns step() -> loss running fwd+bwd on `device`
-    (bench.py itself only uses the CPU; tests/test_decoder_gpu.py also times the port on the GPU)."""
+def oracle_train_step_factory(B, N, rank=0, device="cpu"):
+    """The oracle decoder (oracle/flow_oracle.py: torch restatement of the reference modules, reference-faithful random
+    init from the oracle's own initialiser - no product code on this arm) -> step() running fwd + PointFlowNLL + bwd."""
     from oracle import flow_oracle as fo
-    from dpf_nets_b200.lib.networks._arena import ArenaLayout, init_arena, init_stats
-    specs = fo.decoder_layer_names(N_FLOWS)
-    lay = ArenaLayout(specs, G_LATENT)
-    torch.manual_seed(0)
-    arena, stats = init_arena(lay, 0.01).to(device), init_stats(lay).to(device)
-    arena.requires_grad_(True)
-    layers = []
-    for pre, warp in specs:
-        P = {"eps": torch.tensor([1e-6], device=device)}
-        for key, (off, shape) in lay.param_index.items():
-            if key.startswith(pre):
-                n = 1
-                for s in shape:
-                    n *= s
-                P[key[len(pre):]] = arena[off:off + n].view(shape)
-        for key, (off, shape) in lay.stat_index.items():
-            if key.startswith(pre):
-                P[key[len(pre):]] = stats[off:off + 64]
-        layers.append((P, warp))
+    layers, leaves = fo.init_decoder_layers(N_FLOWS, G_LATENT, F=F_WIDTH, weight_std=0.01, seed=0, device=device)
     p, g = synth_inputs(B, N, G_LATENT, rank)
     p, g = p.to(device), g.to(device)
     g.requires_grad_(True)
     base_mu, base_lv = torch.zeros_like(p), torch.full_like(p, BASE_LOGVAR)
 
     def step():
-        arena.grad = None
+        for t in leaves:
+            t.grad = None
         g.grad = None
         ps, mus, lvs = fo.decoder_forward(layers, p, g, "inverse", training=True)
         nll = fo.point_flow_nll(ps + [p], [base_mu] + mus, [base_lv] + lvs)
         nll.backward()
-        if return_state:     # tests/test_decoder_gpu.py: full-size outputs and gradients of the port
-            return float(nll.detach()), {"arena": arena.detach(), "z": ps[0].detach(), "sum_logvar": sum(lvs).detach(),
-                                         "darena": arena.grad.detach(), "dg": g.grad.detach()}
         return float(nll.detach())
     return step
 
@@ -180,6 +176,9 @@ def time_cpu(step, steps, warmup):
 
 
 def run_reference(args):
+    """Reference arm: the reference algorithm (oracle port, torch CPU fp32) on the box's host cores.  Under torchrun
+    only rank 0 runs it - ONE process, one batch_per_gpu x points batch per step whatever --gpus says - and the
+    config says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -198,12 +197,14 @@ def run_reference(args):
     ts = time_cpu(step, args.steps, args.warmup)
     ms = 1e3 * sum(ts) / len(ts)
     val = B * N / (ms * 1e-3)
+    cfg = workload_config(args, "fp32")
+    cfg.update(global_batch=B, parallelism="host CPU, 1 process x %d threads (rank 0 only; --gpus %d does not add work)" % (torch.get_num_threads(), args.gpus))
     line = {
         "impl": "reference", "metric": "decoder points/s (train fwd+bwd)", "value": val, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, "fp32"),
-        "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -335,6 +336,7 @@ def run_ours(args):
     lib.dpf_profile_enable(0)
     classes = {k: {"ms_per_step": ms[i] / prof_steps, "launches_per_step": cnt[i] / prof_steps,
                    "us_per_launch": (1e3 * ms[i] / cnt[i]) if cnt[i] else None} for i, k in enumerate(KERNEL_CLASSES)}
+    traffic, traffic_src = ncu_traffic()
     dom = max(("fwd_stats", "fwd_apply", "bwd_p1", "bwd_p2"), key=lambda k: classes[k]["ms_per_step"])
     dom_us = classes[dom]["us_per_launch"] or float("inf")
     tensor_peak = pk["bf16_tflops_sustained"]
@@ -342,8 +344,8 @@ def run_ours(args):
     whole = 3 * FLOP_PER_POINT_LAYER_FWD * 3 * N_FLOWS * B * N / (ms_per_step * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if (B, N) == (32, 2048) else None,
-                "traffic_source": "ncu --set full capture of this kernel on this workload, profiles/r01_ncu_coupling_*_summary.txt",
+                "traffic": traffic.get(dom) if (B, N) == (32, 2048) else None,
+                "traffic_source": ("ncu --set full capture of this kernel on this workload: %s" % traffic_src) if traffic_src else None,
                 "peak_source": pk["source"] + " (sustained bf16)",
                 "algorithmic_flop_per_launch": ALGO_FLOP[dom] * B * N,
                 "whole_step": {"achieved": whole, "frac": whole / tensor_peak,
@@ -360,28 +362,90 @@ def run_ours(args):
         "gpu_launches": l1 - l0, "clocks": clocks, "roofline": roofline,
     }
 
-    sweep = None
-    if not args.no_extras and args.sweep_clouds > 0:     # every rank takes part in the sharded sweep
-        sweep = eval_sweep(dev, args.sweep_clouds, N, world, rank, flush)
-    if rank == 0 and not args.no_extras:
-        line["extra"] = extras(model, dev, B, N, pk, flush)
-        if sweep is not None:
-            line["extra"]["eval_sweep"] = sweep
-        line["extra"]["full_model_step"] = full_model_step(dev, B, N, precision, flush)
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        cstep = oracle_train_step_factory(B, N)
-        ts = time_cpu(cstep, 2, 1)
-        cms = 1e3 * sum(ts) / len(ts)
-        line["cpu_baseline"] = {"value": B * N / (cms * 1e-3), "unit": "points/s", "cores": cores, "kind": "port",
-                                "sample": "full batch %dx%d, 1 warm-up + 2 timed steps of the oracle port "
-                                          "(torch CPU fp32 restatement of the reference modules)" % (B, N),
-                                "ms_per_step": cms}
+    if not args.no_extras:
+        extra = {}
+        if args.sweep_clouds > 0:                       # every rank takes part in the sharded sweep
+            extra["eval_sweep"] = eval_sweep(dev, args.sweep_clouds, N, world, rank, flush)
+        # whole-model training steps of the three BASELINE model families, batch-sharded over the ranks (gradient
+        # averaging: dist.GradSync - decoder arena all-reduce overlapped with the rest of the backward)
+        extra["full_model_step"] = full_model_step(dev, B, N, precision, flush, "generation/chair", world, graphed=True)
+        extra["full_model_step_ae_all_original"] = full_model_step(dev, B, N, precision, flush, "autoencoding/all_original", world)
+        extra["full_model_step_svr_all"] = full_model_step(dev, B, N, precision, flush, "svr/all", world)
+        if world == 1:
+            # single-GPU legs and the CPU baseline only in the N = 1 run (under torchrun the other ranks would idle in a
+            # barrier while rank 0 works, and the driver's N = 1 line already carries them)
+            extra.update(extras(model, dev, B, N, pk, flush))
+            extra["decoder_b64"] = decoder_step_b64(dev, N, args.precision, flush)
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cstep = oracle_train_step_factory(B, N)
+            ts = time_cpu(cstep, 2, 1)
+            cms = 1e3 * sum(ts) / len(ts)
+            line["cpu_baseline"] = {"value": B * N / (cms * 1e-3), "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "full batch %dx%d, 1 warm-up + 2 timed steps of the oracle port "
+                                              "(torch CPU fp32 restatement of the reference modules)" % (B, N),
+                                    "ms_per_step": cms}
+        if rank == 0:
+            line["extra"] = extra
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()          # rank 0's single-GPU extras / cpu_baseline legs run while the others wait here
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def decoder_step_b64(dev, N, precision, flush, steps=5, warmup=3):
+    """The YAML default batch (batch_size: 64, configs/generation/*.yaml): 1024 tiles do not fit the merged forward's
+    TMEM-resident form (592 tile slots), so the forward runs as statistics + apply launches with a recompute."""
+    from dpf_nets_b200.lib.networks.decoders import LocalCondRNVPDecoder, prepend
+    from dpf_nets_b200.lib.networks.losses import PointFlowNLL
+    B = 64
+    torch.manual_seed(0)
+    model = LocalCondRNVPDecoder(N_FLOWS, F_WIDTH, G_LATENT).to(dev).train()
+    model.precision = precision
+    p, g = synth_inputs(B, N, G_LATENT, 0)
+    p, g = p.to(dev), g.to(dev).requires_grad_(True)
+    base_mu, base_lv = torch.zeros_like(p), torch.full_like(p, BASE_LOGVAR)
+    crit = PointFlowNLL()
+
+    def step():
+        model.arena.grad = None
+        g.grad = None
+        ps, mus, lvs = model(p, g, mode="inverse")
+        crit(prepend(None, ps)[1:] + [p], prepend(base_mu, mus), prepend(base_lv, lvs)).backward()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sum(ts) / len(ts)
+    return {"value": B * N / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "batch": B, "points": N,
+            "forward_form": "two launches per layer (statistics + apply): 1024 tiles exceed the merged forward's 592 resident tile slots"}
+
+
+def measured_pipe_ceilings(dev):
+    """MUFU (ex2.approx) results/s and packed-fp32 FMA lanes/s of this GPU, measured with dpf_throughput_probe."""
+    from dpf_nets_b200 import _lib
+    lib = _lib.lib()
+    scratch = torch.zeros(4, device=dev)
+    out = {}
+    for name, which in (("mufu_ex2_per_s", 0), ("fp32_fma_lanes_per_s", 1)):
+        n = ctypes.c_longlong(0)
+        best = 0.0
+        for it in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(lib.dpf_throughput_probe(which, 148 * 8, 4096, _lib.ptr(scratch), ctypes.byref(n), _lib.stream_ptr(dev)), "dpf_throughput_probe")
+            b.record()
+            torch.cuda.synchronize()
+            if it:
+                best = max(best, n.value / (a.elapsed_time(b) * 1e-3))
+        out[name] = best
+    return out
 
 
 def extras(model, dev, B, N, pk, flush):
@@ -419,15 +483,20 @@ def extras(model, dev, B, N, pk, flush):
         ts.append(a.elapsed_time(b))
     sec = sum(ts) / len(ts) * 1e-3
     pairs = S * S / sec
-    # distance evals/s the FP32 (FMA) pipe allows: 128 lanes per SM per clock, 6 fp32 lane-operations per evaluation
-    # (3 sub, 1 mul, 2 fma; packed FADD2/FMUL2/FFMA2 halve the ISSUE slots, not the pipe work; the min runs on the ALU pipe)
-    fp32_pipe_peak = 148 * 128 * 1.965e9 / 6.0
+    # Bound: the FP32 (FMA) pipe.  One evaluation of a point pair = 6 fp32 lane-operations (3 sub, 1 mul, 2 fma; the packed
+    # FADD2 / FMUL2 / FFMA2 halve the ISSUE slots, not the pipe work; the mins run on the ALU pipe); SURVEY 8d counts the
+    # algorithmic N^2 evaluations per cloud pair (one evaluation serves both Chamfer directions in the shipped kernel).
+    ceil = measured_pipe_ceilings(dev)
+    fp32_nominal = 148 * 128 * 1.965e9 / 6.0
+    fp32_measured = ceil["fp32_fma_lanes_per_s"] / 6.0
     out["chamfer"] = {"value": pairs, "unit": "cloud-pair CD evals/s", "clouds": "%dx%d of %d points" % (S, S, N),
                       "point_pair_evals_per_s": pairs * N * N,
                       "hbm": {"achieved_gbs": pairs * (2 * N * 12 + 4) / 1e9, "peak_gbs": pk["hbm_gbs"],
                               "frac": pairs * (2 * N * 12 + 4) / 1e9 / pk["hbm_gbs"]},
-                      "fp32_pipe": {"achieved_dist_evals_per_s": 2 * pairs * N * N, "bound": fp32_pipe_peak,
-                                    "frac": 2 * pairs * N * N / fp32_pipe_peak}}
+                      "fp32_pipe": {"achieved_dist_evals_per_s": pairs * N * N, "evals_per_cloud_pair": N * N,
+                                    "bound_nominal": fp32_nominal, "bound_measured": fp32_measured,
+                                    "measured_fp32_fma_lanes_per_s": ceil["fp32_fma_lanes_per_s"],
+                                    "frac": pairs * N * N / fp32_measured, "frac_of_nominal": pairs * N * N / fp32_nominal}}
     # approximate EMD, fused all-pairs cost (match never materialised): MUFU(ex2)-bound, 27 sweeps x N^2 exps per pair
     from dpf_nets_b200.ops import pairwise_emd
     Se = 64
@@ -440,12 +509,13 @@ def extras(model, dev, B, N, pk, flush):
         ts.append(a.elapsed_time(b))
     sec = sum(ts) / len(ts) * 1e-3
     epairs = Se * Se / sec
-    mufu_peak = 148 * 16 * 1.965e9                          # ex2 results/s, assuming 16 MUFU lanes per SM (4 per sub-partition)
+    mufu = ceil["mufu_ex2_per_s"]                           # measured on this GPU (dpf_throughput_probe), not assumed
     out["emd"] = {"value": epairs, "unit": "cloud-pair approximate-EMD evals/s", "clouds": "%dx%d of %d points" % (Se, Se, N),
-                  "exp_per_pair": 27 * N * N, "mufu": {"achieved_ex2_per_s": epairs * 27 * N * N, "bound_assumed": mufu_peak,
-                                                        "frac": epairs * 27 * N * N / mufu_peak,
+                  "exp_per_pair": 27 * N * N, "mufu": {"achieved_ex2_per_s": epairs * 27 * N * N, "bound_measured": mufu,
+                                                        "mufu_results_per_clk_per_sm": mufu / (148 * 1.965e9),
+                                                        "frac": epairs * 27 * N * N / mufu,
                                                         "executed_mufu_per_pair": 36 * N * N,   # + 9 N^2 rsqrt of the fused cost
-                                                        "frac_executed": epairs * 36 * N * N / mufu_peak}}
+                                                        "frac_executed": epairs * 36 * N * N / mufu}}
     return out
 
 
@@ -515,31 +585,42 @@ def encoder_eval(dev, B, N, flush):
     return res
 
 
-def full_model_step(dev, B, N, precision, flush, steps=5, warmup=3):
-    """Whole training step of the chair generation model ('also report whole-model step'):
-    PointNet encoder + latent flows + priors + point decoder + VAE loss + backward + AMSGrad Adam."""
+def full_model_step(dev, B, N, precision, flush, config_name, world, graphed=False, steps=5, warmup=3):
+    """Whole training step of one of the BASELINE model families ('also report whole-model step'):
+    encoders + latent flows + priors + point decoder + VAE loss + backward + gradient averaging across the ranks
+    (batch sharding, B shapes per rank) + AMSGrad Adam.  Timed on every rank, max over ranks.
+      generation/chair           BASELINE config 2 (G = 128)
+      autoencoding/all_original  BASELINE config 3 (G = 512), 'batch-sharded training with gradient allreduce'
+      svr/all                    BASELINE config 4 (ResNet-18 image encoder + G = 512), 224 x 224 synthetic images"""
+    import torch.distributed as dist
     from dpf_nets_b200 import configs
+    from dpf_nets_b200 import dist as ddist
     from dpf_nets_b200.lib.networks.losses import Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss
-    from dpf_nets_b200.lib.networks.models import Local_Cond_RNVP_MC_Global_RNVP_VAE
+    from dpf_nets_b200.lib.networks.models import Local_Cond_RNVP_MC_Global_RNVP_VAE, Local_Cond_RNVP_MC_Global_RNVP_VAE_IC
     from dpf_nets_b200.lib.networks.optimizers import Adam
-    config = configs.load("generation/chair")
+    config = configs.load(config_name)
+    ic = config["train_mode"] == "p_rnvp_mc_g_rnvp_vae_ic"
+    rank = int(os.environ.get("RANK", "0"))
     torch.manual_seed(0)
-    model = Local_Cond_RNVP_MC_Global_RNVP_VAE(**config).to(dev)
+    model = (Local_Cond_RNVP_MC_Global_RNVP_VAE_IC if ic else Local_Cond_RNVP_MC_Global_RNVP_VAE)(**config).to(dev)
     model.pc_decoder.precision = precision
     model.train()
     crit = Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss(**config).to(dev)
     opt = Adam(model.parameters(), lr=config["max_lr"], weight_decay=config["wd"], betas=(config["beta1"], config["max_beta2"]),
                amsgrad=True)
-    gen = torch.Generator().manual_seed(99)
-    clouds = [(torch.rand((B, 3, N), generator=gen) - 0.5).pin_memory() for _ in range(2)]
+    sync = ddist.GradSync(model)
+    gen = torch.Generator().manual_seed(99 + rank)
+    host = [(torch.rand((B, 3, N), generator=gen) - 0.5).pin_memory() for _ in range(2)]
+    if ic:
+        host.append(torch.randn((B, 4, 224, 224), generator=gen).pin_memory())
 
     def step():
-        g_clouds = clouds[0].to(dev, non_blocking=True)
-        p_clouds = clouds[1].to(dev, non_blocking=True)
-        out = model(g_clouds, p_clouds)
-        loss, pnll, gnll, gent = crit(g_clouds, p_clouds, out)
+        inp = [t.to(dev, non_blocking=True) for t in host]
+        out = model(*inp)
+        loss, pnll, gnll, gent = crit(inp[0], inp[1], out)
         opt.zero_grad()
         loss.backward()
+        sync.finish()
         opt.step()
         return loss
 
@@ -547,29 +628,41 @@ def full_model_step(dev, B, N, precision, flush, steps=5, warmup=3):
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         ts, loss = [], None
         for _ in range(steps):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); loss = fn(); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        return sum(ts) / len(ts), float(loss.detach())
+        t = torch.tensor([sum(ts) / len(ts)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(loss.detach())
 
     ms, loss = timed(step)
-    res = {"value": B * N / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "loss": loss,
-           "model": "generation/chair VAE, %d params" % sum(p.numel() for p in model.parameters()),
-           "includes": "H2D of both clouds, encoder, latent flows, priors, decoder, loss, backward, AMSGrad step"}
-    # the same step as two CUDA graphs (config key cuda_graph: forward+loss+backward | optimizer), _graphstep.py
-    try:
-        from dpf_nets_b200.lib.networks._graphstep import GraphedTrainStep
-        gstep = GraphedTrainStep(model, crit, opt, eager_steps=0)
+    n_params = sum(p.numel() for p in model.parameters())
+    res = {"value": world * B * N / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "loss_rank0": loss, "n_gpus": world,
+           "model": "%s, %d params" % (config_name, n_params), "batch_per_gpu": B, "points": N,
+           "gradient_bytes_allreduced_per_step": 4 * n_params if world > 1 else 0,
+           "includes": "H2D of the inputs, encoders, latent flows, priors, decoder, loss, backward, gradient all-reduce "
+                       "(decoder arena overlapped with the rest of the backward), AMSGrad step"}
+    if graphed:
+        # the same step as two CUDA graphs (config key cuda_graph: forward+loss+backward | optimizer), _graphstep.py
+        try:
+            from dpf_nets_b200.lib.networks._graphstep import GraphedTrainStep
+            gstep = GraphedTrainStep(model, crit, opt, allreduce=sync.finish, eager_steps=0)
 
-        def graphed():
-            return gstep(clouds[0].to(dev, non_blocking=True), clouds[1].to(dev, non_blocking=True))[0]
-        gms, gloss = timed(graphed)
-        res["cuda_graph"] = {"value": B * N / (gms * 1e-3), "unit": "points/s", "ms_per_step": gms, "loss": gloss}
-    except Exception as e:      # reported, never fatal for the headline line
-        res["cuda_graph"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            def run_graphed():
+                return gstep(*[t.to(dev, non_blocking=True) for t in host])[0]
+            gms, gloss = timed(run_graphed)
+            res["cuda_graph"] = {"value": world * B * N / (gms * 1e-3), "unit": "points/s", "ms_per_step": gms, "loss_rank0": gloss}
+        except Exception as e:      # reported, never fatal for the headline line
+            res["cuda_graph"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    sync.remove()
+    del model, opt
+    torch.cuda.empty_cache()
     return res
 
 

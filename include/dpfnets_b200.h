@@ -186,6 +186,11 @@ int dpf_umma_selftest(const void* a_img, int a_bytes, const void* b_img, int b_b
                       int num_k, int a_kstep, int b_kstep, int ncols, int use_bulk, float* d_out,
                       void* stream);
 
+/* Measured pipe ceilings for bench.py's roofline fractions: `ctas` CTAs x 256 threads x `iters` rounds of 8 independent
+ * operations per thread; which = 0: ex2.approx (MUFU; the EMD kernels' bound), 1: fma.rn.f32x2 (packed fp32 FMA; the
+ * Chamfer kernels' bound).  *ops_per_launch = MUFU results / fp32 FMA lanes executed; time the call with CUDA events. */
+int dpf_throughput_probe(int which, int ctas, int iters, float* scratch, long long* ops_per_launch, void* stream);
+
 /* Debug probe: CTAs/SM the runtime reports for the merged (0) / plain (1) forward kernel at `smem` bytes. */
 int dpf_debug_occupancy(int which, int smem, int* out);
 

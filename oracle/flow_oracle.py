@@ -364,3 +364,50 @@ def apply_pending(dp_stored, p, pending):
     dp = dp_stored.clone()
     dp[:, kidx, :] -= cvec.view(1, -1, 1) + torch.einsum("jk,bkn->bjn", Q, p[:, kidx, :])
     return dp
+
+
+def init_decoder_layers(n_flows, G, F=64, weight_std=0.01, seed=0, device="cpu", requires_grad=True):
+    """Random-init parameters of a LocalCondRNVPDecoder with the reference's initialisation
+    (flows.py:25-93, layers.py:29-39, decoders.py:49-52): kaiming-uniform SharedDots and nn.Linear defaults,
+    N(0, weight_std) final layers with zero bias, BN weight 1 / bias 0 / running stats (0, 1).
+    -> (layers = [(param dict keyed like one CondRealNVPFlow3D, warp_inds)], leaves = list of trainable tensors).
+    Used by bench.py's reference arm, which must not touch product code."""
+    gen = torch.Generator().manual_seed(seed)
+    layers, leaves = [], []
+
+    def uni(shape, bound):
+        return (torch.rand(shape, generator=gen) * 2.0 - 1.0) * bound
+
+    def leaf(t):
+        t = t.to(device)
+        if requires_grad:
+            t.requires_grad_(True)
+            leaves.append(t)
+        return t
+
+    for _, warp in decoder_layer_names(n_flows):
+        k, w = 3 - len(warp), len(warp)
+        P = {"eps": torch.tensor([1e-6], device=device)}
+        for br in BRANCHES:
+            t0 = "T_%s_0.%s_" % (br, br)
+            P[t0 + "sd0.weight"] = leaf(uni((1, F, k), math.sqrt(6.0 / (F * k))))
+            P[t0 + "sd0_bn.weight"] = leaf(torch.ones(F))
+            P[t0 + "sd0_bn.bias"] = leaf(torch.zeros(F))
+            P[t0 + "sd1.weight"] = leaf(uni((1, F, F), math.sqrt(6.0 / (F * F))))
+            for bn in (t0 + "sd0_bn", t0 + "sd1_bn"):
+                P[bn + ".running_mean"] = torch.zeros(F, device=device)
+                P[bn + ".running_var"] = torch.ones(F, device=device)
+            for kind in ("w", "b"):
+                f = "T_%s_0_cond_%s.%s_sd1_film_%s" % (br, kind, br, kind)
+                P[f + "0.weight"] = leaf(uni((F, G), 1.0 / math.sqrt(G)))
+                P[f + "0_bn.weight"] = leaf(torch.ones(F))
+                P[f + "0_bn.bias"] = leaf(torch.zeros(F))
+                P[f + "0_bn.running_mean"] = torch.zeros(F, device=device)
+                P[f + "0_bn.running_var"] = torch.ones(F, device=device)
+                P[f + "1.weight"] = leaf(torch.randn((F, F), generator=gen) * weight_std)
+                P[f + "1.bias"] = leaf(torch.zeros(F))
+            t1 = "T_%s_1.%s_sd2." % (br, br)
+            P[t1 + "weight"] = leaf(torch.randn((1, w, F), generator=gen) * weight_std)
+            P[t1 + "bias"] = leaf(torch.zeros((1, w)))
+        layers.append((P, warp))
+    return layers, leaves

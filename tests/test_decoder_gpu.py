@@ -580,8 +580,8 @@ def test_speed_vs_eager_torch_port_on_this_gpu(mods, cuda):
     import os
     import sys
     import time
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import bench
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _oracle_arena as bench
     from dpf_nets_b200.lib.networks.losses import PointFlowNLL
     _, decoders = mods
     B, N = 32, 2048
@@ -591,7 +591,7 @@ def test_speed_vs_eager_torch_port_on_this_gpu(mods, cuda):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(3):
-        loss_ref = step_ref()
+        loss_ref = step_ref()[0]
     torch.cuda.synchronize()
     ms_ref = (time.perf_counter() - t0) / 3 * 1e3
 
@@ -782,12 +782,12 @@ def test_full_size_train_outputs_and_gradients_vs_port(mods, cuda):
     re-association noise), NLL 1e-5, gradients 2e-2 per tensor for tensors holding at least 1e-3 of the largest
     gradient norm (tiny-norm tensors are compared in absolute terms against that scale)."""
     import sys
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import bench
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _oracle_arena as bench
     _, decoders = mods
     from dpf_nets_b200.lib.networks.losses import PointFlowNLL
     B, N, G = 32, 2048, 128
-    step_ref = bench.oracle_train_step_factory(B, N, device=cuda, return_state=True)
+    step_ref = bench.oracle_train_step_factory(B, N, device=cuda)
     loss_ref, st = step_ref()
     torch.manual_seed(0)
     m = decoders.LocalCondRNVPDecoder(21, 64, G).to(cuda).train()
