@@ -27,7 +27,8 @@ namespace {
 constexpr int NT = 256;
 
 struct EvalLayerTab {              // DPF_EVAL_LTAB_BYTES, 16-byte multiple (bulk-copied)
-  float4 A0[2][F];                 // folded eval BN_a: {A00, A01, c0, -}
+  float4 PA[2][F / 2][2];          // folded eval BN_a in CHANNEL-PAIR layout (a = channel 2j, b = 2j+1) for the packed fp32x2 math:
+                                   //   {A00_a, A00_b, c0_a, c0_b}, {A01_a, A01_b, -, -}
   float b2[2][2];
   int k, w, keep0, keep1, warp0, warp1;
   int pad[6];
@@ -51,7 +52,12 @@ eval_tables_kernel(const float* __restrict__ arena, const float* __restrict__ st
     const float w1 = (k == 2) ? prm[lay.W0 + c * k + 1] : 0.f;
     const float istd = 1.f / sqrtf(st[ST_BNA_RV * F + c] + DPF_BN_EPS);
     const float gi = prm[lay.bnA_w + c] * istd;
-    lt->A0[br][c] = make_float4(gi * w0, gi * w1, prm[lay.bnA_b + c] - gi * st[ST_BNA_RM * F + c], 0.f);
+    float* pa = reinterpret_cast<float*>(&lt->PA[br][c >> 1][0]);
+    const int ln = c & 1;
+    pa[ln] = gi * w0;
+    pa[2 + ln] = prm[lay.bnA_b + c] - gi * st[ST_BNA_RM * F + c];
+    pa[4 + ln] = gi * w1;
+    pa[6 + ln] = 0.f;
     if (c < 2) lt->b2[br][c] = (c < w) ? prm[lay.b2 + c] : 0.f;
     if (threadIdx.x == 0) {
       lt->k = k; lt->w = w;
@@ -63,8 +69,13 @@ eval_tables_kernel(const float* __restrict__ arena, const float* __restrict__ st
   const float sc = film[(((size_t)l * 4 + br * 2 + 0) * B + b) * F + c];
   const float sh = film[(((size_t)l * 4 + br * 2 + 1) * B + b) * F + c];
   const float S = sc * ib;
-  epi_out[(((size_t)l * B + b) * 2 + br) * F + c] =
-      make_float4(S, fmaf(-S, mb, sh), prm[lay.W2 + c], (w == 2) ? prm[lay.W2 + F + c] : 0.f);
+  // channel-pair layout: [l][b][br][F/2] x {S_a, S_b, T_a, T_b}, {W20_a, W20_b, W21_a, W21_b}
+  float* pe = reinterpret_cast<float*>(epi_out + ((((size_t)l * B + b) * 2 + br) * (F / 2) + (c >> 1)) * 2);
+  const int ln = c & 1;
+  pe[ln] = S;
+  pe[2 + ln] = fmaf(-S, mb, sh);
+  pe[4 + ln] = prm[lay.W2 + c];
+  pe[6 + ln] = (w == 2) ? prm[lay.W2 + F + c] : 0.f;
 }
 
 struct EvalArgs {
@@ -82,32 +93,40 @@ template <bool SPLIT>
 struct EvalSmem {
   unsigned char W[(SPLIT ? 4 : 2) * IMG_W];     // [br][W1 hi (, W1 lo)] of the layer in flight
   unsigned char H[(SPLIT ? 2 : 1) * IMG_H];     // h1 tile (hi (, lo)) of the branch in flight
-  struct Tab { EvalLayerTab lt; float4 epi[2][F]; } tab[2];
+  struct Tab { EvalLayerTab lt; float4 epi[2][F / 2][2]; } tab[2];
   float4 obuf[2][DPF_TILE];                     // partial last-SharedDot sums of the two parts
   uint64_t bar_mma, bar_w;
   uint32_t tmem_base;
 };
 
-// 32 channels of one branch: h3 = relu(S * acc + T), partial sums of the last SharedDot
-__device__ __forceinline__ void eval_epilogue32(const float4* __restrict__ epi, uint32_t taddr, float& o0, float& o1) {
+// 32 channels (16 pairs) of one branch: h3 = relu(S * acc + T), partial sums of the last SharedDot; packed fp32x2 math
+// (FFMA2: two IEEE fp32 lanes per instruction), even / odd channels accumulate in the two lanes of o0_2 / o1_2
+template <bool W2ND>
+__device__ __forceinline__ void eval_epilogue32(const float4 (*__restrict__ epi)[2], uint32_t taddr, f32x2& o0_2, f32x2& o1_2) {
   uint32_t ra[16], rb[16];
   umma::tmem_ld16_issue(taddr, ra);
   umma::tmem_ld16_issue(taddr + 16, rb);
   umma::tmem_ld_wait16(ra);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float4 e = epi[i];
-    const float h3 = fmaxf(fmaf(e.x, __uint_as_float(ra[i]), e.y), 0.f);
-    o0 = fmaf(e.z, h3, o0);
-    o1 = fmaf(e.w, h3, o1);
+  for (int j = 0; j < 8; ++j) {
+    const float4 E0 = epi[j][0], E1 = epi[j][1];
+    const f32x2 a2 = f2_fma(f2_pack(E0.x, E0.y), f2_pack(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1])), f2_pack(E0.z, E0.w));
+    float ha, hb;
+    f2_unpack(a2, ha, hb);
+    const f32x2 h2 = f2_pack(fmaxf(ha, 0.f), fmaxf(hb, 0.f));
+    o0_2 = f2_fma(f2_pack(E1.x, E1.y), h2, o0_2);
+    if (W2ND) o1_2 = f2_fma(f2_pack(E1.z, E1.w), h2, o1_2);
   }
   umma::tmem_ld_wait16(rb);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float4 e = epi[16 + i];
-    const float h3 = fmaxf(fmaf(e.x, __uint_as_float(rb[i]), e.y), 0.f);
-    o0 = fmaf(e.z, h3, o0);
-    o1 = fmaf(e.w, h3, o1);
+  for (int j = 0; j < 8; ++j) {
+    const float4 E0 = epi[8 + j][0], E1 = epi[8 + j][1];
+    const f32x2 a2 = f2_fma(f2_pack(E0.x, E0.y), f2_pack(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1])), f2_pack(E0.z, E0.w));
+    float ha, hb;
+    f2_unpack(a2, ha, hb);
+    const f32x2 h2 = f2_pack(fmaxf(ha, 0.f), fmaxf(hb, 0.f));
+    o0_2 = f2_fma(f2_pack(E1.x, E1.y), h2, o0_2);
+    if (W2ND) o1_2 = f2_fma(f2_pack(E1.z, E1.w), h2, o1_2);
   }
 }
 
@@ -170,19 +189,27 @@ decoder_eval_tc_kernel(const EvalArgs a) {
       const int k = tb.lt.k;
       const float xk0 = pick3(xin, tb.lt.keep0);
       const float xk1 = (k == 2) ? pick3(xin, tb.lt.keep1) : 0.f;
+      const f32x2 xk0_2 = f2_pack(xk0, xk0), xk1_2 = f2_pack(xk1, xk1);
 
 #pragma unroll
       for (int br = 0; br < 2; ++br) {
-        // h1 = relu(A0 . x_keep + c0) of this part's 32 channels -> swizzled bf16 tile (A01 == 0 when k == 1)
+        // h1 = relu(A0 . x_keep + c0) of this part's 32 channels -> swizzled bf16 tile; packed fp32x2 math over channel pairs
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
           const int ch8 = part * 4 + qq;
           uint32_t w[4], wl[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 Aa = tb.lt.A0[br][ch8 * 8 + 2 * i], Ab = tb.lt.A0[br][ch8 * 8 + 2 * i + 1];
-            const float va = fmaxf(fmaf(Aa.y, xk1, fmaf(Aa.x, xk0, Aa.z)), 0.f);
-            const float vb = fmaxf(fmaf(Ab.y, xk1, fmaf(Ab.x, xk0, Ab.z)), 0.f);
+            const float4 P0 = tb.lt.PA[br][ch8 * 4 + i][0];
+            f32x2 v2 = f2_fma(f2_pack(P0.x, P0.y), xk0_2, f2_pack(P0.z, P0.w));
+            if (k == 2) {                   // uniform per layer
+              const float4 P1 = tb.lt.PA[br][ch8 * 4 + i][1];
+              v2 = f2_fma(f2_pack(P1.x, P1.y), xk1_2, v2);
+            }
+            float va, vb;
+            f2_unpack(v2, va, vb);
+            va = fmaxf(va, 0.f);
+            vb = fmaxf(vb, 0.f);
             w[i] = umma::pack_bf16(va, vb);
             if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
           }
@@ -208,12 +235,18 @@ decoder_eval_tc_kernel(const EvalArgs a) {
         else if (tile + 1 < t1) issue_item_loads(tile + 1, 0, stage ^ 1u);
       }
 
+      const int wn = tb.lt.w;
       float o[2][2];
 #pragma unroll
       for (int br = 0; br < 2; ++br) {
-        o[br][0] = part == 0 ? tb.lt.b2[br][0] : 0.f;
-        o[br][1] = part == 0 ? tb.lt.b2[br][1] : 0.f;
-        eval_epilogue32(&tb.epi[br][part * 32], lane_addr + br * F + part * 32, o[br][0], o[br][1]);
+        f32x2 o0_2 = f2_pack(part == 0 ? tb.lt.b2[br][0] : 0.f, 0.f), o1_2 = f2_pack(part == 0 ? tb.lt.b2[br][1] : 0.f, 0.f);
+        if (wn == 2) eval_epilogue32<true>(&tb.epi[br][part * 16], lane_addr + br * F + part * 32, o0_2, o1_2);
+        else eval_epilogue32<false>(&tb.epi[br][part * 16], lane_addr + br * F + part * 32, o0_2, o1_2);
+        float lo, hi;
+        f2_unpack(o0_2, lo, hi);
+        o[br][0] = lo + hi;
+        f2_unpack(o1_2, lo, hi);
+        o[br][1] = lo + hi;
       }
       s.obuf[part][row] = make_float4(o[0][0], o[0][1], o[1][0], o[1][1]);
       umma::fence_before_sync();
@@ -223,7 +256,7 @@ decoder_eval_tc_kernel(const EvalArgs a) {
       const float olv[2] = {u0.z + u1.z, u0.w + u1.w};
 
       // affine transform (both threads of the point keep the new coordinates; part 0 writes P and MU, part 1 LV)
-      const int wn = tb.lt.w, warp0 = tb.lt.warp0, warp1 = tb.lt.warp1;
+      const int warp0 = tb.lt.warp0, warp1 = tb.lt.warp1;
       float yv[3], muv[3] = {0.f, 0.f, 0.f}, lvv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) yv[ch] = (MODE == 0) ? sig1 * xin[ch] : xin[ch] / sig1;

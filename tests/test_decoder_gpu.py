@@ -459,8 +459,8 @@ def test_merged_cooperative_forward_equals_two_launch_form(mods, cuda, native_li
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
 def test_fused_eval_decoder_equals_per_layer_form(mods, cuda, native_lib, precision):
     """Eval mode (running statistics): the one-launch all-layer decoder (coupling_eval.cu) must give
-    the per-layer kernels' outputs bit for bit - same arithmetic, different scheduling - in both
-    directions, with ragged tiles and with more tiles than resident CTAs."""
+    the per-layer kernels' outputs to fp32 re-association - same arithmetic per element, different scheduling and
+    summation order of the last SharedDot - in both directions, with ragged tiles and with more tiles than resident CTAs."""
     _, decoders = mods
     torch.manual_seed(11)
     m = decoders.LocalCondRNVPDecoder(4, 64, 32).to(cuda)   # 12 coupling layers, both patterns
@@ -487,7 +487,10 @@ def test_fused_eval_decoder_equals_per_layer_form(mods, cuda, native_lib, precis
             native_lib.dpf_set_option(1, 1)
             for a, b in zip(*outs):
                 assert torch.isfinite(a).all()
-                assert torch.equal(a, b), (precision, B, N, mode, rel(a, b))
+                # same arithmetic per element; the fused kernel's packed fp32x2 epilogue sums the last SharedDot over even and
+                # odd channels separately (two FFMA2 lanes), so the outputs agree to fp32 re-association (bf16 mode: a flipped
+                # bf16 rounding of h1 in a later layer can amplify that to ~1e-3), not bit for bit
+                assert rel(a, b) < (2e-5 if precision == "bf16x3" else 5e-3), (precision, B, N, mode, rel(a, b))
 
 
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
