@@ -89,6 +89,9 @@ pack_w1_kernel(const float* __restrict__ arena, const LayerMeta* __restrict__ me
 struct TcCommon {                       // small per-CTA tables (after the 1024-aligned image area)
   float4 A0[2][F];                      // folded BN_a: {A00, A01, c0, -}
   float4 epi[2][F];                     // per tile: {S, T, W2_0, W2_1},  a = S*acc + T
+  // the same two tables in CHANNEL-PAIR layout (a = channel 2j, b = 2j+1) for the packed fp32x2 math (FFMA2):
+  float4 A0p[2][F / 2][2];              //   {A00_a, A00_b, c0_a, c0_b}, {A01_a, A01_b, -, -}
+  float4 epip[2][F / 2][2];             //   {S_a, S_b, T_a, T_b}, {W20_a, W20_b, W21_a, W21_b}
   float mb[2][F], ib[2][F], sraw[2][F];
   float W2[2][2][F];
   float b2[2][2];
@@ -105,6 +108,11 @@ __device__ __forceinline__ void tc_prologue_tables(const CouplingArgs& a, const 
   float A00, A01, c0;
   fold_bn_a(a, lay, br, c, writer, A00, A01, c0, nullptr, nullptr);
   s.A0[br][c] = make_float4(A00, A01, c0, 0.f);
+  {
+    float* pa = reinterpret_cast<float*>(&s.A0p[br][c >> 1][0]);
+    const int ln = c & 1;
+    pa[ln] = A00; pa[2 + ln] = c0; pa[4 + ln] = A01; pa[6 + ln] = 0.f;
+  }
   if (need_bnb) {
     float mean, istd;
     bn_b_stats(a, br, c, writer, mean, istd);
@@ -123,6 +131,11 @@ __device__ __forceinline__ void tc_prologue_tables_ltab(const float* __restrict_
   const float4 t0 = reinterpret_cast<const float4*>(ltab)[tid * (DPF_LTAB_ROW / 4) + 0];
   const float4 t1 = reinterpret_cast<const float4*>(ltab)[tid * (DPF_LTAB_ROW / 4) + 1];
   s.A0[br][c] = make_float4(t0.x, t0.y, t0.z, 0.f);
+  {
+    float* pa = reinterpret_cast<float*>(&s.A0p[br][c >> 1][0]);
+    const int ln = c & 1;
+    pa[ln] = t0.x; pa[2 + ln] = t0.z; pa[4 + ln] = t0.y; pa[6 + ln] = 0.f;
+  }
   s.mb[br][c] = t0.w;
   s.ib[br][c] = t1.x;
   s.W2[br][0][c] = t1.y;
@@ -136,7 +149,32 @@ __device__ __forceinline__ void tc_tile_film(const CouplingArgs& a, TcCommon& s,
   const float sh = a.film[((size_t)(br * 2 + 1) * a.B + b) * F + c];
   const float S = sc * s.ib[br][c];
   s.sraw[br][c] = sc;
-  s.epi[br][c] = make_float4(S, fmaf(-S, s.mb[br][c], sh), s.W2[br][0][c], s.W2[br][1][c]);
+  const float T = fmaf(-S, s.mb[br][c], sh);
+  s.epi[br][c] = make_float4(S, T, s.W2[br][0][c], s.W2[br][1][c]);
+  float* pe = reinterpret_cast<float*>(&s.epip[br][c >> 1][0]);
+  const int ln = c & 1;
+  pe[ln] = S; pe[2 + ln] = T; pe[4 + ln] = s.W2[br][0][c]; pe[6 + ln] = s.W2[br][1][c];
+}
+
+// h1 = relu(A0 . x_keep + c0) of the 8 channels of 16-byte chunk q of one branch (packed fp32x2 math over the channel
+// pairs of the pair-layout table) -> bf16 hi (and lo residual) words
+template <int K, bool SPLIT>
+__device__ __forceinline__ void h1_chunk8(const float4 (*__restrict__ A0p)[2], int q, f32x2 xk0_2, f32x2 xk1_2, uint32_t w[4], uint32_t wl[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 P0 = A0p[q * 4 + i][0];
+    f32x2 v2 = f2_fma(f2_pack(P0.x, P0.y), xk0_2, f2_pack(P0.z, P0.w));
+    if (K == 2) {
+      const float4 P1 = A0p[q * 4 + i][1];
+      v2 = f2_fma(f2_pack(P1.x, P1.y), xk1_2, v2);
+    }
+    float va, vb;
+    f2_unpack(v2, va, vb);
+    va = fmaxf(va, 0.f);
+    vb = fmaxf(vb, 0.f);
+    w[i] = umma::pack_bf16(va, vb);
+    if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
+  }
 }
 
 // CTA setup: barriers and TMEM allocation (the weight images are TMA-bulk-loaded by the caller).
@@ -1885,6 +1923,7 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
     if (tile == t0) DPF_STAMP(1, 5);
     const float xk0 = pick3(raw.x, a.f.keep0);
     const float xk1 = (K == 2) ? pick3(raw.x, a.f.keep1) : 0.f;
+    const f32x2 xk0_2 = f2_pack(xk0, xk0), xk1_2 = f2_pack(xk1, xk1);
     TcPoint g;
 #pragma unroll 1
     for (int br = 0; br < 2; ++br) {
@@ -1896,16 +1935,7 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
       for (int qq = 0; qq < 4; ++qq) {
         const int q = part * 4 + qq;
         uint32_t w[4], wl[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 Aa = s.c.A0[br][q * 8 + 2 * i], Ab = s.c.A0[br][q * 8 + 2 * i + 1];
-          float va = fmaf(Aa.x, xk0, Aa.z), vb = fmaf(Ab.x, xk0, Ab.z);
-          if (K == 2) { va = fmaf(Aa.y, xk1, va); vb = fmaf(Ab.y, xk1, vb); }
-          va = fmaxf(va, 0.f);
-          vb = fmaxf(vb, 0.f);
-          w[i] = umma::pack_bf16(va, vb);
-          if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
-        }
+        h1_chunk8<K, SPLIT>(s.c.A0p[br], q, xk0_2, xk1_2, w, wl);
         const uint32_t off = umma::sw128_offset(row, q);
         *reinterpret_cast<uint4*>(s.H + off) = make_uint4(w[0], w[1], w[2], w[3]);
         if (SPLIT) *reinterpret_cast<uint4*>(s.H + IMG_H + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
@@ -1950,9 +1980,12 @@ coupling_bwd_p1_tc2_kernel(const BwdArgs a, const unsigned short* __restrict__ w
           uint32_t wh[4], wl[4], wm[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 ea = s.c.epi[br][part * 32 + q * 8 + 2 * i], eb = s.c.epi[br][part * 32 + q * 8 + 2 * i + 1];
-            const float ha = fmaxf(fmaf(ea.x, v[q * 8 + 2 * i], ea.y), 0.f);
-            const float hb = fmaxf(fmaf(eb.x, v[q * 8 + 2 * i + 1], eb.y), 0.f);
+            const float4 E0 = s.c.epip[br][part * 16 + q * 4 + i][0];
+            const f32x2 a2 = f2_fma(f2_pack(E0.x, E0.y), f2_pack(v[q * 8 + 2 * i], v[q * 8 + 2 * i + 1]), f2_pack(E0.z, E0.w));
+            float ha, hb;
+            f2_unpack(a2, ha, hb);
+            ha = fmaxf(ha, 0.f);
+            hb = fmaxf(hb, 0.f);
             wh[i] = umma::pack_bf16(ha, hb);
             wl[i] = umma::pack_bf16(ha - __uint_as_float(wh[i] << 16), hb - __uint_as_float(wh[i] & 0xffff0000u));
             wm[i] = (ha > 0.f ? 0x3f80u : 0u) | (hb > 0.f ? 0x3f800000u : 0u);
@@ -2051,20 +2084,12 @@ __device__ __forceinline__ void colreduce32_sq_part(float* scratch, const float 
 // h1 chunks of this part for one branch -> tiles, then UMMA chain into TMEM columns [tcol, tcol+64)
 template <int K, bool SPLIT>
 __device__ __forceinline__ void fwd2_gemm(TcFwdSmem2& s, int br, uint32_t tcol, float xk0, float xk1, int row, int part, uint32_t& phase) {
+  const f32x2 xk0_2 = f2_pack(xk0, xk0), xk1_2 = f2_pack(xk1, xk1);
 #pragma unroll
   for (int qq = 0; qq < 4; ++qq) {
     const int q = part * 4 + qq;
     uint32_t w[4], wl[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 Aa = s.c.A0[br][q * 8 + 2 * i], Ab = s.c.A0[br][q * 8 + 2 * i + 1];
-      float va = fmaf(Aa.x, xk0, Aa.z), vb = fmaf(Ab.x, xk0, Ab.z);
-      if (K == 2) { va = fmaf(Aa.y, xk1, va); vb = fmaf(Ab.y, xk1, vb); }
-      va = fmaxf(va, 0.f);
-      vb = fmaxf(vb, 0.f);
-      w[i] = umma::pack_bf16(va, vb);
-      if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
-    }
+    h1_chunk8<K, SPLIT>(s.c.A0p[br], q, xk0_2, xk1_2, w, wl);
     const uint32_t off = umma::sw128_offset(row, q);
     *reinterpret_cast<uint4*>(s.H + off) = make_uint4(w[0], w[1], w[2], w[3]);
     if (SPLIT) *reinterpret_cast<uint4*>(s.H + IMG_H + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
@@ -2081,17 +2106,27 @@ __device__ __forceinline__ void fwd2_gemm(TcFwdSmem2& s, int br, uint32_t tcol, 
   umma::fence_after_sync();
 }
 
-// partial last-SharedDot sums of this part's 32 channels of one branch from TMEM columns [tcol + 32*part, +32)
+// partial last-SharedDot sums of this part's 32 channels of one branch from TMEM columns [tcol + 32*part, +32):
+// packed fp32x2 math over channel pairs (even / odd channels accumulate in the two lanes, summed at the end)
 __device__ __forceinline__ void fwd2_epilogue(const TcFwdSmem2& s, int br, uint32_t taddr, int part, float& o0, float& o1) {
   float v[32];
   umma::tmem_ld32(taddr + part * 32, v);
+  f32x2 o0_2 = f2_pack(o0, 0.f), o1_2 = f2_pack(o1, 0.f);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float4 e = s.c.epi[br][part * 32 + i];
-    const float h3 = fmaxf(fmaf(e.x, v[i], e.y), 0.f);
-    o0 = fmaf(e.z, h3, o0);
-    o1 = fmaf(e.w, h3, o1);
+  for (int j = 0; j < 16; ++j) {
+    const float4 E0 = s.c.epip[br][part * 16 + j][0], E1 = s.c.epip[br][part * 16 + j][1];
+    const f32x2 a2 = f2_fma(f2_pack(E0.x, E0.y), f2_pack(v[2 * j], v[2 * j + 1]), f2_pack(E0.z, E0.w));
+    float ha, hb;
+    f2_unpack(a2, ha, hb);
+    const f32x2 h2 = f2_pack(fmaxf(ha, 0.f), fmaxf(hb, 0.f));
+    o0_2 = f2_fma(f2_pack(E1.x, E1.y), h2, o0_2);
+    o1_2 = f2_fma(f2_pack(E1.z, E1.w), h2, o1_2);
   }
+  float lo, hi;
+  f2_unpack(o0_2, lo, hi);
+  o0 = lo + hi;
+  f2_unpack(o1_2, lo, hi);
+  o1 = lo + hi;
 }
 
 // transform + outputs + moment accumulation of one point (part 0 threads)
