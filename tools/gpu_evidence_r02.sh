@@ -11,10 +11,14 @@ for k in coupling_fwd_train_tc2_kernel coupling_bwd_p1_tc2_kernel coupling_bwd_p
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 70 -c 1 -f -o gpurun_out/r02_prof_$k \
     python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/r02_ncu_$k.log 2>&1
   tail -1 gpurun_out/r02_ncu_$k.log
+  python tools/ncu_summary.py gpurun_out/r02_prof_$k.ncu-rep > gpurun_out/r02_ncu_${k}_summary.txt; rm -f gpurun_out/r02_prof_$k.ncu-rep
 done
 # merged backward (opt-in form), sampling kernel, Chamfer all-pairs (one-evaluation kernel), fused EMD, score reduction
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:coupling_bwd_merged_kernel -s 70 -c 1 -f -o gpurun_out/r02_prof_coupling_bwd_merged_kernel \
   python bench.py --steps 1 --warmup 3 --no-extras --lib-option 5=1 > gpurun_out/r02_ncu_merged.log 2>&1; tail -1 gpurun_out/r02_ncu_merged.log
+python tools/ncu_summary.py gpurun_out/r02_prof_coupling_bwd_merged_kernel.ncu-rep > gpurun_out/r02_ncu_coupling_bwd_merged_kernel_summary.txt; rm -f gpurun_out/r02_prof_coupling_bwd_merged_kernel.ncu-rep
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'decoder_eval_tc_kernel|pairwise_cd_fused_kernel|pairwise_emd|cd_scores_kernel' -c 6 -f -o gpurun_out/r02_prof_eval_kernels \
   python tools/eval_kernels_probe.py > gpurun_out/r02_ncu_eval_kernels.log 2>&1; tail -2 gpurun_out/r02_ncu_eval_kernels.log
-ls -la gpurun_out/*.ncu-rep
+python tools/ncu_summary.py gpurun_out/r02_prof_eval_kernels.ncu-rep > gpurun_out/r02_ncu_eval_kernels_summary.txt; rm -f gpurun_out/r02_prof_eval_kernels.ncu-rep
+# (the .ncu-rep files are ~17 MB each and gpurun_out/ travels back only up to 64 MiB: the text summaries are what is kept)
+du -sh gpurun_out
