@@ -51,7 +51,7 @@ def ncu_traffic():
     if not files:
         return {}, None
     with open(files[-1]) as f:
-        return json.load(f), os.path.relpath(files[-1], ROOT)
+        return {k: v for k, v in json.load(f).items() if not k.startswith("_")}, os.path.relpath(files[-1], ROOT)
 ALGO_FLOP = {"fwd_stats": 0, "fwd_apply": FLOP_PER_POINT_LAYER_FWD, "bwd_p1": 2 * 2 * 64 * 3,
              "bwd_p2": 2 * FLOP_PER_POINT_LAYER_FWD - 2 * 2 * 64 * 3}
 
