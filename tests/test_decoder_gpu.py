@@ -756,8 +756,11 @@ def test_nll_outputs_equal_list_path(mods, cuda, precision):
         nll.backward()
         res[how] = (nll.item(), m.arena.grad.clone(), g.grad.clone(), pp.grad.clone())
     ref = res["plain_lists"]
-    # noise floor of this fixture: the dense path against itself (float atomics in the backward reorder the sums)
-    floor = [max(2e-3, 3 * rel(a, b)) for a, b in zip(res["plain_lists_again"][1:], ref[1:])]
+    # fp32 path: the variants run the same arithmetic (agreement ~1e-5).  bf16x3 path: float atomics in the backward reorder
+    # the sums from run to run - the dense path against ITSELF differs by up to ~1e-2 on dp - so the gate there is the
+    # measured noise floor with head-room, never tighter than 3e-2
+    again = res["plain_lists_again"]
+    floor = [max(2e-3 if precision == "fp32" else 3e-2, 5 * rel(a, b)) for a, b in zip(again[1:], ref[1:])]
     for how in ("stacked", "fused", "nll_terms"):
         got = res[how]
         assert abs(got[0] - ref[0]) < 1e-5 * abs(ref[0]), how
@@ -774,7 +777,8 @@ def test_nll_outputs_equal_list_path(mods, cuda, precision):
     ps, mus, lvs = m(p, g2, mode="inverse")
     P, LV = ps.stacked, lvs.stacked
     ((P[0] ** 2).sum() + (P[4] * 0.3).sum() + LV.sum() + LV[2].sum()).backward()
-    assert rel(ga, m.arena.grad) < 2e-2 and rel(g.grad, g2.grad) < 2e-2      # run-to-run noise of the float atomics: 2e-3 .. 8e-3 measured
+    tol = 2e-3 if precision == "fp32" else 5e-2           # bf16x3: run-to-run noise of the float atomics, 2e-3 .. 1e-2 measured
+    assert rel(ga, m.arena.grad) < tol and rel(g.grad, g2.grad) < tol
 
 
 def test_full_size_train_outputs_and_gradients_vs_port(mods, cuda):
