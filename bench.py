@@ -345,7 +345,6 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in evs2)
     t = torch.tensor([total_ms, e2e_ms, eager_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
