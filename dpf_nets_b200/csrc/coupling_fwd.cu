@@ -44,30 +44,46 @@ film_forward_kernel(const float* __restrict__ arena, float* __restrict__ stats, 
 
   float* u = sm;                         // [nb][F]
   float* Ws = u + (size_t)cap * F;       // [32][F+1]  (later reused as W1s [F][F+1])
-  float* gs = Ws + F * (F + 1);          // [nb][33]
-  float* mean_s = gs + (size_t)cap * 33;
+  float* gs = Ws + F * (F + 1);          // transposed g chunk [32][4][8] (at least 1024 floats)
+  float* mean_s = gs + ((size_t)cap * 33 > 1024 ? (size_t)cap * 33 : 1024);
   float* istd_s = mean_s + F;
   const int tid = threadIdx.x;
   const int c = tid & 63, bq = tid >> 6;
 
-  for (int e = tid; e < nb * F; e += FILM_THREADS) u[e] = 0.f;
-  for (int i0 = 0; i0 < G; i0 += 32) {
-    const int ni = min(32, G - i0);
-    __syncthreads();
-    for (int e = tid; e < F * 32; e += FILM_THREADS) {
-      const int cc = e >> 5, i = e & 31;
-      Ws[i * (F + 1) + cc] = (i < ni) ? __ldg(W0 + (size_t)cc * G + i0 + i) : 0.f;
-    }
-    for (int e = tid; e < nb * 32; e += FILM_THREADS) {
-      const int b = e >> 5, i = e & 31;
-      gs[b * 33 + i] = (i < ni) ? __ldg(g + (size_t)(b0 + b) * G + i0 + i) : 0.f;
-    }
-    __syncthreads();
-    for (int b = bq; b < nb; b += FILM_THREADS / 64) {
-      float acc = 0.f;
+  // u[b][c] = sum_i g[b][i] W0[c][i]: register tile of 8 shapes per thread (shapes bq + 4 j): one weight load and two
+  // 16-byte broadcast loads of the transposed g chunk feed 8 FMAs (the one-shape-per-thread form was shared-memory-load bound)
+  const int nj = (nb + 3) >> 2;               // shapes per bq group
+  for (int jb = 0; jb < nj; jb += 8) {
+    float acc[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc = fmaf(gs[b * 33 + i], Ws[i * (F + 1) + c], acc);
-      u[b * F + c] += acc;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int i0 = 0; i0 < G; i0 += 32) {
+      const int ni = min(32, G - i0);
+      __syncthreads();
+      for (int e = tid; e < F * 32; e += FILM_THREADS) {
+        const int cc = e >> 5, i = e & 31;
+        Ws[i * (F + 1) + cc] = (i < ni) ? __ldg(W0 + (size_t)cc * G + i0 + i) : 0.f;
+      }
+      // gs (reused as gT): [i][q][8] = g[b0 + q + 4 (jb + j)][i0 + i], zero-padded
+      for (int e = tid; e < 32 * 32; e += FILM_THREADS) {
+        const int i = e & 31, qj = e >> 5, q = qj >> 3, j = qj & 7;
+        const int b = q + 4 * (jb + j);
+        gs[i * 32 + qj] = (i < ni && b < nb) ? __ldg(g + (size_t)(b0 + b) * G + i0 + i) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        const float w = Ws[i * (F + 1) + c];
+        const float4 ga = *reinterpret_cast<const float4*>(gs + i * 32 + bq * 8);
+        const float4 gb = *reinterpret_cast<const float4*>(gs + i * 32 + bq * 8 + 4);
+        acc[0] = fmaf(ga.x, w, acc[0]); acc[1] = fmaf(ga.y, w, acc[1]); acc[2] = fmaf(ga.z, w, acc[2]); acc[3] = fmaf(ga.w, w, acc[3]);
+        acc[4] = fmaf(gb.x, w, acc[4]); acc[5] = fmaf(gb.y, w, acc[5]); acc[6] = fmaf(gb.z, w, acc[6]); acc[7] = fmaf(gb.w, w, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = bq + 4 * (jb + j);
+      if (b < nb) u[b * F + c] = acc[j];
     }
   }
   __syncthreads();
@@ -322,7 +338,7 @@ int launch_film_forward(const float* arena, float* stats, const LayerMeta* meta_
   // shared memory sized for the actual batch: 30 KB at B = 32 -> all L*4 CTAs resident in one wave
   // (at the FILM_BCHUNK cap, 116 KB, it is one CTA per SM and 252 CTAs take two waves)
   const int cap = B < FILM_BCHUNK ? B : FILM_BCHUNK;
-  const size_t smem = sizeof(float) * ((size_t)cap * F + F * (F + 1) + (size_t)cap * 33 + 2 * F);
+  const size_t smem = sizeof(float) * ((size_t)cap * F + F * (F + 1) + ((size_t)cap * 33 > 1024 ? (size_t)cap * 33 : 1024) + 2 * F);
   static bool attr = false;
   if (!attr) {
     const size_t smem_max = sizeof(float) * ((size_t)FILM_BCHUNK * F + F * (F + 1) + (size_t)FILM_BCHUNK * 33 + 2 * F);

@@ -276,6 +276,24 @@ int launch_film_backward(const float* arena, const float* stats, float* darena, 
                          const float* g, const float* film, const float* dfilm, float* dg, int L, int B, int G,
                          int training, float eps, cudaStream_t s);
 
+// side stream + fork / join events for the independent kernels at the tail of the backward (one set per device)
+namespace {
+struct TailStreams { cudaStream_t side; cudaEvent_t fork, join; bool ok; };
+TailStreams* tail_streams() {
+  static TailStreams per_dev[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  TailStreams& t = per_dev[dev];
+  if (!t.ok) {
+    if (cudaStreamCreateWithFlags(&t.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    t.ok = true;
+  }
+  return &t;
+}
+}  // namespace
+
 // Backward of dpf_decoder_forward (what torch.autograd does for the reference modules; formulas in
 // SURVEY.md Appendix F).  `workspace` must be the one the forward call used (FiLM outputs, input
 // moments and BN_b sums live there).  dP / dMU / dLV are the cotangents of the stacked outputs
@@ -367,15 +385,29 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     BwdArgs a{};
     a.f.B = B; a.f.N = N; a.f.G = G; a.f.training = training; a.f.eps = eps;
     set_pending(a, 0);
-    ProfScope ps(CAT_BWD_FINAL, s);
-    rc = launch_coupling_bwd_final(a, p, ws.dx[0], dp, s);
-    if (rc) return rc;
-    if (precision >= 1) {
-      rc = launch_dw1_reduce((const float*)bwd_scratch, p2_ctas, darena, reinterpret_cast<const LayerMeta*>(meta_dev), L, G, s);
-      if (rc) return rc;
+    // The tail of the pass is three independent kernels - the wgrad reduction over the per-CTA partials (305 MB from HBM,
+    // ~52 us), the last layer's finalisation and the backward of all FiLM nets (~89 us): fork the reduction onto a side
+    // stream and join before returning (capturable: the side stream is forked from and joined back into `s`).
+    TailStreams* ts = precision >= 1 ? tail_streams() : nullptr;
+    if (ts) {
+      cudaEventRecord(ts->fork, s);
+      cudaStreamWaitEvent(ts->side, ts->fork, 0);
+      rc = launch_dw1_reduce((const float*)bwd_scratch, p2_ctas, darena, reinterpret_cast<const LayerMeta*>(meta_dev), L, G, ts->side);
+      cudaEventRecord(ts->join, ts->side);
+      if (rc) { cudaStreamWaitEvent(s, ts->join, 0); return rc; }
     }
+    {
+      ProfScope ps(CAT_BWD_FINAL, s);
+      rc = launch_coupling_bwd_final(a, p, ws.dx[0], dp, s);
+    }
+    if (rc == DPF_OK && precision >= 1 && !ts)
+      rc = launch_dw1_reduce((const float*)bwd_scratch, p2_ctas, darena, reinterpret_cast<const LayerMeta*>(meta_dev), L, G, s);
+    if (rc == DPF_OK) {
+      ProfScope ps(CAT_FILM_BWD, s);
+      rc = launch_film_backward(arena, stats, darena, reinterpret_cast<const LayerMeta*>(meta_dev), g, ws.film,
+                                ws.dfilm, dg, L, B, G, training, eps, s);
+    }
+    if (ts) cudaStreamWaitEvent(s, ts->join, 0);
+    return rc;
   }
-  ProfScope ps(CAT_FILM_BWD, s);
-  return launch_film_backward(arena, stats, darena, reinterpret_cast<const LayerMeta*>(meta_dev), g, ws.film,
-                              ws.dfilm, dg, L, B, G, training, eps, s);
 }
