@@ -385,28 +385,28 @@ DPF_API int dpf_decoder_backward(const long long* meta_host, const long long* me
     BwdArgs a{};
     a.f.B = B; a.f.N = N; a.f.G = G; a.f.training = training; a.f.eps = eps;
     set_pending(a, 0);
-    // The tail of the pass is three independent kernels - the wgrad reduction over the per-CTA partials (305 MB from HBM,
-    // ~52 us), the last layer's finalisation and the backward of all FiLM nets (~89 us): fork the reduction onto a side
-    // stream and join before returning (capturable: the side stream is forked from and joined back into `s`).
+    // The tail of the pass is three independent kernels - the backward of all FiLM nets (252 CTAs, ~89 us, latency-bound),
+    // the last layer's finalisation and the wgrad reduction over the per-CTA partials (2016 CTAs streaming 305 MB from
+    // HBM, ~52 us).  The FiLM kernel is launched FIRST on `s` so that its few CTAs are placed before the reduction's
+    // fill the chip from a side stream forked from / joined back into `s` (capturable).
     TailStreams* ts = precision >= 1 ? tail_streams() : nullptr;
     if (ts) {
       cudaEventRecord(ts->fork, s);
       cudaStreamWaitEvent(ts->side, ts->fork, 0);
-      rc = launch_dw1_reduce((const float*)bwd_scratch, p2_ctas, darena, reinterpret_cast<const LayerMeta*>(meta_dev), L, G, ts->side);
-      cudaEventRecord(ts->join, ts->side);
-      if (rc) { cudaStreamWaitEvent(s, ts->join, 0); return rc; }
     }
     {
-      ProfScope ps(CAT_BWD_FINAL, s);
-      rc = launch_coupling_bwd_final(a, p, ws.dx[0], dp, s);
-    }
-    if (rc == DPF_OK && precision >= 1 && !ts)
-      rc = launch_dw1_reduce((const float*)bwd_scratch, p2_ctas, darena, reinterpret_cast<const LayerMeta*>(meta_dev), L, G, s);
-    if (rc == DPF_OK) {
       ProfScope ps(CAT_FILM_BWD, s);
       rc = launch_film_backward(arena, stats, darena, reinterpret_cast<const LayerMeta*>(meta_dev), g, ws.film,
                                 ws.dfilm, dg, L, B, G, training, eps, s);
     }
+    cudaStream_t s2 = ts ? ts->side : s;
+    if (rc == DPF_OK) {
+      ProfScope ps(CAT_BWD_FINAL, s);
+      rc = launch_coupling_bwd_final(a, p, ws.dx[0], dp, s2);
+      if (rc == DPF_OK && precision >= 1)
+        rc = launch_dw1_reduce((const float*)bwd_scratch, p2_ctas, darena, reinterpret_cast<const LayerMeta*>(meta_dev), L, G, s2);
+    }
+    if (ts) cudaEventRecord(ts->join, ts->side);
     if (ts) cudaStreamWaitEvent(s, ts->join, 0);
     return rc;
   }
