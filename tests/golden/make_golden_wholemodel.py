@@ -24,9 +24,12 @@ from _detstate import DetRandn, GRAD_KEYS, det_state, whole_model_inputs  # noqa
 from lib.networks.losses import Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss  # noqa: E402
 from lib.networks.models import Local_Cond_RNVP_MC_Global_RNVP_VAE, Local_Cond_RNVP_MC_Global_RNVP_VAE_IC  # noqa: E402
 
-CASES = [("generation_chair", "configs/generation/chair.yaml", False, 4, 300),
-         ("autoencoding_all_original", "configs/autoencoding/all_original.yaml", False, 4, 256),
-         ("svr_all", "configs/svr/all.yaml", True, 3, 2500 // 10)]
+# batch sizes: BatchNorm over the batch dimension (FiLM nets, latent flows, ResNet) is ill-conditioned in fp32 for B = 3..4
+# (the reference's own fp32 gradients are then several per cent away from its float64 run); 8 / 8 / 6 shapes keep the
+# reference's fp32-vs-fp64 distance small enough for tight gates
+CASES = [("generation_chair", "configs/generation/chair.yaml", False, 8, 512),
+         ("autoencoding_all_original", "configs/autoencoding/all_original.yaml", False, 8, 384),
+         ("svr_all", "configs/svr/all.yaml", True, 6, 2500 // 10)]
 
 
 def cfg(path):
@@ -67,6 +70,9 @@ def main():
                         truth64={"losses": res["f64"]["losses"], "z": res["f64"]["z"].float(), "sum_logvar": res["f64"]["sum_logvar"].float(),
                                  "grads": {k: v.float() for k, v in res["f64"]["grads"].items()}})
         print(name, [float(v) for v in fx[name]["losses"]], [float(v) for v in fx[name]["truth64"]["losses"]])
+        for k in GRAD_KEYS[ic]:
+            a, b = res["f32"]["grads"][k].double(), res["f64"]["grads"][k]
+            print("   reference fp32 vs its float64 run: %-70s %.2e" % (k, float((a - b).abs().max() / b.abs().max())))
     # the key -> shape listing is regenerated on the test side from this package's own model (it is checked against
     # the reference's in tests/test_models_host.py), so it is not stored
     for v in fx.values():

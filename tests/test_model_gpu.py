@@ -198,10 +198,10 @@ def test_wholemodel_training_loss_and_gradients_vs_reference(native_lib, cuda, m
 
     def gate(a, ref32, truth, tol, what):
         """within `tol` of the reference's fp32 result, or no further from the fp64 truth (the same reference modules run
-        in double) than twice the reference's own fp32 result is: batch-statistics BatchNorm over B = 3..4 shapes
+        in double) than three times the reference's own fp32 result is: batch-statistics BatchNorm over B = 6..8 shapes
         (FiLM nets, latent flows, ResNet) makes some gradients ill-conditioned in fp32 on BOTH sides."""
         e = rel(a, ref32)
-        assert e < tol or rel(a, truth) < 2 * rel(ref32, truth) + 1e-6, (what, e, rel(a, truth), rel(ref32, truth))
+        assert e < tol or rel(a, truth) < 3 * rel(ref32, truth) + 1e-6, (what, e, rel(a, truth), rel(ref32, truth))
 
     got = torch.stack([l.detach().double().cpu() for l in losses])
     tol_loss = 1e-4 if fp32 else 5e-3
