@@ -1,7 +1,9 @@
 """PointNet cloud encoder and latent feature heads with the reference's names / state_dict keys
 (lib/networks/encoders.py:9-83).  Eval mode: encoder + max-pool run as ONE fused tcgen05 kernel
-(dpf_pointnet_eval_forward, csrc/pointnet.cu).  Train mode (batch statistics, autograd): the shared-MLP
-GEMMs still go through the library path (cuBLAS bmm + ATen batch-norm) - DESIGN.md section 7."""
+(dpf_pointnet_eval_forward, csrc/pointnet.cu).  Train mode (batch statistics, autograd): the last layer
+(256 -> 512, 76 % of the encoder's FLOPs) + BatchNorm + ReLU + max-pool is one tcgen05 kernel forward and an
+analytic sparse backward (ops/pointnet_pool.py: the (B,512,N) activation is never materialised); the three
+narrow layers before it still go through the library path (cuBLAS bmm + ATen batch-norm) - DESIGN.md section 7."""
 import ctypes
 
 import torch
@@ -33,10 +35,21 @@ class PointNetCloudEncoder(nn.Module):
                 and self.precision != 'fp32' and self.init_n_channels == 3 and self.init_n_features == 64
                 and list(self.n_features) == [128, 256, 512] and input.dim() == 3 and input.shape[1] == 3)
 
+    def _fused_train_ok(self, input):
+        return (self.training and torch.is_grad_enabled() and input.is_cuda and input.dtype == torch.float32
+                and self.precision != 'fp32' and len(self.n_features) >= 2 and self.n_features[-2] == 256
+                and self.n_features[-1] == 512 and input.dim() == 3 and hasattr(self.features, 'sd2')
+                and len(self.features) == 12)
+
     def global_features(self, input):
         """max over the points of forward(input): (B, 3, N) -> (B, n_features[-1]); what the models take
         from the encoder (reference models.py:130-131).  Eval mode without autograd runs the fused kernel
         (bf16 tensor cores, fp32 accumulation)."""
+        if self._fused_train_ok(input):
+            from ...ops.pointnet_pool import pooled_bn_relu_max
+            f = self.features
+            h2 = f[:-3](input)                                   # init_sd .. sd1_relu: (B, 256, N)
+            return pooled_bn_relu_max(h2, f.sd2.weight[0], f.sd2_bn)
         if not self._fused_ok(input):
             return torch.max(self.forward(input), dim=2)[0]
         x = input.contiguous()

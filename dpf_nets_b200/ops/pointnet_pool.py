@@ -1,0 +1,113 @@
+"""Train-mode last layer of the PointNet cloud encoder fused with the max-pool over the points
+(reference: features.{sd2, sd2_bn, sd2_relu} in .train(), lib/networks/encoders.py:9-28, + torch.max over dim 2,
+lib/networks/models.py:130-131).
+
+Forward: ONE pass of a tcgen05 kernel over h2 (dpf_pointnet_pool_forward) yields the batch statistics of h = W h2 and,
+per (shape, channel), max / min of h with their point indices; BatchNorm + ReLU are monotone per channel, so
+    out[b,c] = relu(gamma_c (h* - mu_c) / sigma_c + beta_c),   h* = max_n h (gamma_c >= 0) or min_n h (gamma_c < 0).
+The (B,512,N) activation is never materialised.
+
+Backward: the max-pool gradient is SPARSE (one point per (shape, channel)) and BatchNorm's batch terms are LINEAR in h:
+    dh[p,c] = (1/sigma_c) (gamma_c d'[b,c] [p = n*(b,c)] - a1_c - xhat[p,c] a2_c),     a1 = gamma dbeta / M,  a2 = gamma dgamma / M
+so with S = sum_p h2[p], G = sum_p h2[p] h2[p]^T (256 x 256 Gram matrix) and C = W^T diag(a2 / sigma^2) W
+    dW  = diag(gamma/sigma) T  -  (a1/sigma) S^T  -  diag(a2/sigma^2) (W G - mu S^T),        T[c] = sum_b d'[b,c] h2[b,:,n*(b,c)]
+    dh2 = scatter(coef[b,c] W[c,:] at point n*(b,c))  -  W^T(a1/sigma)  +  W^T(a2 mu/sigma^2)  -  C h2
+i.e. two 256 x 256 GEMMs over the points (library GEMMs) + gathers / scatters of B x 512 rows, instead of the library path's
+512 x 256 dgrad + wgrad and three passes over the 134 MB activation."""
+import ctypes
+
+import torch
+
+from .. import _lib
+
+
+def _pool_stats(h2, W):
+    """h2 (B,256,N), W (512,256) CUDA fp32 -> (sum_h (512,) f64, sum_h2 (512,) f64, vmax, vmin (B,512) f32, imax, imin (B,512) i64)."""
+    _lib.require_cuda(h2, W)
+    B, Cin, N = h2.shape
+    if Cin != 256 or tuple(W.shape) != (512, 256) or h2.dtype != torch.float32 or W.dtype != torch.float32:
+        raise _lib.DpfNativeError("pointnet pool kernel is specialised on a 256 -> 512 last layer (got %s, %s)"
+                                  % (tuple(h2.shape), tuple(W.shape)))
+    dev = h2.device
+    nb = ctypes.c_longlong(0)
+    _lib.check(_lib.lib().dpf_pointnet_pool_workspace_bytes(ctypes.byref(nb)), "dpf_pointnet_pool_workspace_bytes")
+    ws = torch.empty(int(nb.value), dtype=torch.uint8, device=dev)
+    sums = torch.empty((512, 2), dtype=torch.float64, device=dev)
+    vmax = torch.empty((B, 512), dtype=torch.float32, device=dev)
+    vmin = torch.empty((B, 512), dtype=torch.float32, device=dev)
+    imax = torch.empty((B, 512), dtype=torch.int32, device=dev)
+    imin = torch.empty((B, 512), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dpf_pointnet_pool_forward", h2, W, int(B), int(N), ws, sums, vmax, vmin, imax, imin, device=dev)
+    return sums[:, 0], sums[:, 1], vmax, vmin, imax.long(), imin.long()
+
+
+class PooledLastLayer(torch.autograd.Function):
+    """(h2 (B,256,N), W (512,256), gamma, beta (512,)) -> (out (B,512), batch mean (512,), biased batch var (512,))."""
+
+    @staticmethod
+    def forward(ctx, h2, W, gamma, beta, eps):
+        h2 = h2.contiguous()
+        W = W.contiguous()
+        B, _, N = h2.shape
+        M = B * N
+        s1, s2, vmax, vmin, imax, imin = _pool_stats(h2.detach(), W.detach())
+        mean64 = s1 / M
+        var64 = (s2 / M - mean64 * mean64).clamp_min(0.0)
+        mean, var = mean64.to(h2.dtype), var64.to(h2.dtype)
+        sigma = torch.sqrt(var + eps)
+        pos = gamma >= 0
+        hsel = torch.where(pos.unsqueeze(0), vmax.to(h2.dtype), vmin.to(h2.dtype))
+        idx = torch.where(pos.unsqueeze(0), imax, imin)
+        xhat = (hsel - mean) / sigma
+        y = xhat * gamma + beta
+        out = torch.relu(y)
+        ctx.save_for_backward(h2, W, gamma, mean, sigma, xhat, idx, y)
+        ctx.mark_non_differentiable(mean, var)
+        return out, mean, var
+
+    @staticmethod
+    def backward(ctx, dout, _dmean, _dvar):
+        h2, W, gamma, mean, sigma, xhat, idx, y = ctx.saved_tensors
+        B, Cin, N = h2.shape
+        M = B * N
+        d = dout * (y > 0).to(dout.dtype)                       # (B,C): cotangent of y at the selected point
+        dbeta = d.sum(0)
+        dgamma = (d * xhat).sum(0)
+        a1 = gamma * dbeta / M
+        a2 = gamma * dgamma / M
+        inv = 1.0 / sigma
+        coef = d * (gamma * inv)                                 # (B,C): dh at the selected point (before the batch terms)
+        dW = dh2 = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gidx = idx.unsqueeze(1).expand(B, Cin, idx.shape[1])        # (B,Cin,C)
+        if ctx.needs_input_grad[1]:
+            S = h2.sum((0, 2))                                                       # (Cin,)
+            G = torch.matmul(h2, h2.transpose(1, 2)).sum(0)                          # (Cin,Cin) Gram matrix over all points
+            hsel_rows = torch.gather(h2, 2, gidx)                                    # (B,Cin,C): h2 at the selected points
+            T = torch.einsum('bc,bkc->ck', coef, hsel_rows)
+            dW = T - (a1 * inv).unsqueeze(1) * S.unsqueeze(0) \
+                - (a2 * inv * inv).unsqueeze(1) * (torch.matmul(W, G) - mean.unsqueeze(1) * S.unsqueeze(0))
+        if ctx.needs_input_grad[0]:
+            w_scaled = W * (a2 * inv * inv).unsqueeze(1)                             # diag(a2/sigma^2) W
+            Cmat = torch.matmul(W.t(), w_scaled)                                     # (Cin,Cin)
+            const = torch.mv(W.t(), a2 * mean * inv * inv - a1 * inv)                # (Cin,)
+            dh2 = const.view(1, Cin, 1) - torch.matmul(Cmat, h2)
+            contrib = coef.unsqueeze(1) * W.t().unsqueeze(0)                         # (B,Cin,C): coef[b,c] W[c,k]
+            dh2.scatter_add_(2, gidx, contrib)
+        return dh2, dW, dgamma, dbeta, None
+
+
+def pooled_bn_relu_max(h2, weight, bn):
+    """Train-mode  max_n relu(bn(weight @ h2))  with nn.BatchNorm1d `bn`'s parameters; updates its running statistics
+    (momentum, unbiased variance) and num_batches_tracked like the module would."""
+    B, _, N = h2.shape
+    out, mean, var = PooledLastLayer.apply(h2, weight, bn.weight, bn.bias, float(bn.eps))
+    if bn.track_running_stats:
+        with torch.no_grad():
+            M = B * N
+            bn.num_batches_tracked += 1
+            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+            bn.running_var.mul_(1 - mom).add_(var * (M / max(M - 1, 1)), alpha=mom)
+    return out

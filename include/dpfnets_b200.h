@@ -160,6 +160,17 @@ int dpf_pointnet_workspace_bytes(long long* bytes);
 int dpf_pointnet_eval_forward(const float* x, int B, int N, const float* const* weights, const float* const* bn,
                               float bn_eps, void* workspace, float* out, void* stream);
 
+/* ---- PointNet cloud encoder, train mode: last layer + max-pool ------------------------------
+ * Replaces features.{sd2, sd2_bn, sd2_relu} in .train() (lib/networks/encoders.py:9-28: SharedDot 256 -> 512, BatchNorm1d
+ * with batch statistics, ReLU) + the max over the points (lib/networks/models.py:130-131) WITHOUT materialising the
+ * (B,512,N) activation: BatchNorm + ReLU are monotone per channel, so the pooled output is a function of max_n / min_n of
+ * h = W h2 and of the batch statistics.  h2 (B,256,N) fp32 (post-ReLU output of the layer before), W (512,256) fp32 ->
+ * sums (512,2) double {sum_p h, sum_p h^2}, vmax / vmin (B,512) fp32, imax / imin (B,512) int32 (lowest index on ties).
+ * bf16 tensor cores with split operands (hi*hi + lo*hi + hi*lo, fp32 accumulation). */
+int dpf_pointnet_pool_workspace_bytes(long long* bytes);
+int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, double* sums,
+                              float* vmax, float* vmin, int* imax, int* imin, void* stream);
+
 /* Fused AMSGrad step with the reference's exact update (lib/networks/optimizers.py:53-74):
  * denom = sqrt(max_exp_avg_sq or exp_avg_sq)/bc2 + eps; p -= wd*p + lr*(exp_avg/bc1)/denom.
  * vmax may be NULL (amsgrad off); bc1 = 1-beta1^t, bc2 = sqrt(1-beta2^t). */

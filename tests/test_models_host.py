@@ -181,3 +181,38 @@ def test_wholemodel_encoder_side_vs_reference(name, cls, ic):
     with torch.no_grad():
         mus, logvars, _ = m._posterior(inp["cloud"], sample=False)
     assert rel(mus, fx["g_posterior_mus"]) < 1e-5
+
+
+def test_pooled_last_layer_backward_algebra_vs_autograd(monkeypatch):
+    """Train-mode PointNet last layer + max-pool (ops/pointnet_pool.py): the analytic backward - sparse max-pool gradient,
+    BatchNorm batch terms through the Gram matrix of h2 - against torch.autograd of the plain module chain
+    SharedDot -> BatchNorm1d(train) -> ReLU -> max (reference encoders.py:9-28, models.py:130-131) in float64, with the
+    kernel's statistics pass replaced by its torch definition (the kernel itself is checked on the GPU)."""
+    from dpf_nets_b200.ops import pointnet_pool as pp
+
+    def stats(h2, W):
+        h = torch.matmul(W, h2)
+        vmax, imax = h.max(2)
+        vmin, imin = h.min(2)
+        return h.sum((0, 2)).double(), (h * h).sum((0, 2)).double(), vmax, vmin, imax, imin
+    monkeypatch.setattr(pp, "_pool_stats", stats)
+    torch.manual_seed(0)
+    B, Cin, C, N = 3, 256, 512, 40
+    h2 = torch.relu(torch.randn(B, Cin, N, dtype=torch.float64)).requires_grad_(True)
+    W = (torch.randn(C, Cin, dtype=torch.float64) * 0.1).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(C).double()
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(C))             # both signs: max- and min-selected channels
+        bn.bias.copy_(0.3 * torch.randn(C))
+    bn2 = torch.nn.BatchNorm1d(C).double()
+    bn2.load_state_dict(bn.state_dict())
+    ref = torch.max(torch.relu(bn(torch.matmul(W, h2))), dim=2)[0]
+    cot = torch.randn_like(ref)
+    gr = torch.autograd.grad((ref * cot).sum(), [h2, W, bn.weight, bn.bias])
+    out = pp.pooled_bn_relu_max(h2, W, bn2)
+    go = torch.autograd.grad((out * cot).sum(), [h2, W, bn2.weight, bn2.bias])
+    assert rel(out, ref) < 1e-12
+    for a, b in zip(go, gr):
+        assert rel(a, b) < 1e-10
+    assert rel(bn2.running_mean, bn.running_mean) < 1e-12 and rel(bn2.running_var, bn.running_var) < 1e-12
+    assert int(bn2.num_batches_tracked) == int(bn.num_batches_tracked) == 1

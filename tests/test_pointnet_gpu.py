@@ -79,11 +79,88 @@ def test_fused_eval_encoder_is_used_and_fast(native_lib, cuda):
     assert fused < lib_path
 
 
-def test_train_mode_and_autograd_keep_the_library_path(native_lib, cuda):
+def test_eval_mode_autograd_and_no_grad_train_keep_the_library_path(native_lib, cuda):
     enc = make_encoder(cuda, 7)
     x = (torch.rand((4, 3, 256)) - 0.5).to(cuda)
-    out = enc.global_features(x)            # grad enabled -> torch path, differentiable
+    out = enc.global_features(x)            # eval mode with grad enabled -> torch path, differentiable
     assert out.requires_grad
     enc.train()
     with torch.no_grad():
         assert torch.equal(enc.global_features(x), torch.max(enc(x), dim=2)[0])
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (2, 64), (3, 77), (4, 1000), (5, 2049), (32, 2048)])
+def test_pool_statistics_kernel_vs_torch(native_lib, cuda, B, N):
+    """dpf_pointnet_pool_forward (W h2 on the tensor cores with split bf16 operands, one channel per TMEM lane): batch sums,
+    max / min over the points and their indices against the fp32 torch definition.  Values 2e-5 relative to the channel
+    scale (bf16 hi + lo operands: ~2^-17 per operand); an index may differ only where the two candidates are that close."""
+    from dpf_nets_b200.ops.pointnet_pool import _pool_stats
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    h2 = torch.relu(torch.randn((B, 256, N), generator=g)).to(cuda)
+    W = (torch.randn((512, 256), generator=g) * 0.08).to(cuda)
+    s1, s2, vmax, vmin, imax, imin = _pool_stats(h2, W)
+    h = torch.matmul(W.double(), h2.double())                     # (B,512,N) truth
+    scale = h.abs().amax(dim=(0, 2)).clamp_min(1e-6)
+    assert ((s1 - h.sum((0, 2))).abs() <= 2e-5 * scale * B * N).all()
+    assert ((s2 - (h * h).sum((0, 2))).abs() <= 4e-5 * scale * scale * B * N).all()
+    tmax, tmin = h.max(2)[0], h.min(2)[0]
+    assert ((vmax.double() - tmax).abs() <= 2e-5 * scale).all() and ((vmin.double() - tmin).abs() <= 2e-5 * scale).all()
+    # the selected point attains the extremum (up to the same tolerance)
+    assert ((torch.gather(h, 2, imax.unsqueeze(2)).squeeze(2) - tmax).abs() <= 4e-5 * scale).all()
+    assert ((torch.gather(h, 2, imin.unsqueeze(2)).squeeze(2) - tmin).abs() <= 4e-5 * scale).all()
+    assert int(imax.min()) >= 0 and int(imax.max()) < N and int(imin.min()) >= 0 and int(imin.max()) < N
+
+
+@pytest.mark.parametrize("B,N", [(4, 300), (32, 2048)])
+def test_train_mode_fused_last_layer_vs_library_path(native_lib, cuda, B, N):
+    """Train-mode global_features: fused last layer + BatchNorm (batch statistics) + ReLU + max-pool with the analytic
+    backward (ops/pointnet_pool.py) against the library path of the same module (SharedDot -> BatchNorm1d -> ReLU -> max,
+    the reference's chain: encoders.py:9-28, models.py:130-131; pinned to the reference on CPU): pooled features,
+    running statistics and the gradients of EVERY encoder parameter."""
+    enc = make_encoder(cuda, 11)
+    with torch.no_grad():                     # both signs of gamma in the last BatchNorm: max- and min-selected channels
+        enc.features.sd2_bn.weight.mul_(torch.where(torch.rand(512, device=cuda) < 0.3, -1.0, 1.0))
+    x = (torch.rand((B, 3, N), generator=torch.Generator().manual_seed(5)) - 0.5).to(cuda)
+    cot = torch.randn((B, 512), generator=torch.Generator().manual_seed(6)).to(cuda)
+    sd0 = {k: v.clone() for k, v in enc.state_dict().items()}
+    res = {}
+    for prec in ("fp32", "auto"):
+        enc.load_state_dict(sd0)
+        enc.train()
+        enc.precision = prec
+        enc.zero_grad()
+        out = enc.global_features(x)
+        (out * cot).sum().backward()
+        res[prec] = (out.detach().clone(), {k: p.grad.clone() for k, p in enc.named_parameters()},
+                     {k: v.clone() for k, v in enc.state_dict().items() if "running" in k or "num_batches" in k})
+    lib, fused = res["fp32"], res["auto"]
+    assert rel(fused[0], lib[0]) < 1e-4
+    for k, v in lib[2].items():
+        assert (torch.equal(fused[2][k], v) if "num_batches" in k else rel(fused[2][k], v) < 1e-4), k
+    worst = max((rel(fused[1][k], v), k) for k, v in lib[1].items())
+    assert worst[0] < 2e-3, worst        # fp32 re-association through four batch-statistics BatchNorms
+
+
+def test_train_mode_fused_last_layer_is_faster(native_lib, cuda):
+    enc = make_encoder(cuda, 3).train()
+    x = (torch.rand((32, 3, 2048)) - 0.5).to(cuda)
+    cot = torch.randn((32, 512), device=cuda)
+
+    def step():
+        enc.zero_grad()
+        (enc.global_features(x) * cot).sum().backward()
+    times = {}
+    for prec in ("fp32", "auto"):
+        enc.precision = prec
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        times[prec] = a.elapsed_time(b) / 10
+    print("pointnet train fwd+bwd 32x2048: library path %.3f ms, fused last layer %.3f ms" % (times["fp32"], times["auto"]))
+    assert times["auto"] < times["fp32"]
