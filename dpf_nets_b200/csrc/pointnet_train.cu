@@ -5,8 +5,9 @@
 // encoders.py:9-28) followed by torch.max over the points (lib/networks/models.py:130-131).
 //
 // BatchNorm + ReLU are monotone per channel, so  max_n relu(gamma (h - mu)/sigma + beta)  is a function of max_n h (gamma >= 0)
-// or min_n h (gamma < 0): one pass over the points yields, per channel, sum h and sum h^2 (batch statistics) and, per
-// (shape, channel), max / min of h with their point indices (the max-pool's selection for the backward).
+// or min_n h (gamma < 0): one pass over the points yields, per (shape, channel), the mean and the sum of squared deviations of
+// h (merged into the batch statistics by the caller) and max / min of h with their point indices (the max-pool's
+// selection for the backward).
 //
 // One CTA = one shape x one chunk of 128 output channels.  z^T[128 channels x 64 points] = W(chunk) h2(tile) on the tensor
 // cores with ONE CHANNEL PER TMEM LANE, so every reduction over points is a per-thread register reduction:
@@ -50,14 +51,14 @@ pool_pack_kernel(const float* __restrict__ W, unsigned char* __restrict__ img) {
 struct PtSmem {
   unsigned char A[2 * PT_WIMG];         // W chunk hi | lo
   unsigned char Bt[2 * PT_BIMG];        // h2 tile hi | lo
-  float red[2][128][6];                 // part -> {sum, sumsq, max, min, argmax, argmin} hand-over
+  float red[2][128][8];                 // part -> {mean, M2, max, min, argmax, argmin, count} hand-over
   uint64_t bar_w, bar_mma;
   uint32_t tmem_base;
 };
 
 __global__ void __launch_bounds__(PT_T, 1)
 pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restrict__ wimg, int B, int N,
-                    double* __restrict__ sums, float* __restrict__ vmax, float* __restrict__ vmin,
+                    float* __restrict__ stat, float* __restrict__ vmax, float* __restrict__ vmin,
                     int* __restrict__ imax, int* __restrict__ imin) {
   extern __shared__ unsigned char smraw[];
   PtSmem& s = *reinterpret_cast<PtSmem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
@@ -79,8 +80,10 @@ pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restric
     umma::mbar_expect_tx(&s.bar_w, 2 * PT_WIMG);
     umma::bulk_g2s(s.A, wimg + (size_t)chunk * 2 * PT_WIMG, 2 * PT_WIMG, &s.bar_w);
   }
-  float sum = 0.f, sq = 0.f, mx = -CUDART_INF_F, mn = CUDART_INF_F;
-  int amx = 0, amn = 0;
+  // statistics as SHIFTED sums  sum (x - r), sum (x - r)^2  with r = the channel's first value in this thread: the variance
+  // then comes out of numbers of the size of the deviations, not of E[x^2] - mean^2 (batch statistics divide by it)
+  float sum = 0.f, sq = 0.f, mx = -CUDART_INF_F, mn = CUDART_INF_F, shift = 0.f;
+  int amx = 0, amn = 0, cnt = 0;
   const float* hb = h2 + (size_t)b * PT_CIN * N;
   const int n_tiles = (N + PT_NT - 1) / PT_NT;
   uint32_t ph = 0;
@@ -144,8 +147,11 @@ pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restric
       for (int i = 0; i < 32; ++i) {
         if (nbase + i < N) {
           const float x = v[i];
-          sum += x;
-          sq = fmaf(x, x, sq);
+          if (cnt == 0) shift = x;
+          ++cnt;
+          const float dx = x - shift;
+          sum += dx;
+          sq = fmaf(dx, dx, sq);
           if (x > mx) { mx = x; amx = nbase + i; }
           if (x < mn) { mn = x; amn = nbase + i; }
         }
@@ -155,8 +161,13 @@ pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restric
     __syncthreads();          // the accumulator and the tile buffer are free again
   }
   // ---- combine the two point halves (part 0 holds the lower point indices of every tile: ties keep the lower index) ----
-  s.red[part][lane_c][0] = sum; s.red[part][lane_c][1] = sq; s.red[part][lane_c][2] = mx; s.red[part][lane_c][3] = mn;
+  // per thread: count, mean = shift + sum / cnt, M2 = sq - sum^2 / cnt (sum of squared deviations from that mean)
+  const float fc = (float)cnt;
+  const float mean_t = cnt ? shift + sum / fc : 0.f;
+  const float m2_t = cnt ? fmaxf(sq - sum * sum / fc, 0.f) : 0.f;
+  s.red[part][lane_c][0] = mean_t; s.red[part][lane_c][1] = m2_t; s.red[part][lane_c][2] = mx; s.red[part][lane_c][3] = mn;
   s.red[part][lane_c][4] = __int_as_float(amx); s.red[part][lane_c][5] = __int_as_float(amn);
+  s.red[part][lane_c][6] = fc;
   __syncthreads();
   if (part == 0) {
     const float* o = s.red[1][lane_c];
@@ -170,8 +181,13 @@ pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restric
     vmin[(size_t)b * PT_COUT + c] = m0;
     imax[(size_t)b * PT_COUT + c] = a1;
     imin[(size_t)b * PT_COUT + c] = a0;
-    atomicAdd(&sums[c * 2 + 0], (double)sum + (double)o[0]);
-    atomicAdd(&sums[c * 2 + 1], (double)sq + (double)o[1]);
+    // pairwise merge of the two (count, mean, M2) triples (Chan et al.)
+    const float n1 = fc, n2 = o[6], nt = n1 + n2;
+    const float delta = o[0] - mean_t;
+    const float mean = nt > 0.f ? mean_t + delta * (n2 / nt) : 0.f;
+    const float m2 = nt > 0.f ? m2_t + o[1] + delta * delta * (n1 * n2 / nt) : 0.f;
+    stat[((size_t)b * PT_COUT + c) * 2 + 0] = mean;
+    stat[((size_t)b * PT_COUT + c) * 2 + 1] = m2;
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -186,25 +202,25 @@ DPF_API int dpf_pointnet_pool_workspace_bytes(long long* bytes) {
   return DPF_OK;
 }
 
-// h2 (B,256,N) fp32, W (512,256) fp32 ->  sums (512,2) double {sum_p h, sum_p h^2} (zeroed here), vmax / vmin (B,512) fp32 =
-// max / min over the points of h = W h2, imax / imin (B,512) int32 = their point indices (lowest index on exact ties).
+// h2 (B,256,N) fp32, W (512,256) fp32 ->  stat (B,512,2) fp32 {mean_n h, sum_n (h - mean)^2} per (shape, channel) (the caller
+// merges the B equal-sized groups into the batch statistics), vmax / vmin (B,512) fp32 = max / min over the points of
+// h = W h2, imax / imin (B,512) int32 = their point indices (lowest index on exact ties).
 // workspace: dpf_pointnet_pool_workspace_bytes() bytes, 256-byte aligned (weight images).
-DPF_API int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, double* sums,
+DPF_API int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, float* stat,
                                       float* vmax, float* vmin, int* imax, int* imin, void* stream) {
-  DPF_REQUIRE(h2 && W && workspace && sums && vmax && vmin && imax && imin, DPF_ERR_NULL_PTR, "dpf_pointnet_pool_forward: null pointer");
+  DPF_REQUIRE(h2 && W && workspace && stat && vmax && vmin && imax && imin, DPF_ERR_NULL_PTR, "dpf_pointnet_pool_forward: null pointer");
   DPF_REQUIRE(B > 0 && N > 0 && B <= 65535, DPF_ERR_BAD_ARG, "dpf_pointnet_pool_forward: bad sizes B=%d N=%d", B, N);
   DPF_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)h2 & 15) == 0, DPF_ERR_ALIGN, "dpf_pointnet_pool_forward: workspace / h2 alignment");
   cudaStream_t s = (cudaStream_t)stream;
   pool_pack_kernel<<<(PT_COUT * (PT_CIN / 8) + 255) / 256, 256, 0, s>>>(W, (unsigned char*)workspace);
   int rc = dpf_check_launch("pool_pack_kernel");
   if (rc) return rc;
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * PT_COUT, s);
   const size_t smem = sizeof(PtSmem) + 1024;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(pool_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  pool_forward_kernel<<<dim3(B, 4), PT_T, smem, s>>>(h2, (const unsigned char*)workspace, B, N, sums, vmax, vmin, imax, imin);
+  pool_forward_kernel<<<dim3(B, 4), PT_T, smem, s>>>(h2, (const unsigned char*)workspace, B, N, stat, vmax, vmin, imax, imin);
   return dpf_check_launch("pool_forward_kernel");
 }

@@ -10,8 +10,9 @@ The (B,512,N) activation is never materialised.
 Backward: the max-pool gradient is SPARSE (one point per (shape, channel)) and BatchNorm's batch terms are LINEAR in h:
     dh[p,c] = (1/sigma_c) (gamma_c d'[b,c] [p = n*(b,c)] - a1_c - xhat[p,c] a2_c),     a1 = gamma dbeta / M,  a2 = gamma dgamma / M
 so with S = sum_p h2[p], G = sum_p h2[p] h2[p]^T (256 x 256 Gram matrix) and C = W^T diag(a2 / sigma^2) W
-    dW  = diag(gamma/sigma) T  -  (a1/sigma) S^T  -  diag(a2/sigma^2) (W G - mu S^T),        T[c] = sum_b d'[b,c] h2[b,:,n*(b,c)]
-    dh2 = scatter(coef[b,c] W[c,:] at point n*(b,c))  -  W^T(a1/sigma)  +  W^T(a2 mu/sigma^2)  -  C h2
+    dW  = diag(gamma/sigma) T  -  (a1/sigma) S^T  -  diag(a2/sigma^2) W Gc,        T[c] = sum_b d'[b,c] h2[b,:,n*(b,c)]
+    dh2 = scatter(coef[b,c] W[c,:] at point n*(b,c))  -  W^T(a1/sigma)  -  C (h2 - m)
+(m = S / M, Gc = sum_p (h2[p] - m)(h2[p] - m)^T: the centred forms avoid the cancellation of W G - mu S^T in fp32)
 i.e. two 256 x 256 GEMMs over the points (library GEMMs) + gathers / scatters of B x 512 rows, instead of the library path's
 512 x 256 dgrad + wgrad and three passes over the 134 MB activation."""
 import ctypes
@@ -22,7 +23,8 @@ from .. import _lib
 
 
 def _pool_stats(h2, W):
-    """h2 (B,256,N), W (512,256) CUDA fp32 -> (sum_h (512,) f64, sum_h2 (512,) f64, vmax, vmin (B,512) f32, imax, imin (B,512) i64)."""
+    """h2 (B,256,N), W (512,256) CUDA fp32 -> (mean (512,), biased var (512,) of h = W h2 over all B*N points, vmax, vmin
+    (B,512), imax, imin (B,512) i64)."""
     _lib.require_cuda(h2, W)
     B, Cin, N = h2.shape
     if Cin != 256 or tuple(W.shape) != (512, 256) or h2.dtype != torch.float32 or W.dtype != torch.float32:
@@ -32,14 +34,18 @@ def _pool_stats(h2, W):
     nb = ctypes.c_longlong(0)
     _lib.check(_lib.lib().dpf_pointnet_pool_workspace_bytes(ctypes.byref(nb)), "dpf_pointnet_pool_workspace_bytes")
     ws = torch.empty(int(nb.value), dtype=torch.uint8, device=dev)
-    sums = torch.empty((512, 2), dtype=torch.float64, device=dev)
+    stat = torch.empty((B, 512, 2), dtype=torch.float32, device=dev)
     vmax = torch.empty((B, 512), dtype=torch.float32, device=dev)
     vmin = torch.empty((B, 512), dtype=torch.float32, device=dev)
     imax = torch.empty((B, 512), dtype=torch.int32, device=dev)
     imin = torch.empty((B, 512), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        _lib.call("dpf_pointnet_pool_forward", h2, W, int(B), int(N), ws, sums, vmax, vmin, imax, imin, device=dev)
-    return sums[:, 0], sums[:, 1], vmax, vmin, imax.long(), imin.long()
+        _lib.call("dpf_pointnet_pool_forward", h2, W, int(B), int(N), ws, stat, vmax, vmin, imax, imin, device=dev)
+    # merge the B equal-sized groups (count N, mean, M2) into the batch statistics (Chan et al.), in double
+    gm, gm2 = stat[..., 0].double(), stat[..., 1].double()
+    mean = gm.mean(0)
+    var = (gm2.sum(0) + N * ((gm - mean) ** 2).sum(0)) / float(B * N)
+    return mean, var, vmax, vmin, imax.long(), imin.long()
 
 
 class PooledLastLayer(torch.autograd.Function):
@@ -51,10 +57,8 @@ class PooledLastLayer(torch.autograd.Function):
         W = W.contiguous()
         B, _, N = h2.shape
         M = B * N
-        s1, s2, vmax, vmin, imax, imin = _pool_stats(h2.detach(), W.detach())
-        mean64 = s1 / M
-        var64 = (s2 / M - mean64 * mean64).clamp_min(0.0)
-        mean, var = mean64.to(h2.dtype), var64.to(h2.dtype)
+        mean64, var64, vmax, vmin, imax, imin = _pool_stats(h2.detach(), W.detach())
+        mean, var = mean64.to(h2.dtype), var64.clamp_min(0.0).to(h2.dtype)
         sigma = torch.sqrt(var + eps)
         pos = gamma >= 0
         hsel = torch.where(pos.unsqueeze(0), vmax.to(h2.dtype), vmin.to(h2.dtype))
@@ -81,18 +85,20 @@ class PooledLastLayer(torch.autograd.Function):
         dW = dh2 = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             gidx = idx.unsqueeze(1).expand(B, Cin, idx.shape[1])        # (B,Cin,C)
-        if ctx.needs_input_grad[1]:
             S = h2.sum((0, 2))                                                       # (Cin,)
-            G = torch.matmul(h2, h2.transpose(1, 2)).sum(0)                          # (Cin,Cin) Gram matrix over all points
+            # CENTRED activations: h - mu = W (h2 - m) exactly, so the batch terms are formed from deviations and not from
+            # differences of large sums (W G - mu S^T cancels catastrophically in fp32 over 65 536 points)
+            hc = h2 - (S / M).view(1, Cin, 1)
+        if ctx.needs_input_grad[1]:
+            Gc = torch.matmul(hc, hc.transpose(1, 2)).sum(0)                         # (Cin,Cin) covariance-form Gram matrix
             hsel_rows = torch.gather(h2, 2, gidx)                                    # (B,Cin,C): h2 at the selected points
             T = torch.einsum('bc,bkc->ck', coef, hsel_rows)
-            dW = T - (a1 * inv).unsqueeze(1) * S.unsqueeze(0) \
-                - (a2 * inv * inv).unsqueeze(1) * (torch.matmul(W, G) - mean.unsqueeze(1) * S.unsqueeze(0))
+            dW = T - (a1 * inv).unsqueeze(1) * S.unsqueeze(0) - (a2 * inv * inv).unsqueeze(1) * torch.matmul(W, Gc)
         if ctx.needs_input_grad[0]:
             w_scaled = W * (a2 * inv * inv).unsqueeze(1)                             # diag(a2/sigma^2) W
             Cmat = torch.matmul(W.t(), w_scaled)                                     # (Cin,Cin)
-            const = torch.mv(W.t(), a2 * mean * inv * inv - a1 * inv)                # (Cin,)
-            dh2 = const.view(1, Cin, 1) - torch.matmul(Cmat, h2)
+            const = torch.mv(W.t(), a1 * inv)                                        # (Cin,)
+            dh2 = -const.view(1, Cin, 1) - torch.matmul(Cmat, hc)
             contrib = coef.unsqueeze(1) * W.t().unsqueeze(0)                         # (B,Cin,C): coef[b,c] W[c,k]
             dh2.scatter_add_(2, gidx, contrib)
         return dh2, dW, dgamma, dbeta, None

@@ -165,10 +165,11 @@ int dpf_pointnet_eval_forward(const float* x, int B, int N, const float* const* 
  * with batch statistics, ReLU) + the max over the points (lib/networks/models.py:130-131) WITHOUT materialising the
  * (B,512,N) activation: BatchNorm + ReLU are monotone per channel, so the pooled output is a function of max_n / min_n of
  * h = W h2 and of the batch statistics.  h2 (B,256,N) fp32 (post-ReLU output of the layer before), W (512,256) fp32 ->
- * sums (512,2) double {sum_p h, sum_p h^2}, vmax / vmin (B,512) fp32, imax / imin (B,512) int32 (lowest index on ties).
+ * stat (B,512,2) fp32 {mean_n h, sum_n (h - mean)^2} per (shape, channel), vmax / vmin (B,512) fp32, imax / imin (B,512)
+ * int32 (lowest index on ties).
  * bf16 tensor cores with split operands (hi*hi + lo*hi + hi*lo, fp32 accumulation). */
 int dpf_pointnet_pool_workspace_bytes(long long* bytes);
-int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, double* sums,
+int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, float* stat,
                               float* vmax, float* vmin, int* imax, int* imin, void* stream);
 
 /* Fused AMSGrad step with the reference's exact update (lib/networks/optimizers.py:53-74):

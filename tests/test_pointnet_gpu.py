@@ -98,16 +98,17 @@ def test_pool_statistics_kernel_vs_torch(native_lib, cuda, B, N):
     g = torch.Generator().manual_seed(B * 1000 + N)
     h2 = torch.relu(torch.randn((B, 256, N), generator=g)).to(cuda)
     W = (torch.randn((512, 256), generator=g) * 0.08).to(cuda)
-    s1, s2, vmax, vmin, imax, imin = _pool_stats(h2, W)
+    mean, var, vmax, vmin, imax, imin = _pool_stats(h2, W)
     h = torch.matmul(W.double(), h2.double())                     # (B,512,N) truth
     scale = h.abs().amax(dim=(0, 2)).clamp_min(1e-6)
-    assert ((s1 - h.sum((0, 2))).abs() <= 2e-5 * scale * B * N).all()
-    assert ((s2 - (h * h).sum((0, 2))).abs() <= 4e-5 * scale * scale * B * N).all()
+    assert ((mean - h.mean((0, 2))).abs() <= 1e-4 * scale).all()
+    tvar = h.var((0, 2), unbiased=False)
+    assert ((var - tvar).abs() <= 2e-4 * tvar + 1e-4 * scale * scale * 1e-3).all()
     tmax, tmin = h.max(2)[0], h.min(2)[0]
-    assert ((vmax.double() - tmax).abs() <= 2e-5 * scale).all() and ((vmin.double() - tmin).abs() <= 2e-5 * scale).all()
+    assert ((vmax.double() - tmax).abs() <= 1e-4 * scale).all() and ((vmin.double() - tmin).abs() <= 1e-4 * scale).all()
     # the selected point attains the extremum (up to the same tolerance)
-    assert ((torch.gather(h, 2, imax.unsqueeze(2)).squeeze(2) - tmax).abs() <= 4e-5 * scale).all()
-    assert ((torch.gather(h, 2, imin.unsqueeze(2)).squeeze(2) - tmin).abs() <= 4e-5 * scale).all()
+    assert ((torch.gather(h, 2, imax.unsqueeze(2)).squeeze(2) - tmax).abs() <= 2e-4 * scale).all()
+    assert ((torch.gather(h, 2, imin.unsqueeze(2)).squeeze(2) - tmin).abs() <= 2e-4 * scale).all()
     assert int(imax.min()) >= 0 and int(imax.max()) < N and int(imin.min()) >= 0 and int(imin.max()) < N
 
 
