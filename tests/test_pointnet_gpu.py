@@ -100,7 +100,7 @@ def test_pool_statistics_kernel_vs_torch(native_lib, cuda, B, N):
     W = (torch.randn((512, 256), generator=g) * 0.08).to(cuda)
     mean, var, vmax, vmin, imax, imin = _pool_stats(h2, W)
     h = torch.matmul(W.double(), h2.double())                     # (B,512,N) truth
-    scale = h.abs().amax(dim=(0, 2)).clamp_min(1e-6)
+    scale = h.abs().max().clamp_min(1e-6)                         # one scale for all channels (split-bf16 products: ~1e-5 of it)
     assert ((mean - h.mean((0, 2))).abs() <= 1e-4 * scale).all()
     tvar = h.var((0, 2), unbiased=False)
     assert ((var - tvar).abs() <= 2e-4 * tvar + 1e-4 * scale * scale * 1e-3).all()
@@ -138,8 +138,46 @@ def test_train_mode_fused_last_layer_vs_library_path(native_lib, cuda, B, N):
     assert rel(fused[0], lib[0]) < 1e-4
     for k, v in lib[2].items():
         assert (torch.equal(fused[2][k], v) if "num_batches" in k else rel(fused[2][k], v) < 1e-4), k
-    worst = max((rel(fused[1][k], v), k) for k, v in lib[1].items())
-    assert worst[0] < 2e-3, worst        # fp32 re-association through four batch-statistics BatchNorms
+    # Gradients: the max-pool routes each (shape, channel) cotangent to ONE point; where two points of a cloud are within
+    # fp32 rounding of each other (a few hundred of the 16 384 (shape, channel) pairs at 2048 points) the kernel's split-bf16
+    # products and cuBLAS' fp32 products may pick different ones - both are argmaxes to fp32 accuracy and the gradient
+    # legitimately differs there.  Gate: L2-relative error (a few flipped selections barely move it); the exact algebra is
+    # checked in float64 at full width below and on the CPU (tests/test_models_host.py).
+    def l2(a, b):
+        return float((a - b).norm() / b.norm().clamp_min(1e-30))
+    worst = max((l2(fused[1][k], v), k) for k, v in lib[1].items())
+    assert worst[0] < (2e-3 if N <= 300 else 3e-2), worst
+
+
+def test_pooled_last_layer_float64_on_gpu_at_full_width(native_lib, cuda, monkeypatch):
+    """The op's forward selection logic and analytic backward at 2048 points per cloud in float64 (statistics pass replaced
+    by its torch definition, exact argmax) against autograd of the module chain in float64: 1e-9."""
+    from dpf_nets_b200.ops import pointnet_pool as pp
+
+    def stats(h2, W):
+        h = torch.matmul(W, h2)
+        vmax, imax = h.max(2)
+        vmin, imin = h.min(2)
+        return h.mean((0, 2)), h.var((0, 2), unbiased=False), vmax, vmin, imax, imin
+    monkeypatch.setattr(pp, "_pool_stats", stats)
+    g = torch.Generator().manual_seed(2)
+    B, N = 6, 2048
+    h2 = torch.relu(torch.randn((B, 256, N), generator=g, dtype=torch.float64)).to(cuda).requires_grad_(True)
+    W = (torch.randn((512, 256), generator=g, dtype=torch.float64) * 0.08).to(cuda).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(512).double().to(cuda)
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(512, generator=g, dtype=torch.float64))
+        bn.bias.copy_(0.3 * torch.randn(512, generator=g, dtype=torch.float64))
+    bn2 = torch.nn.BatchNorm1d(512).double().to(cuda)
+    bn2.load_state_dict(bn.state_dict())
+    cot = torch.randn((B, 512), generator=g, dtype=torch.float64).to(cuda)
+    ref = torch.max(torch.relu(bn(torch.matmul(W, h2))), dim=2)[0]
+    gr = torch.autograd.grad((ref * cot).sum(), [h2, W, bn.weight, bn.bias])
+    out = pp.pooled_bn_relu_max(h2, W, bn2)
+    go = torch.autograd.grad((out * cot).sum(), [h2, W, bn2.weight, bn2.bias])
+    assert rel(out, ref) < 1e-12
+    for a, b in zip(go, gr):
+        assert rel(a, b) < 1e-9
 
 
 def test_train_mode_fused_last_layer_is_faster(native_lib, cuda):
