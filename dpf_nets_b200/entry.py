@@ -51,6 +51,7 @@ def _model(config, svr, dev, precision):
     from .lib.networks.models import Local_Cond_RNVP_MC_Global_RNVP_VAE, Local_Cond_RNVP_MC_Global_RNVP_VAE_IC
     model = (Local_Cond_RNVP_MC_Global_RNVP_VAE_IC if svr else Local_Cond_RNVP_MC_Global_RNVP_VAE)(**config).to(dev)
     model.pc_decoder.precision = precision
+    model.pc_encoder.precision = 'fp32' if precision == 'fp32' else 'auto'      # --precision fp32: the exact paths everywhere
     return model
 
 

@@ -184,6 +184,7 @@ def test_wholemodel_training_loss_and_gradients_vs_reference(native_lib, cuda, m
     m.load_state_dict(det_state({k: list(v.shape) for k, v in m.state_dict().items()}))
     m = m.to(cuda).train()
     m.pc_decoder.precision = precision
+    m.pc_encoder.precision = "fp32" if precision == "fp32" else "auto"     # fp32 = the exact paths everywhere; auto = tensor paths
     crit = Local_Cond_RNVP_MC_Global_RNVP_VAE_Loss(**c)
     inp = {k: v.to(cuda) for k, v in whole_model_inputs(fx["B"], fx["N"], 77, ic).items()}
     with DetRandn(5):
