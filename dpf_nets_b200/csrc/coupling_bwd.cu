@@ -500,6 +500,7 @@ coupling_bwd_final_kernel(const BwdArgs a, const float* __restrict__ p_in, const
 // ------------------------------------------------------------------------------------------
 constexpr int FB_THREADS = 256;
 constexpr int FB_MAXB = 128;
+constexpr int GS_LD = 36;               // leading dimension of the g chunk rows (32 + padding, multiple of 4 floats)
 
 __global__ void __launch_bounds__(FB_THREADS)
 film_backward_kernel(const float* __restrict__ arena, const float* __restrict__ stats, float* __restrict__ darena,
@@ -521,31 +522,47 @@ film_backward_kernel(const float* __restrict__ arena, const float* __restrict__ 
   float* DO = XH + (size_t)B * F;       // [B][F]  cotangent of the net output
   float* DU = DO + (size_t)B * F;       // [B][F]  v (swish output), then dxhat, then du
   float* Ws = DU + (size_t)B * F;       // [F][F+1] / [32][F+1]
-  float* gs = Ws + F * (F + 1);         // [B][33]
-  float* vec = gs + (size_t)B * 33;     // mean, istd, m1, m2, dgam[4][F], dbet[4][F]
+  float* gs = Ws + F * (F + 1);         // [B][GS_LD] g chunk, rows 16-byte aligned
+  float* gT = gs + (size_t)B * GS_LD;   // [32][4][8] transposed g chunk (register-tiled recompute)
+  float* vec = gT + 1024;               // mean, istd, m1, m2, dgam[4][F], dbet[4][F]
   float* mean_s = vec, *istd_s = vec + F, *m1_s = vec + 2 * F, *m2_s = vec + 3 * F;
   float* dgam_s = vec + 4 * F, *dbet_s = vec + 8 * F;
   const int tid = threadIdx.x, c = tid & 63, bq = tid >> 6;
 
-  // ---- recompute u = g W0^T ----
-  for (int e = tid; e < B * F; e += FB_THREADS) XH[e] = 0.f;
-  for (int i0 = 0; i0 < G; i0 += 32) {
-    const int ni = min(32, G - i0);
-    __syncthreads();
-    for (int e = tid; e < F * 32; e += FB_THREADS) {
-      const int cc = e >> 5, i = e & 31;
-      Ws[i * (F + 1) + cc] = (i < ni) ? prm[oW0 + (size_t)cc * G + i0 + i] : 0.f;
-    }
-    for (int e = tid; e < B * 32; e += FB_THREADS) {
-      const int b = e >> 5, i = e & 31;
-      gs[b * 33 + i] = (i < ni) ? g[(size_t)b * G + i0 + i] : 0.f;
-    }
-    __syncthreads();
-    for (int b = bq; b < B; b += 4) {
-      float acc = 0.f;
+  // ---- recompute u = g W0^T: register tile of 8 shapes per thread (shapes bq + 4 j), like film_forward_kernel ----
+  {
+    const int nj = (B + 3) >> 2;
+    for (int jb = 0; jb < nj; jb += 8) {
+      float acc[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc = fmaf(gs[b * 33 + i], Ws[i * (F + 1) + c], acc);
-      XH[b * F + c] += acc;
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int i0 = 0; i0 < G; i0 += 32) {
+        const int ni = min(32, G - i0);
+        __syncthreads();
+        for (int e = tid; e < F * 32; e += FB_THREADS) {
+          const int cc = e >> 5, i = e & 31;
+          Ws[i * (F + 1) + cc] = (i < ni) ? prm[oW0 + (size_t)cc * G + i0 + i] : 0.f;
+        }
+        for (int e = tid; e < 32 * 32; e += FB_THREADS) {        // gT[i][q][8] = g[q + 4 (jb + j)][i0 + i]
+          const int i = e & 31, qj = e >> 5, q = qj >> 3, j = qj & 7;
+          const int b = q + 4 * (jb + j);
+          gT[i * 32 + qj] = (i < ni && b < B) ? g[(size_t)b * G + i0 + i] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const float w = Ws[i * (F + 1) + c];
+          const float4 ga = *reinterpret_cast<const float4*>(gT + i * 32 + bq * 8);
+          const float4 gb = *reinterpret_cast<const float4*>(gT + i * 32 + bq * 8 + 4);
+          acc[0] = fmaf(ga.x, w, acc[0]); acc[1] = fmaf(ga.y, w, acc[1]); acc[2] = fmaf(ga.z, w, acc[2]); acc[3] = fmaf(ga.w, w, acc[3]);
+          acc[4] = fmaf(gb.x, w, acc[4]); acc[5] = fmaf(gb.y, w, acc[5]); acc[6] = fmaf(gb.z, w, acc[6]); acc[7] = fmaf(gb.w, w, acc[7]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int b = bq + 4 * (jb + j);
+        if (b < B) XH[b * F + c] = acc[j];
+      }
     }
   }
   __syncthreads();
@@ -646,30 +663,45 @@ film_backward_kernel(const float* __restrict__ arena, const float* __restrict__ 
     }
     for (int e = tid; e < B * 32; e += FB_THREADS) {
       const int b = e >> 5, i = e & 31;
-      gs[b * 33 + i] = (i < ni) ? g[(size_t)b * G + i0 + i] : 0.f;
+      gs[b * GS_LD + i] = (i < ni) ? g[(size_t)b * G + i0 + i] : 0.f;
     }
     __syncthreads();
     {
-      const int iq = tid >> 6;   // 8 consecutive i per thread
+      const int iq = tid >> 6;   // 8 consecutive i per thread: two 16-byte broadcast loads of g feed 8 FMAs
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
       for (int b = 0; b < B; ++b) {
         const float d = DU[b * F + c];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(d, gs[b * 33 + iq * 8 + i], acc[i]);
+        const float4 ga = *reinterpret_cast<const float4*>(gs + b * GS_LD + iq * 8);
+        const float4 gb = *reinterpret_cast<const float4*>(gs + b * GS_LD + iq * 8 + 4);
+        acc[0] = fmaf(d, ga.x, acc[0]); acc[1] = fmaf(d, ga.y, acc[1]); acc[2] = fmaf(d, ga.z, acc[2]); acc[3] = fmaf(d, ga.w, acc[3]);
+        acc[4] = fmaf(d, gb.x, acc[4]); acc[5] = fmaf(d, gb.y, acc[5]); acc[6] = fmaf(d, gb.z, acc[6]); acc[7] = fmaf(d, gb.w, acc[7]);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (iq * 8 + i < ni) dprm[oW0 + (size_t)c * G + i0 + iq * 8 + i] = acc[i];
     }
     {
+      // dg[b][i] += sum_c du[b][c] W0[c][i]: 4 shapes (b = bb + 8 j) per thread, du rows read as 16-byte broadcasts
       const int i = tid & 31, bb = tid >> 5;
-      for (int b = bb; b < B; b += 8) {
-        float acc = 0.f;
-#pragma unroll 16
-        for (int cc = 0; cc < F; ++cc) acc = fmaf(DU[b * F + cc], Ws[i * (F + 1) + cc], acc);
-        if (i < ni) atomicAdd(&dg[(size_t)b * G + i0 + i], acc);
+      for (int b0 = bb; b0 < B; b0 += 32) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int cc = 0; cc < F; cc += 4) {
+          const float w0 = Ws[i * (F + 1) + cc], w1 = Ws[i * (F + 1) + cc + 1], w2 = Ws[i * (F + 1) + cc + 2], w3 = Ws[i * (F + 1) + cc + 3];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int b = min(b0 + 8 * j, B - 1);
+            const float4 d = *reinterpret_cast<const float4*>(DU + b * F + cc);
+            acc[j] = fmaf(d.x, w0, fmaf(d.y, w1, fmaf(d.z, w2, fmaf(d.w, w3, acc[j]))));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int b = b0 + 8 * j;
+          if (b < B && i < ni) atomicAdd(&dg[(size_t)b * G + i0 + i], acc[j]);
+        }
       }
     }
   }
@@ -712,10 +744,10 @@ int launch_film_backward(const float* arena, const float* stats, float* darena, 
   DPF_REQUIRE(B <= FB_MAXB, DPF_ERR_UNSUPPORTED, "film backward supports B <= %d (got %d)", FB_MAXB, B);
   // shared memory sized for the actual batch: 48 KB at B = 32 -> 4 CTAs per SM, all L*4 CTAs in one wave
   // (at the FB_MAXB cap, 137 KB, it is one CTA per SM and 252 CTAs take two waves)
-  const size_t smem = sizeof(float) * ((size_t)3 * B * F + F * (F + 1) + (size_t)B * 33 + 12 * F);
+  const size_t smem = sizeof(float) * ((size_t)3 * B * F + F * (F + 1) + (size_t)B * GS_LD + 1024 + 12 * F);
   static bool attr = false;
   if (!attr) {
-    const size_t smem_max = sizeof(float) * ((size_t)3 * FB_MAXB * F + F * (F + 1) + (size_t)FB_MAXB * 33 + 12 * F);
+    const size_t smem_max = sizeof(float) * ((size_t)3 * FB_MAXB * F + F * (F + 1) + (size_t)FB_MAXB * GS_LD + 1024 + 12 * F);
     cudaFuncSetAttribute(film_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     attr = true;
   }
