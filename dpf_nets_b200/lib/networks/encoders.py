@@ -98,8 +98,18 @@ class FeatureEncoder(nn.Module):
                     lin.weight.normal_(std=std)
                     lin.bias.fill_(bias)
 
+    fused = True      # class switch: False keeps the plain module chain on the GPU too (tests compare both)
+
+    def _features(self, x):
+        if not (self.fused and self.batch_norm and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+            return self.features(x)
+        from ...ops.latent import bn_swish      # Linear -> [BatchNorm1d + Swish as one fused kernel] per layer
+        for i in range(self.n_layers):
+            x = bn_swish(getattr(self.features, 'mlp%d' % i)(x), getattr(self.features, 'mlp%d_bn' % i))
+        return x
+
     def forward(self, input):
-        feats = self.features(input) if self.n_layers > 0 else input
+        feats = self._features(input) if self.n_layers > 0 else input
         if self.deterministic:
             return self.mus(feats)
         return self.mus(feats), self.logvars(feats)

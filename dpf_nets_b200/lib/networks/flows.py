@@ -68,6 +68,10 @@ class RealNVPFlow(_nn.Module):
         # index tensor and copy it to the GPU on every call - a sync per layer, and illegal under graph capture
         self.register_buffer('_keep_idx', _torch.tensor(self.keep_inds, dtype=_torch.long), persistent=False)
         self.register_buffer('_warp_idx', _torch.tensor(self.warp_inds, dtype=_torch.long), persistent=False)
+        pos = _np.full(g_n_features, -1, dtype=_np.int32)
+        pos[_np.asarray(self.warp_inds, dtype=_np.int64)] = _np.arange(len(self.warp_inds), dtype=_np.int32)
+        self.register_buffer('_pos', _torch.from_numpy(pos), persistent=False)     # latent position -> index in the warp list / -1
+        self.eps_value = float(_np.float32(eps))
         for br in ('mu', 'logvar'):
             net = _nn.Sequential()
             net.add_module(br + '_mlp0', _nn.Linear(len(self.keep_inds), n_features, bias=False))
@@ -79,7 +83,22 @@ class RealNVPFlow(_nn.Module):
                 net[-1].bias.zero_()
             setattr(self, 'T_%s_0' % br, net)
 
+    fused = True      # class switch: False keeps the plain module chain on the GPU too (tests compare both)
+
+    def _net(self, net, br, kept):
+        """Linear -> BatchNorm1d + Swish (one fused kernel) -> Linear of one branch."""
+        from ...ops.latent import bn_swish
+        h = getattr(net, br + '_mlp0')(kept)
+        return getattr(net, br + '_mlp1')(bn_swish(h, getattr(net, br + '_mlp0_bn')))
+
     def forward(self, g, mode='direct'):
+        if self.fused and g.is_cuda and g.dtype == _torch.float32 and g.dim() == 2:
+            # fused path (csrc/latent.cu): BatchNorm + Swish and the whole transform are one kernel each, forward and backward
+            from ...ops.latent import latent_affine
+            kept = g.index_select(1, self._keep_idx)
+            raw_lv = self._net(self.T_logvar_0, 'logvar', kept)
+            raw_mu = self._net(self.T_mu_0, 'mu', kept)
+            return latent_affine(g, raw_mu, raw_lv, self._pos, self.eps_value, mode)
         kept = g.index_select(1, self._keep_idx)
         logvar = _torch.zeros_like(g).index_copy(1, self._warp_idx, _torch.log(self.eps + _torch.exp(self.T_logvar_0(kept))))
         mu = _torch.zeros_like(g).index_copy(1, self._warp_idx, self.T_mu_0(kept))

@@ -172,6 +172,25 @@ int dpf_pointnet_pool_workspace_bytes(long long* bytes);
 int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, float* stat,
                               float* vmax, float* vmin, int* imax, int* imin, void* stream);
 
+/* ---- Latent-side fused blocks -------------------------------------------
+ * The shape-latent flows and feature heads work on (B,F) matrices with B = 32..64 rows; their module chains
+ * (RealNVPFlow lib/networks/flows.py:163-213, FeatureEncoder lib/networks/encoders.py:31-83) are launch-bound.
+ * dpf_bn_swish_*: y = swish(BatchNorm1d(x)) over the batch dimension (training: batch statistics, biased variance, running
+ *   statistics updated with `momentum` and the unbiased variance when rm / rv are given; eval: rm / rv are used) and its
+ *   backward (dx, dgamma, dbeta); save_mean / save_istd (F) carry the statistics from forward to backward.
+ * dpf_latent_affine_*: flows.py:196-211 - logvar = log(eps + exp(raw_lv)), mu / logvar scattered to the warped positions
+ *   (pos (G) int32: index into the warp list, -1 = kept), g_out = exp(-logvar/2)(g - mu) (inverse != 0) or
+ *   exp(logvar/2) g + mu; backward from the cotangents of g_out / mu / logvar (each nullable). */
+int dpf_bn_swish_forward(const float* x, const float* gamma, const float* beta, float* rm, float* rv, int B, int F,
+                         float eps, float momentum, int training, float* y, float* save_mean, float* save_istd, void* stream);
+int dpf_bn_swish_backward(const float* dy, const float* x, const float* gamma, const float* beta, const float* save_mean,
+                          const float* save_istd, int B, int F, int training, float* dx, float* dgamma, float* dbeta, void* stream);
+int dpf_latent_affine_forward(const float* g, const float* raw_mu, const float* raw_lv, const int* pos, int B, int G, int W,
+                              float eps, int inverse, float* g_out, float* mu, float* lv, void* stream);
+int dpf_latent_affine_backward(const float* dgo, const float* dmu_f, const float* dlv_f, const float* g, const float* raw_mu,
+                               const float* raw_lv, const int* pos, int B, int G, int W, float eps, int inverse, float* dg,
+                               float* draw_mu, float* draw_lv, void* stream);
+
 /* Fused AMSGrad step with the reference's exact update (lib/networks/optimizers.py:53-74):
  * denom = sqrt(max_exp_avg_sq or exp_avg_sq)/bc2 + eps; p -= wd*p + lr*(exp_avg/bc1)/denom.
  * vmax may be NULL (amsgrad off); bc1 = 1-beta1^t, bc2 = sqrt(1-beta2^t). */
