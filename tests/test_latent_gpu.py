@@ -30,7 +30,7 @@ def test_global_rnvp_decoder_fused_vs_module_chain(native_lib, cuda, G, B, mode,
     from dpf_nets_b200.lib.networks.decoders import GlobalRNVPDecoder
     from dpf_nets_b200.lib.networks.flows import RealNVPFlow
     torch.manual_seed(G + B)
-    m = GlobalRNVPDecoder(3, 64 if G < 128 else 128, G, weight_std=0.3).to(cuda)
+    m = GlobalRNVPDecoder(3, 64 if G < 128 else 128, G, weight_std=0.05).to(cuda)
     with torch.no_grad():
         for n, p in m.named_parameters():
             if "bn.weight" in n:
