@@ -21,6 +21,9 @@ def _sum_over_layers(logvars):
             return logvars[0] + src.sum(0)
         if stacked is not None:
             return logvars[0] + stacked.sum(0)
+    if len(logvars) > 2 and all(lv.shape == logvars[1].shape for lv in logvars[2:]) and logvars[1].is_cuda:
+        # latent flows: 14 (B,G) tensors - one stack + one reduction instead of a chain of launch-bound adds
+        return logvars[0] + torch.stack(list(logvars[1:])).sum(0)
     acc = logvars[0]
     for lv in logvars[1:]:
         acc = acc + lv
