@@ -132,7 +132,7 @@ class GradSync:
 
     def _hook(self, p):
         rank, R = world(self.group)
-        if R == 1 or torch.cuda.is_current_stream_capturing():
+        if R == 1 or (p.is_cuda and torch.cuda.is_current_stream_capturing()):
             return
         self.pending[id(p)] = dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 

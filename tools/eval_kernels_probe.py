@@ -26,4 +26,14 @@ pairwise_cd(A, A, symmetric=True)
 pairwise_emd(A[:8].contiguous(), B[:8].contiguous())
 M = [torch.rand((1000, 1000), generator=g).to(dev) for _ in range(3)]
 print(cd_scores((M[0] + M[0].t()) / 2, M[1], (M[2] + M[2].t()) / 2).tolist())
+# train-mode PointNet last layer + max-pool (statistics / max kernel) and the fused latent blocks
+from dpf_nets_b200.lib.networks.decoders import GlobalRNVPDecoder  # noqa: E402
+from dpf_nets_b200.ops.pointnet_pool import _pool_stats  # noqa: E402
+h2 = torch.relu(torch.randn((32, 256, 2048), generator=g)).to(dev)
+W3 = (torch.randn((512, 256), generator=g) * 0.08).to(dev)
+_pool_stats(h2, W3)
+gp = GlobalRNVPDecoder(7, 128, 128).to(dev).train()
+lat = torch.randn((32, 128), generator=g).to(dev).requires_grad_(True)
+out = gp(lat, mode="inverse")
+(out[0][0].sum() + sum(t.sum() for t in out[2])).backward()
 torch.cuda.synchronize()
