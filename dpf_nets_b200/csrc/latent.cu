@@ -8,76 +8,117 @@
 //   latent_affine   logvar = log(eps + exp(raw_lv)), scatter of (mu, logvar) to the warped positions,
 //                   g_out = exp(+-logvar/2) g (+-) mu   (flows.py:196-211)
 //
-// One thread owns one column (feature) and walks over the B rows: every reduction is a per-thread loop, accesses are
-// coalesced across the threads of a warp.
+// bn_swish: a CTA covers 32 columns x 8 row groups, every thread keeps its rows in registers (one coalesced read of the
+// matrix, independent loads), the batch reductions are small shared-memory trees.
 #include "common.cuh"
 
 namespace {
 
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
 
-__global__ void __launch_bounds__(128)
+// Thread layout: a CTA covers 32 columns (threadIdx.x) with 8 row groups (threadIdx.y); a thread keeps its rows
+// ty, ty + 8, ... (up to BN_MAXR of them) in registers, so the matrix is read once with independent coalesced loads and
+// the two batch reductions go through a small shared-memory tree.
+constexpr int BN_TY = 8;       // row groups; the kernels are instantiated for 4 / 8 / 32 rows per thread (B <= 32 / 64 / 256)
+
+__device__ __forceinline__ float col_sum(float v, float (*red)[33]) {      // sum over the 8 row groups of a column
+  __syncthreads();
+  red[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < BN_TY; ++i) s += red[i][threadIdx.x];
+  return s;
+}
+
+template <int BN_MAXR>
+__global__ void __launch_bounds__(32 * BN_TY)
 bn_swish_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float* __restrict__ rm, float* __restrict__ rv, int B, int F, float eps, float momentum, int training,
                     float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_istd) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= F) return;
+  __shared__ float red[BN_TY][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+  const bool ok = c < F;
+  float v[BN_MAXR];
+#pragma unroll
+  for (int r = 0; r < BN_MAXR; ++r) {
+    const int b = ty + r * BN_TY;
+    v[r] = (ok && b < B) ? x[(size_t)b * F + c] : 0.f;
+  }
   float mean, var;
   if (training) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += x[(size_t)b * F + c];
-    mean = s / (float)B;
+#pragma unroll
+    for (int r = 0; r < BN_MAXR; ++r) s += v[r];
+    mean = col_sum(s, red) / (float)B;
     float q = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float d = x[(size_t)b * F + c] - mean;
+#pragma unroll
+    for (int r = 0; r < BN_MAXR; ++r) {
+      const float d = (ty + r * BN_TY < B) ? v[r] - mean : 0.f;
       q = fmaf(d, d, q);
     }
-    var = q / (float)B;
-    if (rm) {
+    var = col_sum(q, red) / (float)B;
+    if (rm && ok && ty == 0) {
       rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
       rv[c] = (1.f - momentum) * rv[c] + momentum * var * ((float)B / (float)max(B - 1, 1));
     }
   } else {
-    mean = rm[c];
-    var = rv[c];
+    mean = ok ? rm[c] : 0.f;
+    var = ok ? rv[c] : 1.f;
   }
+  if (!ok) return;
   const float istd = 1.f / sqrtf(var + eps);
   const float g = gamma[c], bt = beta[c];
-  for (int b = 0; b < B; ++b) {
-    const float z = fmaf((x[(size_t)b * F + c] - mean) * istd, g, bt);
-    y[(size_t)b * F + c] = z * sigmoidf_(z);
+#pragma unroll
+  for (int r = 0; r < BN_MAXR; ++r) {
+    const int b = ty + r * BN_TY;
+    if (b < B) {
+      const float z = fmaf((v[r] - mean) * istd, g, bt);
+      y[(size_t)b * F + c] = z * sigmoidf_(z);
+    }
   }
-  save_mean[c] = mean;
-  save_istd[c] = istd;
+  if (ty == 0) {
+    save_mean[c] = mean;
+    save_istd[c] = istd;
+  }
 }
 
-__global__ void __launch_bounds__(128)
+template <int BN_MAXR>
+__global__ void __launch_bounds__(32 * BN_TY)
 bn_swish_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ save_mean, const float* __restrict__ save_istd,
                     int B, int F, int training, float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= F) return;
-  const float mean = save_mean[c], istd = save_istd[c], g = gamma[c], bt = beta[c];
+  __shared__ float red[BN_TY][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+  const bool ok = c < F;
+  const float mean = ok ? save_mean[c] : 0.f, istd = ok ? save_istd[c] : 0.f, g = ok ? gamma[c] : 0.f, bt = ok ? beta[c] : 0.f;
+  float xh[BN_MAXR], dz[BN_MAXR];
   float dg = 0.f, db = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float xh = (x[(size_t)b * F + c] - mean) * istd;
-    const float z = fmaf(xh, g, bt);
+#pragma unroll
+  for (int r = 0; r < BN_MAXR; ++r) {
+    const int b = ty + r * BN_TY;
+    const bool in = ok && b < B;
+    xh[r] = in ? (x[(size_t)b * F + c] - mean) * istd : 0.f;
+    const float z = fmaf(xh[r], g, bt);
     const float s = sigmoidf_(z);
-    const float dz = dy[(size_t)b * F + c] * (s + z * s * (1.f - s));
-    dg = fmaf(dz, xh, dg);
-    db += dz;
+    dz[r] = in ? dy[(size_t)b * F + c] * (s + z * s * (1.f - s)) : 0.f;
+    dg = fmaf(dz[r], xh[r], dg);
+    db += dz[r];
   }
-  dgamma[c] = dg;
-  dbeta[c] = db;
+  dg = col_sum(dg, red);
+  db = col_sum(db, red);
+  if (!ok) return;
+  if (ty == 0) {
+    dgamma[c] = dg;
+    dbeta[c] = db;
+  }
   // d xhat = dz * gamma;  training: dx = istd (d xhat - mean_b(d xhat) - xhat mean_b(d xhat xhat))
   const float m1 = training ? g * db / (float)B : 0.f;
   const float m2 = training ? g * dg / (float)B : 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float xh = (x[(size_t)b * F + c] - mean) * istd;
-    const float z = fmaf(xh, g, bt);
-    const float s = sigmoidf_(z);
-    const float dz = dy[(size_t)b * F + c] * (s + z * s * (1.f - s));
-    dx[(size_t)b * F + c] = istd * (dz * g - m1 - xh * m2);
+#pragma unroll
+  for (int r = 0; r < BN_MAXR; ++r) {
+    const int b = ty + r * BN_TY;
+    if (b < B) dx[(size_t)b * F + c] = istd * (dz[r] * g - m1 - xh[r] * m2);
   }
 }
 
@@ -151,8 +192,12 @@ DPF_API int dpf_bn_swish_forward(const float* x, const float* gamma, const float
   DPF_REQUIRE(x && gamma && beta && y && save_mean && save_istd, DPF_ERR_NULL_PTR, "dpf_bn_swish_forward: null pointer");
   DPF_REQUIRE(training || (rm && rv), DPF_ERR_NULL_PTR, "dpf_bn_swish_forward: eval mode needs running statistics");
   DPF_REQUIRE(B > 0 && F > 0, DPF_ERR_BAD_ARG, "dpf_bn_swish_forward: bad sizes");
-  bn_swish_fwd_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, gamma, beta, rm, rv, B, F, eps, momentum, training, y,
-                                                                        save_mean, save_istd);
+  DPF_REQUIRE(B <= BN_TY * 32, DPF_ERR_UNSUPPORTED, "dpf_bn_swish_forward: B <= %d (got %d)", BN_TY * 32, B);
+  const dim3 grid((F + 31) / 32), block(32, BN_TY);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B <= BN_TY * 4) bn_swish_fwd_kernel<4><<<grid, block, 0, st>>>(x, gamma, beta, rm, rv, B, F, eps, momentum, training, y, save_mean, save_istd);
+  else if (B <= BN_TY * 8) bn_swish_fwd_kernel<8><<<grid, block, 0, st>>>(x, gamma, beta, rm, rv, B, F, eps, momentum, training, y, save_mean, save_istd);
+  else bn_swish_fwd_kernel<32><<<grid, block, 0, st>>>(x, gamma, beta, rm, rv, B, F, eps, momentum, training, y, save_mean, save_istd);
   return dpf_check_launch("bn_swish_fwd_kernel");
 }
 
@@ -162,8 +207,12 @@ DPF_API int dpf_bn_swish_backward(const float* dy, const float* x, const float* 
   DPF_REQUIRE(dy && x && gamma && beta && save_mean && save_istd && dx && dgamma && dbeta, DPF_ERR_NULL_PTR,
               "dpf_bn_swish_backward: null pointer");
   DPF_REQUIRE(B > 0 && F > 0, DPF_ERR_BAD_ARG, "dpf_bn_swish_backward: bad sizes");
-  bn_swish_bwd_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dy, x, gamma, beta, save_mean, save_istd, B, F, training, dx,
-                                                                        dgamma, dbeta);
+  DPF_REQUIRE(B <= BN_TY * 32, DPF_ERR_UNSUPPORTED, "dpf_bn_swish_backward: B <= %d (got %d)", BN_TY * 32, B);
+  const dim3 grid((F + 31) / 32), block(32, BN_TY);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B <= BN_TY * 4) bn_swish_bwd_kernel<4><<<grid, block, 0, st>>>(dy, x, gamma, beta, save_mean, save_istd, B, F, training, dx, dgamma, dbeta);
+  else if (B <= BN_TY * 8) bn_swish_bwd_kernel<8><<<grid, block, 0, st>>>(dy, x, gamma, beta, save_mean, save_istd, B, F, training, dx, dgamma, dbeta);
+  else bn_swish_bwd_kernel<32><<<grid, block, 0, st>>>(dy, x, gamma, beta, save_mean, save_istd, B, F, training, dx, dgamma, dbeta);
   return dpf_check_launch("bn_swish_bwd_kernel");
 }
 

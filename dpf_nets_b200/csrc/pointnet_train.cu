@@ -88,22 +88,35 @@ pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restric
   const int n_tiles = (N + PT_NT - 1) / PT_NT;
   uint32_t ph = 0;
   const bool vec_ok = (N % 4) == 0;
+  // thread k owns input channel k: its 64 consecutive points of a tile are 16 independent 16-byte loads, all issued before
+  // the first use and - for the NEXT tile - before this tile's UMMA wait and epilogue, so the global-load latency (the
+  // kernel's top stall in ncu) overlaps the tensor-core work
+  float4 buf[16];
+  auto load_tile = [&](int tile) {
+    const int n0 = tile * PT_NT;
+    const float* src = hb + (size_t)tid * N + n0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if (vec_ok && n0 + q * 4 + 4 <= N) {
+        buf[q] = __ldg(reinterpret_cast<const float4*>(src + q * 4));
+      } else {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (n0 + q * 4 + e < N) ? __ldg(src + q * 4 + e) : 0.f;
+        buf[q] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  };
+  load_tile(0);
   for (int tile = 0; tile < n_tiles; ++tile) {
     const int n0 = tile * PT_NT;
-    // ---- h2 tile -> bf16 hi | lo, MN-major: thread k owns input channel k (64 consecutive points = 8 chunks of 16 bytes) ----
+    // ---- h2 tile -> bf16 hi | lo, MN-major (8 chunks of 16 bytes per K-row) ----
     {
       const int k = tid;
-      const float* src = hb + (size_t)k * N + n0;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float v[8];
-        if (vec_ok && n0 + q * 8 + 8 <= N) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(src + q * 8)), c = __ldg(reinterpret_cast<const float4*>(src + q * 8 + 4));
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = (n0 + q * 8 + e < N) ? __ldg(src + q * 8 + e) : 0.f;
-        }
+        const float4 a = buf[2 * q], c = buf[2 * q + 1];
+        const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -135,6 +148,7 @@ pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restric
       }
       umma::mma_commit(&s.bar_mma);
     }
+    if (tile + 1 < n_tiles) load_tile(tile + 1);      // in flight during the UMMA chain and the epilogue
     umma::mbar_wait(&s.bar_mma, ph);
     ph ^= 1;
     umma::fence_after_sync();

@@ -106,3 +106,29 @@ def test_latent_blocks_launch_counts(native_lib, cuda):
     (out[0].sum() + out[2].sum()).backward()
     native_lib.dpf_launch_count(ctypes.byref(n2))
     assert n1.value - n0.value == 3 and n2.value - n1.value == 3
+
+
+@pytest.mark.parametrize("B,F", [(2, 7), (32, 128), (33, 100), (64, 512), (65, 40), (256, 64)])
+def test_bn_swish_kernel_shapes(native_lib, cuda, B, F):
+    """Every instantiation of the fused BatchNorm1d + Swish pair (4 / 8 / 32 rows per thread, ragged column tiles) against
+    torch: values, saved running statistics, gradients."""
+    from dpf_nets_b200.ops.latent import bn_swish
+    torch.manual_seed(B * 31 + F)
+    x0 = torch.randn((B, F), device=cuda)
+    cot = torch.randn((B, F), device=cuda)
+    bn_a, bn_b = torch.nn.BatchNorm1d(F).to(cuda), torch.nn.BatchNorm1d(F).to(cuda)
+    with torch.no_grad():
+        bn_a.weight.copy_(1 + 0.3 * torch.randn(F, device=cuda)); bn_a.bias.copy_(0.3 * torch.randn(F, device=cuda))
+    bn_b.load_state_dict(bn_a.state_dict())
+    for training in (True, False):
+        bn_a.train(training); bn_b.train(training)
+        xa, xb = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        za = bn_a(xa)
+        ya = za * torch.sigmoid(za)
+        yb = bn_swish(xb, bn_b)
+        (ya * cot).sum().backward()
+        (yb * cot).sum().backward()
+        assert rel(yb, ya) < 1e-5 and rel(xb.grad, xa.grad) < 1e-4
+        assert rel(bn_b.weight.grad, bn_a.weight.grad) < 1e-4 and rel(bn_b.bias.grad, bn_a.bias.grad) < 1e-4
+        assert rel(bn_b.running_mean, bn_a.running_mean) < 1e-5 and rel(bn_b.running_var, bn_a.running_var) < 1e-5
+        bn_a.zero_grad(); bn_b.zero_grad()
