@@ -513,7 +513,7 @@ def extras(model, dev, B, N, pk, flush):
             ts.append(a.elapsed_time(b))
     ms = sum(ts) / len(ts)
     samp = B * N / (ms * 1e-3)
-    out["sampling"] = {"value": samp, "unit": "points/s", "ms_per_pass": ms,
+    out["sampling"] = {"value": samp, "unit": "points/s", "ms_per_pass": ms, "precision": "bf16 ('auto' = plain bf16 in eval mode, 2e-2 gate)",
                        "tensor_frac": samp * FLOP_PER_POINT_LAYER_FWD * 3 * N_FLOWS / 1e12 / pk["bf16_tflops_sustained"]}
     model.train()
     out["encoder_eval"] = encoder_eval(dev, B, N, flush)

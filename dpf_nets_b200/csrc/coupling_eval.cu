@@ -208,10 +208,14 @@ decoder_eval_tc_kernel(const EvalArgs a) {
             }
             float va, vb;
             f2_unpack(v2, va, vb);
-            va = fmaxf(va, 0.f);
-            vb = fmaxf(vb, 0.f);
-            w[i] = umma::pack_bf16(va, vb);
-            if (SPLIT) wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
+            if (SPLIT) {
+              va = fmaxf(va, 0.f);
+              vb = fmaxf(vb, 0.f);
+              w[i] = umma::pack_bf16(va, vb);
+              wl[i] = umma::pack_bf16(va - __uint_as_float(w[i] << 16), vb - __uint_as_float(w[i] & 0xffff0000u));
+            } else {
+              w[i] = umma::pack_bf16_relu(va, vb);     // ReLU inside the conversion
+            }
           }
           const uint32_t off = umma::sw128_offset(row, ch8);
           *reinterpret_cast<uint4*>(s.H + off) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -155,4 +155,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// {bf16(max(lo, 0)), bf16(max(hi, 0))} in one conversion (SASS: F2FP.RELU.BF16): the ReLU of an activation that is only
+// ever consumed as a bf16 UMMA operand costs no instruction of its own
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 }  // namespace umma
