@@ -1,0 +1,596 @@
+// Train-mode PointNet cloud encoder, the narrow layers (init_sd 3 -> 64, sd0 64 -> 128, sd1 128 -> 256) forward AND backward.
+// Reference: PointNetCloudEncoder.features.{init_sd, sd0, sd1}{, _bn, _relu} in .train() (lib/networks/encoders.py:9-28) and
+// torch.autograd through them; the library path is one bmm + a batch-norm + a clamp per layer forward and twice that backward
+// (15 passes over (B, C, N) activations, fp32 SIMT GEMMs).
+//
+// What is stored per layer is only the PRE-BatchNorm output Z_l = W_l A_{l-1}; the activation A_l = relu(sc_l Z_l + sh_l) is
+// recomputed by whoever loads Z_l (sc, sh = the folded batch statistics).  Layer 0 is never stored at all: its batch
+// statistics follow analytically from the first and second moments of the input cloud (mean_c = W0[c] . E[x],
+// var_c = W0[c]^T Cov(x) W0[c]), so A_0 is recomputed from the three coordinates wherever it is an operand.
+//
+// Two tcgen05 kernels, both with ONE CHANNEL PER TMEM LANE (a reduction over points is a per-thread register reduction, a
+// store is 128 contiguous bytes per thread) and operand tiles [channels x 64 points] built by the CTA from fp32 global data
+// as bf16 hi | lo images (three UMMA chains hi*hi + lo*hi + hi*lo: fp32-class accuracy):
+//   pl_gemm_kernel    Out[M x pts] = Wimg[M x K] f(In[K x pts])      forward layers (f = BN + ReLU of the previous layer, output
+//                     statistics in the epilogue) and the backward dgrads (f = BatchNorm/ReLU backward of (dA, Z), Wimg = W^T)
+//   pl_wgrad_kernel   D[MP x NQ] += sum_pts P[MP x pts] Q[NQ x pts]^T   weight gradients (P = BN/ReLU backward of (dA, Z),
+//                     Q = recomputed activations) and the Gram matrix of the last layer's analytic backward (P = Q)
+// The [channels x 64 points] tile with 128-byte swizzled rows is at the same time a K-major operand over the points (wgrad) and
+// an MN-major operand over the channels (forward / dgrad): one shared-memory image serves both descriptors.
+// Plus two streaming reductions (BatchNorm-backward sums; layer 0's backward sums).
+#include "common.cuh"
+#include "umma.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int PL_T = 256;                       // threads per CTA
+constexpr int PL_NT = 64;                       // points per tile
+constexpr uint32_t PL_KB = 128 * 128;           // 16 KB: [128 rows x 64 bf16] block of a K-major image
+constexpr int PL_TAB = 8;                       // floats per channel in a loader table
+constexpr uint64_t PL_DESC_K = umma::make_desc_template(16, 1024, umma::LAYOUT_SW128);        // K-major, 8-row groups 1024 B apart
+constexpr uint64_t PL_DESC_MN = umma::make_desc_template(1024, 1024, umma::LAYOUT_SW128);     // MN-major, one 64-wide block
+
+enum { LD_X3 = 0, LD_AFFINE = 1, LD_BNBWD = 2 };
+// loader tables, PL_TAB floats per channel:
+//   LD_X3     {a0, a1, a2, c, sub}:       v = relu(a0 x0 + a1 x1 + a2 x2 + c) - sub          (layer 0 with its BatchNorm folded in)
+//   LD_AFFINE {sc, sh, sub}:              v = relu(sc z + sh) - sub                          (sub: centring for the Gram form)
+//   LD_BNBWD  {sc, sh, g, gm1, k2, mu}:   v = (sc z + sh > 0 ? g dA : 0) - gm1 - k2 (z - mu) (BatchNorm + ReLU backward)
+template <int LOADER> struct LoaderInputs { static constexpr int n = LOADER == LD_X3 ? 3 : LOADER == LD_BNBWD ? 2 : 1; };
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight images: matrix [R x K] (element (r, k) at W[r * rs + k * cs], so that W and W^T share the code) ->
+// [ceil(R / 128) chunks][hi, lo][K / 64 blocks][128 x 64] swizzled bf16, rows beyond R zero
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pl_pack_kernel(const float* __restrict__ W, int R, int K, long long rs, long long cs, unsigned char* __restrict__ img) {
+  const int qpr = K / 8;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int rpad = ((R + 127) / 128) * 128;
+  if (i >= rpad * qpr) return;
+  const int r = i / qpr, q = i % qpr;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float a = r < R ? W[(long long)r * rs + (long long)(q * 8 + 2 * e) * cs] : 0.f;
+    const float b = r < R ? W[(long long)r * rs + (long long)(q * 8 + 2 * e + 1) * cs] : 0.f;
+    hi[e] = umma::pack_bf16(a, b);
+    lo[e] = umma::pack_bf16(a - __uint_as_float(hi[e] << 16), b - __uint_as_float(hi[e] & 0xffff0000u));
+  }
+  const uint32_t half = (uint32_t)(K / 64) * PL_KB;
+  unsigned char* base = img + (size_t)(r >> 7) * 2 * half + (size_t)(q >> 3) * PL_KB + umma::sw128_offset(r & 127, q & 7);
+  *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(base + half) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// operand tile builder: C channel rows x 64 points, this thread owns channel `ch` and PPT consecutive points
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, int LOADER>
+struct TileLoader {
+  static constexpr int SEGS = PL_T / C;           // threads per channel row
+  static constexpr int PPT = PL_NT / SEGS;        // points per thread
+  static constexpr int NV = PPT / 4;              // float4 loads per input
+  static constexpr int NIN = LoaderInputs<LOADER>::n;
+  static_assert(C == 64 || C == 128 || C == 256, "channel rows per tile");
+  float4 buf[NIN][NV];
+  float t[6];
+  int ch, seg;
+  const float* src[NIN];
+  int N;
+  bool vec_ok;
+
+  __device__ __forceinline__ void init(const float* in0, const float* in1, const float* tab, int b, int Nn, int tid) {
+    ch = tid % C;
+    seg = tid / C;
+    N = Nn;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) t[j] = tab[ch * PL_TAB + j];
+    if (LOADER == LD_X3) {
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) src[j] = in0 + ((size_t)b * 3 + j) * N;
+    } else {
+      src[0] = in0 + ((size_t)b * C + ch) * N;
+      if (NIN > 1) src[1] = in1 + ((size_t)b * C + ch) * N;
+    }
+    vec_ok = (N % 4) == 0;
+  }
+  __device__ __forceinline__ void load(int n0) {
+    const int base = n0 + seg * PPT;
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) {
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        const int n = base + q * 4;
+        if (vec_ok && n + 4 <= N) {
+          buf[j][q] = __ldg(reinterpret_cast<const float4*>(src[j] + n));
+        } else {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = (n + e < N) ? __ldg(src[j] + n + e) : 0.f;
+          buf[j][q] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ float value(float i0, float i1, float i2) const {
+    if (LOADER == LD_X3) return fmaxf(fmaf(t[0], i0, fmaf(t[1], i1, fmaf(t[2], i2, t[3]))), 0.f) - t[4];
+    if (LOADER == LD_AFFINE) return fmaxf(fmaf(t[0], i0, t[1]), 0.f) - t[2];
+    // LD_BNBWD: i0 = dA, i1 = z
+    const float y = fmaf(t[0], i1, t[1]);
+    return (y > 0.f ? t[2] * i0 : 0.f) - t[3] - t[4] * (i1 - t[5]);
+  }
+  // bf16 hi | lo images of the tile; points beyond N are ZERO operands (they would otherwise enter the sums over points)
+  __device__ __forceinline__ void convert(unsigned char* hi_img, unsigned char* lo_img, int n0) const {
+    const int base = n0 + seg * PPT;
+#pragma unroll
+    for (int q = 0; q < NV / 2; ++q) {
+      float v[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 a0 = buf[0][2 * q + h];
+        const float4 a1 = NIN > 1 ? buf[NIN > 1 ? 1 : 0][2 * q + h] : a0;
+        const float4 a2 = NIN > 2 ? buf[NIN > 2 ? 2 : 0][2 * q + h] : a0;
+        v[4 * h + 0] = value(a0.x, a1.x, a2.x);
+        v[4 * h + 1] = value(a0.y, a1.y, a2.y);
+        v[4 * h + 2] = value(a0.z, a1.z, a2.z);
+        v[4 * h + 3] = value(a0.w, a1.w, a2.w);
+      }
+      if (base + q * 8 + 8 > N) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (base + q * 8 + e >= N) v[e] = 0.f;
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        hi[e] = umma::pack_bf16(v[2 * e], v[2 * e + 1]);
+        lo[e] = umma::pack_bf16(v[2 * e] - __uint_as_float(hi[e] << 16), v[2 * e + 1] - __uint_as_float(hi[e] & 0xffff0000u));
+      }
+      const uint32_t off = umma::sw128_offset(ch, seg * (PPT / 8) + q);
+      *reinterpret_cast<uint4*>(hi_img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(lo_img + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Out[M x pts] = Wimg[M x K] f(In[K x pts]) per tile of 64 points; CTA = (shape b, group of tiles) x (chunk of 128 output rows)
+// ---------------------------------------------------------------------------------------------------------------
+struct PlGemmArgs {
+  const float* in0;             // LD_X3: x (B,3,N); LD_AFFINE: Z (B,K,N); LD_BNBWD: dA (B,K,N)
+  const float* in1;             // LD_BNBWD: Z (B,K,N)
+  const float* tab;             // (K, PL_TAB)
+  const unsigned char* wimg;    // pl_pack_kernel image of the [Mout x K] matrix
+  float* out;                   // (B, Mout, N) or null
+  const float* row_off;         // (Mout,) added to every element of a row, or null
+  float* stat;                  // (B * groups, Mout, 3) {count, mean, sum of squared deviations} or null
+  int B, N, Mout, tiles_per_cta, groups;
+};
+
+template <int K, int LOADER, bool STATS>
+__global__ void __launch_bounds__(PL_T, 1)
+pl_gemm_kernel(const PlGemmArgs a) {
+  constexpr int NST = K == 256 ? 1 : 2;           // operand stages (K = 256: the 128 KB weight image leaves room for one)
+  constexpr int LAG = NST - 1;                    // the epilogue of tile i - LAG runs under the UMMAs of tile i
+  constexpr uint32_t WHALF = (K / 64) * PL_KB, BHALF = K * 128;
+  extern __shared__ unsigned char smraw[];
+  unsigned char* sm = smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u);
+  unsigned char* sA = sm;                                       // weight chunk hi | lo
+  unsigned char* sB = sm + 2 * WHALF;                           // NST x (tile hi | lo)
+  float (*red)[128][4] = reinterpret_cast<float (*)[128][4]>(sB + NST * 2 * BHALF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + 2 * 128 * 4 * sizeof(float));   // [0] weights, [1..2] TMEM buffers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int lane_c = tid & 127, part = tid >> 7, quarter = warp & 3;
+  const int b = blockIdx.x / a.groups, grp = blockIdx.x % a.groups, chunk = blockIdx.y;
+  const int n_tiles = (a.N + PL_NT - 1) / PL_NT;
+  const int t0 = grp * a.tiles_per_cta;
+  const int nt = max(0, min(a.tiles_per_cta, n_tiles - t0));
+  if (tid == 0) {
+    umma::mbar_init(&bars[0], 1);
+    umma::mbar_init(&bars[1], 1);
+    umma::mbar_init(&bars[2], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 128);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+  if (tid == 0) {
+    umma::mbar_expect_tx(&bars[0], 2 * WHALF);
+    umma::bulk_g2s(sA, a.wimg + (size_t)chunk * 2 * WHALF, 2 * WHALF, &bars[0]);
+  }
+  TileLoader<K, LOADER> ld;
+  ld.init(a.in0, a.in1, a.tab, b, a.N, tid);
+  constexpr uint32_t IDESC = umma::make_idesc_bf16(128, PL_NT, 0, 1);
+
+  const int row = chunk * 128 + lane_c;
+  const bool row_ok = row < a.Mout;
+  const float roff = (a.row_off && row_ok) ? a.row_off[row] : 0.f;
+  float sum = 0.f, sq = 0.f, shift = 0.f;
+  int cnt = 0;
+  uint32_t par[2] = {0u, 0u};
+  const bool vec_ok = (a.N % 4) == 0;
+
+  if (nt > 0) ld.load(t0 * PL_NT);
+  for (int i = 0; i < nt + LAG; ++i) {
+    if (i < nt) {
+      unsigned char* st = sB + (size_t)(i % NST) * 2 * BHALF;
+      ld.convert(st, st + BHALF, (t0 + i) * PL_NT);
+      umma::fence_async_smem();
+      if (i + 1 < nt) ld.load((t0 + i + 1) * PL_NT);       // in flight under the UMMAs and the epilogue
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (i < nt && tid == 0) {
+      if (i == 0) umma::mbar_wait(&bars[0], 0);
+      umma::fence_after_sync();
+      const uint32_t d = tmem + (uint32_t)(i & 1) * PL_NT;
+      const uint32_t b0 = umma::smem_u32(sB + (size_t)(i % NST) * 2 * BHALF);
+#pragma unroll
+      for (int chain = 0; chain < 3; ++chain) {           // hi*hi, lo*hi, hi*lo
+        const uint32_t a_base = umma::smem_u32(sA) + (chain == 1 ? WHALF : 0);
+        const uint32_t b_base = b0 + (chain == 2 ? BHALF : 0);
+#pragma unroll
+        for (int kb = 0; kb < K / 64; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma::mma_bf16(d, umma::desc_at(PL_DESC_K, a_base + kb * PL_KB + 32 * k),
+                           umma::desc_at(PL_DESC_MN, b_base + (kb * 4 + k) * 2048), IDESC, (chain | kb | k) > 0);
+      }
+      umma::mma_commit(&bars[1 + (i & 1)]);
+    }
+    const int e = i - LAG;
+    if (e >= 0) {
+      umma::mbar_wait(&bars[1 + (e & 1)], par[e & 1]);
+      par[e & 1] ^= 1u;
+      umma::fence_after_sync();
+      float v[32];
+      umma::tmem_ld32(tmem + lane_off + (uint32_t)(e & 1) * PL_NT + part * 32, v);
+      const int nbase = (t0 + e) * PL_NT + part * 32;
+      if (STATS) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (nbase + j < a.N) {
+            const float x = v[j];
+            if (cnt == 0) shift = x;
+            ++cnt;
+            const float dx = x - shift;
+            sum += dx;
+            sq = fmaf(dx, dx, sq);
+          }
+        }
+      }
+      if (a.out && row_ok) {
+        float* dst = a.out + ((size_t)b * a.Mout + row) * a.N + nbase;
+        if (vec_ok && nbase + 32 <= a.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j] + roff, v[4 * j + 1] + roff, v[4 * j + 2] + roff, v[4 * j + 3] + roff);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nbase + j < a.N) dst[j] = v[j] + roff;
+        }
+      }
+    }
+  }
+  if (STATS) {
+    // this thread: count, mean = shift + sum / cnt, M2 = sq - sum^2 / cnt; the two point halves merge pairwise (Chan et al.)
+    const float fc = (float)cnt;
+    const float mean_t = cnt ? shift + sum / fc : 0.f;
+    const float m2_t = cnt ? fmaxf(sq - sum * sum / fc, 0.f) : 0.f;
+    red[part][lane_c][0] = fc; red[part][lane_c][1] = mean_t; red[part][lane_c][2] = m2_t;
+    __syncthreads();
+    if (part == 0 && row_ok) {
+      const float n2 = red[1][lane_c][0], mean2 = red[1][lane_c][1], m22 = red[1][lane_c][2];
+      const float ntot = fc + n2;
+      const float delta = mean2 - mean_t;
+      float* o = a.stat + ((size_t)blockIdx.x * a.Mout + row) * 3;
+      o[0] = ntot;
+      o[1] = ntot > 0.f ? mean_t + delta * (n2 / ntot) : 0.f;
+      o[2] = ntot > 0.f ? m2_t + m22 + delta * delta * (fc * n2 / ntot) : 0.f;
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+}
+
+template <int K>
+constexpr size_t pl_gemm_smem() {
+  return 1024 + 2 * (size_t)(K / 64) * PL_KB + (K == 256 ? 1 : 2) * 2 * (size_t)K * 128 + 2 * 128 * 4 * sizeof(float) + 64;
+}
+
+template <int K, int LOADER, bool STATS>
+int pl_launch_gemm(const PlGemmArgs& a, cudaStream_t s) {
+  constexpr size_t smem = pl_gemm_smem<K>();
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pl_gemm_kernel<K, LOADER, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  pl_gemm_kernel<K, LOADER, STATS><<<dim3(a.B * a.groups, (a.Mout + 127) / 128), PL_T, smem, s>>>(a);
+  return dpf_check_launch("pl_gemm_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// D[MP x NQ] += sum over the CTA's points of P[MP x pts] Q[NQ x pts]^T ; accumulated in TMEM over the CTA's tiles, then
+// added to `out` (MP x NQ row-major fp32) with float atomics.  GRAM: Q is P (one image, MP == NQ).
+// ---------------------------------------------------------------------------------------------------------------
+struct PlWgradArgs {
+  const float* p_in0; const float* p_in1; const float* p_tab;
+  const float* q_in0; const float* q_tab;
+  float* out;                   // (MP, NQ), zero-initialised by the caller
+  int B, N, tiles_per_cta, groups;
+};
+
+template <int MP, int PLOADER, int NQ, int QLOADER, bool GRAM>
+__global__ void __launch_bounds__(PL_T, 1)
+pl_wgrad_kernel(const PlWgradArgs a) {
+  constexpr uint32_t PHALF = MP * 128, QHALF = GRAM ? 0 : NQ * 128;
+  constexpr uint32_t STAGE = 2 * PHALF + 2 * QHALF;
+  constexpr uint32_t COLS = (MP / 128) * NQ;                   // fp32 accumulator columns
+  constexpr uint32_t TCOLS = COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
+  extern __shared__ unsigned char smraw[];
+  unsigned char* sm = smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 2 * STAGE);      // [0..1] stage free, [2] all done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int lane_c = tid & 127, part = tid >> 7, quarter = warp & 3;
+  const int b = blockIdx.x / a.groups, grp = blockIdx.x % a.groups;
+  const int n_tiles = (a.N + PL_NT - 1) / PL_NT;
+  const int t0 = grp * a.tiles_per_cta;
+  const int nt = max(0, min(a.tiles_per_cta, n_tiles - t0));
+  if (tid == 0) {
+    umma::mbar_init(&bars[0], 1);
+    umma::mbar_init(&bars[1], 1);
+    umma::mbar_init(&bars[2], 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, TCOLS);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+
+  TileLoader<MP, PLOADER> lp;
+  lp.init(a.p_in0, a.p_in1, a.p_tab, b, a.N, tid);
+  TileLoader<GRAM ? MP : NQ, GRAM ? PLOADER : QLOADER> lq;
+  if (!GRAM) lq.init(a.q_in0, nullptr, a.q_tab, b, a.N, tid);
+  constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NQ, 0, 0);
+  uint32_t par[2] = {0u, 0u};
+
+  if (nt > 0) {
+    lp.load(t0 * PL_NT);
+    if (!GRAM) lq.load(t0 * PL_NT);
+  }
+  for (int i = 0; i < nt; ++i) {
+    unsigned char* st = sm + (size_t)(i & 1) * STAGE;
+    if (i >= 2) {                                   // the UMMAs of tile i - 2 read this stage
+      umma::mbar_wait(&bars[i & 1], par[i & 1]);
+      par[i & 1] ^= 1u;
+    }
+    lp.convert(st, st + PHALF, (t0 + i) * PL_NT);
+    if (!GRAM) lq.convert(st + 2 * PHALF, st + 2 * PHALF + QHALF, (t0 + i) * PL_NT);
+    umma::fence_async_smem();
+    if (i + 1 < nt) {
+      lp.load((t0 + i + 1) * PL_NT);
+      if (!GRAM) lq.load((t0 + i + 1) * PL_NT);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+      const uint32_t p0 = umma::smem_u32(st), q0 = GRAM ? p0 : umma::smem_u32(st + 2 * PHALF);
+      constexpr uint32_t QH = GRAM ? PHALF : QHALF;
+#pragma unroll
+      for (int mc = 0; mc < MP / 128; ++mc) {
+#pragma unroll
+        for (int chain = 0; chain < 3; ++chain) {         // hi*hi, lo*hi, hi*lo
+          const uint32_t pa = p0 + (chain == 1 ? PHALF : 0) + mc * PL_KB;
+          const uint32_t qa = q0 + (chain == 2 ? QH : 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma::mma_bf16(tmem + mc * NQ, umma::desc_at(PL_DESC_K, pa + 32 * k), umma::desc_at(PL_DESC_K, qa + 32 * k), IDESC,
+                           (i | chain | k) > 0);
+        }
+      }
+      umma::mma_commit(i + 1 < nt ? &bars[i & 1] : &bars[2]);
+    }
+  }
+  if (nt > 0) {
+    umma::mbar_wait(&bars[2], 0);
+    umma::fence_after_sync();
+    // lane = P row; this part adds half of the columns, 32 at a time
+#pragma unroll 1
+    for (int mc = 0; mc < MP / 128; ++mc) {
+#pragma unroll 1
+      for (int c0 = part * 32; c0 < NQ; c0 += 64) {
+        float v[32];
+        umma::tmem_ld32(tmem + lane_off + mc * NQ + c0, v);
+        float* dst = a.out + (size_t)(mc * 128 + lane_c) * NQ + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
+}
+
+template <int MP, int PLOADER, int NQ, int QLOADER, bool GRAM>
+int pl_launch_wgrad(const PlWgradArgs& a, cudaStream_t s) {
+  constexpr size_t smem = 1024 + 2 * (2 * (size_t)MP * 128 + (GRAM ? 0 : 2 * (size_t)NQ * 128)) + 64;
+  static_assert(smem <= 232448, "wgrad stages exceed the shared memory of an SM");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pl_wgrad_kernel<MP, PLOADER, NQ, QLOADER, GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  pl_wgrad_kernel<MP, PLOADER, NQ, QLOADER, GRAM><<<a.B * a.groups, PL_T, smem, s>>>(a);
+  return dpf_check_launch("pl_wgrad_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// streaming reductions.  One block per (shape, channel) row of N points.
+//   BatchNorm + ReLU backward sums:  s[c] = {sum dA [y > 0], sum dA [y > 0] (z - mu)},  y = sc z + sh
+//   layer 0 backward sums:           s[c] = {sum dA m, sum dA m x0, sum dA m x1, sum dA m x2},  m = [a . x + c > 0]
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_add_double(double* dst, const float* v, int nv, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = 0; j < nv; ++j) {
+    const double w = warp_sum_d((double)v[j]);
+    if (lane == 0) scratch[warp * 4 + j] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < nv) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += scratch[w * 4 + threadIdx.x];
+    atomicAdd(dst + threadIdx.x, t);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+pl_bn_bwd_sums_kernel(const float* __restrict__ dA, const float* __restrict__ Z, const float* __restrict__ tab, int C, int N,
+                      double* __restrict__ sums) {
+  __shared__ double scratch[4 * 4];
+  const int c = blockIdx.x % C;
+  const size_t base = (size_t)blockIdx.x * N;
+  const float sc = tab[c * PL_TAB + 0], sh = tab[c * PL_TAB + 1], mu = tab[c * PL_TAB + 5];
+  float acc[2] = {0.f, 0.f};
+  for (int n = threadIdx.x; n < N; n += 128) {
+    const float z = Z[base + n], d = dA[base + n];
+    const float dm = fmaf(sc, z, sh) > 0.f ? d : 0.f;
+    acc[0] += dm;
+    acc[1] = fmaf(dm, z - mu, acc[1]);
+  }
+  block_add_double(sums + (size_t)c * 2, acc, 2, scratch);
+}
+
+__global__ void __launch_bounds__(128)
+pl_layer0_bwd_sums_kernel(const float* __restrict__ dA, const float* __restrict__ x, const float* __restrict__ tab, int C, int N,
+                          double* __restrict__ sums) {
+  __shared__ double scratch[4 * 4];
+  const int c = blockIdx.x % C, b = blockIdx.x / C;
+  const size_t base = (size_t)blockIdx.x * N;
+  const float* xb = x + (size_t)b * 3 * N;
+  const float a0 = tab[c * PL_TAB + 0], a1 = tab[c * PL_TAB + 1], a2 = tab[c * PL_TAB + 2], cc = tab[c * PL_TAB + 3];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n = threadIdx.x; n < N; n += 128) {
+    const float x0 = xb[n], x1 = xb[N + n], x2 = xb[2 * (size_t)N + n];
+    const float dm = fmaf(a0, x0, fmaf(a1, x1, fmaf(a2, x2, cc))) > 0.f ? dA[base + n] : 0.f;
+    acc[0] += dm;
+    acc[1] = fmaf(dm, x0, acc[1]);
+    acc[2] = fmaf(dm, x1, acc[2]);
+    acc[3] = fmaf(dm, x2, acc[3]);
+  }
+  block_add_double(sums + (size_t)c * 4, acc, 4, scratch);
+}
+
+int pick_groups(int B, int N, int* tiles_per_cta, int waves = 2) {
+  // ~`waves` CTAs per SM worth of (shape, tile group) work items, at least 2 tiles per CTA (the weight image load and, for
+  // the weight gradients, the atomic flush of the accumulator are amortised)
+  const int n_tiles = (N + PL_NT - 1) / PL_NT;
+  int groups = (waves * dpf_num_sms() + B - 1) / B;
+  groups = max(1, min(groups, (n_tiles + 1) / 2));
+  *tiles_per_cta = (n_tiles + groups - 1) / groups;
+  return (n_tiles + *tiles_per_cta - 1) / *tiles_per_cta;
+}
+
+}  // namespace
+
+// ===============================================================================================================
+// C ABI
+// ===============================================================================================================
+// bytes of the packed image of an [R x K] matrix (K in {64, 128, 256})
+DPF_API int dpf_pointnet_layer_image_bytes(int R, int K, long long* bytes) {
+  DPF_REQUIRE(bytes, DPF_ERR_NULL_PTR, "dpf_pointnet_layer_image_bytes: null out pointer");
+  DPF_REQUIRE(R > 0 && (K == 64 || K == 128 || K == 256), DPF_ERR_BAD_ARG, "dpf_pointnet_layer_image_bytes: R=%d K=%d", R, K);
+  *bytes = (long long)((R + 127) / 128) * 2 * (K / 64) * PL_KB;
+  return DPF_OK;
+}
+
+// W: matrix [R x K], element (r, k) at W[r * row_stride + k * col_stride] (so W^T needs no copy) -> image (256-byte aligned)
+DPF_API int dpf_pointnet_layer_pack(const float* W, int R, int K, long long row_stride, long long col_stride, void* image, void* stream) {
+  DPF_REQUIRE(W && image, DPF_ERR_NULL_PTR, "dpf_pointnet_layer_pack: null pointer");
+  DPF_REQUIRE(R > 0 && (K == 64 || K == 128 || K == 256), DPF_ERR_BAD_ARG, "dpf_pointnet_layer_pack: R=%d K=%d", R, K);
+  DPF_REQUIRE(((uintptr_t)image & 255) == 0, DPF_ERR_ALIGN, "dpf_pointnet_layer_pack: image alignment");
+  const int n = ((R + 127) / 128) * 128 * (K / 8);
+  pl_pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, R, K, row_stride, col_stride, (unsigned char*)image);
+  return dpf_check_launch("pl_pack_kernel");
+}
+
+// how the points of a shape are split over CTAs: `groups` work items per shape (the stat buffer has B * groups rows)
+DPF_API int dpf_pointnet_layer_groups(int B, int N, int* groups) {
+  DPF_REQUIRE(groups, DPF_ERR_NULL_PTR, "dpf_pointnet_layer_groups: null out pointer");
+  DPF_REQUIRE(B > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer_groups: B=%d N=%d", B, N);
+  int tpc;
+  *groups = pick_groups(B, N, &tpc);
+  return DPF_OK;
+}
+
+// Out (B, Mout, N) = image[Mout x K] f(in) with the loader `loader` (0 layer 0 from x (B,3,N), K = 64; 1 relu(sc z + sh) - sub of
+// in0 (B,K,N); 2 BatchNorm + ReLU backward of (in0 = dA, in1 = Z), both (B,K,N)); tab (K, 8) fp32 per-channel loader constants;
+// out nullable; row_off (Mout,) nullable; stat (B * groups, Mout, 3) {count, mean, M2} nullable (forward layers).
+DPF_API int dpf_pointnet_layer_gemm(int loader, int K, const float* in0, const float* in1, const float* tab, const void* image,
+                                    int B, int N, int Mout, float* out, const float* row_off, float* stat, void* stream) {
+  DPF_REQUIRE(in0 && tab && image && (out || stat), DPF_ERR_NULL_PTR, "dpf_pointnet_layer_gemm: null pointer");
+  DPF_REQUIRE(loader != LD_BNBWD || in1, DPF_ERR_NULL_PTR, "dpf_pointnet_layer_gemm: the backward loader needs Z");
+  DPF_REQUIRE(B > 0 && N > 0 && Mout > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer_gemm: bad sizes B=%d N=%d Mout=%d", B, N, Mout);
+  DPF_REQUIRE(((uintptr_t)image & 255) == 0 && ((uintptr_t)in0 & 15) == 0 && ((uintptr_t)in1 & 15) == 0 && ((uintptr_t)out & 15) == 0,
+              DPF_ERR_ALIGN, "dpf_pointnet_layer_gemm: alignment");
+  PlGemmArgs a{in0, in1, tab, (const unsigned char*)image, out, row_off, stat, B, N, Mout, 0, 0};
+  a.groups = pick_groups(B, N, &a.tiles_per_cta);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool st = stat != nullptr;
+  if (loader == LD_X3 && K == 64) return st ? pl_launch_gemm<64, LD_X3, true>(a, s) : pl_launch_gemm<64, LD_X3, false>(a, s);
+  if (loader == LD_AFFINE && K == 128) return st ? pl_launch_gemm<128, LD_AFFINE, true>(a, s) : pl_launch_gemm<128, LD_AFFINE, false>(a, s);
+  if (loader == LD_AFFINE && K == 256 && !st) return pl_launch_gemm<256, LD_AFFINE, false>(a, s);
+  if (loader == LD_BNBWD && K == 128 && !st) return pl_launch_gemm<128, LD_BNBWD, false>(a, s);
+  if (loader == LD_BNBWD && K == 256 && !st) return pl_launch_gemm<256, LD_BNBWD, false>(a, s);
+  DPF_REQUIRE(false, DPF_ERR_UNSUPPORTED, "dpf_pointnet_layer_gemm: no kernel for loader %d, K = %d, stats %d", loader, K, (int)st);
+  return DPF_ERR_UNSUPPORTED;
+}
+
+// out (MP, NQ) += sum over all points of P Q^T; P = BatchNorm + ReLU backward of (dA, Z) (B,MP,N) with p_tab, or (gram != 0)
+// the centred activations relu(sc z + sh) - sub of Z (B,MP,N) with Q = P; Q = layer 0 from x (NQ = 64, q_loader 0) or
+// relu(sc z + sh) - sub of q_in (B,NQ,N) (q_loader 1).  out is accumulated with float atomics: zero it first.
+DPF_API int dpf_pointnet_layer_wgrad(int MP, int NQ, int gram, int q_loader, const float* p_in0, const float* p_in1, const float* p_tab,
+                                     const float* q_in, const float* q_tab, int B, int N, float* out, void* stream) {
+  DPF_REQUIRE(p_in0 && p_tab && out && (gram || (p_in1 && q_in && q_tab)), DPF_ERR_NULL_PTR, "dpf_pointnet_layer_wgrad: null pointer");
+  DPF_REQUIRE(B > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer_wgrad: bad sizes B=%d N=%d", B, N);
+  DPF_REQUIRE(((uintptr_t)p_in0 & 15) == 0 && ((uintptr_t)p_in1 & 15) == 0 && ((uintptr_t)q_in & 15) == 0, DPF_ERR_ALIGN,
+              "dpf_pointnet_layer_wgrad: alignment");
+  PlWgradArgs a{p_in0, p_in1, p_tab, q_in, q_tab, out, B, N, 0, 0};
+  a.groups = pick_groups(B, N, &a.tiles_per_cta, 1);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (gram && MP == 256 && NQ == 256) return pl_launch_wgrad<256, LD_AFFINE, 256, LD_AFFINE, true>(a, s);
+  if (!gram && MP == 256 && NQ == 128 && q_loader == LD_AFFINE) return pl_launch_wgrad<256, LD_BNBWD, 128, LD_AFFINE, false>(a, s);
+  if (!gram && MP == 128 && NQ == 64 && q_loader == LD_X3) return pl_launch_wgrad<128, LD_BNBWD, 64, LD_X3, false>(a, s);
+  DPF_REQUIRE(false, DPF_ERR_UNSUPPORTED, "dpf_pointnet_layer_wgrad: no kernel for MP = %d, NQ = %d, gram %d, q_loader %d", MP, NQ, gram, q_loader);
+  return DPF_ERR_UNSUPPORTED;
+}
+
+// sums (C, 2) double += {sum dA [y > 0], sum dA [y > 0] (z - mu)} over all points, y = sc z + sh (tab as for loader 2)
+DPF_API int dpf_pointnet_bn_bwd_sums(const float* dA, const float* Z, const float* tab, int B, int C, int N, double* sums, void* stream) {
+  DPF_REQUIRE(dA && Z && tab && sums, DPF_ERR_NULL_PTR, "dpf_pointnet_bn_bwd_sums: null pointer");
+  DPF_REQUIRE(B > 0 && C > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_bn_bwd_sums: bad sizes");
+  pl_bn_bwd_sums_kernel<<<B * C, 128, 0, (cudaStream_t)stream>>>(dA, Z, tab, C, N, sums);
+  return dpf_check_launch("pl_bn_bwd_sums_kernel");
+}
+
+// sums (C, 4) double += {sum dA m, sum dA m x0, sum dA m x1, sum dA m x2}, m = [a . x + c > 0] (tab as for loader 0)
+DPF_API int dpf_pointnet_layer0_bwd_sums(const float* dA, const float* x, const float* tab, int B, int C, int N, double* sums, void* stream) {
+  DPF_REQUIRE(dA && x && tab && sums, DPF_ERR_NULL_PTR, "dpf_pointnet_layer0_bwd_sums: null pointer");
+  DPF_REQUIRE(B > 0 && C > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer0_bwd_sums: bad sizes");
+  pl_layer0_bwd_sums_kernel<<<B * C, 128, 0, (cudaStream_t)stream>>>(dA, x, tab, C, N, sums);
+  return dpf_check_launch("pl_layer0_bwd_sums_kernel");
+}

@@ -57,7 +57,7 @@ struct PtSmem {
 };
 
 __global__ void __launch_bounds__(PT_T, 1)
-pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restrict__ wimg, int B, int N,
+pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab, const unsigned char* __restrict__ wimg, int B, int N,
                     float* __restrict__ stat, float* __restrict__ vmax, float* __restrict__ vmin,
                     int* __restrict__ imax, int* __restrict__ imin) {
   extern __shared__ unsigned char smraw[];
@@ -91,6 +91,10 @@ pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restric
   // thread k owns input channel k: its 64 consecutive points of a tile are 16 independent 16-byte loads, all issued before
   // the first use and - for the NEXT tile - before this tile's UMMA wait and epilogue, so the global-load latency (the
   // kernel's top stall in ncu) overlaps the tensor-core work
+  // tab != null: h2 is the layer's PRE-BatchNorm input Z and the operand is relu(sc z + sh) (8 floats per channel, {sc, sh, ..});
+  // columns beyond N then hold relu(sh) instead of 0, which is harmless: the epilogue never reads them
+  const float in_sc = tab ? tab[tid * 8] : 1.f, in_sh = tab ? tab[tid * 8 + 1] : 0.f;
+  const bool in_act = tab != nullptr;
   float4 buf[16];
   auto load_tile = [&](int tile) {
     const int n0 = tile * PT_NT;
@@ -116,7 +120,11 @@ pool_forward_kernel(const float* __restrict__ h2, const unsigned char* __restric
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 a = buf[2 * q], c = buf[2 * q + 1];
-        const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        if (in_act) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(in_sc, v[e], in_sh), 0.f);
+        }
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -220,8 +228,10 @@ DPF_API int dpf_pointnet_pool_workspace_bytes(long long* bytes) {
 // merges the B equal-sized groups into the batch statistics), vmax / vmin (B,512) fp32 = max / min over the points of
 // h = W h2, imax / imin (B,512) int32 = their point indices (lowest index on exact ties).
 // workspace: dpf_pointnet_pool_workspace_bytes() bytes, 256-byte aligned (weight images).
-DPF_API int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, float* stat,
-                                      float* vmax, float* vmin, int* imax, int* imin, void* stream) {
+// in_tab (256, 8) fp32 nullable: per input channel {sc, sh, ...}: the operand is relu(sc h2 + sh) (h2 = the pre-BatchNorm
+// output of the layer before, its BatchNorm + ReLU applied on load)
+DPF_API int dpf_pointnet_pool_forward_ex(const float* h2, const float* in_tab, const float* W, int B, int N, void* workspace, float* stat,
+                                         float* vmax, float* vmin, int* imax, int* imin, void* stream) {
   DPF_REQUIRE(h2 && W && workspace && stat && vmax && vmin && imax && imin, DPF_ERR_NULL_PTR, "dpf_pointnet_pool_forward: null pointer");
   DPF_REQUIRE(B > 0 && N > 0 && B <= 65535, DPF_ERR_BAD_ARG, "dpf_pointnet_pool_forward: bad sizes B=%d N=%d", B, N);
   DPF_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)h2 & 15) == 0, DPF_ERR_ALIGN, "dpf_pointnet_pool_forward: workspace / h2 alignment");
@@ -235,6 +245,11 @@ DPF_API int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, in
     cudaFuncSetAttribute(pool_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  pool_forward_kernel<<<dim3(B, 4), PT_T, smem, s>>>(h2, (const unsigned char*)workspace, B, N, stat, vmax, vmin, imax, imin);
+  pool_forward_kernel<<<dim3(B, 4), PT_T, smem, s>>>(h2, in_tab, (const unsigned char*)workspace, B, N, stat, vmax, vmin, imax, imin);
   return dpf_check_launch("pool_forward_kernel");
+}
+
+DPF_API int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, float* stat,
+                                      float* vmax, float* vmin, int* imax, int* imin, void* stream) {
+  return dpf_pointnet_pool_forward_ex(h2, nullptr, W, B, N, workspace, stat, vmax, vmin, imax, imin, stream);
 }

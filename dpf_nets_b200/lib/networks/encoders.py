@@ -1,9 +1,10 @@
 """PointNet cloud encoder and latent feature heads with the reference's names / state_dict keys
 (lib/networks/encoders.py:9-83).  Eval mode: encoder + max-pool run as ONE fused tcgen05 kernel
-(dpf_pointnet_eval_forward, csrc/pointnet.cu).  Train mode (batch statistics, autograd): the last layer
-(256 -> 512, 76 % of the encoder's FLOPs) + BatchNorm + ReLU + max-pool is one tcgen05 kernel forward and an
-analytic sparse backward (ops/pointnet_pool.py: the (B,512,N) activation is never materialised); the three
-narrow layers before it still go through the library path (cuBLAS bmm + ATen batch-norm) - DESIGN.md section 7."""
+(dpf_pointnet_eval_forward, csrc/pointnet.cu).  Train mode (batch statistics, autograd): the whole encoder + max-pool is
+one autograd function over the library's own tcgen05 kernels (ops/pointnet_train.py: layer 0 analytic from the input
+moments, layers 1-2 as GEMM kernels with the BatchNorm + ReLU of the previous layer applied on load and the output
+statistics in the epilogue, the last layer + max-pool without materialising the (B,512,N) activation, fused dgrad / wgrad
+kernels backward); other widths, or an input that needs a gradient, keep the narrow layers on the library path."""
 import ctypes
 
 import torch
@@ -41,13 +42,22 @@ class PointNetCloudEncoder(nn.Module):
                 and self.n_features[-1] == 512 and input.dim() == 3 and hasattr(self.features, 'sd2')
                 and len(self.features) == 12)
 
+    fused_layers = True     # class switch: False keeps init_sd .. sd1 on the library path in train mode (tests compare both)
+
+    def _fused_all_layers_ok(self, input):
+        return (self.fused_layers and not input.requires_grad and self.init_n_channels == 3 and self.init_n_features == 64
+                and list(self.n_features) == [128, 256, 512])
+
     def global_features(self, input):
         """max over the points of forward(input): (B, 3, N) -> (B, n_features[-1]); what the models take
         from the encoder (reference models.py:130-131).  Eval mode without autograd runs the fused kernel
         (bf16 tensor cores, fp32 accumulation)."""
         if self._fused_train_ok(input):
-            from ...ops.pointnet_pool import pooled_bn_relu_max
             f = self.features
+            if self._fused_all_layers_ok(input):
+                from ...ops.pointnet_train import pointnet_train_forward
+                return pointnet_train_forward(input, [f.init_sd, f.sd0, f.sd1, f.sd2], [f.init_sd_bn, f.sd0_bn, f.sd1_bn, f.sd2_bn])
+            from ...ops.pointnet_pool import pooled_bn_relu_max
             h2 = f[:-3](input)                                   # init_sd .. sd1_relu: (B, 256, N)
             return pooled_bn_relu_max(h2, f.sd2.weight[0], f.sd2_bn)
         if not self._fused_ok(input):

@@ -22,10 +22,10 @@ import torch
 from .. import _lib
 
 
-def _pool_stats(h2, W):
-    """h2 (B,256,N), W (512,256) CUDA fp32 -> (mean (512,), biased var (512,) of h = W h2 over all B*N points, vmax, vmin
-    (B,512), imax, imin (B,512) i64)."""
-    _lib.require_cuda(h2, W)
+def pool_stats(h2, W, in_tab=None):
+    """h2 (B,256,N), W (512,256) CUDA fp32 -> (mean (512,), biased var (512,) of h = W a over all B*N points (double), vmax,
+    vmin (B,512), imax, imin (B,512) i64); a = h2, or relu(sc h2 + sh) with the per-channel table in_tab (256, 8) {sc, sh, ..}."""
+    _lib.require_cuda(h2, W, in_tab)
     B, Cin, N = h2.shape
     if Cin != 256 or tuple(W.shape) != (512, 256) or h2.dtype != torch.float32 or W.dtype != torch.float32:
         raise _lib.DpfNativeError("pointnet pool kernel is specialised on a 256 -> 512 last layer (got %s, %s)"
@@ -40,12 +40,62 @@ def _pool_stats(h2, W):
     imax = torch.empty((B, 512), dtype=torch.int32, device=dev)
     imin = torch.empty((B, 512), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        _lib.call("dpf_pointnet_pool_forward", h2, W, int(B), int(N), ws, stat, vmax, vmin, imax, imin, device=dev)
+        _lib.call("dpf_pointnet_pool_forward_ex", h2, in_tab, W, int(B), int(N), ws, stat, vmax, vmin, imax, imin, device=dev)
     # merge the B equal-sized groups (count N, mean, M2) into the batch statistics (Chan et al.), in double
     gm, gm2 = stat[..., 0].double(), stat[..., 1].double()
     mean = gm.mean(0)
     var = (gm2.sum(0) + N * ((gm - mean) ** 2).sum(0)) / float(B * N)
     return mean, var, vmax, vmin, imax.long(), imin.long()
+
+
+_pool_stats = pool_stats
+
+
+def pool_select(gamma, beta, mean64, var64, vmax, vmin, imax, imin, eps, dtype):
+    """BatchNorm + ReLU + max over the points from the per-(shape, channel) extrema -> (out (B,512), saved tensors
+    (mean, sigma, xhat, idx, y) for pool_backward)."""
+    mean, var = mean64.to(dtype), var64.clamp_min(0.0).to(dtype)
+    sigma = torch.sqrt(var + eps)
+    pos = gamma >= 0
+    hsel = torch.where(pos.unsqueeze(0), vmax.to(dtype), vmin.to(dtype))
+    idx = torch.where(pos.unsqueeze(0), imax, imin)
+    xhat = (hsel - mean) / sigma
+    y = xhat * gamma + beta
+    return torch.relu(y), (mean, sigma, xhat, idx, y)
+
+
+def pool_backward(h2, W, gamma, sel, dout, need_input=True, need_weight=True):
+    """-> (dh2 (B,256,N) | None, dW (512,256) | None, dgamma, dbeta); h2 = the layer's (post-ReLU) input activations."""
+    mean, sigma, xhat, idx, y = sel
+    B, Cin, N = h2.shape
+    M = B * N
+    d = dout * (y > 0).to(dout.dtype)                       # (B,C): cotangent of y at the selected point
+    dbeta = d.sum(0)
+    dgamma = (d * xhat).sum(0)
+    a1 = gamma * dbeta / M
+    a2 = gamma * dgamma / M
+    inv = 1.0 / sigma
+    coef = d * (gamma * inv)                                 # (B,C): dh at the selected point (before the batch terms)
+    dW = dh2 = None
+    if need_input or need_weight:
+        gidx = idx.unsqueeze(1).expand(B, Cin, idx.shape[1])        # (B,Cin,C)
+        S = h2.sum((0, 2))                                                       # (Cin,)
+        # CENTRED activations: h - mu = W (h2 - m) exactly, so the batch terms are formed from deviations and not from
+        # differences of large sums (W G - mu S^T cancels catastrophically in fp32 over 65 536 points)
+        hc = h2 - (S / M).view(1, Cin, 1)
+    if need_weight:
+        Gc = torch.matmul(hc, hc.transpose(1, 2)).sum(0)                         # (Cin,Cin) covariance-form Gram matrix
+        hsel_rows = torch.gather(h2, 2, gidx)                                    # (B,Cin,C): h2 at the selected points
+        T = torch.einsum('bc,bkc->ck', coef, hsel_rows)
+        dW = T - (a1 * inv).unsqueeze(1) * S.unsqueeze(0) - (a2 * inv * inv).unsqueeze(1) * torch.matmul(W, Gc)
+    if need_input:
+        w_scaled = W * (a2 * inv * inv).unsqueeze(1)                             # diag(a2/sigma^2) W
+        Cmat = torch.matmul(W.t(), w_scaled)                                     # (Cin,Cin)
+        const = torch.mv(W.t(), a1 * inv)                                        # (Cin,)
+        dh2 = -const.view(1, Cin, 1) - torch.matmul(Cmat, hc)
+        contrib = coef.unsqueeze(1) * W.t().unsqueeze(0)                         # (B,Cin,C): coef[b,c] W[c,k]
+        dh2.scatter_add_(2, gidx, contrib)
+    return dh2, dW, dgamma, dbeta
 
 
 class PooledLastLayer(torch.autograd.Function):
@@ -55,52 +105,17 @@ class PooledLastLayer(torch.autograd.Function):
     def forward(ctx, h2, W, gamma, beta, eps):
         h2 = h2.contiguous()
         W = W.contiguous()
-        B, _, N = h2.shape
-        M = B * N
-        mean64, var64, vmax, vmin, imax, imin = _pool_stats(h2.detach(), W.detach())
-        mean, var = mean64.to(h2.dtype), var64.clamp_min(0.0).to(h2.dtype)
-        sigma = torch.sqrt(var + eps)
-        pos = gamma >= 0
-        hsel = torch.where(pos.unsqueeze(0), vmax.to(h2.dtype), vmin.to(h2.dtype))
-        idx = torch.where(pos.unsqueeze(0), imax, imin)
-        xhat = (hsel - mean) / sigma
-        y = xhat * gamma + beta
-        out = torch.relu(y)
-        ctx.save_for_backward(h2, W, gamma, mean, sigma, xhat, idx, y)
+        mean64, var64, vmax, vmin, imax, imin = _pool_stats(h2.detach(), W.detach())     # module attribute: tests substitute it
+        out, sel = pool_select(gamma, beta, mean64, var64, vmax, vmin, imax, imin, eps, h2.dtype)
+        ctx.save_for_backward(h2, W, gamma, *sel)
+        mean, var = sel[0], var64.clamp_min(0.0).to(h2.dtype)
         ctx.mark_non_differentiable(mean, var)
         return out, mean, var
 
     @staticmethod
     def backward(ctx, dout, _dmean, _dvar):
-        h2, W, gamma, mean, sigma, xhat, idx, y = ctx.saved_tensors
-        B, Cin, N = h2.shape
-        M = B * N
-        d = dout * (y > 0).to(dout.dtype)                       # (B,C): cotangent of y at the selected point
-        dbeta = d.sum(0)
-        dgamma = (d * xhat).sum(0)
-        a1 = gamma * dbeta / M
-        a2 = gamma * dgamma / M
-        inv = 1.0 / sigma
-        coef = d * (gamma * inv)                                 # (B,C): dh at the selected point (before the batch terms)
-        dW = dh2 = None
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            gidx = idx.unsqueeze(1).expand(B, Cin, idx.shape[1])        # (B,Cin,C)
-            S = h2.sum((0, 2))                                                       # (Cin,)
-            # CENTRED activations: h - mu = W (h2 - m) exactly, so the batch terms are formed from deviations and not from
-            # differences of large sums (W G - mu S^T cancels catastrophically in fp32 over 65 536 points)
-            hc = h2 - (S / M).view(1, Cin, 1)
-        if ctx.needs_input_grad[1]:
-            Gc = torch.matmul(hc, hc.transpose(1, 2)).sum(0)                         # (Cin,Cin) covariance-form Gram matrix
-            hsel_rows = torch.gather(h2, 2, gidx)                                    # (B,Cin,C): h2 at the selected points
-            T = torch.einsum('bc,bkc->ck', coef, hsel_rows)
-            dW = T - (a1 * inv).unsqueeze(1) * S.unsqueeze(0) - (a2 * inv * inv).unsqueeze(1) * torch.matmul(W, Gc)
-        if ctx.needs_input_grad[0]:
-            w_scaled = W * (a2 * inv * inv).unsqueeze(1)                             # diag(a2/sigma^2) W
-            Cmat = torch.matmul(W.t(), w_scaled)                                     # (Cin,Cin)
-            const = torch.mv(W.t(), a1 * inv)                                        # (Cin,)
-            dh2 = -const.view(1, Cin, 1) - torch.matmul(Cmat, hc)
-            contrib = coef.unsqueeze(1) * W.t().unsqueeze(0)                         # (B,Cin,C): coef[b,c] W[c,k]
-            dh2.scatter_add_(2, gidx, contrib)
+        h2, W, gamma, *sel = ctx.saved_tensors
+        dh2, dW, dgamma, dbeta = pool_backward(h2, W, gamma, sel, dout, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dh2, dW, dgamma, dbeta, None
 
 

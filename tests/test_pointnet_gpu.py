@@ -112,12 +112,17 @@ def test_pool_statistics_kernel_vs_torch(native_lib, cuda, B, N):
     assert int(imax.min()) >= 0 and int(imax.max()) < N and int(imin.min()) >= 0 and int(imin.max()) < N
 
 
+@pytest.mark.parametrize("fused_layers", [False, True])
 @pytest.mark.parametrize("B,N", [(4, 300), (32, 2048)])
-def test_train_mode_fused_last_layer_vs_library_path(native_lib, cuda, B, N):
+def test_train_mode_fused_last_layer_vs_library_path(native_lib, cuda, B, N, fused_layers, monkeypatch):
     """Train-mode global_features: fused last layer + BatchNorm (batch statistics) + ReLU + max-pool with the analytic
     backward (ops/pointnet_pool.py) against the library path of the same module (SharedDot -> BatchNorm1d -> ReLU -> max,
     the reference's chain: encoders.py:9-28, models.py:130-131; pinned to the reference on CPU): pooled features,
     running statistics and the gradients of EVERY encoder parameter."""
+    from dpf_nets_b200.lib.networks.encoders import PointNetCloudEncoder
+    # fused_layers: the whole encoder as one autograd function over the library's kernels (ops/pointnet_train.py: narrow layers
+    # forward + backward as tcgen05 kernels); False: only the last layer + max-pool fused (ops/pointnet_pool.py)
+    monkeypatch.setattr(PointNetCloudEncoder, "fused_layers", fused_layers)
     enc = make_encoder(cuda, 11)
     with torch.no_grad():                     # both signs of gamma in the last BatchNorm: max- and min-selected channels
         enc.features.sd2_bn.weight.mul_(torch.where(torch.rand(512, device=cuda) < 0.3, -1.0, 1.0))
@@ -203,3 +208,132 @@ def test_train_mode_fused_last_layer_is_faster(native_lib, cuda):
         times[prec] = a.elapsed_time(b) / 10
     print("pointnet train fwd+bwd 32x2048: library path %.3f ms, fused last layer %.3f ms" % (times["fp32"], times["auto"]))
     assert times["auto"] < times["fp32"]
+
+
+def _tables(gen, C, cuda):
+    sc = (torch.rand(C, generator=gen) + 0.5) * torch.where(torch.rand(C, generator=gen) < 0.2, -1.0, 1.0)
+    sh = torch.randn(C, generator=gen) * 0.3
+    return sc.to(cuda), sh.to(cuda)
+
+
+@pytest.mark.parametrize("B,N", [(3, 200), (2, 333), (5, 1024)])
+def test_pointnet_layer_kernels_vs_float64(native_lib, cuda, B, N):
+    """csrc/pointnet_layers.cu unit by unit against float64 torch on the same tables: the three operand loaders (layer 0 from
+    the coordinates, BatchNorm + ReLU on load, BatchNorm + ReLU backward on load), the GEMM kernel (outputs, per-work-item
+    statistics merged like the product does, row offsets, padded output rows), the weight-gradient / Gram kernel and the two
+    streaming reductions.  Ragged tiles (N % 64 != 0) and the unaligned scalar path (N % 4 != 0) included."""
+    from dpf_nets_b200 import _lib
+    from dpf_nets_b200.ops import pointnet_train as pt
+    gen = torch.Generator().manual_seed(B * 1000 + N)
+    r = lambda *s: torch.randn(s, generator=gen)
+    x = (torch.rand((B, 3, N), generator=gen) - 0.5).to(cuda)
+    tol = 2e-5
+
+    def relerr(a, b):
+        return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+    # ---- loader 0 (layer 0 from x), K = 64 -> 128, statistics ----
+    a = (r(64, 3) * 1.5).to(cuda)
+    c = (r(64) * 0.3).to(cuda)
+    tab0 = pt._table(a[:, 0], a[:, 1], a[:, 2], c)
+    W1 = (r(128, 64) * 0.2).to(cuda)
+    Z1, st1 = pt._gemm(pt.LD_X3, 64, x, None, tab0, pt._image(W1, 128, 64, False), B, N, 128, want_stat=True)
+    A0 = torch.relu(torch.einsum('ci,bin->bcn', a.double(), x.double()) + c.double().view(1, -1, 1))
+    Z1_ref = torch.einsum('oc,bcn->bon', W1.double(), A0)
+    assert relerr(Z1, Z1_ref) < tol
+    mean1, var1 = pt._merge_stats(st1)
+    assert relerr(mean1, Z1_ref.mean((0, 2))) < 1e-5 and relerr(var1, Z1_ref.var((0, 2), unbiased=False)) < 1e-5
+    # ---- loader 1 (BatchNorm + ReLU on load), K = 128 -> 256, statistics ----
+    sc1, sh1 = _tables(gen, 128, cuda)
+    mu1 = Z1_ref.mean((0, 2))
+    tab1 = pt._table(sc1, sh1, None, None, None, mu1)
+    W2 = (r(256, 128) * 0.15).to(cuda)
+    Z1f = Z1_ref.float().contiguous()
+    Z2, st2 = pt._gemm(pt.LD_AFFINE, 128, Z1f, None, tab1, pt._image(W2, 256, 128, False), B, N, 256, want_stat=True)
+    A1 = torch.relu(Z1f.double() * sc1.double().view(1, -1, 1) + sh1.double().view(1, -1, 1))
+    Z2_ref = torch.einsum('oc,bcn->bon', W2.double(), A1)
+    assert relerr(Z2, Z2_ref) < tol
+    mean2, var2 = pt._merge_stats(st2)
+    assert relerr(mean2, Z2_ref.mean((0, 2))) < 1e-5 and relerr(var2, Z2_ref.var((0, 2), unbiased=False)) < 1e-5
+    # ---- loader 2 (BatchNorm + ReLU backward on load): dgrads K = 256 -> 128 and K = 128 -> 64 (padded rows), row offsets ----
+    Z2f = Z2_ref.float().contiguous()
+    sc2, sh2 = _tables(gen, 256, cuda)
+    mu2 = Z2_ref.mean((0, 2))
+    dA2 = r(B, 256, N).to(cuda)
+    g2, gm12, k22 = (r(256) * 0.5).to(cuda), (r(256) * 0.1).to(cuda), (r(256) * 0.1).to(cuda)
+    tabb2 = pt._table(sc2, sh2, g2, gm12, k22, mu2)
+
+    def bnbwd(dA, Z, sc, sh, g, gm1, k2, mu):
+        v = lambda t: t.double().view(1, -1, 1)
+        y = Z.double() * v(sc) + v(sh)
+        return torch.where(y > 0, v(g) * dA.double(), torch.zeros_like(y)) - v(gm1) - v(k2) * (Z.double() - v(mu))
+    dZ2 = bnbwd(dA2, Z2f, sc2, sh2, g2, gm12, k22, mu2)
+    roff = (r(128) * 0.2).to(cuda)
+    dA1, _ = pt._gemm(pt.LD_BNBWD, 256, dA2, Z2f, tabb2, pt._image(W2, 128, 256, True), B, N, 128, row_off=roff)
+    dA1_ref = torch.einsum('oc,bon->bcn', W2.double(), dZ2) + roff.double().view(1, -1, 1)
+    assert relerr(dA1, dA1_ref) < tol
+    g1, gm11, k21 = (r(128) * 0.5).to(cuda), (r(128) * 0.1).to(cuda), (r(128) * 0.1).to(cuda)
+    tabb1 = pt._table(sc1, sh1, g1, gm11, k21, mu1)
+    dA1f = dA1_ref.float().contiguous()
+    dZ1 = bnbwd(dA1f, Z1f, sc1, sh1, g1, gm11, k21, mu1)
+    dA0, _ = pt._gemm(pt.LD_BNBWD, 128, dA1f, Z1f, tabb1, pt._image(W1, 64, 128, True), B, N, 64)
+    assert relerr(dA0, torch.einsum('oc,bon->bcn', W1.double(), dZ1)) < tol
+    # ---- weight gradients and the Gram matrix ----
+    dW2 = torch.zeros((256, 128), device=cuda)
+    _lib.call("dpf_pointnet_layer_wgrad", 256, 128, 0, pt.LD_AFFINE, dA2, Z2f, tabb2, Z1f, tab1, B, N, dW2, device=cuda)
+    assert relerr(dW2, torch.einsum('bon,bcn->oc', dZ2, A1)) < tol
+    dW1 = torch.zeros((128, 64), device=cuda)
+    _lib.call("dpf_pointnet_layer_wgrad", 128, 64, 0, pt.LD_X3, dA1f, Z1f, tabb1, x, tab0, B, N, dW1, device=cuda)
+    assert relerr(dW1, torch.einsum('bon,bcn->oc', dZ1, A0)) < tol
+    sub = (r(256) * 0.2).to(cuda)
+    tabg = pt._table(sc2, sh2, sub)
+    G = torch.zeros((256, 256), device=cuda)
+    _lib.call("dpf_pointnet_layer_wgrad", 256, 256, 1, pt.LD_AFFINE, Z2f, None, tabg, None, None, B, N, G, device=cuda)
+    hc = torch.relu(Z2f.double() * sc2.double().view(1, -1, 1) + sh2.double().view(1, -1, 1)) - sub.double().view(1, -1, 1)
+    assert relerr(G, torch.einsum('bin,bjn->ij', hc, hc)) < tol
+    # ---- streaming reductions ----
+    s2 = torch.zeros((256, 2), dtype=torch.float64, device=cuda)
+    _lib.call("dpf_pointnet_bn_bwd_sums", dA2, Z2f, tabb2, B, 256, N, s2, device=cuda)
+    y2 = Z2f.double() * sc2.double().view(1, -1, 1) + sh2.double().view(1, -1, 1)
+    dm = torch.where(y2 > 0, dA2.double(), torch.zeros_like(y2))
+    assert relerr(s2[:, 0], dm.sum((0, 2))) < 1e-5 and relerr(s2[:, 1], (dm * (Z2f.double() - mu2.view(1, -1, 1))).sum((0, 2))) < 1e-5
+    s0 = torch.zeros((64, 4), dtype=torch.float64, device=cuda)
+    dA0f = dA0.contiguous()
+    _lib.call("dpf_pointnet_layer0_bwd_sums", dA0f, x, tab0, B, 64, N, s0, device=cuda)
+    y0 = torch.einsum('ci,bin->bcn', a.double(), x.double()) + c.double().view(1, -1, 1)
+    dm0 = torch.where(y0 > 0, dA0f.double(), torch.zeros_like(y0))
+    assert relerr(s0[:, 0], dm0.sum((0, 2))) < 1e-5
+    assert relerr(s0[:, 1:], torch.einsum('bcn,bjn->cj', dm0, x.double())) < 1e-5
+
+
+def test_pointnet_train_function_float64_truth(native_lib, cuda):
+    """The fused train-mode encoder (ops/pointnet_train.py) and the library chain of the same module, both against the SAME
+    module evaluated in float64: the fused path may be no further from the truth than a small multiple of the library's own
+    fp32 result (pooled features, running statistics, gradients of all twelve parameter tensors in L2)."""
+    import copy
+    B, N = 8, 1024
+    enc = make_encoder(cuda, 21)
+    x = (torch.rand((B, 3, N), generator=torch.Generator().manual_seed(8)) - 0.5).to(cuda)
+    cot = torch.randn((B, 512), generator=torch.Generator().manual_seed(9)).to(cuda)
+    sd0 = {k: v.clone() for k, v in enc.state_dict().items()}
+
+    def run(module, xin, cotin, prec):
+        module.train()
+        module.precision = prec
+        module.zero_grad()
+        out = module.global_features(xin)
+        (out * cotin).sum().backward()
+        return out.detach(), {k: p.grad.clone() for k, p in module.named_parameters()}
+    enc64 = copy.deepcopy(enc).double()
+    truth = run(enc64, x.double(), cot.double(), "fp32")
+    res = {}
+    for prec in ("fp32", "auto"):
+        enc.load_state_dict(sd0)
+        res[prec] = run(enc, x, cot, prec)
+
+    def l2(a, b):
+        return float((a.double() - b).norm() / b.norm().clamp_min(1e-30))
+    for k in truth[1]:
+        e_lib, e_fused = l2(res["fp32"][1][k], truth[1][k]), l2(res["auto"][1][k], truth[1][k])
+        assert e_fused < max(5e-3, 4 * e_lib), (k, e_fused, e_lib)
+    assert l2(res["auto"][0], truth[0]) < max(1e-4, 4 * l2(res["fp32"][0], truth[0]))
