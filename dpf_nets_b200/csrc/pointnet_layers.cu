@@ -20,23 +20,19 @@
 // Plus two streaming reductions (BatchNorm-backward sums; layer 0's backward sums).
 #include "common.cuh"
 #include "umma.cuh"
+#include "pointnet_tiles.cuh"
 #include <math_constants.h>
 
 namespace {
 
-constexpr int PL_T = 256;                       // threads per CTA
-constexpr int PL_NT = 64;                       // points per tile
+constexpr int PL_T = pnt::T;                    // threads per CTA
+constexpr int PL_NT = pnt::NT;                  // points per tile
 constexpr uint32_t PL_KB = 128 * 128;           // 16 KB: [128 rows x 64 bf16] block of a K-major image
-constexpr int PL_TAB = 8;                       // floats per channel in a loader table
+constexpr int PL_TAB = pnt::TAB;                // floats per channel in a loader table (pointnet_tiles.cuh)
 constexpr uint64_t PL_DESC_K = umma::make_desc_template(16, 1024, umma::LAYOUT_SW128);        // K-major, 8-row groups 1024 B apart
 constexpr uint64_t PL_DESC_MN = umma::make_desc_template(1024, 1024, umma::LAYOUT_SW128);     // MN-major, one 64-wide block
 
-enum { LD_X3 = 0, LD_AFFINE = 1, LD_BNBWD = 2 };
-// loader tables, PL_TAB floats per channel:
-//   LD_X3     {a0, a1, a2, c, sub}:       v = relu(a0 x0 + a1 x1 + a2 x2 + c) - sub          (layer 0 with its BatchNorm folded in)
-//   LD_AFFINE {sc, sh, sub}:              v = relu(sc z + sh) - sub                          (sub: centring for the Gram form)
-//   LD_BNBWD  {sc, sh, g, gm1, k2, mu}:   v = (sc z + sh > 0 ? g dA : 0) - gm1 - k2 (z - mu) (BatchNorm + ReLU backward)
-template <int LOADER> struct LoaderInputs { static constexpr int n = LOADER == LD_X3 ? 3 : LOADER == LD_BNBWD ? 2 : 1; };
+using pnt::LD_X3; using pnt::LD_AFFINE; using pnt::LD_BNBWD;
 
 // ---------------------------------------------------------------------------------------------------------------
 // weight images: matrix [R x K] (element (r, k) at W[r * rs + k * cs], so that W and W^T share the code) ->
@@ -63,96 +59,13 @@ pl_pack_kernel(const float* __restrict__ W, int R, int K, long long rs, long lon
   *reinterpret_cast<uint4*>(base + half) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// operand tile builder: C channel rows x 64 points, this thread owns channel `ch` and PPT consecutive points
-// ---------------------------------------------------------------------------------------------------------------
-template <int C, int LOADER>
-struct TileLoader {
-  static constexpr int SEGS = PL_T / C;           // threads per channel row
-  static constexpr int PPT = PL_NT / SEGS;        // points per thread
-  static constexpr int NV = PPT / 4;              // float4 loads per input
-  static constexpr int NIN = LoaderInputs<LOADER>::n;
-  static_assert(C == 64 || C == 128 || C == 256, "channel rows per tile");
-  float4 buf[NIN][NV];
-  float t[6];
-  int ch, seg;
-  const float* src[NIN];
-  int N;
-  bool vec_ok;
-
-  __device__ __forceinline__ void init(const float* in0, const float* in1, const float* tab, int b, int Nn, int tid) {
-    ch = tid % C;
-    seg = tid / C;
-    N = Nn;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) t[j] = tab[ch * PL_TAB + j];
-    if (LOADER == LD_X3) {
-#pragma unroll
-      for (int j = 0; j < NIN; ++j) src[j] = in0 + ((size_t)b * 3 + j) * N;
-    } else {
-      src[0] = in0 + ((size_t)b * C + ch) * N;
-      if (NIN > 1) src[1] = in1 + ((size_t)b * C + ch) * N;
-    }
-    vec_ok = (N % 4) == 0;
-  }
-  __device__ __forceinline__ void load(int n0) {
-    const int base = n0 + seg * PPT;
-#pragma unroll
-    for (int j = 0; j < NIN; ++j) {
-#pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        const int n = base + q * 4;
-        if (vec_ok && n + 4 <= N) {
-          buf[j][q] = __ldg(reinterpret_cast<const float4*>(src[j] + n));
-        } else {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = (n + e < N) ? __ldg(src[j] + n + e) : 0.f;
-          buf[j][q] = make_float4(v[0], v[1], v[2], v[3]);
-        }
-      }
-    }
-  }
-  __device__ __forceinline__ float value(float i0, float i1, float i2) const {
-    if (LOADER == LD_X3) return fmaxf(fmaf(t[0], i0, fmaf(t[1], i1, fmaf(t[2], i2, t[3]))), 0.f) - t[4];
-    if (LOADER == LD_AFFINE) return fmaxf(fmaf(t[0], i0, t[1]), 0.f) - t[2];
-    // LD_BNBWD: i0 = dA, i1 = z
-    const float y = fmaf(t[0], i1, t[1]);
-    return (y > 0.f ? t[2] * i0 : 0.f) - t[3] - t[4] * (i1 - t[5]);
-  }
-  // bf16 hi | lo images of the tile; points beyond N are ZERO operands (they would otherwise enter the sums over points)
-  __device__ __forceinline__ void convert(unsigned char* hi_img, unsigned char* lo_img, int n0) const {
-    const int base = n0 + seg * PPT;
-#pragma unroll
-    for (int q = 0; q < NV / 2; ++q) {
-      float v[8];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 a0 = buf[0][2 * q + h];
-        const float4 a1 = NIN > 1 ? buf[NIN > 1 ? 1 : 0][2 * q + h] : a0;
-        const float4 a2 = NIN > 2 ? buf[NIN > 2 ? 2 : 0][2 * q + h] : a0;
-        v[4 * h + 0] = value(a0.x, a1.x, a2.x);
-        v[4 * h + 1] = value(a0.y, a1.y, a2.y);
-        v[4 * h + 2] = value(a0.z, a1.z, a2.z);
-        v[4 * h + 3] = value(a0.w, a1.w, a2.w);
-      }
-      if (base + q * 8 + 8 > N) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (base + q * 8 + e >= N) v[e] = 0.f;
-      }
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        hi[e] = umma::pack_bf16(v[2 * e], v[2 * e + 1]);
-        lo[e] = umma::pack_bf16(v[2 * e] - __uint_as_float(hi[e] << 16), v[2 * e + 1] - __uint_as_float(hi[e] & 0xffff0000u));
-      }
-      const uint32_t off = umma::sw128_offset(ch, seg * (PPT / 8) + q);
-      *reinterpret_cast<uint4*>(hi_img + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(lo_img + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-  }
-};
+// CTAs along the point tiles: the kernels hold an SM's shared memory (nearly) alone, so one CTA per SM and output chunk in
+// total, each with a contiguous range of the B * ceil(N / 64) tiles (at least 2 per CTA: the weight image load and the
+// weight gradients' atomic flush are amortised)
+int pl_ctas(int B, int N, int chunks) {
+  const int total = B * ((N + PL_NT - 1) / PL_NT);
+  return max(1, min((total + 1) / 2, max(1, dpf_num_sms() / chunks)));
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Out[M x pts] = Wimg[M x K] f(In[K x pts]) per tile of 64 points; CTA = (shape b, group of tiles) x (chunk of 128 output rows)
@@ -164,8 +77,8 @@ struct PlGemmArgs {
   const unsigned char* wimg;    // pl_pack_kernel image of the [Mout x K] matrix
   float* out;                   // (B, Mout, N) or null
   const float* row_off;         // (Mout,) added to every element of a row, or null
-  float* stat;                  // (B * groups, Mout, 3) {count, mean, sum of squared deviations} or null
-  int B, N, Mout, tiles_per_cta, groups;
+  float* stat;                  // (gridDim.x, Mout, 3) {count, mean, sum of squared deviations} or null
+  int B, N, Mout;
 };
 
 template <int K, int LOADER, bool STATS>
@@ -184,10 +97,12 @@ pl_gemm_kernel(const PlGemmArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int lane_c = tid & 127, part = tid >> 7, quarter = warp & 3;
-  const int b = blockIdx.x / a.groups, grp = blockIdx.x % a.groups, chunk = blockIdx.y;
+  const int chunk = blockIdx.y;
+  // the CTA's contiguous range of the B * n_tiles point tiles (tiles of all shapes in one flat index: balanced to one tile)
   const int n_tiles = (a.N + PL_NT - 1) / PL_NT;
-  const int t0 = grp * a.tiles_per_cta;
-  const int nt = max(0, min(a.tiles_per_cta, n_tiles - t0));
+  const int total = a.B * n_tiles;
+  const int t0 = (int)((long long)total * blockIdx.x / gridDim.x);
+  const int nt = (int)((long long)total * (blockIdx.x + 1) / gridDim.x) - t0;
   if (tid == 0) {
     umma::mbar_init(&bars[0], 1);
     umma::mbar_init(&bars[1], 1);
@@ -204,8 +119,8 @@ pl_gemm_kernel(const PlGemmArgs a) {
     umma::mbar_expect_tx(&bars[0], 2 * WHALF);
     umma::bulk_g2s(sA, a.wimg + (size_t)chunk * 2 * WHALF, 2 * WHALF, &bars[0]);
   }
-  TileLoader<K, LOADER> ld;
-  ld.init(a.in0, a.in1, a.tab, b, a.N, tid);
+  typename pnt::LoaderFor<K, LOADER>::type ld;
+  ld.init(a.in0, a.in1, a.tab, a.N, tid);
   constexpr uint32_t IDESC = umma::make_idesc_bf16(128, PL_NT, 0, 1);
 
   const int row = chunk * 128 + lane_c;
@@ -216,13 +131,13 @@ pl_gemm_kernel(const PlGemmArgs a) {
   uint32_t par[2] = {0u, 0u};
   const bool vec_ok = (a.N % 4) == 0;
 
-  if (nt > 0) ld.load(t0 * PL_NT);
+  if (nt > 0) ld.load(t0);
   for (int i = 0; i < nt + LAG; ++i) {
     if (i < nt) {
       unsigned char* st = sB + (size_t)(i % NST) * 2 * BHALF;
-      ld.convert(st, st + BHALF, (t0 + i) * PL_NT);
+      ld.template convert<false, false>(st, st + BHALF, t0 + i, nullptr);     // tail columns are never read back
       umma::fence_async_smem();
-      if (i + 1 < nt) ld.load((t0 + i + 1) * PL_NT);       // in flight under the UMMAs and the epilogue
+      if (i + 1 < nt) ld.load(t0 + i + 1);       // in flight under the UMMAs and the epilogue
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -251,7 +166,8 @@ pl_gemm_kernel(const PlGemmArgs a) {
       umma::fence_after_sync();
       float v[32];
       umma::tmem_ld32(tmem + lane_off + (uint32_t)(e & 1) * PL_NT + part * 32, v);
-      const int nbase = (t0 + e) * PL_NT + part * 32;
+      const int b = (t0 + e) / n_tiles;
+      const int nbase = (t0 + e - b * n_tiles) * PL_NT + part * 32;
       if (STATS) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -314,19 +230,20 @@ int pl_launch_gemm(const PlGemmArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(pl_gemm_kernel<K, LOADER, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  pl_gemm_kernel<K, LOADER, STATS><<<dim3(a.B * a.groups, (a.Mout + 127) / 128), PL_T, smem, s>>>(a);
+  pl_gemm_kernel<K, LOADER, STATS><<<dim3(pl_ctas(a.B, a.N, (a.Mout + 127) / 128), (a.Mout + 127) / 128), PL_T, smem, s>>>(a);
   return dpf_check_launch("pl_gemm_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // D[MP x NQ] += sum over the CTA's points of P[MP x pts] Q[NQ x pts]^T ; accumulated in TMEM over the CTA's tiles, then
-// added to `out` (MP x NQ row-major fp32) with float atomics.  GRAM: Q is P (one image, MP == NQ).
+// written as this CTA's partial sum (MP x NQ row-major fp32); a small kernel adds the partials to `out`.  GRAM: Q is P
+// (one image, MP == NQ).
 // ---------------------------------------------------------------------------------------------------------------
 struct PlWgradArgs {
   const float* p_in0; const float* p_in1; const float* p_tab;
   const float* q_in0; const float* q_tab;
-  float* out;                   // (MP, NQ), zero-initialised by the caller
-  int B, N, tiles_per_cta, groups;
+  float* partial;               // (gridDim.x, MP, NQ): this CTA's sum over its tiles (summed by pl_reduce_partials_kernel)
+  int B, N;
 };
 
 template <int MP, int PLOADER, int NQ, int QLOADER, bool GRAM>
@@ -343,10 +260,10 @@ pl_wgrad_kernel(const PlWgradArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int lane_c = tid & 127, part = tid >> 7, quarter = warp & 3;
-  const int b = blockIdx.x / a.groups, grp = blockIdx.x % a.groups;
   const int n_tiles = (a.N + PL_NT - 1) / PL_NT;
-  const int t0 = grp * a.tiles_per_cta;
-  const int nt = max(0, min(a.tiles_per_cta, n_tiles - t0));
+  const int total = a.B * n_tiles;
+  const int t0 = (int)((long long)total * blockIdx.x / gridDim.x);
+  const int nt = (int)((long long)total * (blockIdx.x + 1) / gridDim.x) - t0;
   if (tid == 0) {
     umma::mbar_init(&bars[0], 1);
     umma::mbar_init(&bars[1], 1);
@@ -360,16 +277,16 @@ pl_wgrad_kernel(const PlWgradArgs a) {
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
 
-  TileLoader<MP, PLOADER> lp;
-  lp.init(a.p_in0, a.p_in1, a.p_tab, b, a.N, tid);
-  TileLoader<GRAM ? MP : NQ, GRAM ? PLOADER : QLOADER> lq;
-  if (!GRAM) lq.init(a.q_in0, nullptr, a.q_tab, b, a.N, tid);
+  typename pnt::LoaderFor<MP, PLOADER>::type lp;
+  lp.init(a.p_in0, a.p_in1, a.p_tab, a.N, tid);
+  typename pnt::LoaderFor<GRAM ? MP : NQ, GRAM ? PLOADER : QLOADER>::type lq;
+  if (!GRAM) lq.init(a.q_in0, nullptr, a.q_tab, a.N, tid);
   constexpr uint32_t IDESC = umma::make_idesc_bf16(128, NQ, 0, 0);
   uint32_t par[2] = {0u, 0u};
 
   if (nt > 0) {
-    lp.load(t0 * PL_NT);
-    if (!GRAM) lq.load(t0 * PL_NT);
+    lp.load(t0);
+    if (!GRAM) lq.load(t0);
   }
   for (int i = 0; i < nt; ++i) {
     unsigned char* st = sm + (size_t)(i & 1) * STAGE;
@@ -377,12 +294,12 @@ pl_wgrad_kernel(const PlWgradArgs a) {
       umma::mbar_wait(&bars[i & 1], par[i & 1]);
       par[i & 1] ^= 1u;
     }
-    lp.convert(st, st + PHALF, (t0 + i) * PL_NT);
-    if (!GRAM) lq.convert(st + 2 * PHALF, st + 2 * PHALF + QHALF, (t0 + i) * PL_NT);
+    lp.template convert<true, false>(st, st + PHALF, t0 + i, nullptr);          // points beyond N must not enter the sums
+    if (!GRAM) lq.template convert<true, false>(st + 2 * PHALF, st + 2 * PHALF + QHALF, t0 + i, nullptr);
     umma::fence_async_smem();
     if (i + 1 < nt) {
-      lp.load((t0 + i + 1) * PL_NT);
-      if (!GRAM) lq.load((t0 + i + 1) * PL_NT);
+      lp.load(t0 + i + 1);
+      if (!GRAM) lq.load(t0 + i + 1);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -408,17 +325,24 @@ pl_wgrad_kernel(const PlWgradArgs a) {
   if (nt > 0) {
     umma::mbar_wait(&bars[2], 0);
     umma::fence_after_sync();
-    // lane = P row; this part adds half of the columns, 32 at a time
+  }
+  // lane = P row; this part stores half of the columns, 32 at a time (128 contiguous bytes per thread).  Per-CTA partials
+  // + a reduction kernel instead of float atomics: 148 CTAs x 32 768 .. 65 536 atomics on the same addresses were half
+  // of this kernel's time (ncu: lg_throttle on the REDs).
 #pragma unroll 1
-    for (int mc = 0; mc < MP / 128; ++mc) {
+  for (int mc = 0; mc < MP / 128; ++mc) {
 #pragma unroll 1
-      for (int c0 = part * 32; c0 < NQ; c0 += 64) {
-        float v[32];
+    for (int c0 = part * 32; c0 < NQ; c0 += 64) {
+      float v[32];
+      if (nt > 0) {
         umma::tmem_ld32(tmem + lane_off + mc * NQ + c0, v);
-        float* dst = a.out + (size_t)(mc * 128 + lane_c) * NQ + c0;
+      } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
+      float4* dst = reinterpret_cast<float4*>(a.partial + ((size_t)blockIdx.x * MP + mc * 128 + lane_c) * NQ + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
   }
   umma::fence_before_sync();
@@ -426,8 +350,26 @@ pl_wgrad_kernel(const PlWgradArgs a) {
   if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
 }
 
+// out[j] += sum over the CTAs' partials; the CTA range is split over blockIdx.y (4 atomics per address instead of 148)
+__global__ void __launch_bounds__(128)
+pl_reduce_partials_kernel(const float* __restrict__ partial, int n_ctas, int n4, float* __restrict__ out) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= n4) return;
+  const int c0 = (int)((long long)n_ctas * blockIdx.y / gridDim.y), c1 = (int)((long long)n_ctas * (blockIdx.y + 1) / gridDim.y);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int c = c0; c < c1; ++c) {
+    const float4 v = reinterpret_cast<const float4*>(partial)[(size_t)c * n4 + j];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  atomicAdd(out + 4 * j + 0, acc.x);
+  atomicAdd(out + 4 * j + 1, acc.y);
+  atomicAdd(out + 4 * j + 2, acc.z);
+  atomicAdd(out + 4 * j + 3, acc.w);
+}
+
 template <int MP, int PLOADER, int NQ, int QLOADER, bool GRAM>
-int pl_launch_wgrad(const PlWgradArgs& a, cudaStream_t s) {
+int pl_launch_wgrad(const PlWgradArgs& a, float* out, cudaStream_t s) {
   constexpr size_t smem = 1024 + 2 * (2 * (size_t)MP * 128 + (GRAM ? 0 : 2 * (size_t)NQ * 128)) + 64;
   static_assert(smem <= 232448, "wgrad stages exceed the shared memory of an SM");
   static bool attr = false;
@@ -435,8 +377,13 @@ int pl_launch_wgrad(const PlWgradArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(pl_wgrad_kernel<MP, PLOADER, NQ, QLOADER, GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  pl_wgrad_kernel<MP, PLOADER, NQ, QLOADER, GRAM><<<a.B * a.groups, PL_T, smem, s>>>(a);
-  return dpf_check_launch("pl_wgrad_kernel");
+  const int ctas = pl_ctas(a.B, a.N, 1);
+  pl_wgrad_kernel<MP, PLOADER, NQ, QLOADER, GRAM><<<ctas, PL_T, smem, s>>>(a);
+  int rc = dpf_check_launch("pl_wgrad_kernel");
+  if (rc) return rc;
+  const int n4 = MP * NQ / 4;
+  pl_reduce_partials_kernel<<<dim3((n4 + 127) / 128, 4), 128, 0, s>>>(a.partial, ctas, n4, out);
+  return dpf_check_launch("pl_reduce_partials_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -495,14 +442,140 @@ pl_layer0_bwd_sums_kernel(const float* __restrict__ dA, const float* __restrict_
   block_add_double(sums + (size_t)c * 4, acc, 4, scratch);
 }
 
-int pick_groups(int B, int N, int* tiles_per_cta, int waves = 2) {
-  // ~`waves` CTAs per SM worth of (shape, tile group) work items, at least 2 tiles per CTA (the weight image load and, for
-  // the weight gradients, the atomic flush of the accumulator are amortised)
-  const int n_tiles = (N + PL_NT - 1) / PL_NT;
-  int groups = (waves * dpf_num_sms() + B - 1) / B;
-  groups = max(1, min(groups, (n_tiles + 1) / 2));
-  *tiles_per_cta = (n_tiles + groups - 1) / groups;
-  return (n_tiles + *tiles_per_cta - 1) / *tiles_per_cta;
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-channel finalisation kernels (one thread per channel, double arithmetic): what would otherwise be ~150 tiny
+// library launches per training step between the big kernels
+// ---------------------------------------------------------------------------------------------------------------
+// moments of the cloud: sums[0..2] = sum x_i, sums[3..8] = sum x_i x_j (00 01 02 11 12 22) over all B * N points
+__global__ void __launch_bounds__(256)
+pl_input_moments_kernel(const float* __restrict__ x, int B, int N, double* __restrict__ sums) {
+  __shared__ double scratch[8 * 9];
+  double acc[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc[j] = 0.0;
+  const long long total = (long long)B * N;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < total; p += (long long)gridDim.x * 256) {
+    const int b = (int)(p / N), n = (int)(p - (long long)b * N);
+    const float* xb = x + (size_t)b * 3 * N + n;
+    const double x0 = xb[0], x1 = xb[N], x2 = xb[2 * (size_t)N];
+    acc[0] += x0; acc[1] += x1; acc[2] += x2;
+    acc[3] += x0 * x0; acc[4] += x0 * x1; acc[5] += x0 * x2; acc[6] += x1 * x1; acc[7] += x1 * x2; acc[8] += x2 * x2;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const double w = warp_sum_d(acc[j]);
+    if (lane == 0) scratch[warp * 9 + j] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += scratch[w * 9 + threadIdx.x];
+    atomicAdd(sums + threadIdx.x, t);
+  }
+}
+
+__device__ __forceinline__ void load_moments(const double* sums, double M, double xm[3], double cov[3][3]) {
+  for (int i = 0; i < 3; ++i) xm[i] = sums[i] / M;
+  const double s2[3][3] = {{sums[3], sums[4], sums[5]}, {sums[4], sums[6], sums[7]}, {sums[5], sums[7], sums[8]}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) cov[i][j] = s2[i][j] / M - xm[i] * xm[j];      // double: no cancellation issue at |x| ~ 1
+}
+
+// layer 0: analytic batch statistics mean_c = W0[c] . E[x], var_c = W0[c]^T Cov(x) W0[c] -> loader table {sc W0[c,:], beta - sc mean},
+// stats (C, 3) fp32 {mean, biased var, istd}
+__global__ void pl_layer0_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ W0, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, int C, double M, float eps, float* __restrict__ tab,
+                                          float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double xm[3], cov[3][3];
+  load_moments(sums, M, xm, cov);
+  const double w[3] = {W0[c * 3], W0[c * 3 + 1], W0[c * 3 + 2]};
+  double mean = 0.0, var = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    mean += w[i] * xm[i];
+    for (int j = 0; j < 3; ++j) var += w[i] * cov[i][j] * w[j];
+  }
+  var = fmax(var, 0.0);
+  const double istd = rsqrt(var + (double)eps);
+  const double sc = (double)gamma[c] * istd;
+  float* t = tab + (size_t)c * PL_TAB;
+  t[0] = (float)(sc * w[0]); t[1] = (float)(sc * w[1]); t[2] = (float)(sc * w[2]); t[3] = (float)((double)beta[c] - sc * mean);
+  t[4] = 0.f; t[5] = 0.f; t[6] = 0.f; t[7] = 0.f;
+  stats[c * 3] = (float)mean; stats[c * 3 + 1] = (float)var; stats[c * 3 + 2] = (float)istd;
+}
+
+// merge of the per-CTA {count, mean, M2} triples (Chan et al.) -> loader table {sc, sh, 0, 0, 0, mean}, stats (C, 3) {mean, biased var, istd}.
+// stride3 = 3: stat (G, C, 3) of pl_gemm_kernel; stride3 = 2: stat (G, C, 2) {mean, M2} of the pool kernel with `count` points each.
+__global__ void pl_stats_finalize_kernel(const float* __restrict__ stat, int G, int C, int stride3, float count, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float eps, float* __restrict__ tab, float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int g = 0; g < G; ++g) {
+    const float* e = stat + ((size_t)g * C + c) * stride3;
+    const double ng = stride3 == 3 ? (double)e[0] : (double)count;
+    const double mg = e[stride3 - 2], m2g = e[stride3 - 1];
+    if (ng > 0.0) {
+      const double nt = n + ng, delta = mg - mean;
+      mean += delta * (ng / nt);
+      m2 += m2g + delta * delta * (n * ng / nt);
+      n = nt;
+    }
+  }
+  const double var = n > 0.0 ? fmax(m2 / n, 0.0) : 0.0;
+  const double istd = rsqrt(var + (double)eps);
+  if (tab) {
+    const double sc = (double)gamma[c] * istd;
+    float* t = tab + (size_t)c * PL_TAB;
+    t[0] = (float)sc; t[1] = (float)((double)beta[c] - sc * mean); t[2] = 0.f; t[3] = 0.f; t[4] = 0.f; t[5] = (float)mean; t[6] = 0.f; t[7] = 0.f;
+  }
+  stats[c * 3] = (float)mean; stats[c * 3 + 1] = (float)var; stats[c * 3 + 2] = (float)istd;
+}
+
+// BatchNorm backward of a layer from the two sums: dbeta = s1, dgamma = s2 istd; loader-2 table {sc, sh, g, g m1, g m2 istd, mu}
+__global__ void pl_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ tab_fwd, const float* __restrict__ gamma,
+                                       const float* __restrict__ stats, int C, double M, float* __restrict__ tab_bwd,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double istd = stats[c * 3 + 2];
+  const double s1 = sums[c * 2], dg = sums[c * 2 + 1] * istd;
+  const double g = (double)gamma[c] * istd;
+  const float* tf = tab_fwd + (size_t)c * PL_TAB;
+  float* t = tab_bwd + (size_t)c * PL_TAB;
+  t[0] = tf[0]; t[1] = tf[1]; t[2] = (float)g; t[3] = (float)(g * s1 / M); t[4] = (float)(g * dg / M * istd); t[5] = tf[5]; t[6] = 0.f; t[7] = 0.f;
+  dgamma[c] = (float)dg;
+  dbeta[c] = (float)s1;
+}
+
+// layer 0 backward from its four sums per channel {S, T_0, T_1, T_2} and the input moments
+__global__ void pl_layer0_bwd_finalize_kernel(const double* __restrict__ sums4, const double* __restrict__ moments, const float* __restrict__ W0,
+                                              const float* __restrict__ gamma, const float* __restrict__ stats, int C, double M,
+                                              float* __restrict__ dW0, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double xm[3], cov[3][3];
+  load_moments(moments, M, xm, cov);
+  const double istd = stats[c * 3 + 2];
+  const double w[3] = {W0[c * 3], W0[c * 3 + 1], W0[c * 3 + 2]};
+  const double S = sums4[c * 4];
+  double Tc[3], dg = 0.0;
+  for (int j = 0; j < 3; ++j) {
+    Tc[j] = sums4[c * 4 + 1 + j] - S * xm[j];          // sum dy (x_j - mean_j)
+    dg += w[j] * Tc[j];
+  }
+  dg *= istd;
+  const double gi = (double)gamma[c] * istd;
+  for (int j = 0; j < 3; ++j) {
+    double wc = 0.0;
+    for (int i = 0; i < 3; ++i) wc += w[i] * cov[i][j];
+    dW0[c * 3 + j] = (float)(gi * (Tc[j] - dg * istd * wc));      // m2 istd M (W0 cov)_j with m2 = dg / M
+  }
+  dgamma[c] = (float)dg;
+  dbeta[c] = (float)S;
 }
 
 }  // namespace
@@ -528,18 +601,17 @@ DPF_API int dpf_pointnet_layer_pack(const float* W, int R, int K, long long row_
   return dpf_check_launch("pl_pack_kernel");
 }
 
-// how the points of a shape are split over CTAs: `groups` work items per shape (the stat buffer has B * groups rows)
-DPF_API int dpf_pointnet_layer_groups(int B, int N, int* groups) {
+// rows of the stat buffer of dpf_pointnet_layer_gemm: one per CTA along the point tiles
+DPF_API int dpf_pointnet_layer_groups(int B, int N, int Mout, int* groups) {
   DPF_REQUIRE(groups, DPF_ERR_NULL_PTR, "dpf_pointnet_layer_groups: null out pointer");
-  DPF_REQUIRE(B > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer_groups: B=%d N=%d", B, N);
-  int tpc;
-  *groups = pick_groups(B, N, &tpc);
+  DPF_REQUIRE(B > 0 && N > 0 && Mout > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer_groups: B=%d N=%d Mout=%d", B, N, Mout);
+  *groups = pl_ctas(B, N, (Mout + 127) / 128);
   return DPF_OK;
 }
 
 // Out (B, Mout, N) = image[Mout x K] f(in) with the loader `loader` (0 layer 0 from x (B,3,N), K = 64; 1 relu(sc z + sh) - sub of
 // in0 (B,K,N); 2 BatchNorm + ReLU backward of (in0 = dA, in1 = Z), both (B,K,N)); tab (K, 8) fp32 per-channel loader constants;
-// out nullable; row_off (Mout,) nullable; stat (B * groups, Mout, 3) {count, mean, M2} nullable (forward layers).
+// out nullable; row_off (Mout,) nullable; stat (dpf_pointnet_layer_groups, Mout, 3) {count, mean, M2} nullable (forward layers).
 DPF_API int dpf_pointnet_layer_gemm(int loader, int K, const float* in0, const float* in1, const float* tab, const void* image,
                                     int B, int N, int Mout, float* out, const float* row_off, float* stat, void* stream) {
   DPF_REQUIRE(in0 && tab && image && (out || stat), DPF_ERR_NULL_PTR, "dpf_pointnet_layer_gemm: null pointer");
@@ -547,8 +619,7 @@ DPF_API int dpf_pointnet_layer_gemm(int loader, int K, const float* in0, const f
   DPF_REQUIRE(B > 0 && N > 0 && Mout > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer_gemm: bad sizes B=%d N=%d Mout=%d", B, N, Mout);
   DPF_REQUIRE(((uintptr_t)image & 255) == 0 && ((uintptr_t)in0 & 15) == 0 && ((uintptr_t)in1 & 15) == 0 && ((uintptr_t)out & 15) == 0,
               DPF_ERR_ALIGN, "dpf_pointnet_layer_gemm: alignment");
-  PlGemmArgs a{in0, in1, tab, (const unsigned char*)image, out, row_off, stat, B, N, Mout, 0, 0};
-  a.groups = pick_groups(B, N, &a.tiles_per_cta);
+  PlGemmArgs a{in0, in1, tab, (const unsigned char*)image, out, row_off, stat, B, N, Mout};
   cudaStream_t s = (cudaStream_t)stream;
   const bool st = stat != nullptr;
   if (loader == LD_X3 && K == 64) return st ? pl_launch_gemm<64, LD_X3, true>(a, s) : pl_launch_gemm<64, LD_X3, false>(a, s);
@@ -560,21 +631,30 @@ DPF_API int dpf_pointnet_layer_gemm(int loader, int K, const float* in0, const f
   return DPF_ERR_UNSUPPORTED;
 }
 
+// bytes of the scratch buffer of dpf_pointnet_layer_wgrad (per-CTA partial sums)
+DPF_API int dpf_pointnet_layer_wgrad_scratch_bytes(int MP, int NQ, int B, int N, long long* bytes) {
+  DPF_REQUIRE(bytes, DPF_ERR_NULL_PTR, "dpf_pointnet_layer_wgrad_scratch_bytes: null out pointer");
+  DPF_REQUIRE(MP > 0 && NQ > 0 && B > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer_wgrad_scratch_bytes: bad sizes");
+  *bytes = (long long)pl_ctas(B, N, 1) * MP * NQ * (long long)sizeof(float);
+  return DPF_OK;
+}
+
 // out (MP, NQ) += sum over all points of P Q^T; P = BatchNorm + ReLU backward of (dA, Z) (B,MP,N) with p_tab, or (gram != 0)
 // the centred activations relu(sc z + sh) - sub of Z (B,MP,N) with Q = P; Q = layer 0 from x (NQ = 64, q_loader 0) or
-// relu(sc z + sh) - sub of q_in (B,NQ,N) (q_loader 1).  out is accumulated with float atomics: zero it first.
+// relu(sc z + sh) - sub of q_in (B,NQ,N) (q_loader 1).  out is ACCUMULATED into (zero it first); scratch:
+// dpf_pointnet_layer_wgrad_scratch_bytes() bytes, 16-byte aligned.
 DPF_API int dpf_pointnet_layer_wgrad(int MP, int NQ, int gram, int q_loader, const float* p_in0, const float* p_in1, const float* p_tab,
-                                     const float* q_in, const float* q_tab, int B, int N, float* out, void* stream) {
-  DPF_REQUIRE(p_in0 && p_tab && out && (gram || (p_in1 && q_in && q_tab)), DPF_ERR_NULL_PTR, "dpf_pointnet_layer_wgrad: null pointer");
+                                     const float* q_in, const float* q_tab, int B, int N, void* scratch, float* out, void* stream) {
+  DPF_REQUIRE(p_in0 && p_tab && out && scratch && (gram || (p_in1 && q_in && q_tab)), DPF_ERR_NULL_PTR, "dpf_pointnet_layer_wgrad: null pointer");
+  DPF_REQUIRE(((uintptr_t)scratch & 15) == 0 && ((uintptr_t)out & 15) == 0, DPF_ERR_ALIGN, "dpf_pointnet_layer_wgrad: scratch / out alignment");
   DPF_REQUIRE(B > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer_wgrad: bad sizes B=%d N=%d", B, N);
   DPF_REQUIRE(((uintptr_t)p_in0 & 15) == 0 && ((uintptr_t)p_in1 & 15) == 0 && ((uintptr_t)q_in & 15) == 0, DPF_ERR_ALIGN,
               "dpf_pointnet_layer_wgrad: alignment");
-  PlWgradArgs a{p_in0, p_in1, p_tab, q_in, q_tab, out, B, N, 0, 0};
-  a.groups = pick_groups(B, N, &a.tiles_per_cta, 1);
+  PlWgradArgs a{p_in0, p_in1, p_tab, q_in, q_tab, (float*)scratch, B, N};
   cudaStream_t s = (cudaStream_t)stream;
-  if (gram && MP == 256 && NQ == 256) return pl_launch_wgrad<256, LD_AFFINE, 256, LD_AFFINE, true>(a, s);
-  if (!gram && MP == 256 && NQ == 128 && q_loader == LD_AFFINE) return pl_launch_wgrad<256, LD_BNBWD, 128, LD_AFFINE, false>(a, s);
-  if (!gram && MP == 128 && NQ == 64 && q_loader == LD_X3) return pl_launch_wgrad<128, LD_BNBWD, 64, LD_X3, false>(a, s);
+  if (gram && MP == 256 && NQ == 256) return pl_launch_wgrad<256, LD_AFFINE, 256, LD_AFFINE, true>(a, out, s);
+  if (!gram && MP == 256 && NQ == 128 && q_loader == LD_AFFINE) return pl_launch_wgrad<256, LD_BNBWD, 128, LD_AFFINE, false>(a, out, s);
+  if (!gram && MP == 128 && NQ == 64 && q_loader == LD_X3) return pl_launch_wgrad<128, LD_BNBWD, 64, LD_X3, false>(a, out, s);
   DPF_REQUIRE(false, DPF_ERR_UNSUPPORTED, "dpf_pointnet_layer_wgrad: no kernel for MP = %d, NQ = %d, gram %d, q_loader %d", MP, NQ, gram, q_loader);
   return DPF_ERR_UNSUPPORTED;
 }
@@ -593,4 +673,50 @@ DPF_API int dpf_pointnet_layer0_bwd_sums(const float* dA, const float* x, const 
   DPF_REQUIRE(B > 0 && C > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_layer0_bwd_sums: bad sizes");
   pl_layer0_bwd_sums_kernel<<<B * C, 128, 0, (cudaStream_t)stream>>>(dA, x, tab, C, N, sums);
   return dpf_check_launch("pl_layer0_bwd_sums_kernel");
+}
+
+// ---- per-channel finalisation (tiny kernels; everything stays on the device) -------------------------------------
+// moments (9,) double += {sum x_i, sum x_i x_j (00 01 02 11 12 22)} over the B * N points of x (B,3,N): zero it first
+DPF_API int dpf_pointnet_input_moments(const float* x, int B, int N, double* moments, void* stream) {
+  DPF_REQUIRE(x && moments, DPF_ERR_NULL_PTR, "dpf_pointnet_input_moments: null pointer");
+  DPF_REQUIRE(B > 0 && N > 0, DPF_ERR_BAD_ARG, "dpf_pointnet_input_moments: bad sizes");
+  const long long total = (long long)B * N;
+  const int blocks = (int)((total + 256 * 4 - 1) / (256 * 4) < 2 * dpf_num_sms() ? (total + 256 * 4 - 1) / (256 * 4) : 2 * dpf_num_sms());
+  pl_input_moments_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, B, N, moments);
+  return dpf_check_launch("pl_input_moments_kernel");
+}
+
+// layer 0 (W0 (C,3)): tab (C,8) loader-0 table, stats (C,3) {mean, biased var, istd} from the input moments
+DPF_API int dpf_pointnet_layer0_finalize(const double* moments, const float* W0, const float* gamma, const float* beta, int C, int B, int N,
+                                         float eps, float* tab, float* stats, void* stream) {
+  DPF_REQUIRE(moments && W0 && gamma && beta && tab && stats, DPF_ERR_NULL_PTR, "dpf_pointnet_layer0_finalize: null pointer");
+  pl_layer0_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(moments, W0, gamma, beta, C, (double)B * N, eps, tab, stats);
+  return dpf_check_launch("pl_layer0_finalize_kernel");
+}
+
+// stat: (G, C, 3) {count, mean, M2} of dpf_pointnet_layer_gemm (width 3) or (G, C, 2) {mean, M2} with `count` points each of the
+// pool kernel (width 2) -> tab (C,8) loader-1 table {sc, sh, 0, 0, 0, mean} (nullable), stats (C,3) {mean, biased var, istd}
+DPF_API int dpf_pointnet_stats_finalize(const float* stat, int G, int C, int width, float count, const float* gamma, const float* beta, float eps,
+                                        float* tab, float* stats, void* stream) {
+  DPF_REQUIRE(stat && stats && (!tab || (gamma && beta)), DPF_ERR_NULL_PTR, "dpf_pointnet_stats_finalize: null pointer");
+  DPF_REQUIRE(G > 0 && C > 0 && (width == 2 || width == 3), DPF_ERR_BAD_ARG, "dpf_pointnet_stats_finalize: bad sizes");
+  pl_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stat, G, C, width, count, gamma, beta, eps, tab, stats);
+  return dpf_check_launch("pl_stats_finalize_kernel");
+}
+
+// sums (C,2) of dpf_pointnet_bn_bwd_sums -> dgamma, dbeta (C,) and the loader-2 table tab_bwd (C,8); tab_fwd: the layer's
+// loader-1 table, stats: its {mean, var, istd}
+DPF_API int dpf_pointnet_bwd_finalize(const double* sums, const float* tab_fwd, const float* gamma, const float* stats, int C, int B, int N,
+                                      float* tab_bwd, float* dgamma, float* dbeta, void* stream) {
+  DPF_REQUIRE(sums && tab_fwd && gamma && stats && tab_bwd && dgamma && dbeta, DPF_ERR_NULL_PTR, "dpf_pointnet_bwd_finalize: null pointer");
+  pl_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, tab_fwd, gamma, stats, C, (double)B * N, tab_bwd, dgamma, dbeta);
+  return dpf_check_launch("pl_bwd_finalize_kernel");
+}
+
+// layer 0 backward: sums4 (C,4) of dpf_pointnet_layer0_bwd_sums + the input moments -> dW0 (C,3), dgamma, dbeta (C,)
+DPF_API int dpf_pointnet_layer0_bwd_finalize(const double* sums4, const double* moments, const float* W0, const float* gamma, const float* stats,
+                                             int C, int B, int N, float* dW0, float* dgamma, float* dbeta, void* stream) {
+  DPF_REQUIRE(sums4 && moments && W0 && gamma && stats && dW0 && dgamma && dbeta, DPF_ERR_NULL_PTR, "dpf_pointnet_layer0_bwd_finalize: null pointer");
+  pl_layer0_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums4, moments, W0, gamma, stats, C, (double)B * N, dW0, dgamma, dbeta);
+  return dpf_check_launch("pl_layer0_bwd_finalize_kernel");
 }

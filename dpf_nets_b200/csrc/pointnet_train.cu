@@ -16,6 +16,7 @@
 //   three UMMA chains hi*hi + lo*hi + hi*lo (fp32-class accuracy: batch statistics divide by small deviations).
 #include "coupling.cuh"
 #include "umma.cuh"
+#include "pointnet_tiles.cuh"
 #include <math_constants.h>
 
 namespace {
@@ -56,10 +57,11 @@ struct PtSmem {
   uint32_t tmem_base;
 };
 
+template <bool IN_ACT>
 __global__ void __launch_bounds__(PT_T, 1)
 pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab, const unsigned char* __restrict__ wimg, int B, int N,
                     float* __restrict__ stat, float* __restrict__ vmax, float* __restrict__ vmin,
-                    int* __restrict__ imax, int* __restrict__ imin) {
+                    int* __restrict__ imax, int* __restrict__ imin, float* __restrict__ asum) {
   extern __shared__ unsigned char smraw[];
   PtSmem& s = *reinterpret_cast<PtSmem*>(smraw + ((1024u - (umma::smem_u32(smraw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -84,58 +86,28 @@ pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab,
   // then comes out of numbers of the size of the deviations, not of E[x^2] - mean^2 (batch statistics divide by it)
   float sum = 0.f, sq = 0.f, mx = -CUDART_INF_F, mn = CUDART_INF_F, shift = 0.f;
   int amx = 0, amn = 0, cnt = 0;
-  const float* hb = h2 + (size_t)b * PT_CIN * N;
   const int n_tiles = (N + PT_NT - 1) / PT_NT;
   uint32_t ph = 0;
-  const bool vec_ok = (N % 4) == 0;
   // thread k owns input channel k: its 64 consecutive points of a tile are 16 independent 16-byte loads, all issued before
   // the first use and - for the NEXT tile - before this tile's UMMA wait and epilogue, so the global-load latency (the
   // kernel's top stall in ncu) overlaps the tensor-core work
-  // tab != null: h2 is the layer's PRE-BatchNorm input Z and the operand is relu(sc z + sh) (8 floats per channel, {sc, sh, ..});
-  // columns beyond N then hold relu(sh) instead of 0, which is harmless: the epilogue never reads them
-  const float in_sc = tab ? tab[tid * 8] : 1.f, in_sh = tab ? tab[tid * 8 + 1] : 0.f;
-  const bool in_act = tab != nullptr;
-  float4 buf[16];
-  auto load_tile = [&](int tile) {
-    const int n0 = tile * PT_NT;
-    const float* src = hb + (size_t)tid * N + n0;
+  // tab != null: h2 is the layer's PRE-BatchNorm input Z and the operand is relu(sc z + sh) (8 floats per channel, {sc, sh, 0, ..});
+  // columns beyond N then hold relu(sh) instead of 0, which is harmless: the epilogue never reads them.
+  // Coalesced row loads + neighbour swap (pointnet_tiles.cuh); the NEXT tile's loads are issued before this tile's UMMA wait
+  // and epilogue, so the global-load latency overlaps the tensor-core work.
+  const bool want_asum = asum != nullptr && chunk == 0;
+  pnt::TileLoader<PT_CIN, IN_ACT ? pnt::LD_AFFINE : pnt::LD_RAW> ld;
+  ld.init(h2, nullptr, tab, N, tid);
+  float act_sum[PT_CIN / 32];       // per-slot sums of the operand over the valid points (the analytic backward's S)
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      if (vec_ok && n0 + q * 4 + 4 <= N) {
-        buf[q] = __ldg(reinterpret_cast<const float4*>(src + q * 4));
-      } else {
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = (n0 + q * 4 + e < N) ? __ldg(src + q * 4 + e) : 0.f;
-        buf[q] = make_float4(v[0], v[1], v[2], v[3]);
-      }
-    }
-  };
-  load_tile(0);
+  for (int i = 0; i < PT_CIN / 32; ++i) act_sum[i] = 0.f;
+  const int tile0 = b * n_tiles;    // flat tile index of the loaders
+  ld.load(tile0);
   for (int tile = 0; tile < n_tiles; ++tile) {
     const int n0 = tile * PT_NT;
     // ---- h2 tile -> bf16 hi | lo, MN-major (8 chunks of 16 bytes per K-row) ----
-    {
-      const int k = tid;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 a = buf[2 * q], c = buf[2 * q + 1];
-        float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-        if (in_act) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(in_sc, v[e], in_sh), 0.f);
-        }
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          hi[e] = umma::pack_bf16(v[2 * e], v[2 * e + 1]);
-          lo[e] = umma::pack_bf16(v[2 * e] - __uint_as_float(hi[e] << 16), v[2 * e + 1] - __uint_as_float(hi[e] & 0xffff0000u));
-        }
-        const uint32_t off = umma::sw128_offset(k, q);
-        *reinterpret_cast<uint4*>(s.Bt + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(s.Bt + PT_BIMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
-    }
+    if (want_asum) ld.template convert<false, true>(s.Bt, s.Bt + PT_BIMG, tile0 + tile, act_sum);
+    else ld.template convert<false, false>(s.Bt, s.Bt + PT_BIMG, tile0 + tile, nullptr);
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
@@ -156,7 +128,9 @@ pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab,
       }
       umma::mma_commit(&s.bar_mma);
     }
-    if (tile + 1 < n_tiles) load_tile(tile + 1);      // in flight during the UMMA chain and the epilogue
+    if (tile + 1 < n_tiles) {                         // in flight during the UMMA chain and the epilogue
+      ld.load(tile0 + tile + 1);
+    }
     umma::mbar_wait(&s.bar_mma, ph);
     ph ^= 1;
     umma::fence_after_sync();
@@ -181,6 +155,16 @@ pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab,
     }
     umma::fence_before_sync();
     __syncthreads();          // the accumulator and the tile buffer are free again
+  }
+  if (want_asum) {      // a slot's row is shared by the 8 lanes of the same parity in the same half-warp
+#pragma unroll
+    for (int i = 0; i < PT_CIN / 32; ++i) {
+      float v = act_sum[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      if ((tid & 14) == 0) asum[(size_t)b * PT_CIN + ld.slot_row(i)] = v;
+    }
   }
   // ---- combine the two point halves (part 0 holds the lower point indices of every tile: ties keep the lower index) ----
   // per thread: count, mean = shift + sum / cnt, M2 = sq - sum^2 / cnt (sum of squared deviations from that mean)
@@ -230,8 +214,9 @@ DPF_API int dpf_pointnet_pool_workspace_bytes(long long* bytes) {
 // workspace: dpf_pointnet_pool_workspace_bytes() bytes, 256-byte aligned (weight images).
 // in_tab (256, 8) fp32 nullable: per input channel {sc, sh, ...}: the operand is relu(sc h2 + sh) (h2 = the pre-BatchNorm
 // output of the layer before, its BatchNorm + ReLU applied on load)
+// asum (B, 256) fp32 nullable: per (shape, input channel) sum of the operand over the points.
 DPF_API int dpf_pointnet_pool_forward_ex(const float* h2, const float* in_tab, const float* W, int B, int N, void* workspace, float* stat,
-                                         float* vmax, float* vmin, int* imax, int* imin, void* stream) {
+                                         float* vmax, float* vmin, int* imax, int* imin, float* asum, void* stream) {
   DPF_REQUIRE(h2 && W && workspace && stat && vmax && vmin && imax && imin, DPF_ERR_NULL_PTR, "dpf_pointnet_pool_forward: null pointer");
   DPF_REQUIRE(B > 0 && N > 0 && B <= 65535, DPF_ERR_BAD_ARG, "dpf_pointnet_pool_forward: bad sizes B=%d N=%d", B, N);
   DPF_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)h2 & 15) == 0, DPF_ERR_ALIGN, "dpf_pointnet_pool_forward: workspace / h2 alignment");
@@ -242,14 +227,16 @@ DPF_API int dpf_pointnet_pool_forward_ex(const float* h2, const float* in_tab, c
   const size_t smem = sizeof(PtSmem) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(pool_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(pool_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(pool_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  pool_forward_kernel<<<dim3(B, 4), PT_T, smem, s>>>(h2, in_tab, (const unsigned char*)workspace, B, N, stat, vmax, vmin, imax, imin);
+  if (in_tab) pool_forward_kernel<true><<<dim3(B, 4), PT_T, smem, s>>>(h2, in_tab, (const unsigned char*)workspace, B, N, stat, vmax, vmin, imax, imin, asum);
+  else pool_forward_kernel<false><<<dim3(B, 4), PT_T, smem, s>>>(h2, in_tab, (const unsigned char*)workspace, B, N, stat, vmax, vmin, imax, imin, asum);
   return dpf_check_launch("pool_forward_kernel");
 }
 
 DPF_API int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, float* stat,
                                       float* vmax, float* vmin, int* imax, int* imin, void* stream) {
-  return dpf_pointnet_pool_forward_ex(h2, nullptr, W, B, N, workspace, stat, vmax, vmin, imax, imin, stream);
+  return dpf_pointnet_pool_forward_ex(h2, nullptr, W, B, N, workspace, stat, vmax, vmin, imax, imin, nullptr, stream);
 }

@@ -22,9 +22,10 @@ import torch
 from .. import _lib
 
 
-def pool_stats(h2, W, in_tab=None):
+def pool_stats(h2, W, in_tab=None, want_asum=False, merge=True):
     """h2 (B,256,N), W (512,256) CUDA fp32 -> (mean (512,), biased var (512,) of h = W a over all B*N points (double), vmax,
-    vmin (B,512), imax, imin (B,512) i64); a = h2, or relu(sc h2 + sh) with the per-channel table in_tab (256, 8) {sc, sh, ..}."""
+    vmin (B,512), imax, imin (B,512) i64[, asum (B,256): sum of a over the points]); a = h2, or relu(sc h2 + sh) with the
+    per-channel table in_tab (256, 8) {sc, sh, ..}."""
     _lib.require_cuda(h2, W, in_tab)
     B, Cin, N = h2.shape
     if Cin != 256 or tuple(W.shape) != (512, 256) or h2.dtype != torch.float32 or W.dtype != torch.float32:
@@ -39,13 +40,18 @@ def pool_stats(h2, W, in_tab=None):
     vmin = torch.empty((B, 512), dtype=torch.float32, device=dev)
     imax = torch.empty((B, 512), dtype=torch.int32, device=dev)
     imin = torch.empty((B, 512), dtype=torch.int32, device=dev)
+    asum = torch.empty((B, 256), dtype=torch.float32, device=dev) if want_asum else None
     with torch.cuda.device(dev):
-        _lib.call("dpf_pointnet_pool_forward_ex", h2, in_tab, W, int(B), int(N), ws, stat, vmax, vmin, imax, imin, device=dev)
+        _lib.call("dpf_pointnet_pool_forward_ex", h2, in_tab, W, int(B), int(N), ws, stat, vmax, vmin, imax, imin, asum, device=dev)
+    if not merge:       # raw per-shape {mean, M2} (B,512,2): the caller merges them (dpf_pointnet_stats_finalize)
+        res = (stat, vmax, vmin, imax.long(), imin.long())
+        return res + (asum,) if want_asum else res
     # merge the B equal-sized groups (count N, mean, M2) into the batch statistics (Chan et al.), in double
     gm, gm2 = stat[..., 0].double(), stat[..., 1].double()
     mean = gm.mean(0)
     var = (gm2.sum(0) + N * ((gm - mean) ** 2).sum(0)) / float(B * N)
-    return mean, var, vmax, vmin, imax.long(), imin.long()
+    res = (mean, var, vmax, vmin, imax.long(), imin.long())
+    return res + (asum,) if want_asum else res
 
 
 _pool_stats = pool_stats

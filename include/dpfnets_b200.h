@@ -172,9 +172,10 @@ int dpf_pointnet_pool_workspace_bytes(long long* bytes);
 int dpf_pointnet_pool_forward(const float* h2, const float* W, int B, int N, void* workspace, float* stat,
                               float* vmax, float* vmin, int* imax, int* imin, void* stream);
 /* in_tab (256, 8) fp32, nullable: per input channel {sc, sh, ...}; the operand is relu(sc h2 + sh), i.e. h2 is the
- * PRE-BatchNorm output of the layer before and its BatchNorm + ReLU are applied while the tile is loaded. */
+ * PRE-BatchNorm output of the layer before and its BatchNorm + ReLU are applied while the tile is loaded.
+ * asum (B, 256) fp32, nullable: per (shape, input channel) sum of the operand over the points (the analytic backward's S). */
 int dpf_pointnet_pool_forward_ex(const float* h2, const float* in_tab, const float* W, int B, int N, void* workspace, float* stat,
-                                 float* vmax, float* vmin, int* imax, int* imin, void* stream);
+                                 float* vmax, float* vmin, int* imax, int* imin, float* asum, void* stream);
 
 /* ---- PointNet cloud encoder, train mode: the narrow layers, forward and backward -------------
  * Replaces features.{init_sd, sd0, sd1}{, _bn, _relu} in .train() (lib/networks/encoders.py:9-28: SharedDot 3 -> 64 -> 128
@@ -187,20 +188,36 @@ int dpf_pointnet_pool_forward_ex(const float* h2, const float* in_tab, const flo
 int dpf_pointnet_layer_image_bytes(int R, int K, long long* bytes);
 /* W: matrix [R x K], element (r, k) at W[r * row_stride + k * col_stride] (W^T needs no copy); K in {64, 128, 256} */
 int dpf_pointnet_layer_pack(const float* W, int R, int K, long long row_stride, long long col_stride, void* image, void* stream);
-int dpf_pointnet_layer_groups(int B, int N, int* groups);
-/* out (B, Mout, N) = image[Mout x K] f(in); out nullable; row_off (Mout,) nullable; stat (B * groups, Mout, 3)
+int dpf_pointnet_layer_groups(int B, int N, int Mout, int* groups);   /* rows of the stat buffer below */
+/* out (B, Mout, N) = image[Mout x K] f(in); out nullable; row_off (Mout,) nullable; stat (groups, Mout, 3)
  * {count, mean, sum of squared deviations} per CTA work item, nullable (forward layers: loader 0 with K = 64, loader 1 with K = 128) */
 int dpf_pointnet_layer_gemm(int loader, int K, const float* in0, const float* in1, const float* tab, const void* image,
                             int B, int N, int Mout, float* out, const float* row_off, float* stat, void* stream);
-/* out (MP, NQ) += sum over all points of P Q^T (float atomics: zero it first).  gram = 0: P = loader 2 of (p_in0 = dA,
+int dpf_pointnet_layer_wgrad_scratch_bytes(int MP, int NQ, int B, int N, long long* bytes);
+/* out (MP, NQ) += sum over all points of P Q^T (accumulated: zero it first; scratch: per-CTA partial sums, 16-byte aligned).  gram = 0: P = loader 2 of (p_in0 = dA,
  * p_in1 = Z) (B,MP,N), Q = loader q_loader of q_in ((B,NQ,N), or x (B,3,N) with q_loader 0 and NQ = 64); gram = 1: P = Q =
  * loader 1 of p_in0 (B,256,N).  (MP, NQ, q_loader) in {(256,128,1), (128,64,0)} or gram with 256 x 256. */
 int dpf_pointnet_layer_wgrad(int MP, int NQ, int gram, int q_loader, const float* p_in0, const float* p_in1, const float* p_tab,
-                             const float* q_in, const float* q_tab, int B, int N, float* out, void* stream);
+                             const float* q_in, const float* q_tab, int B, int N, void* scratch, float* out, void* stream);
 /* sums (C, 2) double += {sum dA [y > 0], sum dA [y > 0] (z - mu)} over all points, y = sc z + sh (table of loader 2) */
 int dpf_pointnet_bn_bwd_sums(const float* dA, const float* Z, const float* tab, int B, int C, int N, double* sums, void* stream);
 /* sums (C, 4) double += {sum dA m, sum dA m x0, sum dA m x1, sum dA m x2}, m = [a . x + c > 0] (table of loader 0) */
 int dpf_pointnet_layer0_bwd_sums(const float* dA, const float* x, const float* tab, int B, int C, int N, double* sums, void* stream);
+
+/* per-channel finalisation kernels (everything between the big kernels stays on the device):
+ * input moments (9,) double {sum x_i, sum x_i x_j (00 01 02 11 12 22)} (accumulated: zero first); layer 0's analytic statistics
+ * and loader-0 table; merge of the per-CTA statistics into {mean, biased var, istd} + loader-1 table; BatchNorm-backward sums
+ * -> dgamma, dbeta, loader-2 table; layer 0's backward from its four sums per channel. */
+int dpf_pointnet_input_moments(const float* x, int B, int N, double* moments, void* stream);
+int dpf_pointnet_layer0_finalize(const double* moments, const float* W0, const float* gamma, const float* beta, int C, int B, int N,
+                                 float eps, float* tab, float* stats, void* stream);
+int dpf_pointnet_stats_finalize(const float* stat, int G, int C, int width, float count, const float* gamma, const float* beta, float eps,
+                                float* tab, float* stats, void* stream);
+int dpf_pointnet_bwd_finalize(const double* sums, const float* tab_fwd, const float* gamma, const float* stats, int C, int B, int N,
+                              float* tab_bwd, float* dgamma, float* dbeta, void* stream);
+int dpf_pointnet_layer0_bwd_finalize(const double* sums4, const double* moments, const float* W0, const float* gamma, const float* stats,
+                                     int C, int B, int N, float* dW0, float* dgamma, float* dbeta, void* stream);
+
 
 /* ---- Latent-side fused blocks -------------------------------------------
  * The shape-latent flows and feature heads work on (B,F) matrices with B = 32..64 rows; their module chains
