@@ -509,22 +509,32 @@ __global__ void pl_layer0_finalize_kernel(const double* __restrict__ sums, const
 
 // merge of the per-CTA {count, mean, M2} triples (Chan et al.) -> loader table {sc, sh, 0, 0, 0, mean}, stats (C, 3) {mean, biased var, istd}.
 // stride3 = 3: stat (G, C, 3) of pl_gemm_kernel; stride3 = 2: stat (G, C, 2) {mean, M2} of the pool kernel with `count` points each.
-__global__ void pl_stats_finalize_kernel(const float* __restrict__ stat, int G, int C, int stride3, float count, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, float eps, float* __restrict__ tab, float* __restrict__ stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+pl_stats_finalize_kernel(const float* __restrict__ stat, int G, int C, int stride3, float count, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, float* __restrict__ tab, float* __restrict__ stats) {
+  // one WARP per channel, the G groups strided over its lanes; two passes of plain sums (no serial dependency):
+  //   n = sum n_g, mean = sum n_g m_g / n, M2 = sum [M2_g + n_g (m_g - mean)^2]
+  const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int g = 0; g < G; ++g) {
+  double n = 0.0, nm = 0.0;
+  for (int g = lane; g < G; g += 32) {
     const float* e = stat + ((size_t)g * C + c) * stride3;
     const double ng = stride3 == 3 ? (double)e[0] : (double)count;
-    const double mg = e[stride3 - 2], m2g = e[stride3 - 1];
-    if (ng > 0.0) {
-      const double nt = n + ng, delta = mg - mean;
-      mean += delta * (ng / nt);
-      m2 += m2g + delta * delta * (n * ng / nt);
-      n = nt;
-    }
+    n += ng;
+    nm += ng * (double)e[stride3 - 2];
   }
+  n = warp_sum_d(n);
+  nm = warp_sum_d(nm);
+  const double mean = n > 0.0 ? nm / n : 0.0;
+  double m2 = 0.0;
+  for (int g = lane; g < G; g += 32) {
+    const float* e = stat + ((size_t)g * C + c) * stride3;
+    const double ng = stride3 == 3 ? (double)e[0] : (double)count;
+    const double d = (double)e[stride3 - 2] - mean;
+    m2 += (double)e[stride3 - 1] + ng * d * d;
+  }
+  m2 = warp_sum_d(m2);
+  if (lane != 0) return;
   const double var = n > 0.0 ? fmax(m2 / n, 0.0) : 0.0;
   const double istd = rsqrt(var + (double)eps);
   if (tab) {
@@ -700,7 +710,7 @@ DPF_API int dpf_pointnet_stats_finalize(const float* stat, int G, int C, int wid
                                         float* tab, float* stats, void* stream) {
   DPF_REQUIRE(stat && stats && (!tab || (gamma && beta)), DPF_ERR_NULL_PTR, "dpf_pointnet_stats_finalize: null pointer");
   DPF_REQUIRE(G > 0 && C > 0 && (width == 2 || width == 3), DPF_ERR_BAD_ARG, "dpf_pointnet_stats_finalize: bad sizes");
-  pl_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stat, G, C, width, count, gamma, beta, eps, tab, stats);
+  pl_stats_finalize_kernel<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(stat, G, C, width, count, gamma, beta, eps, tab, stats);
   return dpf_check_launch("pl_stats_finalize_kernel");
 }
 

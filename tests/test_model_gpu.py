@@ -207,7 +207,9 @@ def test_wholemodel_training_loss_and_gradients_vs_reference(native_lib, cuda, m
     got = torch.stack([l.detach().double().cpu() for l in losses])
     tol_loss = 1e-4 if fp32 else 5e-3
     assert ((got - fx["losses"]).abs() <= tol_loss * fx["losses"].abs()).all(), (got, fx["losses"])
-    assert rel(out["g_posterior_mus"], fx["g_posterior_mus"]) < 1e-4
+    # tensor path: the whole PointNet encoder runs on split-bf16 GEMMs (~1e-5 per layer), then the posterior head's
+    # batch-statistics BatchNorm over B = 6..8 shapes amplifies it (measured 4e-5 .. 1.1e-4)
+    assert rel(out["g_posterior_mus"], fx["g_posterior_mus"]) < (1e-4 if fp32 else 1e-3)
     gate(out["p_prior_samples"][0], fx["z"], t64["z"], 1e-3 if fp32 else 2e-2, "z")
     gate(out["p_prior_logvars"].tail_total, fx["sum_logvar"], t64["sum_logvar"], 1e-3 if fp32 else 2e-2, "sum_logvar")
     named = dict(m.named_parameters())
