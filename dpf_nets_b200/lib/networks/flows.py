@@ -68,6 +68,7 @@ class RealNVPFlow(_nn.Module):
         # index tensor and copy it to the GPU on every call - a sync per layer, and illegal under graph capture
         self.register_buffer('_keep_idx', _torch.tensor(self.keep_inds, dtype=_torch.long), persistent=False)
         self.register_buffer('_warp_idx', _torch.tensor(self.warp_inds, dtype=_torch.long), persistent=False)
+        self.register_buffer('_keep_idx32', _torch.tensor(self.keep_inds, dtype=_torch.int32), persistent=False)
         pos = _np.full(g_n_features, -1, dtype=_np.int32)
         pos[_np.asarray(self.warp_inds, dtype=_np.int64)] = _np.arange(len(self.warp_inds), dtype=_np.int32)
         self.register_buffer('_pos', _torch.from_numpy(pos), persistent=False)     # latent position -> index in the warp list / -1
@@ -84,6 +85,7 @@ class RealNVPFlow(_nn.Module):
             setattr(self, 'T_%s_0' % br, net)
 
     fused = True      # class switch: False keeps the plain module chain on the GPU too (tests compare both)
+    fused_layer = True      # class switch: False keeps the per-block fused kernels (BatchNorm + Swish, transform) with library GEMMs
 
     def _net(self, net, br, kept):
         """Linear -> BatchNorm1d + Swish (one fused kernel) -> Linear of one branch."""
@@ -94,7 +96,12 @@ class RealNVPFlow(_nn.Module):
     def forward(self, g, mode='direct'):
         if self.fused and g.is_cuda and g.dtype == _torch.float32 and g.dim() == 2:
             # fused path (csrc/latent.cu): BatchNorm + Swish and the whole transform are one kernel each, forward and backward
-            from ...ops.latent import latent_affine
+            from ...ops.latent import latent_affine, latent_flow_layer, latent_flow_layer_ok
+            nets = tuple((getattr(n, b + '_mlp0'), getattr(n, b + '_mlp0_bn'), getattr(n, b + '_mlp1'))
+                         for n, b in ((self.T_mu_0, 'mu'), (self.T_logvar_0, 'logvar')))
+            if self.fused_layer and latent_flow_layer_ok(g, nets):
+                # the whole layer, forward and backward, as one kernel each (csrc/latent_flow.cu)
+                return latent_flow_layer(g, nets, self._pos, self._keep_idx32, self.eps_value, mode)
             kept = g.index_select(1, self._keep_idx)
             raw_lv = self._net(self.T_logvar_0, 'logvar', kept)
             raw_mu = self._net(self.T_mu_0, 'mu', kept)

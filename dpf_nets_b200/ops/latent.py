@@ -88,3 +88,83 @@ def latent_affine(g, raw_mu, raw_lv, pos, eps, mode):
     if mode not in ("direct", "inverse"):
         raise ValueError(mode)
     return _LatentAffine.apply(g, raw_mu, raw_lv, pos, float(eps), mode == "inverse")
+
+
+def _ptrs(ts):
+    return (ctypes.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+
+
+class _LatentFlowLayer(torch.autograd.Function):
+    """One RealNVPFlow layer (csrc/latent_flow.cu): (g, [Wa, gamma, beta, Wb, bb] x {mu, logvar}) -> (g_out, mu, logvar)."""
+
+    @staticmethod
+    def forward(ctx, g, Wa0, ga0, be0, Wb0, bb0, Wa1, ga1, be1, Wb1, bb1, pos, keep_idx, rms, rvs, bn_eps, momentum, training, eps, inverse):
+        g = g.contiguous()
+        par = [t.detach().contiguous() for t in (Wa0, ga0, be0, Wb0, bb0, Wa1, ga1, be1, Wb1, bb1)]
+        B, D = g.shape
+        H, Kk = par[0].shape
+        Wn = par[3].shape[0]
+        dev = g.device
+        g_out, mu, lv = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g)
+        hpre = torch.empty((2, B, H), dtype=torch.float32, device=dev)
+        stat = torch.empty((2, 2, H), dtype=torch.float32, device=dev)
+        raw = torch.empty((2, B, Wn), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("dpf_latent_flow_forward", g, pos, keep_idx, _ptrs([par[0], par[5]]), _ptrs([par[1], par[6]]), _ptrs([par[2], par[7]]),
+                      _ptrs(rms), _ptrs(rvs), _ptrs([par[3], par[8]]), _ptrs([par[4], par[9]]), int(B), int(D), int(H), int(Kk), int(Wn),
+                      ctypes.c_float(bn_eps), ctypes.c_float(momentum), bool(training), ctypes.c_float(eps), bool(inverse),
+                      g_out, mu, lv, hpre, stat, raw, device=dev)
+        ctx.save_for_backward(g, pos, keep_idx, hpre, stat, raw, *par)
+        ctx.cfg = (bool(training), float(eps), bool(inverse))
+        ctx.set_materialize_grads(False)
+        return g_out, mu, lv
+
+    @staticmethod
+    def backward(ctx, dgo, dmu, dlv):
+        g, pos, keep_idx, hpre, stat, raw, *par = ctx.saved_tensors
+        training, eps, inverse = ctx.cfg
+        B, D = g.shape
+        H, Kk = par[0].shape
+        Wn = par[3].shape[0]
+        dev = g.device
+        dg = torch.empty_like(g)
+        grads = [torch.empty_like(t) for t in par]
+        c = lambda t: None if t is None else t.contiguous()
+        with torch.cuda.device(dev):
+            _lib.call("dpf_latent_flow_backward", c(dgo), c(dmu), c(dlv), g, pos, keep_idx, _ptrs([par[0], par[5]]), _ptrs([par[1], par[6]]),
+                      _ptrs([par[2], par[7]]), _ptrs([par[3], par[8]]), int(B), int(D), int(H), int(Kk), int(Wn), training,
+                      ctypes.c_float(eps), inverse, hpre, stat, raw, dg, _ptrs([grads[0], grads[5]]), _ptrs([grads[1], grads[6]]),
+                      _ptrs([grads[2], grads[7]]), _ptrs([grads[3], grads[8]]), _ptrs([grads[4], grads[9]]), device=dev)
+        return (dg, *grads, None, None, None, None, None, None, None, None, None)
+
+
+def latent_flow_layer_ok(g, nets):
+    """the one-kernel layer handles B <= 64 rows, hidden width % 8 == 0, kept / warped widths % 32 == 0, affine BatchNorm with
+    the same momentum in both branches."""
+    (l0a, bn_a, l1a), (l0b, bn_b, l1b) = nets
+    H, Kk = l0a.weight.shape
+    Wn = l1a.weight.shape[0]
+    return (g.shape[0] <= 64 and H % 8 == 0 and Kk % 32 == 0 and Wn % 32 == 0 and l0a.bias is None and l0b.bias is None
+            and l1a.bias is not None and l1b.bias is not None and bn_a.affine and bn_b.affine and bn_a.momentum == bn_b.momentum
+            and bn_a.eps == bn_b.eps and bn_a.training == bn_b.training and bn_a.track_running_stats == bn_b.track_running_stats
+            and (g.shape[0] > 1 or not bn_a.training))
+
+
+def latent_flow_layer(g, nets, pos, keep_idx, eps, mode):
+    """nets = ((Linear, BatchNorm1d, Linear) of the mu branch, the same of the logvar branch) -> (g_out, mu, logvar) with the
+    modules' train / eval semantics (running-statistics update, num_batches_tracked)."""
+    if mode not in ("direct", "inverse"):
+        raise ValueError(mode)
+    (l0a, bn_a, l1a), (l0b, bn_b, l1b) = nets
+    training = bn_a.training or not bn_a.track_running_stats
+    rms = rvs = [None, None]
+    momentum = 0.0
+    if bn_a.track_running_stats:
+        if bn_a.training:
+            bn_a.num_batches_tracked += 1
+            bn_b.num_batches_tracked += 1
+            momentum = bn_a.momentum if bn_a.momentum is not None else 1.0 / float(bn_a.num_batches_tracked)
+        rms, rvs = [bn_a.running_mean, bn_b.running_mean], [bn_a.running_var, bn_b.running_var]
+    return _LatentFlowLayer.apply(g, l0a.weight, bn_a.weight, bn_a.bias, l1a.weight, l1a.bias, l0b.weight, bn_b.weight, bn_b.bias,
+                                  l1b.weight, l1b.bias, pos, keep_idx, rms, rvs, float(bn_a.eps), float(momentum), training, float(eps),
+                                  mode == "inverse")

@@ -238,6 +238,26 @@ int dpf_latent_affine_backward(const float* dgo, const float* dmu_f, const float
                                const float* raw_lv, const int* pos, int B, int G, int W, float eps, int inverse, float* dg,
                                float* draw_mu, float* draw_lv, void* stream);
 
+/* ---- shape-latent flows: one RealNVPFlow coupling layer per kernel ----------------------------
+ * Replaces RealNVPFlow.forward (lib/networks/flows.py:163-213: per branch Linear -> BatchNorm1d -> Swish -> Linear, then
+ * logvar = log(eps + exp(.)), g_out = exp(+-logvar/2) g (+-) mu) and torch.autograd through it.  g (B,D), B <= 64; pos (D,)
+ * int32: index in the warp list or -1; keep_idx (Kk,) int32; per branch b in {0: mu, 1: logvar}: Wa[b] (H,Kk), gamma[b],
+ * beta[b] (H), rm[b], rv[b] (H; running statistics, updated in place in training mode when not null, read in eval mode),
+ * Wb[b] (Wn,H), bb[b] (Wn).  H % 8 == 0, Kk % 32 == 0, Wn % 32 == 0, else DPF_ERR_UNSUPPORTED.  The forward saves hpre
+ * (2,B,H), stat (2,2,H) {mean, istd} and raw (2,B,Wn) for the backward; fp32 CUDA-core arithmetic. */
+int dpf_latent_flow_forward(const float* g, const int* pos, const int* keep_idx, const float* const* Wa, const float* const* gamma,
+                            const float* const* beta, float* const* rm, float* const* rv, const float* const* Wb,
+                            const float* const* bb, int B, int D, int H, int Kk, int Wn, float bn_eps, float momentum, int training,
+                            float eps, int inverse, float* g_out, float* mu, float* lv, float* hpre, float* stat, float* raw,
+                            void* stream);
+/* cotangents dgo, dmu_f, dlv_f (B,D; each nullable = zero) -> dg (B,D) and per branch dWa (H,Kk), dgamma, dbeta (H), dWb (Wn,H), dbb (Wn) */
+int dpf_latent_flow_backward(const float* dgo, const float* dmu_f, const float* dlv_f, const float* g, const int* pos,
+                             const int* keep_idx, const float* const* Wa, const float* const* gamma, const float* const* beta,
+                             const float* const* Wb, int B, int D, int H, int Kk, int Wn, int training, float eps, int inverse,
+                             const float* hpre, const float* stat, const float* raw, float* dg, float* const* dWa,
+                             float* const* dgamma, float* const* dbeta, float* const* dWb, float* const* dbb, void* stream);
+
+
 /* Fused AMSGrad step with the reference's exact update (lib/networks/optimizers.py:53-74):
  * denom = sqrt(max_exp_avg_sq or exp_avg_sq)/bc2 + eps; p -= wd*p + lr*(exp_avg/bc1)/denom.
  * vmax may be NULL (amsgrad off); bc1 = 1-beta1^t, bc2 = sqrt(1-beta2^t). */

@@ -23,12 +23,17 @@ def _run(module, fused_classes, fused, fn):
             c.fused = o
 
 
-@pytest.mark.parametrize("G,B", [(16, 5), (128, 32), (512, 32)])
+@pytest.mark.parametrize("fused_layer", [True, False])
+@pytest.mark.parametrize("G,B", [(16, 5), (128, 32), (512, 32), (128, 64), (128, 33), (128, 2)])
 @pytest.mark.parametrize("mode", ["inverse", "direct"])
 @pytest.mark.parametrize("training", [True, False])
-def test_global_rnvp_decoder_fused_vs_module_chain(native_lib, cuda, G, B, mode, training):
+def test_global_rnvp_decoder_fused_vs_module_chain(native_lib, cuda, G, B, mode, training, fused_layer, monkeypatch):
     from dpf_nets_b200.lib.networks.decoders import GlobalRNVPDecoder
     from dpf_nets_b200.lib.networks.flows import RealNVPFlow
+    # fused_layer: every coupling layer as ONE kernel forward and ONE backward (csrc/latent_flow.cu; B <= 64, kept / warped
+    # widths multiples of 32 - G = 16 falls back to the block kernels); False: BatchNorm + Swish and the transform as
+    # kernels, the four Linear layers through the library
+    monkeypatch.setattr(RealNVPFlow, "fused_layer", fused_layer)
     torch.manual_seed(G + B)
     m = GlobalRNVPDecoder(3, 64 if G < 128 else 128, G, weight_std=0.05).to(cuda)
     with torch.no_grad():
@@ -93,10 +98,13 @@ def test_feature_encoder_fused_vs_module_chain(native_lib, cuda, deterministic, 
         assert (torch.equal(got[3][k], v) if "num_batches" in k else rel(got[3][k], v) < 1e-5), k
 
 
-def test_latent_blocks_launch_counts(native_lib, cuda):
-    """One coupling layer of the latent flow = 2 x bn_swish + 1 transform kernel forward, the same backward."""
+@pytest.mark.parametrize("fused_layer,n_launch", [(True, 1), (False, 3)])
+def test_latent_blocks_launch_counts(native_lib, cuda, fused_layer, n_launch, monkeypatch):
+    """One coupling layer of the latent flow = ONE kernel forward and ONE backward (csrc/latent_flow.cu); with the block
+    kernels only: 2 x bn_swish + 1 transform kernel forward, the same backward."""
     import ctypes
     from dpf_nets_b200.lib.networks.flows import RealNVPFlow
+    monkeypatch.setattr(RealNVPFlow, "fused_layer", fused_layer)
     m = RealNVPFlow(128, 128, warp_inds=list(range(0, 128, 2))).to(cuda).train()
     g = torch.randn((32, 128), device=cuda, requires_grad=True)
     n0, n1, n2 = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_longlong(0)
@@ -105,7 +113,7 @@ def test_latent_blocks_launch_counts(native_lib, cuda):
     native_lib.dpf_launch_count(ctypes.byref(n1))
     (out[0].sum() + out[2].sum()).backward()
     native_lib.dpf_launch_count(ctypes.byref(n2))
-    assert n1.value - n0.value == 3 and n2.value - n1.value == 3
+    assert n1.value - n0.value == n_launch and n2.value - n1.value == n_launch
 
 
 @pytest.mark.parametrize("B,F", [(2, 7), (32, 128), (33, 100), (64, 512), (65, 40), (256, 64)])
