@@ -517,6 +517,7 @@ def extras(model, dev, B, N, pk, flush):
                        "tensor_frac": samp * FLOP_PER_POINT_LAYER_FWD * 3 * N_FLOWS / 1e12 / pk["bf16_tflops_sustained"]}
     model.train()
     out["encoder_eval"] = encoder_eval(dev, B, N, flush)
+    out["encoder_train"] = encoder_train(dev, B, N, flush)
     S = 256
     A = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
     Bc = (torch.rand((S, N, 3), generator=gen) - 0.5).to(dev)
@@ -628,6 +629,34 @@ def encoder_eval(dev, B, N, flush):
     ms = res["fused_ms"]
     flop = 2.0 * (3 * 64 + 64 * 128 + 128 * 256 + 256 * 512) * B * N
     res.update({"value": B * N / (ms * 1e-3), "unit": "points/s", "tflops": flop / (ms * 1e-3) / 1e12})
+    return res
+
+
+def encoder_train(dev, B, N, flush):
+    """PointNet encoder + max-pool in TRAIN mode, forward + backward: the whole encoder as one autograd
+    function over the library's own tcgen05 kernels vs the library path of the same module (bmm + ATen batch-norm + clamp)."""
+    from dpf_nets_b200.lib.networks.encoders import PointNetCloudEncoder
+    torch.manual_seed(0)
+    enc = PointNetCloudEncoder(3, 64, [128, 256, 512]).to(dev).train()
+    x = (torch.rand((B, 3, N), generator=torch.Generator().manual_seed(3)) - 0.5).to(dev)
+    cot = torch.randn((B, 512), generator=torch.Generator().manual_seed(4)).to(dev)
+    res = {}
+    for name, prec in (("fused", "auto"), ("library_path", "fp32")):
+        enc.precision = prec
+
+        def step():
+            enc.zero_grad()
+            (enc.global_features(x) * cot).sum().backward()
+        for _ in range(3):
+            step()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        res[name + "_ms"] = sum(ts) / len(ts)
+    res.update({"value": B * N / (res["fused_ms"] * 1e-3), "unit": "points/s", "what": "forward + backward, eager launches"})
     return res
 
 

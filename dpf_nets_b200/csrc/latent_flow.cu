@@ -4,16 +4,27 @@
 //     logvar = log(eps + exp(raw_lv)),  g_out[warp] = exp(+-logvar / 2) g[warp] (+-) mu,  g_out[keep] = g[keep]
 // The library path is 4 GEMMs of 32 x 64 x 128 (SIMT sgemm, ~5 us of pure latency each), 2 BatchNorm + Swish kernels, the
 // transform and a handful of index ops per layer forward, and three times that backward: ~100 launches of a few us for a
-// MFLOP of work, 14 layers per training step.  Here the batch (B <= 64 shapes) lives in one CTA: LANE = BATCH ROW for every
-// product with a weight matrix (the weight elements are warp-uniform 16-byte loads straight from global memory / L2: each
-// element is read by exactly one warp, once), THREAD = COLUMN for the reductions over the batch (BatchNorm statistics, the
-// weight gradients).  fp32 CUDA-core arithmetic throughout: same accuracy class as the library path.
+// MFLOP of work, 14 layers per training step.
+//
+// Here a layer is one THREAD-BLOCK CLUSTER of 8 CTAs (a first version with one CTA per layer measured 27 / 70 us forward /
+// backward: one SM's instruction issue is the bound).  The hidden width is split over the CTAs: every CTA owns H / 8 hidden
+// columns per branch - its slices of Wa, of the BatchNorm statistics (the whole batch, B <= 64 shapes, lives in every CTA,
+// so the statistics need no exchange) and of Wb's columns - and the two places where all hidden columns meet go through
+// DISTRIBUTED SHARED MEMORY: forward, every CTA pushes its slice of s = swish(bn(hpre)) into all eight CTAs' copies before
+// the second product (each CTA then forms Wn / 8 output columns per branch and transforms those positions); backward, the
+// partial sums of d kept = d hpre Wa over the hidden slices are reduced by reading the eight CTAs' buffers.
+// LANE = BATCH ROW for the products with weight matrices (weight elements are warp-uniform shared-memory reads) and for the
+// BatchNorm reductions (warp shuffles); fp32 CUDA-core arithmetic throughout: same accuracy class as the library path.
 #include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int LF_T = 512;            // 16 warps
-constexpr int LF_CH = 8;             // columns per register-blocked chunk
+constexpr int LC_NC = 8;             // CTAs per cluster
+constexpr int LC_T = 256;            // threads per CTA (8 warps)
+constexpr int LC_CH = 4;             // columns per register-blocked chunk
 
 struct LfBranch {
   const float* Wa;                   // (H, Kk)
@@ -54,22 +65,23 @@ struct LfBwdArgs {
 
 __device__ __forceinline__ float sigmoid_(float z) { return 1.f / (1.f + expf(-z)); }
 
-// C[b][c] = sum_k A[b][k] W[c][k] for the rows b = lane + 32 r of a shared-memory matrix A (leading dimension lda, 16-byte
-// aligned rows) and 8 weight rows c (global memory, K contiguous floats each, 16-byte aligned): warp-uniform weight loads
+// acc[r][j] = sum_k A[lane + 32 r][k] W[j][k]: A in shared memory (leading dimension lda), 4 weight rows in shared memory
+// (warp-uniform 16-byte reads), K a multiple of 4
 template <int RB>
-__device__ __forceinline__ void rows_times_wrows(const float* __restrict__ A, int lda, int K, const float* (&w)[LF_CH], int lane,
-                                                 float (&acc)[RB][LF_CH]) {
+__device__ __forceinline__ void rows_times_wrows(const float* __restrict__ A, int lda, int K, const float* w0, int ldw, int lane,
+                                                 float (&acc)[RB][LC_CH]) {
 #pragma unroll
   for (int r = 0; r < RB; ++r)
 #pragma unroll
-    for (int j = 0; j < LF_CH; ++j) acc[r][j] = 0.f;
+    for (int j = 0; j < LC_CH; ++j) acc[r][j] = 0.f;
+#pragma unroll 2
   for (int k = 0; k < K; k += 4) {
     float4 av[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) av[r] = *reinterpret_cast<const float4*>(A + (size_t)(lane + 32 * r) * lda + k);
 #pragma unroll
-    for (int j = 0; j < LF_CH; ++j) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w[j] + k));
+    for (int j = 0; j < LC_CH; ++j) {
+      const float4 wv = *reinterpret_cast<const float4*>(w0 + (size_t)j * ldw + k);
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         acc[r][j] = fmaf(av[r].x, wv.x, acc[r][j]);
@@ -81,63 +93,73 @@ __device__ __forceinline__ void rows_times_wrows(const float* __restrict__ A, in
   }
 }
 
+__device__ __forceinline__ void copy4(float* dst, const float* __restrict__ src, int n4, int tid) {
+  for (int i = tid; i < n4; i += LC_T) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+}
+
 template <int RB>
-__global__ void __launch_bounds__(LF_T, 1)
+__global__ void __cluster_dims__(LC_NC, 1, 1) __launch_bounds__(LC_T, 1)
 latent_flow_fwd_kernel(const LfFwdArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rk = (int)cluster.block_rank();
   extern __shared__ __align__(16) float sm[];
   const int B = a.B, D = a.D, H = a.H, Kk = a.Kk, Wn = a.Wn;
   constexpr int BR = 32 * RB;
-  const int ldk = Kk + 4, ldh = H + 4, ldw = Wn + 4;
+  const int JS = H / LC_NC, WS = Wn / LC_NC;        // hidden / output columns per branch owned by this CTA
+  const int ldk = Kk + 4, ldh = H + 4;
   float* kept = sm;                          // [BR][ldk]
-  float* h = kept + BR * ldk;                // [2][BR][ldh]
-  float* raw = h + 2 * BR * ldh;             // [2][BR][ldw]
+  float* sW1 = kept + BR * ldk;              // [2][JS][Kk]   rows rk*JS.. of Wa
+  float* sW2 = sW1 + 2 * JS * Kk;            // [2][WS][H]    rows rk*WS.. of Wb
+  float* hl = sW2 + 2 * WS * H;              // [2][BR][JS]   own hidden slice: hpre -> s
+  float* s_all = hl + 2 * BR * JS;           // [2][BR][ldh]  all hidden columns (pushed by the eight CTAs)
+  float* rawl = s_all + 2 * BR * ldh;        // [2][BR][WS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < BR * Kk; i += LF_T) {
+  for (int i = tid; i < BR * Kk; i += LC_T) {
     const int b = i / Kk, k = i - b * Kk;
     kept[b * ldk + k] = b < B ? a.g[(size_t)b * D + a.keep_idx[k]] : 0.f;
   }
-  __syncthreads();
-  // ---- hpre = kept Wa^T, both branches: 2 H columns in chunks of 8 over the warps ----
-  for (int c0 = warp * LF_CH; c0 < 2 * H; c0 += (LF_T / 32) * LF_CH) {
-    const int br = c0 / H, j0 = c0 - br * H;
-    const float* Wa = br ? a.br[1].Wa : a.br[0].Wa;
-    const float* w[LF_CH];
 #pragma unroll
-    for (int j = 0; j < LF_CH; ++j) w[j] = Wa + (size_t)(j0 + j) * Kk;
-    float acc[RB][LF_CH];
-    rows_times_wrows<RB>(kept, ldk, Kk, w, lane, acc);
+  for (int br = 0; br < 2; ++br) {
+    copy4(sW1 + br * JS * Kk, (br ? a.br[1].Wa : a.br[0].Wa) + (size_t)rk * JS * Kk, JS * Kk / 4, tid);
+    copy4(sW2 + br * WS * H, (br ? a.br[1].Wb : a.br[0].Wb) + (size_t)rk * WS * H, WS * H / 4, tid);
+  }
+  cluster.sync();       // every CTA of the cluster has started (its shared memory may be written remotely from here on)
+  // ---- hpre = kept Wa^T on the own 2 JS columns ----
+  for (int c0 = warp * LC_CH; c0 < 2 * JS; c0 += (LC_T / 32) * LC_CH) {
+    const int br = c0 / JS, jl = c0 - br * JS;
+    float acc[RB][LC_CH];
+    rows_times_wrows<RB>(kept, ldk, Kk, sW1 + (size_t)(br * JS + jl) * Kk, Kk, lane, acc);
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       const int b = lane + 32 * r;
-      float* hr = h + ((size_t)br * BR + b) * ldh + j0;
-      *reinterpret_cast<float4*>(hr) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      *reinterpret_cast<float4*>(hr + 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
-      if (b < B) {
-        float* gp = a.hpre + ((size_t)br * B + b) * H + j0;
-        *reinterpret_cast<float4*>(gp) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-        *reinterpret_cast<float4*>(gp + 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
-      }
+      const float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      *reinterpret_cast<float4*>(hl + ((size_t)br * BR + b) * JS + jl) = v;
+      if (b < B) *reinterpret_cast<float4*>(a.hpre + ((size_t)br * B + b) * H + rk * JS + jl) = v;
     }
   }
   __syncthreads();
-  // ---- BatchNorm1d + Swish, one thread per (branch, feature) column ----
-  for (int c = tid; c < 2 * H; c += LF_T) {
-    const int br = c / H, j = c - br * H;
+  // ---- BatchNorm1d + Swish: a warp per column, lane = batch row, statistics by warp shuffles ----
+  for (int c = warp; c < 2 * JS; c += LC_T / 32) {
+    const int br = c / JS, jl = c - br * JS, j = rk * JS + jl;
     const LfBranch& P = br ? a.br[1] : a.br[0];
-    float* col = h + (size_t)br * BR * ldh + j;
+    float v[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) v[r] = (lane + 32 * r < B) ? hl[((size_t)br * BR + lane + 32 * r) * JS + jl] : 0.f;
     float mean, var;
     if (a.training) {
       float s = 0.f;
-      for (int b = 0; b < B; ++b) s += col[(size_t)b * ldh];
-      mean = s / (float)B;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) s += v[r];
+      mean = warp_sum(s) / (float)B;
       float q = 0.f;
-      for (int b = 0; b < B; ++b) {
-        const float d = col[(size_t)b * ldh] - mean;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float d = (lane + 32 * r < B) ? v[r] - mean : 0.f;
         q = fmaf(d, d, q);
       }
-      var = q / (float)B;
-      if (P.rm) {
+      var = warp_sum(q) / (float)B;
+      if (P.rm && lane == 0) {
         P.rm[j] = (1.f - a.momentum) * P.rm[j] + a.momentum * mean;
         P.rv[j] = (1.f - a.momentum) * P.rv[j] + a.momentum * var * ((float)B / (float)max(B - 1, 1));
       }
@@ -147,49 +169,58 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     }
     const float istd = 1.f / sqrtf(var + a.bn_eps);
     const float ga = P.gamma[j], be = P.beta[j];
-    a.stat[(size_t)(br * 2 + 0) * H + j] = mean;
-    a.stat[(size_t)(br * 2 + 1) * H + j] = istd;
-    for (int b = 0; b < B; ++b) {
-      const float z = fmaf((col[(size_t)b * ldh] - mean) * istd, ga, be);
-      col[(size_t)b * ldh] = z * sigmoid_(z);
+    if (lane == 0) {
+      a.stat[(size_t)(br * 2 + 0) * H + j] = mean;
+      a.stat[(size_t)(br * 2 + 1) * H + j] = istd;
     }
-    for (int b = B; b < BR; ++b) col[(size_t)b * ldh] = 0.f;
-  }
-  __syncthreads();
-  // ---- raw = s Wb^T + bb, both branches: 2 Wn columns ----
-  for (int c0 = warp * LF_CH; c0 < 2 * Wn; c0 += (LF_T / 32) * LF_CH) {
-    const int br = c0 / Wn, j0 = c0 - br * Wn;
-    const LfBranch& P = br ? a.br[1] : a.br[0];
-    const float* w[LF_CH];
-#pragma unroll
-    for (int j = 0; j < LF_CH; ++j) w[j] = P.Wb + (size_t)(j0 + j) * H;
-    float acc[RB][LF_CH];
-    rows_times_wrows<RB>(h + (size_t)br * BR * ldh, ldh, H, w, lane, acc);
-    float bias[LF_CH];
-#pragma unroll
-    for (int j = 0; j < LF_CH; ++j) bias[j] = P.bb[j0 + j];
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      const int b = lane + 32 * r;
-      float* rr = raw + ((size_t)br * BR + b) * ldw + j0;
+      const float z = fmaf((v[r] - mean) * istd, ga, be);
+      hl[((size_t)br * BR + lane + 32 * r) * JS + jl] = (lane + 32 * r < B) ? z * sigmoid_(z) : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- push the own slice of s into every CTA's copy (distributed shared memory, 16-byte stores) ----
+  {
+    const int q4 = JS / 4, n4 = 2 * BR * q4;
+    for (int i = tid; i < n4; i += LC_T) {
+      const int q = i % q4, row = i / q4;                       // row = br * BR + b
+      const float4 v = *reinterpret_cast<const float4*>(hl + (size_t)row * JS + 4 * q);
 #pragma unroll
-      for (int j = 0; j < LF_CH; ++j) rr[j] = acc[r][j] + bias[j];
-      if (b < B) {
-        float* gp = a.raw + ((size_t)br * B + b) * Wn + j0;
-#pragma unroll
-        for (int j = 0; j < LF_CH; ++j) gp[j] = acc[r][j] + bias[j];
+      for (int t = 0; t < LC_NC; ++t) {
+        float* dst = cluster.map_shared_rank(s_all, (unsigned)((rk + t) % LC_NC));
+        *reinterpret_cast<float4*>(dst + (size_t)row * ldh + rk * JS + 4 * q) = v;
       }
     }
   }
+  cluster.sync();
+  // ---- raw = s Wb^T + bb on the own 2 WS output columns ----
+  for (int c0 = warp * LC_CH; c0 < 2 * WS; c0 += (LC_T / 32) * LC_CH) {
+    const int br = c0 / WS, wl = c0 - br * WS;
+    const LfBranch& P = br ? a.br[1] : a.br[0];
+    float acc[RB][LC_CH];
+    rows_times_wrows<RB>(s_all + (size_t)br * BR * ldh, ldh, H, sW2 + (size_t)(br * WS + wl) * H, H, lane, acc);
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(P.bb + rk * WS + wl));
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int b = lane + 32 * r;
+      const float4 v = make_float4(acc[r][0] + bias.x, acc[r][1] + bias.y, acc[r][2] + bias.z, acc[r][3] + bias.w);
+      *reinterpret_cast<float4*>(rawl + ((size_t)br * BR + b) * WS + wl) = v;
+      if (b < B) *reinterpret_cast<float4*>(a.raw + ((size_t)br * B + b) * Wn + rk * WS + wl) = v;
+    }
+  }
   __syncthreads();
-  // ---- the transform (same arithmetic as latent_affine_fwd_kernel) ----
-  for (int e = tid; e < B * D; e += LF_T) {
+  // ---- the transform (same arithmetic as latent_affine_fwd_kernel): warped positions whose raw columns this CTA formed,
+  //      kept positions dealt round-robin ----
+  for (int e = tid; e < B * D; e += LC_T) {
     const int b = e / D, j = e - b * D;
     const int p = a.pos[j];
+    if (p >= 0 ? (p / WS != rk) : (j % LC_NC != rk)) continue;
     float m = 0.f, l = 0.f;
     if (p >= 0) {
-      m = raw[((size_t)0 * BR + b) * ldw + p];
-      l = logf(a.eps + expf(raw[((size_t)1 * BR + b) * ldw + p]));
+      const int wl = p - rk * WS;
+      m = rawl[((size_t)0 * BR + b) * WS + wl];
+      l = logf(a.eps + expf(rawl[((size_t)1 * BR + b) * WS + wl]));
     }
     const float gv = a.g[e];
     a.mu[e] = m;
@@ -199,45 +230,68 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
 }
 
 template <int RB>
-__global__ void __launch_bounds__(LF_T, 1)
+__global__ void __cluster_dims__(LC_NC, 1, 1) __launch_bounds__(LC_T, 1)
 latent_flow_bwd_kernel(const LfBwdArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rk = (int)cluster.block_rank();
   extern __shared__ __align__(16) float sm[];
   const int B = a.B, D = a.D, H = a.H, Kk = a.Kk, Wn = a.Wn;
   constexpr int BR = 32 * RB;
-  const int ldk = Kk + 4, ldh = H + 4, ldw = Wn + 4;
+  const int JS = H / LC_NC, KS = Kk / LC_NC;
+  const int ldk = Kk + 4, ldw = Wn + 4;
   float* kept = sm;                          // [BR][ldk]
-  float* S = kept + BR * ldk;                // [2][BR][ldh]   s = swish(y)
-  float* DY = S + 2 * BR * ldh;              // [2][BR][ldh]   swish'(y) -> d y -> d hpre
-  float* DR = DY + 2 * BR * ldh;             // [2][BR][ldw]   d raw
+  float* DR = kept + BR * ldk;               // [2][BR][ldw]  d raw, all output columns (formed by every CTA)
+  float* Sl = DR + 2 * BR * ldw;             // [2][BR][JS]   s = swish(y) of the own hidden columns
+  float* XH = Sl + 2 * BR * JS;              // [2][BR][JS]   xhat
+  float* DY = XH + 2 * BR * JS;              // [2][BR][JS]   swish'(y) -> d y -> d hpre
+  float* sWbT = DY + 2 * BR * JS;            // [2][Wn][JS]   columns rk*JS.. of Wb
+  float* sWa = sWbT + 2 * Wn * JS;           // [2][JS][Kk]   rows rk*JS.. of Wa
+  float* dkp = sWa + 2 * JS * Kk;            // [BR][ldk]     this CTA's partial d kept
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- 0. kept rows, recomputed activations ----
-  for (int i = tid; i < BR * Kk; i += LF_T) {
+  // ---- 0. operands ----
+  for (int i = tid; i < BR * Kk; i += LC_T) {
     const int b = i / Kk, k = i - b * Kk;
     kept[b * ldk + k] = b < B ? a.g[(size_t)b * D + a.keep_idx[k]] : 0.f;
   }
-  for (int i = tid; i < 2 * BR * H; i += LF_T) {
-    const int j = i % H, b = (i / H) % BR, br = i / (H * BR);
-    float s = 0.f, ds = 0.f;
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    copy4(sWa + br * JS * Kk, (br ? a.br[1].Wa : a.br[0].Wa) + (size_t)rk * JS * Kk, JS * Kk / 4, tid);
+    const float* Wb = br ? a.br[1].Wb : a.br[0].Wb;
+    const int q4 = JS / 4;
+    for (int i = tid; i < Wn * q4; i += LC_T) {
+      const int q = i % q4, w = i / q4;
+      *reinterpret_cast<float4*>(sWbT + ((size_t)br * Wn + w) * JS + 4 * q) =
+          __ldg(reinterpret_cast<const float4*>(Wb + (size_t)w * H + rk * JS + 4 * q));
+    }
+  }
+  for (int i = tid; i < 2 * BR * JS; i += LC_T) {
+    const int jl = i % JS, b = (i / JS) % BR, br = i / (JS * BR), j = rk * JS + jl;
+    float s = 0.f, ds = 0.f, xh = 0.f;
     if (b < B) {
       const LfBranch& P = br ? a.br[1] : a.br[0];
       const float mean = a.stat[(size_t)(br * 2 + 0) * H + j], istd = a.stat[(size_t)(br * 2 + 1) * H + j];
-      const float z = fmaf((a.hpre[((size_t)br * B + b) * H + j] - mean) * istd, P.gamma[j], P.beta[j]);
+      xh = (a.hpre[((size_t)br * B + b) * H + j] - mean) * istd;
+      const float z = fmaf(xh, P.gamma[j], P.beta[j]);
       const float sg = sigmoid_(z);
       s = z * sg;
       ds = sg + z * sg * (1.f - sg);
     }
-    S[((size_t)br * BR + b) * ldh + j] = s;
-    DY[((size_t)br * BR + b) * ldh + j] = ds;
+    Sl[i] = s;
+    XH[i] = xh;
+    DY[i] = ds;
   }
-  for (int i = tid; i < 2 * BR * ldw; i += LF_T) DR[i] = 0.f;
-  __syncthreads();
-  // ---- 1. the transform backward (same arithmetic as latent_affine_bwd_kernel): d raw, dg of the warped positions ----
-  for (int e = tid; e < B * D; e += LF_T) {
+  for (int i = tid; i < 2 * (BR - B) * ldw; i += LC_T) {        // rows beyond the batch are zero operands
+    const int br = i / ((BR - B) * ldw), rest = i - br * (BR - B) * ldw;
+    DR[((size_t)br * BR + B) * ldw + rest] = 0.f;
+  }
+  // ---- 1. the transform backward (same arithmetic as latent_affine_bwd_kernel): d raw in every CTA; dg of the warped
+  //         positions dealt round-robin (the kept ones are written in step 6) ----
+  for (int e = tid; e < B * D; e += LC_T) {
     const int b = e / D, j = e - b * D;
     const int p = a.pos[j];
+    if (p < 0) continue;
     const float d = a.dgo ? a.dgo[e] : 0.f;
-    if (p < 0) continue;                 // kept positions: written in step 6
     const float rw = a.raw[((size_t)1 * B + b) * Wn + p];
     const float ex = expf(rw);
     const float l = logf(a.eps + ex);
@@ -255,180 +309,173 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
       dm += d;
       dl += 0.5f * d * sc * gv;
     }
-    a.dg[e] = dgv;
+    if (j % LC_NC == rk) a.dg[e] = dgv;
     DR[((size_t)0 * BR + b) * ldw + p] = dm;
     DR[((size_t)1 * BR + b) * ldw + p] = dl * ex / (a.eps + ex);
   }
   __syncthreads();
-  // ---- 2. dbb = sum_b d raw;  dWb[w][j] = sum_b d raw[b][w] s[b][j]   (thread = (branch, j) column x 32 values of w) ----
-  for (int c = tid; c < 2 * Wn; c += LF_T) {
+  // ---- 2. dbb (its columns dealt over the CTAs);  dWb[w][own j] = sum_b d raw[b][w] s[b][j] ----
+  for (int c = rk * (2 * Wn / LC_NC) + tid; c < (rk + 1) * (2 * Wn / LC_NC); c += LC_T) {
     const int br = c / Wn, w = c - br * Wn;
     float s = 0.f;
     for (int b = 0; b < B; ++b) s += DR[((size_t)br * BR + b) * ldw + w];
     (br ? a.gr[1].dbb : a.gr[0].dbb)[w] = s;
   }
-  for (int item = tid; item < 2 * H * ((Wn + 31) / 32); item += LF_T) {
-    const int c = item % (2 * H), wblk = item / (2 * H);
-    const int br = c / H, j = c - br * H, w0 = wblk * 32;
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    const float* sc = S + (size_t)br * BR * ldh + j;
-    const float* dr = DR + (size_t)br * BR * ldw + w0;
-    for (int b = 0; b < B; ++b) {
-      const float sv = sc[(size_t)b * ldh];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 d4 = *reinterpret_cast<const float4*>(dr + (size_t)b * ldw + 4 * i);
-        acc[4 * i + 0] = fmaf(d4.x, sv, acc[4 * i + 0]);
-        acc[4 * i + 1] = fmaf(d4.y, sv, acc[4 * i + 1]);
-        acc[4 * i + 2] = fmaf(d4.z, sv, acc[4 * i + 2]);
-        acc[4 * i + 3] = fmaf(d4.w, sv, acc[4 * i + 3]);
+  {
+    const int q4 = JS / 4;
+    for (int i = tid; i < 2 * Wn * q4; i += LC_T) {
+      const int q = i % q4, w = (i / q4) % Wn, br = i / (q4 * Wn);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b = 0; b < B; ++b) {
+        const float d = DR[((size_t)br * BR + b) * ldw + w];
+        const float4 s4 = *reinterpret_cast<const float4*>(Sl + ((size_t)br * BR + b) * JS + 4 * q);
+        acc.x = fmaf(d, s4.x, acc.x); acc.y = fmaf(d, s4.y, acc.y); acc.z = fmaf(d, s4.z, acc.z); acc.w = fmaf(d, s4.w, acc.w);
       }
+      *reinterpret_cast<float4*>((br ? a.gr[1].dWb : a.gr[0].dWb) + (size_t)w * H + rk * JS + 4 * q) = acc;
     }
-    float* dWb = br ? a.gr[1].dWb : a.gr[0].dWb;
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (w0 + i < Wn) dWb[(size_t)(w0 + i) * H + j] = acc[i];
   }
-  // ---- 3. d y = swish'(y) * (d raw Wb): lanes = rows, 8 columns j per chunk, K = Wn ----
-  for (int c0 = warp * LF_CH; c0 < 2 * H; c0 += (LF_T / 32) * LF_CH) {
-    const int br = c0 / H, j0 = c0 - br * H;
-    const float* Wb = br ? a.br[1].Wb : a.br[0].Wb;
-    float acc[RB][LF_CH];
+  // ---- 3. d y = swish'(y) * (d raw Wb) on the own columns: lanes = rows, K = Wn ----
+  for (int c0 = warp * LC_CH; c0 < 2 * JS; c0 += (LC_T / 32) * LC_CH) {
+    const int br = c0 / JS, jl = c0 - br * JS;
+    float acc[RB][LC_CH];
 #pragma unroll
     for (int r = 0; r < RB; ++r)
 #pragma unroll
-      for (int j = 0; j < LF_CH; ++j) acc[r][j] = 0.f;
+      for (int j = 0; j < LC_CH; ++j) acc[r][j] = 0.f;
     const float* dr = DR + (size_t)br * BR * ldw;
+    const float* wt = sWbT + (size_t)br * Wn * JS + jl;
     for (int w = 0; w < Wn; w += 4) {
       float4 dv[RB];
 #pragma unroll
       for (int r = 0; r < RB; ++r) dv[r] = *reinterpret_cast<const float4*>(dr + (size_t)(lane + 32 * r) * ldw + w);
 #pragma unroll
       for (int ww = 0; ww < 4; ++ww) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wb + (size_t)(w + ww) * H + j0));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wb + (size_t)(w + ww) * H + j0 + 4));
+        const float4 wv = *reinterpret_cast<const float4*>(wt + (size_t)(w + ww) * JS);
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
           const float d = ww == 0 ? dv[r].x : ww == 1 ? dv[r].y : ww == 2 ? dv[r].z : dv[r].w;
-          acc[r][0] = fmaf(d, w0.x, acc[r][0]); acc[r][1] = fmaf(d, w0.y, acc[r][1]);
-          acc[r][2] = fmaf(d, w0.z, acc[r][2]); acc[r][3] = fmaf(d, w0.w, acc[r][3]);
-          acc[r][4] = fmaf(d, w1.x, acc[r][4]); acc[r][5] = fmaf(d, w1.y, acc[r][5]);
-          acc[r][6] = fmaf(d, w1.z, acc[r][6]); acc[r][7] = fmaf(d, w1.w, acc[r][7]);
+          acc[r][0] = fmaf(d, wv.x, acc[r][0]); acc[r][1] = fmaf(d, wv.y, acc[r][1]);
+          acc[r][2] = fmaf(d, wv.z, acc[r][2]); acc[r][3] = fmaf(d, wv.w, acc[r][3]);
         }
       }
     }
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      float* dy = DY + ((size_t)br * BR + lane + 32 * r) * ldh + j0;
-#pragma unroll
-      for (int j = 0; j < LF_CH; ++j) dy[j] *= acc[r][j];
+      float4* dy = reinterpret_cast<float4*>(DY + ((size_t)br * BR + lane + 32 * r) * JS + jl);
+      float4 v = *dy;
+      v.x *= acc[r][0]; v.y *= acc[r][1]; v.z *= acc[r][2]; v.w *= acc[r][3];
+      *dy = v;
     }
   }
   __syncthreads();
-  // ---- 4. BatchNorm backward per (branch, feature) column: dgamma, dbeta, d hpre (in place) ----
-  for (int c = tid; c < 2 * H; c += LF_T) {
-    const int br = c / H, j = c - br * H;
+  // ---- 4. BatchNorm backward: a warp per column, lane = batch row ----
+  for (int c = warp; c < 2 * JS; c += LC_T / 32) {
+    const int br = c / JS, jl = c - br * JS, j = rk * JS + jl;
     const LfBranch& P = br ? a.br[1] : a.br[0];
-    const float mean = a.stat[(size_t)(br * 2 + 0) * H + j], istd = a.stat[(size_t)(br * 2 + 1) * H + j];
-    const float ga = P.gamma[j];
-    float* col = DY + (size_t)br * BR * ldh + j;
-    const float* hp = a.hpre + (size_t)br * B * H + j;
+    const float istd = a.stat[(size_t)(br * 2 + 1) * H + j], ga = P.gamma[j];
+    float dz[RB], xh[RB];
     float dgam = 0.f, dbet = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float xh = (hp[(size_t)b * H] - mean) * istd;
-      const float dz = col[(size_t)b * ldh];
-      dgam = fmaf(dz, xh, dgam);
-      dbet += dz;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const size_t o = ((size_t)br * BR + lane + 32 * r) * JS + jl;
+      dz[r] = DY[o];            // zero beyond the batch (swish' was stored as 0 there)
+      xh[r] = XH[o];
+      dgam = fmaf(dz[r], xh[r], dgam);
+      dbet += dz[r];
     }
-    (br ? a.gr[1].dgamma : a.gr[0].dgamma)[j] = dgam;
-    (br ? a.gr[1].dbeta : a.gr[0].dbeta)[j] = dbet;
+    dgam = warp_sum(dgam);
+    dbet = warp_sum(dbet);
+    if (lane == 0) {
+      (br ? a.gr[1].dgamma : a.gr[0].dgamma)[j] = dgam;
+      (br ? a.gr[1].dbeta : a.gr[0].dbeta)[j] = dbet;
+    }
     const float m1 = a.training ? ga * dbet / (float)B : 0.f;
     const float m2 = a.training ? ga * dgam / (float)B : 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float xh = (hp[(size_t)b * H] - mean) * istd;
-      col[(size_t)b * ldh] = istd * (col[(size_t)b * ldh] * ga - m1 - xh * m2);
-    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+      DY[((size_t)br * BR + lane + 32 * r) * JS + jl] = (lane + 32 * r < B) ? istd * (dz[r] * ga - m1 - xh[r] * m2) : 0.f;
   }
   __syncthreads();
-  // ---- 5. dWa[j][k] = sum_b d hpre[b][j] kept[b][k]   (thread = (branch, j) column x 32 values of k) ----
-  for (int item = tid; item < 2 * H * ((Kk + 31) / 32); item += LF_T) {
-    const int c = item % (2 * H), kblk = item / (2 * H);
-    const int br = c / H, j = c - br * H, k0 = kblk * 32;
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    const float* dc = DY + (size_t)br * BR * ldh + j;
-    for (int b = 0; b < B; ++b) {
-      const float dv = dc[(size_t)b * ldh];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 k4 = *reinterpret_cast<const float4*>(kept + (size_t)b * ldk + k0 + 4 * i);
-        acc[4 * i + 0] = fmaf(k4.x, dv, acc[4 * i + 0]);
-        acc[4 * i + 1] = fmaf(k4.y, dv, acc[4 * i + 1]);
-        acc[4 * i + 2] = fmaf(k4.z, dv, acc[4 * i + 2]);
-        acc[4 * i + 3] = fmaf(k4.w, dv, acc[4 * i + 3]);
+  // ---- 5. dWa[own j][k] = sum_b d hpre[b][j] kept[b][k] ----
+  {
+    const int q4 = Kk / 4;
+    for (int i = tid; i < 2 * JS * q4; i += LC_T) {
+      const int q = i % q4, jl = (i / q4) % JS, br = i / (q4 * JS);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b = 0; b < B; ++b) {
+        const float dv = DY[((size_t)br * BR + b) * JS + jl];
+        const float4 k4 = *reinterpret_cast<const float4*>(kept + (size_t)b * ldk + 4 * q);
+        acc.x = fmaf(dv, k4.x, acc.x); acc.y = fmaf(dv, k4.y, acc.y); acc.z = fmaf(dv, k4.z, acc.z); acc.w = fmaf(dv, k4.w, acc.w);
       }
+      *reinterpret_cast<float4*>((br ? a.gr[1].dWa : a.gr[0].dWa) + (size_t)(rk * JS + jl) * Kk + 4 * q) = acc;
     }
-    float* dWa = (br ? a.gr[1].dWa : a.gr[0].dWa) + (size_t)j * Kk + k0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (k0 + i < Kk) dWa[i] = acc[i];
   }
-  // ---- 6. d kept = d hpre Wa (both branches): lanes = rows, 4 columns k per warp item; dg[keep] = dgo[keep] + d kept ----
-  for (int k0 = warp * 4; k0 < Kk; k0 += (LF_T / 32) * 4) {
+  // ---- 6. partial d kept over the own hidden columns of both branches: lanes = rows, 4 columns k per warp item ----
+  for (int k0 = warp * 4; k0 < Kk; k0 += (LC_T / 32) * 4) {
     float acc[RB][4];
 #pragma unroll
     for (int r = 0; r < RB; ++r)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[r][i] = 0.f;
     for (int br = 0; br < 2; ++br) {
-      const float* Wa = br ? a.br[1].Wa : a.br[0].Wa;
-      const float* dh = DY + (size_t)br * BR * ldh;
-      for (int j = 0; j < H; j += 4) {
+      for (int jl = 0; jl < JS; jl += 4) {
         float4 dv[RB];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) dv[r] = *reinterpret_cast<const float4*>(dh + (size_t)(lane + 32 * r) * ldh + j);
+        for (int r = 0; r < RB; ++r) dv[r] = *reinterpret_cast<const float4*>(DY + ((size_t)br * BR + lane + 32 * r) * JS + jl);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(Wa + (size_t)(j + jj) * Kk + k0));
+          const float4 wv = *reinterpret_cast<const float4*>(sWa + (size_t)(br * JS + jl + jj) * Kk + k0);
 #pragma unroll
           for (int r = 0; r < RB; ++r) {
             const float d = jj == 0 ? dv[r].x : jj == 1 ? dv[r].y : jj == 2 ? dv[r].z : dv[r].w;
-            acc[r][0] = fmaf(d, wv.x, acc[r][0]);
-            acc[r][1] = fmaf(d, wv.y, acc[r][1]);
-            acc[r][2] = fmaf(d, wv.z, acc[r][2]);
-            acc[r][3] = fmaf(d, wv.w, acc[r][3]);
+            acc[r][0] = fmaf(d, wv.x, acc[r][0]); acc[r][1] = fmaf(d, wv.y, acc[r][1]);
+            acc[r][2] = fmaf(d, wv.z, acc[r][2]); acc[r][3] = fmaf(d, wv.w, acc[r][3]);
           }
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const int b = lane + 32 * r;
-      if (b < B) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const size_t e = (size_t)b * D + a.keep_idx[k0 + i];
-          a.dg[e] = (a.dgo ? a.dgo[e] : 0.f) + acc[r][i];
-        }
-      }
-    }
+    for (int r = 0; r < RB; ++r)
+      *reinterpret_cast<float4*>(dkp + (size_t)(lane + 32 * r) * ldk + k0) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
   }
+  cluster.sync();
+  // ---- 7. reduce the eight partials on the own KS kept columns (distributed shared memory reads): dg[keep] = dgo[keep] + d kept ----
+  for (int i = tid; i < B * KS; i += LC_T) {
+    const int kl = i % KS, b = i / KS, k = rk * KS + kl;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < LC_NC; ++t) s += cluster.map_shared_rank(dkp, (unsigned)t)[(size_t)b * ldk + k];
+    const size_t e = (size_t)b * D + a.keep_idx[k];
+    a.dg[e] = (a.dgo ? a.dgo[e] : 0.f) + s;
+  }
+  cluster.sync();          // no CTA may exit while its partial is still being read
 }
 
-size_t lf_fwd_smem(int RB, int H, int Kk, int Wn) { return sizeof(float) * (size_t)(32 * RB) * ((Kk + 4) + 2 * (H + 4) + 2 * (Wn + 4)); }
-size_t lf_bwd_smem(int RB, int H, int Kk, int Wn) { return sizeof(float) * (size_t)(32 * RB) * ((Kk + 4) + 4 * (H + 4) + 2 * (Wn + 4)); }
+size_t lf_fwd_smem(int RB, int H, int Kk, int Wn) {
+  const size_t BR = 32 * RB, JS = H / LC_NC, WS = Wn / LC_NC;
+  return sizeof(float) * (BR * (Kk + 4) + 2 * JS * Kk + 2 * WS * H + 2 * BR * JS + 2 * BR * (H + 4) + 2 * BR * WS);
+}
+size_t lf_bwd_smem(int RB, int H, int Kk, int Wn) {
+  const size_t BR = 32 * RB, JS = H / LC_NC;
+  return sizeof(float) * (2 * BR * (Kk + 4) + 2 * BR * (Wn + 4) + 6 * BR * JS + 2 * (size_t)Wn * JS + 2 * JS * Kk);
+}
+constexpr size_t LF_SMEM_MAX = 227 * 1024;
+
+template <typename K, typename A>
+int lf_launch(K kernel, const A& a, size_t smem, cudaStream_t s, const char* what) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kernel<<<LC_NC, LC_T, smem, s>>>(a);
+  return dpf_check_launch(what);
+}
 
 int lf_check_dims(const char* what, int B, int D, int H, int Kk, int Wn) {
   DPF_REQUIRE(B > 0 && D > 0 && H > 0 && Kk > 0 && Wn > 0 && Kk <= D && Wn <= D, DPF_ERR_BAD_ARG, "%s: bad sizes", what);
-  DPF_REQUIRE(B <= 64 && H % 8 == 0 && Kk % 32 == 0 && Wn % 32 == 0, DPF_ERR_UNSUPPORTED,
-              "%s: needs B <= 64, H %% 8 == 0, kept / warped widths multiples of 32 (got B=%d H=%d kept=%d warped=%d)", what, B, H, Kk, Wn);
+  DPF_REQUIRE(B <= 64 && H % 32 == 0 && Kk % 32 == 0 && Wn % 32 == 0, DPF_ERR_UNSUPPORTED,
+              "%s: needs B <= 64 and hidden / kept / warped widths multiples of 32 (got B=%d H=%d kept=%d warped=%d)", what, B, H, Kk, Wn);
   return DPF_OK;
 }
 
-bool lf_aligned(const LfBranch& b) { return (((uintptr_t)b.Wa | (uintptr_t)b.Wb) & 15) == 0; }
+bool lf_aligned(const LfBranch& b) { return (((uintptr_t)b.Wa | (uintptr_t)b.Wb | (uintptr_t)b.bb) & 15) == 0; }
 
 }  // namespace
 
@@ -459,16 +506,10 @@ DPF_API int dpf_latent_flow_forward(const float* g, const int* pos, const int* k
   a.g_out = g_out; a.mu = mu; a.lv = lv; a.hpre = hpre; a.stat = stat; a.raw = raw;
   const int RB = B <= 32 ? 1 : 2;
   const size_t smem = lf_fwd_smem(RB, H, Kk, Wn);
-  DPF_REQUIRE(smem <= 227 * 1024, DPF_ERR_UNSUPPORTED, "dpf_latent_flow_forward: layer too wide for one CTA (%zu bytes of shared memory)", smem);
+  DPF_REQUIRE(smem <= LF_SMEM_MAX, DPF_ERR_UNSUPPORTED, "dpf_latent_flow_forward: layer too wide (%zu bytes of shared memory per CTA)", smem);
   cudaStream_t s = (cudaStream_t)stream;
-  if (RB == 1) {
-    cudaFuncSetAttribute(latent_flow_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    latent_flow_fwd_kernel<1><<<1, LF_T, smem, s>>>(a);
-  } else {
-    cudaFuncSetAttribute(latent_flow_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    latent_flow_fwd_kernel<2><<<1, LF_T, smem, s>>>(a);
-  }
-  return dpf_check_launch("latent_flow_fwd_kernel");
+  return RB == 1 ? lf_launch(latent_flow_fwd_kernel<1>, a, smem, s, "latent_flow_fwd_kernel")
+                 : lf_launch(latent_flow_fwd_kernel<2>, a, smem, s, "latent_flow_fwd_kernel");
 }
 
 // One RealNVPFlow layer backward: cotangents dgo, dmu_f, dlv_f (B,D; each nullable = zero) of g_out, mu, logvar -> dg (B,D) and,
@@ -489,20 +530,14 @@ DPF_API int dpf_latent_flow_backward(const float* dgo, const float* dmu_f, const
                 "dpf_latent_flow_backward: null branch pointer");
     a.br[b] = LfBranch{Wa[b], gamma[b], beta[b], nullptr, nullptr, Wb[b], nullptr};
     a.gr[b] = LfGrads{dWa[b], dgamma[b], dbeta[b], dWb[b], dbb[b]};
-    DPF_REQUIRE(lf_aligned(a.br[b]), DPF_ERR_ALIGN, "dpf_latent_flow_backward: weight matrices must be 16-byte aligned");
+    DPF_REQUIRE(lf_aligned(a.br[b]) && (((uintptr_t)dWa[b] | (uintptr_t)dWb[b]) & 15) == 0, DPF_ERR_ALIGN, "dpf_latent_flow_backward: weight matrices must be 16-byte aligned");
   }
   a.B = B; a.D = D; a.H = H; a.Kk = Kk; a.Wn = Wn; a.eps = eps; a.training = training; a.inverse = inverse;
   a.hpre = hpre; a.stat = stat; a.raw = raw; a.dg = dg;
   const int RB = B <= 32 ? 1 : 2;
   const size_t smem = lf_bwd_smem(RB, H, Kk, Wn);
-  DPF_REQUIRE(smem <= 227 * 1024, DPF_ERR_UNSUPPORTED, "dpf_latent_flow_backward: layer too wide for one CTA (%zu bytes of shared memory)", smem);
+  DPF_REQUIRE(smem <= LF_SMEM_MAX, DPF_ERR_UNSUPPORTED, "dpf_latent_flow_backward: layer too wide (%zu bytes of shared memory per CTA)", smem);
   cudaStream_t s = (cudaStream_t)stream;
-  if (RB == 1) {
-    cudaFuncSetAttribute(latent_flow_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    latent_flow_bwd_kernel<1><<<1, LF_T, smem, s>>>(a);
-  } else {
-    cudaFuncSetAttribute(latent_flow_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    latent_flow_bwd_kernel<2><<<1, LF_T, smem, s>>>(a);
-  }
-  return dpf_check_launch("latent_flow_bwd_kernel");
+  return RB == 1 ? lf_launch(latent_flow_bwd_kernel<1>, a, smem, s, "latent_flow_bwd_kernel")
+                 : lf_launch(latent_flow_bwd_kernel<2>, a, smem, s, "latent_flow_bwd_kernel");
 }

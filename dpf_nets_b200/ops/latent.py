@@ -139,12 +139,12 @@ class _LatentFlowLayer(torch.autograd.Function):
 
 
 def latent_flow_layer_ok(g, nets):
-    """the one-kernel layer handles B <= 64 rows, hidden width % 8 == 0, kept / warped widths % 32 == 0, affine BatchNorm with
-    the same momentum in both branches."""
+    """the one-kernel layer handles B <= 64 rows, hidden / kept / warped widths % 32 == 0, affine BatchNorm with the same
+    momentum in both branches."""
     (l0a, bn_a, l1a), (l0b, bn_b, l1b) = nets
     H, Kk = l0a.weight.shape
     Wn = l1a.weight.shape[0]
-    return (g.shape[0] <= 64 and H % 8 == 0 and Kk % 32 == 0 and Wn % 32 == 0 and l0a.bias is None and l0b.bias is None
+    return (g.shape[0] <= 64 and H % 32 == 0 and Kk % 32 == 0 and Wn % 32 == 0 and l0a.bias is None and l0b.bias is None
             and l1a.bias is not None and l1b.bias is not None and bn_a.affine and bn_b.affine and bn_a.momentum == bn_b.momentum
             and bn_a.eps == bn_b.eps and bn_a.training == bn_b.training and bn_a.track_running_stats == bn_b.track_running_stats
             and (g.shape[0] > 1 or not bn_a.training))

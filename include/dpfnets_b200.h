@@ -243,8 +243,9 @@ int dpf_latent_affine_backward(const float* dgo, const float* dmu_f, const float
  * logvar = log(eps + exp(.)), g_out = exp(+-logvar/2) g (+-) mu) and torch.autograd through it.  g (B,D), B <= 64; pos (D,)
  * int32: index in the warp list or -1; keep_idx (Kk,) int32; per branch b in {0: mu, 1: logvar}: Wa[b] (H,Kk), gamma[b],
  * beta[b] (H), rm[b], rv[b] (H; running statistics, updated in place in training mode when not null, read in eval mode),
- * Wb[b] (Wn,H), bb[b] (Wn).  H % 8 == 0, Kk % 32 == 0, Wn % 32 == 0, else DPF_ERR_UNSUPPORTED.  The forward saves hpre
- * (2,B,H), stat (2,2,H) {mean, istd} and raw (2,B,Wn) for the backward; fp32 CUDA-core arithmetic. */
+ * Wb[b] (Wn,H), bb[b] (Wn).  H, Kk, Wn multiples of 32, else DPF_ERR_UNSUPPORTED.  The forward saves hpre (2,B,H), stat
+ * (2,2,H) {mean, istd} and raw (2,B,Wn) for the backward.  One thread-block cluster of 8 CTAs per layer (hidden columns
+ * split over the CTAs, exchange through distributed shared memory); fp32 CUDA-core arithmetic. */
 int dpf_latent_flow_forward(const float* g, const int* pos, const int* keep_idx, const float* const* Wa, const float* const* gamma,
                             const float* const* beta, float* const* rm, float* const* rv, const float* const* Wb,
                             const float* const* bb, int B, int D, int H, int Kk, int Wn, float bn_eps, float momentum, int training,

@@ -1,2 +1,2 @@
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"pl_wgrad_kernel|pl_gemm_kernel" -s 12 -c 6 -f -o gpurun_out/src_pl python tools/encoder_profile.py > gpurun_out/src_pl.log 2>&1
-ls -la gpurun_out/src_pl.ncu-rep
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"latent_flow" -s 30 -c 2 -f -o gpurun_out/src_lf python tools/model_profile.py > gpurun_out/src_lf.log 2>&1
+ls -la gpurun_out/src_lf.ncu-rep
