@@ -113,16 +113,27 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
   float* hl = sW2 + 2 * WS * H;              // [2][BR][JS]   own hidden slice: hpre -> s
   float* s_all = hl + 2 * BR * JS;           // [2][BR][ldh]  all hidden columns (pushed by the eight CTAs)
   float* rawl = s_all + 2 * BR * ldh;        // [2][BR][WS]
+  float* gS = rawl + 2 * BR * WS;            // [B][D]        the layer input (coalesced copy: every later access is shared memory)
+  int* kidx = reinterpret_cast<int*>(gS + (size_t)B * D);      // [Kk] kept positions
+  int* wd = kidx + Kk;                       // [Wn] warped positions (inverse of pos)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < BR * Kk; i += LC_T) {
-    const int b = i / Kk, k = i - b * Kk;
-    kept[b * ldk + k] = b < B ? a.g[(size_t)b * D + a.keep_idx[k]] : 0.f;
+  // all global reads of the prologue are independent of each other (one round trip)
+  copy4(gS, a.g, B * D / 4, tid);
+  for (int k = tid; k < Kk; k += LC_T) kidx[k] = a.keep_idx[k];
+  for (int d = tid; d < D; d += LC_T) {
+    const int p = a.pos[d];
+    if (p >= 0) wd[p] = d;
   }
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
     copy4(sW1 + br * JS * Kk, (br ? a.br[1].Wa : a.br[0].Wa) + (size_t)rk * JS * Kk, JS * Kk / 4, tid);
     copy4(sW2 + br * WS * H, (br ? a.br[1].Wb : a.br[0].Wb) + (size_t)rk * WS * H, WS * H / 4, tid);
+  }
+  __syncthreads();
+  for (int i = tid; i < BR * Kk; i += LC_T) {
+    const int b = i / Kk, k = i - b * Kk;
+    kept[b * ldk + k] = b < B ? gS[(size_t)b * D + kidx[k]] : 0.f;
   }
   cluster.sync();       // every CTA of the cluster has started (its shared memory may be written remotely from here on)
   // ---- hpre = kept Wa^T on the own 2 JS columns ----
@@ -210,26 +221,30 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     }
   }
   __syncthreads();
-  // ---- the transform (same arithmetic as latent_affine_fwd_kernel): warped positions whose raw columns this CTA formed,
-  //      kept positions dealt round-robin ----
-  for (int e = tid; e < B * D; e += LC_T) {
-    const int b = e / D, j = e - b * D;
-    const int p = a.pos[j];
-    if (p >= 0 ? (p / WS != rk) : (j % LC_NC != rk)) continue;
-    float m = 0.f, l = 0.f;
-    if (p >= 0) {
-      const int wl = p - rk * WS;
-      m = rawl[((size_t)0 * BR + b) * WS + wl];
-      l = logf(a.eps + expf(rawl[((size_t)1 * BR + b) * WS + wl]));
-    }
-    const float gv = a.g[e];
+  // ---- the transform (same arithmetic as latent_affine_fwd_kernel) on the warped positions whose raw columns this CTA
+  //      formed; the kept positions are dealt over the CTAs by kept-column range ----
+  for (int i = tid; i < B * WS; i += LC_T) {
+    const int wl = i % WS, b = i / WS;
+    const size_t e = (size_t)b * D + wd[rk * WS + wl];
+    const float m = rawl[((size_t)0 * BR + b) * WS + wl];
+    const float l = logf(a.eps + expf(rawl[((size_t)1 * BR + b) * WS + wl]));
+    const float gv = gS[e];
     a.mu[e] = m;
     a.lv[e] = l;
     a.g_out[e] = a.inverse ? expf(-0.5f * l) * (gv - m) : fmaf(expf(0.5f * l), gv, m);
   }
+  const int KSf = Kk / LC_NC;
+  for (int i = tid; i < B * KSf; i += LC_T) {
+    const int kl = i % KSf, b = i / KSf;
+    const size_t e = (size_t)b * D + kidx[rk * KSf + kl];
+    a.mu[e] = 0.f;
+    a.lv[e] = 0.f;
+    a.g_out[e] = gS[e];
+  }
 }
 
-template <int RB>
+// GS: the layer input g is staged in shared memory (when it fits; wide latents read it from global memory instead)
+template <int RB, bool GS>
 __global__ void __cluster_dims__(LC_NC, 1, 1) __launch_bounds__(LC_T, 1)
 latent_flow_bwd_kernel(const LfBwdArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -247,12 +262,17 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
   float* sWbT = DY + 2 * BR * JS;            // [2][Wn][JS]   columns rk*JS.. of Wb
   float* sWa = sWbT + 2 * Wn * JS;           // [2][JS][Kk]   rows rk*JS.. of Wa
   float* dkp = sWa + 2 * JS * Kk;            // [BR][ldk]     this CTA's partial d kept
+  int* kidx = reinterpret_cast<int*>(dkp + BR * ldk);          // [Kk] kept positions
+  int* wd = kidx + Kk;                       // [Wn] warped positions (inverse of pos)
+  float* gS = reinterpret_cast<float*>(wd + Wn);               // GS: [B][D] the layer input
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- 0. operands ----
-  for (int i = tid; i < BR * Kk; i += LC_T) {
-    const int b = i / Kk, k = i - b * Kk;
-    kept[b * ldk + k] = b < B ? a.g[(size_t)b * D + a.keep_idx[k]] : 0.f;
+  // ---- 0. operands (independent global reads first) ----
+  if (GS) copy4(gS, a.g, B * D / 4, tid);
+  for (int k = tid; k < Kk; k += LC_T) kidx[k] = a.keep_idx[k];
+  for (int d = tid; d < D; d += LC_T) {
+    const int p = a.pos[d];
+    if (p >= 0) wd[p] = d;
   }
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
@@ -265,6 +285,7 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
           __ldg(reinterpret_cast<const float4*>(Wb + (size_t)w * H + rk * JS + 4 * q));
     }
   }
+#pragma unroll 4
   for (int i = tid; i < 2 * BR * JS; i += LC_T) {
     const int jl = i % JS, b = (i / JS) % BR, br = i / (JS * BR), j = rk * JS + jl;
     float s = 0.f, ds = 0.f, xh = 0.f;
@@ -285,19 +306,26 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
     const int br = i / ((BR - B) * ldw), rest = i - br * (BR - B) * ldw;
     DR[((size_t)br * BR + B) * ldw + rest] = 0.f;
   }
-  // ---- 1. the transform backward (same arithmetic as latent_affine_bwd_kernel): d raw in every CTA; dg of the warped
-  //         positions dealt round-robin (the kept ones are written in step 6) ----
-  for (int e = tid; e < B * D; e += LC_T) {
-    const int b = e / D, j = e - b * D;
-    const int p = a.pos[j];
-    if (p < 0) continue;
+  __syncthreads();
+#pragma unroll 4
+  for (int i = tid; i < BR * Kk; i += LC_T) {
+    const int b = i / Kk, k = i - b * Kk;
+    kept[b * ldk + k] = b < B ? (GS ? gS[(size_t)b * D + kidx[k]] : a.g[(size_t)b * D + kidx[k]]) : 0.f;
+  }
+  // ---- 1. the transform backward (same arithmetic as latent_affine_bwd_kernel): d raw of ALL warped columns in every CTA
+  //         (items (b, w): every address is known up front, the loads of several items are in flight together); dg of the
+  //         warped positions dealt round-robin (the kept ones are written in step 7) ----
+#pragma unroll 4
+  for (int i = tid; i < B * Wn; i += LC_T) {
+    const int p = i % Wn, b = i / Wn;
+    const size_t e = (size_t)b * D + wd[p];
     const float d = a.dgo ? a.dgo[e] : 0.f;
     const float rw = a.raw[((size_t)1 * B + b) * Wn + p];
+    const float m = a.raw[((size_t)0 * B + b) * Wn + p];
+    float dm = a.dmu_f ? a.dmu_f[e] : 0.f, dl = a.dlv_f ? a.dlv_f[e] : 0.f, dgv;
     const float ex = expf(rw);
     const float l = logf(a.eps + ex);
-    const float m = a.raw[((size_t)0 * B + b) * Wn + p];
-    const float gv = a.g[e];
-    float dm = a.dmu_f ? a.dmu_f[e] : 0.f, dl = a.dlv_f ? a.dlv_f[e] : 0.f, dgv;
+    const float gv = GS ? gS[e] : a.g[e];
     if (a.inverse) {
       const float sc = expf(-0.5f * l);
       dgv = d * sc;
@@ -309,7 +337,7 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
       dm += d;
       dl += 0.5f * d * sc * gv;
     }
-    if (j % LC_NC == rk) a.dg[e] = dgv;
+    if (p % LC_NC == rk) a.dg[e] = dgv;
     DR[((size_t)0 * BR + b) * ldw + p] = dm;
     DR[((size_t)1 * BR + b) * ldw + p] = dl * ex / (a.eps + ex);
   }
@@ -445,19 +473,19 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
     float s = 0.f;
 #pragma unroll
     for (int t = 0; t < LC_NC; ++t) s += cluster.map_shared_rank(dkp, (unsigned)t)[(size_t)b * ldk + k];
-    const size_t e = (size_t)b * D + a.keep_idx[k];
+    const size_t e = (size_t)b * D + kidx[k];
     a.dg[e] = (a.dgo ? a.dgo[e] : 0.f) + s;
   }
   cluster.sync();          // no CTA may exit while its partial is still being read
 }
 
-size_t lf_fwd_smem(int RB, int H, int Kk, int Wn) {
+size_t lf_fwd_smem(int RB, int B, int D, int H, int Kk, int Wn) {
   const size_t BR = 32 * RB, JS = H / LC_NC, WS = Wn / LC_NC;
-  return sizeof(float) * (BR * (Kk + 4) + 2 * JS * Kk + 2 * WS * H + 2 * BR * JS + 2 * BR * (H + 4) + 2 * BR * WS);
+  return sizeof(float) * (BR * (Kk + 4) + 2 * JS * Kk + 2 * WS * H + 2 * BR * JS + 2 * BR * (H + 4) + 2 * BR * WS + (size_t)B * D + Kk + Wn);
 }
-size_t lf_bwd_smem(int RB, int H, int Kk, int Wn) {
+size_t lf_bwd_smem(int RB, int B, int D, int H, int Kk, int Wn, bool gs) {
   const size_t BR = 32 * RB, JS = H / LC_NC;
-  return sizeof(float) * (2 * BR * (Kk + 4) + 2 * BR * (Wn + 4) + 6 * BR * JS + 2 * (size_t)Wn * JS + 2 * JS * Kk);
+  return sizeof(float) * (2 * BR * (Kk + 4) + 2 * BR * (Wn + 4) + 6 * BR * JS + 2 * (size_t)Wn * JS + 2 * JS * Kk + Kk + Wn + (gs ? (size_t)B * D : 0));
 }
 constexpr size_t LF_SMEM_MAX = 227 * 1024;
 
@@ -470,7 +498,7 @@ int lf_launch(K kernel, const A& a, size_t smem, cudaStream_t s, const char* wha
 
 int lf_check_dims(const char* what, int B, int D, int H, int Kk, int Wn) {
   DPF_REQUIRE(B > 0 && D > 0 && H > 0 && Kk > 0 && Wn > 0 && Kk <= D && Wn <= D, DPF_ERR_BAD_ARG, "%s: bad sizes", what);
-  DPF_REQUIRE(B <= 64 && H % 32 == 0 && Kk % 32 == 0 && Wn % 32 == 0, DPF_ERR_UNSUPPORTED,
+  DPF_REQUIRE(B <= 64 && H % 32 == 0 && Kk % 32 == 0 && Wn % 32 == 0 && D == Kk + Wn, DPF_ERR_UNSUPPORTED,
               "%s: needs B <= 64 and hidden / kept / warped widths multiples of 32 (got B=%d H=%d kept=%d warped=%d)", what, B, H, Kk, Wn);
   return DPF_OK;
 }
@@ -478,6 +506,17 @@ int lf_check_dims(const char* what, int B, int D, int H, int Kk, int Wn) {
 bool lf_aligned(const LfBranch& b) { return (((uintptr_t)b.Wa | (uintptr_t)b.Wb | (uintptr_t)b.bb) & 15) == 0; }
 
 }  // namespace
+
+// DPF_OK when dpf_latent_flow_forward AND _backward handle a layer of these sizes, DPF_ERR_UNSUPPORTED otherwise (the caller
+// then keeps the block kernels + library GEMMs)
+DPF_API int dpf_latent_flow_supported(int B, int D, int H, int Kk, int Wn) {
+  int rc = lf_check_dims("dpf_latent_flow_supported", B, D, H, Kk, Wn);
+  if (rc) return rc;
+  const int RB = B <= 32 ? 1 : 2;
+  DPF_REQUIRE(lf_fwd_smem(RB, B, D, H, Kk, Wn) <= LF_SMEM_MAX && lf_bwd_smem(RB, B, D, H, Kk, Wn, false) <= LF_SMEM_MAX, DPF_ERR_UNSUPPORTED,
+              "dpf_latent_flow_supported: layer too wide for the shared memory of a CTA (B=%d D=%d H=%d)", B, D, H);
+  return DPF_OK;
+}
 
 // One RealNVPFlow layer forward.  g (B,D); pos (D,) int32: index in the warp list or -1; keep_idx (Kk,) int32: the kept
 // positions in order; per branch b in {0: mu, 1: logvar}: Wa[b] (H,Kk), gamma[b], beta[b] (H), rm[b], rv[b] (H) running
@@ -500,12 +539,12 @@ DPF_API int dpf_latent_flow_forward(const float* g, const int* pos, const int* k
     DPF_REQUIRE(training || (rm[b] && rv[b]), DPF_ERR_NULL_PTR, "dpf_latent_flow_forward: eval mode needs running statistics");
     DPF_REQUIRE(lf_aligned(a.br[b]), DPF_ERR_ALIGN, "dpf_latent_flow_forward: weight matrices must be 16-byte aligned");
   }
-  DPF_REQUIRE((((uintptr_t)hpre | (uintptr_t)raw) & 15) == 0, DPF_ERR_ALIGN, "dpf_latent_flow_forward: hpre / raw alignment");
+  DPF_REQUIRE((((uintptr_t)hpre | (uintptr_t)raw | (uintptr_t)g) & 15) == 0, DPF_ERR_ALIGN, "dpf_latent_flow_forward: g / hpre / raw alignment");
   a.B = B; a.D = D; a.H = H; a.Kk = Kk; a.Wn = Wn;
   a.bn_eps = bn_eps; a.momentum = momentum; a.eps = eps; a.training = training; a.inverse = inverse;
   a.g_out = g_out; a.mu = mu; a.lv = lv; a.hpre = hpre; a.stat = stat; a.raw = raw;
   const int RB = B <= 32 ? 1 : 2;
-  const size_t smem = lf_fwd_smem(RB, H, Kk, Wn);
+  const size_t smem = lf_fwd_smem(RB, B, D, H, Kk, Wn);
   DPF_REQUIRE(smem <= LF_SMEM_MAX, DPF_ERR_UNSUPPORTED, "dpf_latent_flow_forward: layer too wide (%zu bytes of shared memory per CTA)", smem);
   cudaStream_t s = (cudaStream_t)stream;
   return RB == 1 ? lf_launch(latent_flow_fwd_kernel<1>, a, smem, s, "latent_flow_fwd_kernel")
@@ -533,11 +572,15 @@ DPF_API int dpf_latent_flow_backward(const float* dgo, const float* dmu_f, const
     DPF_REQUIRE(lf_aligned(a.br[b]) && (((uintptr_t)dWa[b] | (uintptr_t)dWb[b]) & 15) == 0, DPF_ERR_ALIGN, "dpf_latent_flow_backward: weight matrices must be 16-byte aligned");
   }
   a.B = B; a.D = D; a.H = H; a.Kk = Kk; a.Wn = Wn; a.eps = eps; a.training = training; a.inverse = inverse;
+  DPF_REQUIRE(((uintptr_t)g & 15) == 0, DPF_ERR_ALIGN, "dpf_latent_flow_backward: g alignment");
   a.hpre = hpre; a.stat = stat; a.raw = raw; a.dg = dg;
   const int RB = B <= 32 ? 1 : 2;
-  const size_t smem = lf_bwd_smem(RB, H, Kk, Wn);
+  const bool gs = lf_bwd_smem(RB, B, D, H, Kk, Wn, true) <= LF_SMEM_MAX;
+  const size_t smem = lf_bwd_smem(RB, B, D, H, Kk, Wn, gs);
   DPF_REQUIRE(smem <= LF_SMEM_MAX, DPF_ERR_UNSUPPORTED, "dpf_latent_flow_backward: layer too wide (%zu bytes of shared memory per CTA)", smem);
   cudaStream_t s = (cudaStream_t)stream;
-  return RB == 1 ? lf_launch(latent_flow_bwd_kernel<1>, a, smem, s, "latent_flow_bwd_kernel")
-                 : lf_launch(latent_flow_bwd_kernel<2>, a, smem, s, "latent_flow_bwd_kernel");
+  if (RB == 1) return gs ? lf_launch(latent_flow_bwd_kernel<1, true>, a, smem, s, "latent_flow_bwd_kernel")
+                         : lf_launch(latent_flow_bwd_kernel<1, false>, a, smem, s, "latent_flow_bwd_kernel");
+  return gs ? lf_launch(latent_flow_bwd_kernel<2, true>, a, smem, s, "latent_flow_bwd_kernel")
+            : lf_launch(latent_flow_bwd_kernel<2, false>, a, smem, s, "latent_flow_bwd_kernel");
 }

@@ -144,7 +144,9 @@ def latent_flow_layer_ok(g, nets):
     (l0a, bn_a, l1a), (l0b, bn_b, l1b) = nets
     H, Kk = l0a.weight.shape
     Wn = l1a.weight.shape[0]
-    return (g.shape[0] <= 64 and H % 32 == 0 and Kk % 32 == 0 and Wn % 32 == 0 and l0a.bias is None and l0b.bias is None
+    if _lib.lib().dpf_latent_flow_supported(int(g.shape[0]), int(g.shape[1]), int(H), int(Kk), int(Wn)) != 0:
+        return False
+    return (l0a.bias is None and l0b.bias is None
             and l1a.bias is not None and l1b.bias is not None and bn_a.affine and bn_b.affine and bn_a.momentum == bn_b.momentum
             and bn_a.eps == bn_b.eps and bn_a.training == bn_b.training and bn_a.track_running_stats == bn_b.track_running_stats
             and (g.shape[0] > 1 or not bn_a.training))
