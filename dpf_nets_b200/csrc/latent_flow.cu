@@ -116,10 +116,26 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
   float* gS = rawl + 2 * BR * WS;            // [B][D]        the layer input (coalesced copy: every later access is shared memory)
   int* kidx = reinterpret_cast<int*>(gS + (size_t)B * D);      // [Kk] kept positions
   int* wd = kidx + Kk;                       // [Wn] warped positions (inverse of pos)
+  float* colp = reinterpret_cast<float*>(wd + Wn);             // [2 JS][4] {gamma, beta, running mean, running var} of the own columns
+  float* biasl = colp + 8 * JS;              // [2 WS] bias of the own output columns
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  cluster.barrier_arrive();     // "this CTA has started": waited for only right before the first remote write
   // all global reads of the prologue are independent of each other (one round trip)
   copy4(gS, a.g, B * D / 4, tid);
+  for (int c = tid; c < 2 * JS; c += LC_T) {
+    const int br = c / JS, j = rk * JS + (c - br * JS);
+    const LfBranch& P = br ? a.br[1] : a.br[0];
+    const bool stats = !a.training || P.rm;
+    colp[4 * c + 0] = P.gamma[j];
+    colp[4 * c + 1] = P.beta[j];
+    colp[4 * c + 2] = stats ? P.rm[j] : 0.f;
+    colp[4 * c + 3] = stats ? P.rv[j] : 1.f;
+  }
+  for (int c = tid; c < 2 * WS; c += LC_T) {
+    const int br = c / WS;
+    biasl[c] = (br ? a.br[1].bb : a.br[0].bb)[rk * WS + (c - br * WS)];
+  }
   for (int k = tid; k < Kk; k += LC_T) kidx[k] = a.keep_idx[k];
   for (int d = tid; d < D; d += LC_T) {
     const int p = a.pos[d];
@@ -135,7 +151,7 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     const int b = i / Kk, k = i - b * Kk;
     kept[b * ldk + k] = b < B ? gS[(size_t)b * D + kidx[k]] : 0.f;
   }
-  cluster.sync();       // every CTA of the cluster has started (its shared memory may be written remotely from here on)
+  __syncthreads();
   // ---- hpre = kept Wa^T on the own 2 JS columns ----
   for (int c0 = warp * LC_CH; c0 < 2 * JS; c0 += (LC_T / 32) * LC_CH) {
     const int br = c0 / JS, jl = c0 - br * JS;
@@ -171,15 +187,15 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
       }
       var = warp_sum(q) / (float)B;
       if (P.rm && lane == 0) {
-        P.rm[j] = (1.f - a.momentum) * P.rm[j] + a.momentum * mean;
-        P.rv[j] = (1.f - a.momentum) * P.rv[j] + a.momentum * var * ((float)B / (float)max(B - 1, 1));
+        P.rm[j] = (1.f - a.momentum) * colp[4 * c + 2] + a.momentum * mean;
+        P.rv[j] = (1.f - a.momentum) * colp[4 * c + 3] + a.momentum * var * ((float)B / (float)max(B - 1, 1));
       }
     } else {
-      mean = P.rm[j];
-      var = P.rv[j];
+      mean = colp[4 * c + 2];
+      var = colp[4 * c + 3];
     }
     const float istd = 1.f / sqrtf(var + a.bn_eps);
-    const float ga = P.gamma[j], be = P.beta[j];
+    const float ga = colp[4 * c + 0], be = colp[4 * c + 1];
     if (lane == 0) {
       a.stat[(size_t)(br * 2 + 0) * H + j] = mean;
       a.stat[(size_t)(br * 2 + 1) * H + j] = istd;
@@ -192,6 +208,7 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
   }
   __syncthreads();
   // ---- push the own slice of s into every CTA's copy (distributed shared memory, 16-byte stores) ----
+  cluster.barrier_wait();       // every CTA of the cluster has started: its shared memory may be written remotely
   {
     const int q4 = JS / 4, n4 = 2 * BR * q4;
     for (int i = tid; i < n4; i += LC_T) {
@@ -208,10 +225,9 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
   // ---- raw = s Wb^T + bb on the own 2 WS output columns ----
   for (int c0 = warp * LC_CH; c0 < 2 * WS; c0 += (LC_T / 32) * LC_CH) {
     const int br = c0 / WS, wl = c0 - br * WS;
-    const LfBranch& P = br ? a.br[1] : a.br[0];
     float acc[RB][LC_CH];
     rows_times_wrows<RB>(s_all + (size_t)br * BR * ldh, ldh, H, sW2 + (size_t)(br * WS + wl) * H, H, lane, acc);
-    const float4 bias = __ldg(reinterpret_cast<const float4*>(P.bb + rk * WS + wl));
+    const float4 bias = *reinterpret_cast<const float4*>(biasl + br * WS + wl);
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       const int b = lane + 32 * r;
@@ -264,11 +280,20 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
   float* dkp = sWa + 2 * JS * Kk;            // [BR][ldk]     this CTA's partial d kept
   int* kidx = reinterpret_cast<int*>(dkp + BR * ldk);          // [Kk] kept positions
   int* wd = kidx + Kk;                       // [Wn] warped positions (inverse of pos)
-  float* gS = reinterpret_cast<float*>(wd + Wn);               // GS: [B][D] the layer input
+  float* colp = reinterpret_cast<float*>(wd + Wn);             // [2 JS][4] {gamma, beta, mean, istd} of the own columns
+  float* gS = colp + 8 * JS;                 // GS: [B][D] the layer input
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // ---- 0. operands (independent global reads first) ----
   if (GS) copy4(gS, a.g, B * D / 4, tid);
+  for (int c = tid; c < 2 * JS; c += LC_T) {
+    const int br = c / JS, j = rk * JS + (c - br * JS);
+    const LfBranch& P = br ? a.br[1] : a.br[0];
+    colp[4 * c + 0] = P.gamma[j];
+    colp[4 * c + 1] = P.beta[j];
+    colp[4 * c + 2] = a.stat[(size_t)(br * 2 + 0) * H + j];
+    colp[4 * c + 3] = a.stat[(size_t)(br * 2 + 1) * H + j];
+  }
   for (int k = tid; k < Kk; k += LC_T) kidx[k] = a.keep_idx[k];
   for (int d = tid; d < D; d += LC_T) {
     const int p = a.pos[d];
@@ -285,15 +310,15 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
           __ldg(reinterpret_cast<const float4*>(Wb + (size_t)w * H + rk * JS + 4 * q));
     }
   }
+  __syncthreads();
 #pragma unroll 4
   for (int i = tid; i < 2 * BR * JS; i += LC_T) {
     const int jl = i % JS, b = (i / JS) % BR, br = i / (JS * BR), j = rk * JS + jl;
     float s = 0.f, ds = 0.f, xh = 0.f;
     if (b < B) {
-      const LfBranch& P = br ? a.br[1] : a.br[0];
-      const float mean = a.stat[(size_t)(br * 2 + 0) * H + j], istd = a.stat[(size_t)(br * 2 + 1) * H + j];
-      xh = (a.hpre[((size_t)br * B + b) * H + j] - mean) * istd;
-      const float z = fmaf(xh, P.gamma[j], P.beta[j]);
+      const float* cp = colp + 4 * (br * JS + jl);
+      xh = (a.hpre[((size_t)br * B + b) * H + j] - cp[2]) * cp[3];
+      const float z = fmaf(xh, cp[0], cp[1]);
       const float sg = sigmoid_(z);
       s = z * sg;
       ds = sg + z * sg * (1.f - sg);
@@ -306,7 +331,6 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
     const int br = i / ((BR - B) * ldw), rest = i - br * (BR - B) * ldw;
     DR[((size_t)br * BR + B) * ldw + rest] = 0.f;
   }
-  __syncthreads();
 #pragma unroll 4
   for (int i = tid; i < BR * Kk; i += LC_T) {
     const int b = i / Kk, k = i - b * Kk;
@@ -399,8 +423,7 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
   // ---- 4. BatchNorm backward: a warp per column, lane = batch row ----
   for (int c = warp; c < 2 * JS; c += LC_T / 32) {
     const int br = c / JS, jl = c - br * JS, j = rk * JS + jl;
-    const LfBranch& P = br ? a.br[1] : a.br[0];
-    const float istd = a.stat[(size_t)(br * 2 + 1) * H + j], ga = P.gamma[j];
+    const float istd = colp[4 * c + 3], ga = colp[4 * c + 0];
     float dz[RB], xh[RB];
     float dgam = 0.f, dbet = 0.f;
 #pragma unroll
@@ -481,11 +504,11 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
 
 size_t lf_fwd_smem(int RB, int B, int D, int H, int Kk, int Wn) {
   const size_t BR = 32 * RB, JS = H / LC_NC, WS = Wn / LC_NC;
-  return sizeof(float) * (BR * (Kk + 4) + 2 * JS * Kk + 2 * WS * H + 2 * BR * JS + 2 * BR * (H + 4) + 2 * BR * WS + (size_t)B * D + Kk + Wn);
+  return sizeof(float) * (BR * (Kk + 4) + 2 * JS * Kk + 2 * WS * H + 2 * BR * JS + 2 * BR * (H + 4) + 2 * BR * WS + (size_t)B * D + Kk + Wn + 8 * JS + 2 * WS);
 }
 size_t lf_bwd_smem(int RB, int B, int D, int H, int Kk, int Wn, bool gs) {
   const size_t BR = 32 * RB, JS = H / LC_NC;
-  return sizeof(float) * (2 * BR * (Kk + 4) + 2 * BR * (Wn + 4) + 6 * BR * JS + 2 * (size_t)Wn * JS + 2 * JS * Kk + Kk + Wn + (gs ? (size_t)B * D : 0));
+  return sizeof(float) * (2 * BR * (Kk + 4) + 2 * BR * (Wn + 4) + 6 * BR * JS + 2 * (size_t)Wn * JS + 2 * JS * Kk + Kk + Wn + 8 * JS + (gs ? (size_t)B * D : 0));
 }
 constexpr size_t LF_SMEM_MAX = 227 * 1024;
 
