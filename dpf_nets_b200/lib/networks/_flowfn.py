@@ -48,7 +48,8 @@ class CouplingStackFunction(torch.autograd.Function):
                       P, MU, LV, SLV, ws, L, G, B, N, MODES[mode], bool(training), update,
                       PRECISIONS[precision], ctypes.c_float(stack.eps_value), device=dev)
         if training:
-            stack.num_batches_tracked += 1
+            from ...ops._counters import bump
+            bump(stack.num_batches_tracked)
         ctx.stack, ctx.mode, ctx.training, ctx.ws, ctx.precision = stack, mode, bool(training), ws, precision
         stack._last_pass = (ws, L, G, B, N)
         ctx.save_for_backward(p, g, arena, P, LV)

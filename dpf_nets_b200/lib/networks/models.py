@@ -129,6 +129,11 @@ class Local_Cond_RNVP_MC_Global_RNVP_VAE(_DPFBase):
         return out
 
     def forward(self, g_input, p_input, n_sampled_points=None):
+        from ...ops._counters import deferred
+        with deferred():      # the ~35 BatchNorm step counters of the fused paths: one multi-tensor add
+            return self._forward(g_input, p_input, n_sampled_points)
+
+    def _forward(self, g_input, p_input, n_sampled_points=None):
         n = p_input.shape[2] if n_sampled_points is None else n_sampled_points
         B, G = g_input.shape[0], self.g_latent_space_size
         out = {}
@@ -159,6 +164,11 @@ class Local_Cond_RNVP_MC_Global_RNVP_VAE_IC(_DPFBase):
         self._build_common(kwargs, with_base_var=kwargs.get('p_decoder_base_type') == 'fixed')
 
     def forward(self, g_input, p_input, images, n_sampled_points=None):
+        from ...ops._counters import deferred
+        with deferred():
+            return self._forward(g_input, p_input, images, n_sampled_points)
+
+    def _forward(self, g_input, p_input, images, n_sampled_points=None):
         n = p_input.shape[2] if n_sampled_points is None else n_sampled_points
         out = {}
         g0_mu, g0_lv = self.g0_prior(self.img_encoder(images))

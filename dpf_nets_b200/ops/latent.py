@@ -6,6 +6,7 @@ import ctypes
 import torch
 
 from .. import _lib
+from . import _counters
 
 
 def fused_ok(*tensors):
@@ -48,8 +49,8 @@ def bn_swish(x, bn):
     rv = bn.running_var if bn.track_running_stats else None
     momentum = 0.0
     if bn.training and bn.track_running_stats:
-        bn.num_batches_tracked += 1
-        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        _counters.bump(bn.num_batches_tracked)
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
     elif training:
         rm = rv = None
     return _BnSwish.apply(x, bn.weight, bn.bias, rm, rv, float(bn.eps), float(momentum), training)
@@ -163,9 +164,9 @@ def latent_flow_layer(g, nets, pos, keep_idx, eps, mode):
     momentum = 0.0
     if bn_a.track_running_stats:
         if bn_a.training:
-            bn_a.num_batches_tracked += 1
-            bn_b.num_batches_tracked += 1
-            momentum = bn_a.momentum if bn_a.momentum is not None else 1.0 / float(bn_a.num_batches_tracked)
+            _counters.bump(bn_a.num_batches_tracked)
+            _counters.bump(bn_b.num_batches_tracked)
+            momentum = bn_a.momentum if bn_a.momentum is not None else 1.0 / float(bn_a.num_batches_tracked + 1)
         rms, rvs = [bn_a.running_mean, bn_b.running_mean], [bn_a.running_var, bn_b.running_var]
     return _LatentFlowLayer.apply(g, l0a.weight, bn_a.weight, bn_a.bias, l1a.weight, l1a.bias, l0b.weight, bn_b.weight, bn_b.bias,
                                   l1b.weight, l1b.bias, pos, keep_idx, rms, rvs, float(bn_a.eps), float(momentum), training, float(eps),

@@ -20,6 +20,7 @@ import ctypes
 import torch
 
 from .. import _lib
+from . import _counters
 
 
 def pool_stats(h2, W, in_tab=None, want_asum=False, merge=True):
@@ -133,8 +134,8 @@ def pooled_bn_relu_max(h2, weight, bn):
     if bn.track_running_stats:
         with torch.no_grad():
             M = B * N
-            bn.num_batches_tracked += 1
-            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            _counters.bump(bn.num_batches_tracked)
+            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
             bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
             bn.running_var.mul_(1 - mom).add_(var * (M / max(M - 1, 1)), alpha=mom)
     return out

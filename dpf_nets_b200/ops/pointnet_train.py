@@ -18,6 +18,7 @@ import ctypes
 import torch
 
 from .. import _lib
+from . import _counters
 from . import pointnet_pool as _pp
 from .pointnet_pool import pool_select
 
@@ -203,8 +204,8 @@ def pointnet_train_forward(x, sds, bns):
         for st, bn in zip(stats, bns):
             if not bn.track_running_stats:
                 continue
-            bn.num_batches_tracked += 1
-            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            _counters.bump(bn.num_batches_tracked)
+            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
             bn.running_mean.mul_(1 - mom).add_(st[:, 0], alpha=mom)
             bn.running_var.mul_(1 - mom).add_(st[:, 1], alpha=mom * (M / max(M - 1, 1)))
     return out
