@@ -711,7 +711,9 @@ def full_model_step(dev, B, N, precision, flush, config_name, world, graphed=Fal
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); loss = fn(); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        t = torch.tensor([sum(ts) / len(ts)], dtype=torch.float64, device=dev)
+        # median over the steps: the eager legs launch ~1 000 kernels per step from Python and a single descheduled host
+        # thread on a shared box shows up as a multi-ms outlier (the graph-replay leg below is the host-independent figure)
+        t = torch.tensor([sorted(ts)[len(ts) // 2]], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(loss.detach())
@@ -722,7 +724,7 @@ def full_model_step(dev, B, N, precision, flush, config_name, world, graphed=Fal
            "model": "%s, %d params" % (config_name, n_params), "batch_per_gpu": B, "points": N,
            "gradient_bytes_allreduced_per_step": 4 * n_params if world > 1 else 0,
            "includes": "H2D of the inputs, encoders, latent flows, priors, decoder, loss, backward, gradient all-reduce "
-                       "(decoder arena overlapped with the rest of the backward), AMSGrad step"}
+                       "(decoder arena overlapped with the rest of the backward), AMSGrad step; median of the timed steps, max over ranks"}
     if graphed:
         # the same step as two CUDA graphs (config key cuda_graph: forward+loss+backward | optimizer), _graphstep.py
         try:
