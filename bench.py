@@ -415,8 +415,8 @@ def run_ours(args):
         # whole-model training steps of the three BASELINE model families, batch-sharded over the ranks (gradient
         # averaging: dist.GradSync - decoder arena all-reduce overlapped with the rest of the backward)
         extra["full_model_step"] = full_model_step(dev, B, N, precision, flush, "generation/chair", world, graphed=True)
-        extra["full_model_step_ae_all_original"] = full_model_step(dev, B, N, precision, flush, "autoencoding/all_original", world)
-        extra["full_model_step_svr_all"] = full_model_step(dev, B, N, precision, flush, "svr/all", world)
+        extra["full_model_step_ae_all_original"] = full_model_step(dev, B, N, precision, flush, "autoencoding/all_original", world, graphed=True)
+        extra["full_model_step_svr_all"] = full_model_step(dev, B, N, precision, flush, "svr/all", world, graphed=True)
         if world == 1:
             # single-GPU legs and the CPU baseline only in the N = 1 run (under torchrun the other ranks would idle in a
             # barrier while rank 0 works, and the driver's N = 1 line already carries them)

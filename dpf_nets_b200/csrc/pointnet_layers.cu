@@ -169,15 +169,26 @@ pl_gemm_kernel(const PlGemmArgs a) {
       const int b = (t0 + e) / n_tiles;
       const int nbase = (t0 + e - b * n_tiles) * PL_NT + part * 32;
       if (STATS) {
+        if (nbase + 32 <= a.N) {      // all 32 columns valid: no per-element bookkeeping
+          if (cnt == 0) shift = v[0];
+          cnt += 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (nbase + j < a.N) {
-            const float x = v[j];
-            if (cnt == 0) shift = x;
-            ++cnt;
-            const float dx = x - shift;
+          for (int j = 0; j < 32; ++j) {
+            const float dx = v[j] - shift;
             sum += dx;
             sq = fmaf(dx, dx, sq);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nbase + j < a.N) {
+              const float x = v[j];
+              if (cnt == 0) shift = x;
+              ++cnt;
+              const float dx = x - shift;
+              sum += dx;
+              sq = fmaf(dx, dx, sq);
+            }
           }
         }
       }

@@ -46,12 +46,14 @@ __device__ __forceinline__ void store_split_chunk(unsigned char* hi_img, unsigne
 // halves with one shuffle each, so that the even lane owns 8 points of the iteration-i row and the odd lane 8 points of the
 // iteration-(i + 1) row.  The row of a (pair, lane) slot is the same for every tile.
 // ---------------------------------------------------------------------------------------------------------------
-template <int C, int LOADER>
+template <int C, int LOADER, int NW = T / 32>
 struct TileLoader {
-  static constexpr int NIT = C / 16;              // load iterations per tile: 16 rows each (2 per warp)
+  static constexpr int RPI = 2 * NW;              // rows per load iteration (2 per warp)
+  static constexpr int NIT = C / RPI;             // load iterations per tile
   static constexpr int NIN = LoaderInputs<LOADER>::n;
   static_assert(C == 64 || C == 128 || C == 256, "channel rows per tile");
   static_assert(LOADER != LD_X3, "layer 0 has its own builder");
+  static_assert(NIT >= 2 && NIT % 2 == 0, "rows are processed in pairs of load iterations");
   float4 buf[NIN][NIT];
   const float* in[2];
   const float* tab;
@@ -68,7 +70,7 @@ struct TileLoader {
     lane = tid & 31;
     vec_ok = (N % 4) == 0;
   }
-  __device__ __forceinline__ int slot_row(int pair) const { return (2 * pair + (lane & 1)) * 16 + warp * 2 + (lane >> 4); }
+  __device__ __forceinline__ int slot_row(int pair) const { return (2 * pair + (lane & 1)) * RPI + warp * 2 + (lane >> 4); }
   // flat tile index over all shapes: tile -> (shape tile / n_tiles, first point (tile % n_tiles) * 64)
   __device__ __forceinline__ void load(int tile) {
     const int b = tile / n_tiles;
@@ -77,7 +79,7 @@ struct TileLoader {
     for (int j = 0; j < NIN; ++j) {
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {
-        const float* src = in[j] + ((size_t)b * C + i * 16 + warp * 2 + (lane >> 4)) * N + n;
+        const float* src = in[j] + ((size_t)b * C + i * RPI + warp * 2 + (lane >> 4)) * N + n;
         if (vec_ok && n + 4 <= N) {
           buf[j][i] = __ldg(reinterpret_cast<const float4*>(src));
         } else {

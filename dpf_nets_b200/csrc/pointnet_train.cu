@@ -21,8 +21,9 @@
 
 namespace {
 
-constexpr int PT_T = 256;                       // threads: lane = tid & 127 = channel of the chunk, part = tid >> 7 = half of the tile's points
+constexpr int PT_T = 512;                       // threads: lane = tid & 127 = channel of the chunk, part = tid >> 7 = quarter of the tile's points
 constexpr int PT_CIN = 256, PT_COUT = 512, PT_NT = 64;     // input channels, output channels, points per tile
+constexpr int PT_PARTS = PT_T / 128, PT_PC = PT_NT / PT_PARTS;      // 4 parts x 16 columns
 constexpr uint32_t PT_KB = 128 * 128;           // 16 KB: [128 rows x 64 bf16] K-block of the weight chunk
 constexpr uint32_t PT_WIMG = 4 * PT_KB;         // 64 KB: one chunk image (4 K-blocks)
 constexpr uint32_t PT_BIMG = PT_CIN * 128;      // 32 KB: [256 K-rows x 64 points] bf16
@@ -52,7 +53,7 @@ pool_pack_kernel(const float* __restrict__ W, unsigned char* __restrict__ img) {
 struct PtSmem {
   unsigned char A[2 * PT_WIMG];         // W chunk hi | lo
   unsigned char Bt[2 * PT_BIMG];        // h2 tile hi | lo
-  float red[2][128][8];                 // part -> {mean, M2, max, min, argmax, argmin, count} hand-over
+  float red[PT_PARTS][128][8];          // part -> {mean, M2, max, min, argmax, argmin, count} hand-over
   uint64_t bar_w, bar_mma;
   uint32_t tmem_base;
 };
@@ -96,11 +97,12 @@ pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab,
   // Coalesced row loads + neighbour swap (pointnet_tiles.cuh); the NEXT tile's loads are issued before this tile's UMMA wait
   // and epilogue, so the global-load latency overlaps the tensor-core work.
   const bool want_asum = asum != nullptr && chunk == 0;
-  pnt::TileLoader<PT_CIN, IN_ACT ? pnt::LD_AFFINE : pnt::LD_RAW> ld;
+  pnt::TileLoader<PT_CIN, IN_ACT ? pnt::LD_AFFINE : pnt::LD_RAW, PT_T / 32> ld;
   ld.init(h2, nullptr, tab, N, tid);
-  float act_sum[PT_CIN / 32];       // per-slot sums of the operand over the valid points (the analytic backward's S)
+  constexpr int NSLOT = PT_CIN / (4 * (PT_T / 32));       // (pair, lane parity) slots per thread
+  float act_sum[NSLOT];             // per-slot sums of the operand over the valid points (the analytic backward's S)
 #pragma unroll
-  for (int i = 0; i < PT_CIN / 32; ++i) act_sum[i] = 0.f;
+  for (int i = 0; i < NSLOT; ++i) act_sum[i] = 0.f;
   const int tile0 = b * n_tiles;    // flat tile index of the loaders
   ld.load(tile0);
   for (int tile = 0; tile < n_tiles; ++tile) {
@@ -134,22 +136,37 @@ pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab,
     umma::mbar_wait(&s.bar_mma, ph);
     ph ^= 1;
     umma::fence_after_sync();
-    // ---- lane = channel: statistics and max / min over this part's 32 points, in registers ----
+    // ---- lane = channel: statistics and max / min over this part's 16 points, in registers ----
     {
-      float v[32];
-      umma::tmem_ld32(tmem + lane_off + part * 32, v);
-      const int nbase = n0 + part * 32;
+      uint32_t r[PT_PC];
+      umma::tmem_ld16_issue(tmem + lane_off + part * PT_PC, r);
+      umma::tmem_ld_wait16(r);
+      const int nbase = n0 + part * PT_PC;
+      if (nbase + PT_PC <= N) {       // all columns valid (every tile but a ragged last one): no per-element bookkeeping
+        if (cnt == 0) shift = __uint_as_float(r[0]);
+        cnt += PT_PC;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (nbase + i < N) {
-          const float x = v[i];
-          if (cnt == 0) shift = x;
-          ++cnt;
+        for (int i = 0; i < PT_PC; ++i) {
+          const float x = __uint_as_float(r[i]);
           const float dx = x - shift;
           sum += dx;
           sq = fmaf(dx, dx, sq);
           if (x > mx) { mx = x; amx = nbase + i; }
           if (x < mn) { mn = x; amn = nbase + i; }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PT_PC; ++i) {
+          if (nbase + i < N) {
+            const float x = __uint_as_float(r[i]);
+            if (cnt == 0) shift = x;
+            ++cnt;
+            const float dx = x - shift;
+            sum += dx;
+            sq = fmaf(dx, dx, sq);
+            if (x > mx) { mx = x; amx = nbase + i; }
+            if (x < mn) { mn = x; amn = nbase + i; }
+          }
         }
       }
     }
@@ -158,7 +175,7 @@ pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab,
   }
   if (want_asum) {      // a slot's row is shared by the 8 lanes of the same parity in the same half-warp
 #pragma unroll
-    for (int i = 0; i < PT_CIN / 32; ++i) {
+    for (int i = 0; i < NSLOT; ++i) {
       float v = act_sum[i];
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -166,7 +183,7 @@ pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab,
       if ((tid & 14) == 0) asum[(size_t)b * PT_CIN + ld.slot_row(i)] = v;
     }
   }
-  // ---- combine the two point halves (part 0 holds the lower point indices of every tile: ties keep the lower index) ----
+  // ---- combine the four point quarters ----
   // per thread: count, mean = shift + sum / cnt, M2 = sq - sum^2 / cnt (sum of squared deviations from that mean)
   const float fc = (float)cnt;
   const float mean_t = cnt ? shift + sum / fc : 0.f;
@@ -176,24 +193,32 @@ pool_forward_kernel(const float* __restrict__ h2, const float* __restrict__ tab,
   s.red[part][lane_c][6] = fc;
   __syncthreads();
   if (part == 0) {
-    const float* o = s.red[1][lane_c];
+    // parts hold increasing point indices within every tile: on ties the lower index wins
     const int c = chunk * 128 + lane_c;
     float m1 = mx, m0 = mn;
     int a1 = amx, a0 = amn;
-    const int oamx = __float_as_int(o[4]), oamn = __float_as_int(o[5]);
-    if (o[2] > m1 || (o[2] == m1 && oamx < a1)) { m1 = o[2]; a1 = oamx; }
-    if (o[3] < m0 || (o[3] == m0 && oamn < a0)) { m0 = o[3]; a0 = oamn; }
+    float n1 = fc, mean = mean_t, m2 = m2_t;
+#pragma unroll
+    for (int p = 1; p < PT_PARTS; ++p) {
+      const float* o = s.red[p][lane_c];
+      const int oamx = __float_as_int(o[4]), oamn = __float_as_int(o[5]);
+      if (o[2] > m1 || (o[2] == m1 && oamx < a1)) { m1 = o[2]; a1 = oamx; }
+      if (o[3] < m0 || (o[3] == m0 && oamn < a0)) { m0 = o[3]; a0 = oamn; }
+      // pairwise merge of the (count, mean, M2) triples (Chan et al.)
+      const float n2 = o[6], nt = n1 + n2;
+      if (nt > 0.f) {
+        const float delta = o[0] - mean;
+        mean += delta * (n2 / nt);
+        m2 += o[1] + delta * delta * (n1 * n2 / nt);
+        n1 = nt;
+      }
+    }
     vmax[(size_t)b * PT_COUT + c] = m1;
     vmin[(size_t)b * PT_COUT + c] = m0;
     imax[(size_t)b * PT_COUT + c] = a1;
     imin[(size_t)b * PT_COUT + c] = a0;
-    // pairwise merge of the two (count, mean, M2) triples (Chan et al.)
-    const float n1 = fc, n2 = o[6], nt = n1 + n2;
-    const float delta = o[0] - mean_t;
-    const float mean = nt > 0.f ? mean_t + delta * (n2 / nt) : 0.f;
-    const float m2 = nt > 0.f ? m2_t + o[1] + delta * delta * (n1 * n2 / nt) : 0.f;
-    stat[((size_t)b * PT_COUT + c) * 2 + 0] = mean;
-    stat[((size_t)b * PT_COUT + c) * 2 + 1] = m2;
+    stat[((size_t)b * PT_COUT + c) * 2 + 0] = n1 > 0.f ? mean : 0.f;
+    stat[((size_t)b * PT_COUT + c) * 2 + 1] = n1 > 0.f ? m2 : 0.f;
   }
   umma::fence_before_sync();
   __syncthreads();
