@@ -120,9 +120,15 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
   float* biasl = colp + 8 * JS;              // [2 WS] bias of the own output columns
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  pdl_launch_dependents();      // the next layer's kernel may start its own prologue
   cluster.barrier_arrive();     // "this CTA has started": waited for only right before the first remote write
-  // all global reads of the prologue are independent of each other (one round trip)
-  copy4(gS, a.g, B * D / 4, tid);
+  // everything that does not depend on the previous layer's kernel first (programmatic dependent launch: this part
+  // overlaps that kernel's tail); all global reads of the prologue are independent of each other (one round trip)
+  for (int k = tid; k < Kk; k += LC_T) kidx[k] = a.keep_idx[k];
+  for (int d = tid; d < D; d += LC_T) {
+    const int p = a.pos[d];
+    if (p >= 0) wd[p] = d;
+  }
   for (int c = tid; c < 2 * JS; c += LC_T) {
     const int br = c / JS, j = rk * JS + (c - br * JS);
     const LfBranch& P = br ? a.br[1] : a.br[0];
@@ -136,16 +142,13 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     const int br = c / WS;
     biasl[c] = (br ? a.br[1].bb : a.br[0].bb)[rk * WS + (c - br * WS)];
   }
-  for (int k = tid; k < Kk; k += LC_T) kidx[k] = a.keep_idx[k];
-  for (int d = tid; d < D; d += LC_T) {
-    const int p = a.pos[d];
-    if (p >= 0) wd[p] = d;
-  }
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
     copy4(sW1 + br * JS * Kk, (br ? a.br[1].Wa : a.br[0].Wa) + (size_t)rk * JS * Kk, JS * Kk / 4, tid);
     copy4(sW2 + br * WS * H, (br ? a.br[1].Wb : a.br[0].Wb) + (size_t)rk * WS * H, WS * H / 4, tid);
   }
+  pdl_wait();                   // the layer input (and every buffer this kernel writes) belongs to us from here on
+  copy4(gS, a.g, B * D / 4, tid);
   __syncthreads();
   for (int i = tid; i < BR * Kk; i += LC_T) {
     const int b = i / Kk, k = i - b * Kk;
@@ -284,7 +287,9 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
   float* gS = colp + 8 * JS;                 // GS: [B][D] the layer input
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- 0. operands (independent global reads first) ----
+  // ---- 0. operands: all of them were produced by the forward pass, none by the previous backward kernel, so this whole step
+  //         overlaps that kernel's tail (programmatic dependent launch); independent global reads first ----
+  pdl_launch_dependents();
   if (GS) copy4(gS, a.g, B * D / 4, tid);
   for (int c = tid; c < 2 * JS; c += LC_T) {
     const int br = c / JS, j = rk * JS + (c - br * JS);
@@ -339,6 +344,7 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
   // ---- 1. the transform backward (same arithmetic as latent_affine_bwd_kernel): d raw of ALL warped columns in every CTA
   //         (items (b, w): every address is known up front, the loads of several items are in flight together); dg of the
   //         warped positions dealt round-robin (the kept ones are written in step 7) ----
+  pdl_wait();          // the cotangents come from the previous backward kernels; every global write of this kernel follows
 #pragma unroll 4
   for (int i = tid; i < B * Wn; i += LC_T) {
     const int p = i % Wn, b = i / Wn;
@@ -515,7 +521,7 @@ constexpr size_t LF_SMEM_MAX = 227 * 1024;
 template <typename K, typename A>
 int lf_launch(K kernel, const A& a, size_t smem, cudaStream_t s, const char* what) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kernel<<<LC_NC, LC_T, smem, s>>>(a);
+  dpf_launch_pdl(kernel, LC_NC, LC_T, smem, s, a);      // cluster dims come from the kernel's __cluster_dims__
   return dpf_check_launch(what);
 }
 
