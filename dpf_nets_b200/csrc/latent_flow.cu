@@ -65,6 +65,16 @@ struct LfBwdArgs {
 
 __device__ __forceinline__ float sigmoid_(float z) { return 1.f / (1.f + expf(-z)); }
 
+// phase stamps of the most recent launches (thread 0 of cluster rank 0; eight stores per kernel): dpf_latent_flow_stamps()
+__device__ unsigned long long g_lf_stamps[2][12];
+__device__ __forceinline__ void lf_stamp(int which, int i, int rk, int tid) {
+  if (rk == 0 && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_lf_stamps[which][i] = t;
+  }
+}
+
 // acc[r][j] = sum_k A[lane + 32 r][k] W[j][k]: A in shared memory (leading dimension lda), 4 weight rows in shared memory
 // (warp-uniform 16-byte reads), K a multiple of 4
 template <int RB>
@@ -120,6 +130,7 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
   float* biasl = colp + 8 * JS;              // [2 WS] bias of the own output columns
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  lf_stamp(0, 0, rk, tid);
   pdl_launch_dependents();      // the next layer's kernel may start its own prologue
   cluster.barrier_arrive();     // "this CTA has started": waited for only right before the first remote write
   // everything that does not depend on the previous layer's kernel first (programmatic dependent launch: this part
@@ -147,7 +158,9 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     copy4(sW1 + br * JS * Kk, (br ? a.br[1].Wa : a.br[0].Wa) + (size_t)rk * JS * Kk, JS * Kk / 4, tid);
     copy4(sW2 + br * WS * H, (br ? a.br[1].Wb : a.br[0].Wb) + (size_t)rk * WS * H, WS * H / 4, tid);
   }
+  lf_stamp(0, 1, rk, tid);
   pdl_wait();                   // the layer input (and every buffer this kernel writes) belongs to us from here on
+  lf_stamp(0, 2, rk, tid);
   copy4(gS, a.g, B * D / 4, tid);
   __syncthreads();
   for (int i = tid; i < BR * Kk; i += LC_T) {
@@ -155,6 +168,7 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     kept[b * ldk + k] = b < B ? gS[(size_t)b * D + kidx[k]] : 0.f;
   }
   __syncthreads();
+  lf_stamp(0, 3, rk, tid);
   // ---- hpre = kept Wa^T on the own 2 JS columns ----
   for (int c0 = warp * LC_CH; c0 < 2 * JS; c0 += (LC_T / 32) * LC_CH) {
     const int br = c0 / JS, jl = c0 - br * JS;
@@ -169,47 +183,66 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     }
   }
   __syncthreads();
-  // ---- BatchNorm1d + Swish: a warp per column, lane = batch row, statistics by warp shuffles ----
-  for (int c = warp; c < 2 * JS; c += LC_T / 32) {
-    const int br = c / JS, jl = c - br * JS, j = rk * JS + jl;
+  lf_stamp(0, 4, rk, tid);
+  // ---- BatchNorm1d + Swish: four columns per warp item (independent shuffle chains in flight together), lane = batch row ----
+  for (int c0 = warp * 4; c0 < 2 * JS; c0 += (LC_T / 32) * 4) {
+    const int br = c0 / JS, jl = c0 - br * JS, j = rk * JS + jl;
     const LfBranch& P = br ? a.br[1] : a.br[0];
-    float v[RB];
+    float4 v[RB];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) v[r] = (lane + 32 * r < B) ? hl[((size_t)br * BR + lane + 32 * r) * JS + jl] : 0.f;
-    float mean, var;
+    for (int r = 0; r < RB; ++r)
+      v[r] = (lane + 32 * r < B) ? *reinterpret_cast<const float4*>(hl + ((size_t)br * BR + lane + 32 * r) * JS + jl) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mean[4], var[4];
     if (a.training) {
-      float s = 0.f;
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int r = 0; r < RB; ++r) s += v[r];
-      mean = warp_sum(s) / (float)B;
-      float q = 0.f;
+      for (int r = 0; r < RB; ++r) { s[0] += v[r].x; s[1] += v[r].y; s[2] += v[r].z; s[3] += v[r].w; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mean[q] = warp_sum(s[q]) / (float)B;
+      float q2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
-        const float d = (lane + 32 * r < B) ? v[r] - mean : 0.f;
-        q = fmaf(d, d, q);
+        if (lane + 32 * r < B) {
+          const float d0 = v[r].x - mean[0], d1 = v[r].y - mean[1], d2 = v[r].z - mean[2], d3 = v[r].w - mean[3];
+          q2[0] = fmaf(d0, d0, q2[0]); q2[1] = fmaf(d1, d1, q2[1]); q2[2] = fmaf(d2, d2, q2[2]); q2[3] = fmaf(d3, d3, q2[3]);
+        }
       }
-      var = warp_sum(q) / (float)B;
-      if (P.rm && lane == 0) {
-        P.rm[j] = (1.f - a.momentum) * colp[4 * c + 2] + a.momentum * mean;
-        P.rv[j] = (1.f - a.momentum) * colp[4 * c + 3] + a.momentum * var * ((float)B / (float)max(B - 1, 1));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) var[q] = warp_sum(q2[q]) / (float)B;
+      if (P.rm && lane < 4) {
+        const float mq = lane == 0 ? mean[0] : lane == 1 ? mean[1] : lane == 2 ? mean[2] : mean[3];
+        const float vq = lane == 0 ? var[0] : lane == 1 ? var[1] : lane == 2 ? var[2] : var[3];
+        P.rm[j + lane] = (1.f - a.momentum) * colp[4 * (c0 + lane) + 2] + a.momentum * mq;
+        P.rv[j + lane] = (1.f - a.momentum) * colp[4 * (c0 + lane) + 3] + a.momentum * vq * ((float)B / (float)max(B - 1, 1));
       }
     } else {
-      mean = colp[4 * c + 2];
-      var = colp[4 * c + 3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { mean[q] = colp[4 * (c0 + q) + 2]; var[q] = colp[4 * (c0 + q) + 3]; }
     }
-    const float istd = 1.f / sqrtf(var + a.bn_eps);
-    const float ga = colp[4 * c + 0], be = colp[4 * c + 1];
-    if (lane == 0) {
-      a.stat[(size_t)(br * 2 + 0) * H + j] = mean;
-      a.stat[(size_t)(br * 2 + 1) * H + j] = istd;
+    float istd[4], ga[4], be[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      istd[q] = 1.f / sqrtf(var[q] + a.bn_eps);
+      ga[q] = colp[4 * (c0 + q) + 0];
+      be[q] = colp[4 * (c0 + q) + 1];
+    }
+    if (lane < 4) {
+      const float mq = lane == 0 ? mean[0] : lane == 1 ? mean[1] : lane == 2 ? mean[2] : mean[3];
+      const float iq = lane == 0 ? istd[0] : lane == 1 ? istd[1] : lane == 2 ? istd[2] : istd[3];
+      a.stat[(size_t)(br * 2 + 0) * H + j + lane] = mq;
+      a.stat[(size_t)(br * 2 + 1) * H + j + lane] = iq;
     }
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      const float z = fmaf((v[r] - mean) * istd, ga, be);
-      hl[((size_t)br * BR + lane + 32 * r) * JS + jl] = (lane + 32 * r < B) ? z * sigmoid_(z) : 0.f;
+      const bool in = lane + 32 * r < B;
+      const float z0 = fmaf((v[r].x - mean[0]) * istd[0], ga[0], be[0]), z1 = fmaf((v[r].y - mean[1]) * istd[1], ga[1], be[1]);
+      const float z2 = fmaf((v[r].z - mean[2]) * istd[2], ga[2], be[2]), z3 = fmaf((v[r].w - mean[3]) * istd[3], ga[3], be[3]);
+      *reinterpret_cast<float4*>(hl + ((size_t)br * BR + lane + 32 * r) * JS + jl) =
+          in ? make_float4(z0 * sigmoid_(z0), z1 * sigmoid_(z1), z2 * sigmoid_(z2), z3 * sigmoid_(z3)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __syncthreads();
+  lf_stamp(0, 5, rk, tid);
   // ---- push the own slice of s into every CTA's copy (distributed shared memory, 16-byte stores) ----
   cluster.barrier_wait();       // every CTA of the cluster has started: its shared memory may be written remotely
   {
@@ -225,6 +258,7 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     }
   }
   cluster.sync();
+  lf_stamp(0, 6, rk, tid);
   // ---- raw = s Wb^T + bb on the own 2 WS output columns ----
   for (int c0 = warp * LC_CH; c0 < 2 * WS; c0 += (LC_T / 32) * LC_CH) {
     const int br = c0 / WS, wl = c0 - br * WS;
@@ -240,6 +274,7 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     }
   }
   __syncthreads();
+  lf_stamp(0, 7, rk, tid);
   // ---- the transform (same arithmetic as latent_affine_fwd_kernel) on the warped positions whose raw columns this CTA
   //      formed; the kept positions are dealt over the CTAs by kept-column range ----
   for (int i = tid; i < B * WS; i += LC_T) {
@@ -260,6 +295,7 @@ latent_flow_fwd_kernel(const LfFwdArgs a) {
     a.lv[e] = 0.f;
     a.g_out[e] = gS[e];
   }
+  lf_stamp(0, 8, rk, tid);
 }
 
 // GS: the layer input g is staged in shared memory (when it fits; wide latents read it from global memory instead)
@@ -289,7 +325,9 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
 
   // ---- 0. operands: all of them were produced by the forward pass, none by the previous backward kernel, so this whole step
   //         overlaps that kernel's tail (programmatic dependent launch); independent global reads first ----
+  lf_stamp(1, 0, rk, tid);
   pdl_launch_dependents();
+  cluster.barrier_arrive();     // "this CTA has started": waited for right before the first remote write
   if (GS) copy4(gS, a.g, B * D / 4, tid);
   for (int c = tid; c < 2 * JS; c += LC_T) {
     const int br = c / JS, j = rk * JS + (c - br * JS);
@@ -341,37 +379,47 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
     const int b = i / Kk, k = i - b * Kk;
     kept[b * ldk + k] = b < B ? (GS ? gS[(size_t)b * D + kidx[k]] : a.g[(size_t)b * D + kidx[k]]) : 0.f;
   }
-  // ---- 1. the transform backward (same arithmetic as latent_affine_bwd_kernel): d raw of ALL warped columns in every CTA
-  //         (items (b, w): every address is known up front, the loads of several items are in flight together); dg of the
-  //         warped positions dealt round-robin (the kept ones are written in step 7) ----
+  // ---- 1. the transform backward (same arithmetic as latent_affine_bwd_kernel) on the own Wn / 8 warped columns; the two
+  //         d raw values of an item are pushed into every CTA's copy (distributed shared memory); dg of those positions ----
+  lf_stamp(1, 1, rk, tid);
   pdl_wait();          // the cotangents come from the previous backward kernels; every global write of this kernel follows
-#pragma unroll 4
-  for (int i = tid; i < B * Wn; i += LC_T) {
-    const int p = i % Wn, b = i / Wn;
-    const size_t e = (size_t)b * D + wd[p];
-    const float d = a.dgo ? a.dgo[e] : 0.f;
-    const float rw = a.raw[((size_t)1 * B + b) * Wn + p];
-    const float m = a.raw[((size_t)0 * B + b) * Wn + p];
-    float dm = a.dmu_f ? a.dmu_f[e] : 0.f, dl = a.dlv_f ? a.dlv_f[e] : 0.f, dgv;
-    const float ex = expf(rw);
-    const float l = logf(a.eps + ex);
-    const float gv = GS ? gS[e] : a.g[e];
-    if (a.inverse) {
-      const float sc = expf(-0.5f * l);
-      dgv = d * sc;
-      dm -= d * sc;
-      dl -= 0.5f * d * sc * (gv - m);
-    } else {
-      const float sc = expf(0.5f * l);
-      dgv = d * sc;
-      dm += d;
-      dl += 0.5f * d * sc * gv;
+  lf_stamp(1, 2, rk, tid);
+  cluster.barrier_wait();       // every CTA of the cluster has started: remote writes may begin
+  {
+    const int WSb = Wn / LC_NC;
+    for (int i = tid; i < B * WSb; i += LC_T) {
+      const int p = rk * WSb + i % WSb, b = i / WSb;
+      const size_t e = (size_t)b * D + wd[p];
+      const float d = a.dgo ? a.dgo[e] : 0.f;
+      const float rw = a.raw[((size_t)1 * B + b) * Wn + p];
+      const float m = a.raw[((size_t)0 * B + b) * Wn + p];
+      float dm = a.dmu_f ? a.dmu_f[e] : 0.f, dl = a.dlv_f ? a.dlv_f[e] : 0.f, dgv;
+      const float ex = expf(rw);
+      const float l = logf(a.eps + ex);
+      const float gv = GS ? gS[e] : a.g[e];
+      if (a.inverse) {
+        const float sc = expf(-0.5f * l);
+        dgv = d * sc;
+        dm -= d * sc;
+        dl -= 0.5f * d * sc * (gv - m);
+      } else {
+        const float sc = expf(0.5f * l);
+        dgv = d * sc;
+        dm += d;
+        dl += 0.5f * d * sc * gv;
+      }
+      a.dg[e] = dgv;
+      const float dlr = dl * ex / (a.eps + ex);
+#pragma unroll
+      for (int t = 0; t < LC_NC; ++t) {
+        float* dst = cluster.map_shared_rank(DR, (unsigned)((rk + t) % LC_NC));
+        dst[((size_t)0 * BR + b) * ldw + p] = dm;
+        dst[((size_t)1 * BR + b) * ldw + p] = dlr;
+      }
     }
-    if (p % LC_NC == rk) a.dg[e] = dgv;
-    DR[((size_t)0 * BR + b) * ldw + p] = dm;
-    DR[((size_t)1 * BR + b) * ldw + p] = dl * ex / (a.eps + ex);
   }
-  __syncthreads();
+  cluster.sync();
+  lf_stamp(1, 3, rk, tid);
   // ---- 2. dbb (its columns dealt over the CTAs);  dWb[w][own j] = sum_b d raw[b][w] s[b][j] ----
   for (int c = rk * (2 * Wn / LC_NC) + tid; c < (rk + 1) * (2 * Wn / LC_NC); c += LC_T) {
     const int br = c / Wn, w = c - br * Wn;
@@ -392,6 +440,7 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
       *reinterpret_cast<float4*>((br ? a.gr[1].dWb : a.gr[0].dWb) + (size_t)w * H + rk * JS + 4 * q) = acc;
     }
   }
+  lf_stamp(1, 4, rk, tid);
   // ---- 3. d y = swish'(y) * (d raw Wb) on the own columns: lanes = rows, K = Wn ----
   for (int c0 = warp * LC_CH; c0 < 2 * JS; c0 += (LC_T / 32) * LC_CH) {
     const int br = c0 / JS, jl = c0 - br * JS;
@@ -426,33 +475,51 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
     }
   }
   __syncthreads();
-  // ---- 4. BatchNorm backward: a warp per column, lane = batch row ----
-  for (int c = warp; c < 2 * JS; c += LC_T / 32) {
-    const int br = c / JS, jl = c - br * JS, j = rk * JS + jl;
-    const float istd = colp[4 * c + 3], ga = colp[4 * c + 0];
-    float dz[RB], xh[RB];
-    float dgam = 0.f, dbet = 0.f;
+  lf_stamp(1, 5, rk, tid);
+  // ---- 4. BatchNorm backward: four columns per warp item, lane = batch row ----
+  for (int c0 = warp * 4; c0 < 2 * JS; c0 += (LC_T / 32) * 4) {
+    const int br = c0 / JS, jl = c0 - br * JS, j = rk * JS + jl;
+    float4 dz[RB], xh[RB];
+    float dgam[4] = {0.f, 0.f, 0.f, 0.f}, dbet[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       const size_t o = ((size_t)br * BR + lane + 32 * r) * JS + jl;
-      dz[r] = DY[o];            // zero beyond the batch (swish' was stored as 0 there)
-      xh[r] = XH[o];
-      dgam = fmaf(dz[r], xh[r], dgam);
-      dbet += dz[r];
+      dz[r] = *reinterpret_cast<const float4*>(DY + o);            // zero beyond the batch (swish' was stored as 0 there)
+      xh[r] = *reinterpret_cast<const float4*>(XH + o);
+      dgam[0] = fmaf(dz[r].x, xh[r].x, dgam[0]); dgam[1] = fmaf(dz[r].y, xh[r].y, dgam[1]);
+      dgam[2] = fmaf(dz[r].z, xh[r].z, dgam[2]); dgam[3] = fmaf(dz[r].w, xh[r].w, dgam[3]);
+      dbet[0] += dz[r].x; dbet[1] += dz[r].y; dbet[2] += dz[r].z; dbet[3] += dz[r].w;
     }
-    dgam = warp_sum(dgam);
-    dbet = warp_sum(dbet);
-    if (lane == 0) {
-      (br ? a.gr[1].dgamma : a.gr[0].dgamma)[j] = dgam;
-      (br ? a.gr[1].dbeta : a.gr[0].dbeta)[j] = dbet;
-    }
-    const float m1 = a.training ? ga * dbet / (float)B : 0.f;
-    const float m2 = a.training ? ga * dgam / (float)B : 0.f;
 #pragma unroll
-    for (int r = 0; r < RB; ++r)
-      DY[((size_t)br * BR + lane + 32 * r) * JS + jl] = (lane + 32 * r < B) ? istd * (dz[r] * ga - m1 - xh[r] * m2) : 0.f;
+    for (int q = 0; q < 4; ++q) {
+      dgam[q] = warp_sum(dgam[q]);
+      dbet[q] = warp_sum(dbet[q]);
+    }
+    if (lane < 4) {
+      const float gq = lane == 0 ? dgam[0] : lane == 1 ? dgam[1] : lane == 2 ? dgam[2] : dgam[3];
+      const float bq = lane == 0 ? dbet[0] : lane == 1 ? dbet[1] : lane == 2 ? dbet[2] : dbet[3];
+      (br ? a.gr[1].dgamma : a.gr[0].dgamma)[j + lane] = gq;
+      (br ? a.gr[1].dbeta : a.gr[0].dbeta)[j + lane] = bq;
+    }
+    float istd[4], ga[4], m1[4], m2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      istd[q] = colp[4 * (c0 + q) + 3];
+      ga[q] = colp[4 * (c0 + q) + 0];
+      m1[q] = a.training ? ga[q] * dbet[q] / (float)B : 0.f;
+      m2[q] = a.training ? ga[q] * dgam[q] / (float)B : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const bool in = lane + 32 * r < B;
+      *reinterpret_cast<float4*>(DY + ((size_t)br * BR + lane + 32 * r) * JS + jl) =
+          in ? make_float4(istd[0] * (dz[r].x * ga[0] - m1[0] - xh[r].x * m2[0]), istd[1] * (dz[r].y * ga[1] - m1[1] - xh[r].y * m2[1]),
+                           istd[2] * (dz[r].z * ga[2] - m1[2] - xh[r].z * m2[2]), istd[3] * (dz[r].w * ga[3] - m1[3] - xh[r].w * m2[3]))
+             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   __syncthreads();
+  lf_stamp(1, 6, rk, tid);
   // ---- 5. dWa[own j][k] = sum_b d hpre[b][j] kept[b][k] ----
   {
     const int q4 = Kk / 4;
@@ -467,6 +534,7 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
       *reinterpret_cast<float4*>((br ? a.gr[1].dWa : a.gr[0].dWa) + (size_t)(rk * JS + jl) * Kk + 4 * q) = acc;
     }
   }
+  lf_stamp(1, 7, rk, tid);
   // ---- 6. partial d kept over the own hidden columns of both branches: lanes = rows, 4 columns k per warp item ----
   for (int k0 = warp * 4; k0 < Kk; k0 += (LC_T / 32) * 4) {
     float acc[RB][4];
@@ -495,7 +563,9 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
     for (int r = 0; r < RB; ++r)
       *reinterpret_cast<float4*>(dkp + (size_t)(lane + 32 * r) * ldk + k0) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
   }
+  lf_stamp(1, 8, rk, tid);
   cluster.sync();
+  lf_stamp(1, 9, rk, tid);
   // ---- 7. reduce the eight partials on the own KS kept columns (distributed shared memory reads): dg[keep] = dgo[keep] + d kept ----
   for (int i = tid; i < B * KS; i += LC_T) {
     const int kl = i % KS, b = i / KS, k = rk * KS + kl;
@@ -505,7 +575,9 @@ latent_flow_bwd_kernel(const LfBwdArgs a) {
     const size_t e = (size_t)b * D + kidx[k];
     a.dg[e] = (a.dgo ? a.dgo[e] : 0.f) + s;
   }
+  lf_stamp(1, 10, rk, tid);
   cluster.sync();          // no CTA may exit while its partial is still being read
+  lf_stamp(1, 11, rk, tid);
 }
 
 size_t lf_fwd_smem(int RB, int B, int D, int H, int Kk, int Wn) {
@@ -535,6 +607,13 @@ int lf_check_dims(const char* what, int B, int D, int H, int Kk, int Wn) {
 bool lf_aligned(const LfBranch& b) { return (((uintptr_t)b.Wa | (uintptr_t)b.Wb | (uintptr_t)b.bb) & 15) == 0; }
 
 }  // namespace
+
+// development aid: globaltimer stamps (ns) of the phases of the most recent forward (row 0) and backward (row 1) launch
+DPF_API int dpf_latent_flow_stamps(unsigned long long* out24) {
+  DPF_REQUIRE(out24, DPF_ERR_NULL_PTR, "dpf_latent_flow_stamps: null pointer");
+  cudaError_t e = cudaMemcpyFromSymbol(out24, g_lf_stamps, sizeof(unsigned long long) * 24);
+  return e == cudaSuccess ? DPF_OK : (int)e;
+}
 
 // DPF_OK when dpf_latent_flow_forward AND _backward handle a layer of these sizes, DPF_ERR_UNSUPPORTED otherwise (the caller
 // then keeps the block kernels + library GEMMs)

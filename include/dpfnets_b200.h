@@ -246,6 +246,8 @@ int dpf_latent_affine_backward(const float* dgo, const float* dmu_f, const float
  * Wb[b] (Wn,H), bb[b] (Wn).  H, Kk, Wn multiples of 32, else DPF_ERR_UNSUPPORTED.  The forward saves hpre (2,B,H), stat
  * (2,2,H) {mean, istd} and raw (2,B,Wn) for the backward.  One thread-block cluster of 8 CTAs per layer (hidden columns
  * split over the CTAs, exchange through distributed shared memory); fp32 CUDA-core arithmetic. */
+/* development aid: globaltimer stamps (ns) of the phases of the most recent forward (row 0) / backward (row 1) launch, 2 x 12 */
+int dpf_latent_flow_stamps(unsigned long long* out24);
 /* DPF_OK when both calls below handle a layer of these sizes, DPF_ERR_UNSUPPORTED otherwise */
 int dpf_latent_flow_supported(int B, int D, int H, int Kk, int Wn);
 int dpf_latent_flow_forward(const float* g, const int* pos, const int* keep_idx, const float* const* Wa, const float* const* gamma,
