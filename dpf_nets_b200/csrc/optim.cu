@@ -58,20 +58,45 @@ adam_step_multi_kernel(const __grid_constant__ AdamTensors t, float lr, float b1
   float* __restrict__ m = t.m[k];
   float* __restrict__ v = t.v[k];
   float* __restrict__ vmax = t.vmax[k];
-  for (int i = base + threadIdx.x; i < end; i += 256) {
-    const float gi = g[i];
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    float vm = vi;
-    if (vmax) {
-      vm = fmaxf(vmax[i], vi);
-      vmax[i] = vm;
-    }
+  auto upd = [&](float gi, float& mi, float& vi, float& vm, float& pi) {
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    vm = vmax ? fmaxf(vm, vi) : vi;
     const float denom = sqrtf(vm) / bc2 + eps;
-    const float pi = p[i];
-    p[i] = pi - (pi * wd + lr * ((mi / bc1) / denom));
+    pi = pi - (pi * wd + lr * ((mi / bc1) / denom));
+  };
+  // 16-byte accesses when the five arrays allow it (the slab start is a multiple of 4 elements): the update is pure
+  // streaming, 9 arrays' worth of traffic per element
+  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vmax) & 15) == 0);
+  int i = base + 4 * threadIdx.x;
+  if (vec) {
+    for (; i + 4 <= end; i += 4 * 256) {
+      const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+      float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i), p4 = *reinterpret_cast<const float4*>(p + i);
+      float4 x4 = vmax ? *reinterpret_cast<const float4*>(vmax + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      upd(g4.x, m4.x, v4.x, x4.x, p4.x);
+      upd(g4.y, m4.y, v4.y, x4.y, p4.y);
+      upd(g4.z, m4.z, v4.z, x4.z, p4.z);
+      upd(g4.w, m4.w, v4.w, x4.w, p4.w);
+      *reinterpret_cast<float4*>(m + i) = m4;
+      *reinterpret_cast<float4*>(v + i) = v4;
+      if (vmax) *reinterpret_cast<float4*>(vmax + i) = x4;
+      *reinterpret_cast<float4*>(p + i) = p4;
+    }
+    // the (at most 3) elements after the last full group of four: handled by the thread whose group straddles `end`
+    if (i < end) {
+      for (int e = i; e < end; ++e) {
+        float mi = m[e], vi = v[e], vm = vmax ? vmax[e] : 0.f, pi = p[e];
+        upd(g[e], mi, vi, vm, pi);
+        m[e] = mi; v[e] = vi; if (vmax) vmax[e] = vm; p[e] = pi;
+      }
+    }
+  } else {
+    for (int e = base + threadIdx.x; e < end; e += 256) {
+      float mi = m[e], vi = v[e], vm = vmax ? vmax[e] : 0.f, pi = p[e];
+      upd(g[e], mi, vi, vm, pi);
+      m[e] = mi; v[e] = vi; if (vmax) vmax[e] = vm; p[e] = pi;
+    }
   }
 }
 }  // namespace
