@@ -216,3 +216,47 @@ def test_pooled_last_layer_backward_algebra_vs_autograd(monkeypatch):
         assert rel(a, b) < 1e-10
     assert rel(bn2.running_mean, bn.running_mean) < 1e-12 and rel(bn2.running_var, bn.running_var) < 1e-12
     assert int(bn2.num_batches_tracked) == int(bn.num_batches_tracked) == 1
+
+
+def test_deferred_batchnorm_counters():
+    """ops/_counters.py: inside `deferred()` the BatchNorm step counters of the fused paths are collected and bumped once by the
+    outermost context (one multi-tensor add); outside any context `bump` adds immediately; values equal either way."""
+    from dpf_nets_b200.ops import _counters
+    a, b, c = (torch.zeros((), dtype=torch.long) for _ in range(3))
+    _counters.bump(a)
+    assert int(a) == 1
+    with _counters.deferred():
+        _counters.bump(a)
+        _counters.bump(b)
+        with _counters.deferred():          # nested: still pending
+            _counters.bump(c)
+        assert (int(a), int(b), int(c)) == (1, 0, 0)
+    assert (int(a), int(b), int(c)) == (2, 1, 1)
+    try:
+        with _counters.deferred():
+            _counters.bump(b)
+            raise RuntimeError("x")
+    except RuntimeError:
+        pass
+    assert int(b) == 2                      # flushed on the way out, and the context is reset
+    _counters.bump(b)
+    assert int(b) == 3
+
+
+def test_pointnet_stats_merge_host():
+    """ops/pointnet_train.py::_merge_stats (Chan et al. merge of per-work-item {count, mean, M2}) against the direct statistics,
+    including empty work items."""
+    from dpf_nets_b200.ops.pointnet_train import _merge_stats
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn((1000, 7), generator=gen, dtype=torch.float64) * 3 + 5
+    cuts = [0, 0, 130, 131, 600, 1000]
+    rows = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        seg = x[lo:hi]
+        n = float(hi - lo)
+        mean = seg.mean(0) if hi > lo else torch.zeros(7, dtype=torch.float64)
+        m2 = ((seg - mean) ** 2).sum(0) if hi > lo else torch.zeros(7, dtype=torch.float64)
+        rows.append(torch.stack([torch.full((7,), n, dtype=torch.float64), mean, m2], 1))
+    mean, var = _merge_stats(torch.stack(rows).float())
+    assert torch.allclose(mean, x.mean(0), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(var, x.var(0, unbiased=False), rtol=1e-5)
