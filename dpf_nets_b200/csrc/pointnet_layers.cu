@@ -599,6 +599,43 @@ __global__ void pl_layer0_bwd_finalize_kernel(const double* __restrict__ sums4, 
   dbeta[c] = (float)S;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// the SPARSE part of the pooled last layer's backward (ops/pointnet_pool.py): the max-pool routes the cotangent of
+// (shape b, channel c) to ONE point n* = idx[b][c].  Per (b, c) and input channel k:
+//     a = relu(sc_k Z[b][k][n*] + sh_k)          the layer input at the selected point (recomputed)
+//     T[c][k]       += coef[b][c] a              (weight-gradient term; summed over the shapes)
+//     dA[b][k][n*]  += coef[b][c] W[c][k]        (input-gradient term, on top of the dense part already in dA)
+// instead of gather -> affine -> relu -> einsum and outer product -> scatter_add over three (B,256,512) temporaries.
+// Block = (shape, 8 channels), thread = input channel k; several channels of a shape often select the same point: atomics.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PS_CG = 8;
+__global__ void __launch_bounds__(256)
+pl_pool_sparse_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ tab, const long long* __restrict__ idx,
+                          const float* __restrict__ coef, const float* __restrict__ W, int N, int C, float* __restrict__ T,
+                          float* __restrict__ dA) {
+  const int k = threadIdx.x, b = blockIdx.y, c0 = blockIdx.x * PS_CG;
+  const float sc = tab[k * PL_TAB], sh = tab[k * PL_TAB + 1];
+  const float* zrow = Z + ((size_t)b * 256 + k) * N;
+  float* drow = dA + ((size_t)b * 256 + k) * N;
+  float zv[PS_CG], cf[PS_CG];
+  int np[PS_CG];
+#pragma unroll
+  for (int j = 0; j < PS_CG; ++j) {           // all gathers of the block's channels in flight together
+    np[j] = (int)idx[(size_t)b * C + c0 + j];
+    cf[j] = coef[(size_t)b * C + c0 + j];
+    zv[j] = zrow[np[j]];
+  }
+#pragma unroll
+  for (int j = 0; j < PS_CG; ++j) {
+    if (cf[j] != 0.f) {
+      const float a = fmaxf(fmaf(sc, zv[j], sh), 0.f);
+      if (a != 0.f) atomicAdd(T + (size_t)(c0 + j) * 256 + k, cf[j] * a);
+      atomicAdd(drow + np[j], cf[j] * W[(size_t)(c0 + j) * 256 + k]);
+    }
+  }
+}
+
 }  // namespace
 
 // ===============================================================================================================
@@ -740,4 +777,15 @@ DPF_API int dpf_pointnet_layer0_bwd_finalize(const double* sums4, const double* 
   DPF_REQUIRE(sums4 && moments && W0 && gamma && stats && dW0 && dgamma && dbeta, DPF_ERR_NULL_PTR, "dpf_pointnet_layer0_bwd_finalize: null pointer");
   pl_layer0_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums4, moments, W0, gamma, stats, C, (double)B * N, dW0, dgamma, dbeta);
   return dpf_check_launch("pl_layer0_bwd_finalize_kernel");
+}
+
+// The sparse part of the pooled last layer's backward: Z (B,256,N) the layer's pre-BatchNorm input with its loader-1 table tab
+// (256,8), idx (B,C) int64 the selected point per (shape, channel), coef (B,C) the cotangent there, W (C,256).
+// T (C,256) += sum_b coef[b][c] a[b][:][n*] (zero it first), dA (B,256,N) += coef[b][c] W[c][:] at point n* (float atomics).
+DPF_API int dpf_pointnet_pool_sparse_backward(const float* Z, const float* tab, const long long* idx, const float* coef, const float* W,
+                                              int B, int N, int C, float* T, float* dA, void* stream) {
+  DPF_REQUIRE(Z && tab && idx && coef && W && T && dA, DPF_ERR_NULL_PTR, "dpf_pointnet_pool_sparse_backward: null pointer");
+  DPF_REQUIRE(B > 0 && N > 0 && C > 0 && C % PS_CG == 0 && B <= 65535, DPF_ERR_BAD_ARG, "dpf_pointnet_pool_sparse_backward: bad sizes B=%d N=%d C=%d", B, N, C);
+  pl_pool_sparse_bwd_kernel<<<dim3(C / PS_CG, B), 256, 0, (cudaStream_t)stream>>>(Z, tab, idx, coef, W, N, C, T, dA);
+  return dpf_check_launch("pl_pool_sparse_bwd_kernel");
 }

@@ -145,6 +145,11 @@ class PointNetTrainFunction(torch.autograd.Function):
         return (None, dW0, dW1, dW2, dW3, dg0, dg1, dg2, dg3, db0, db1, db2, db3, None)
 
 
+def _sparse_backward(Z2, tab2, idx, coef, W, B, N, T, dA2):
+    """T += sum_b coef a(n*), dA2[.., n*] += coef W (csrc/pointnet_layers.cu::pl_pool_sparse_bwd_kernel)."""
+    _lib.call("dpf_pointnet_pool_sparse_backward", Z2, tab2, idx.contiguous(), coef, W, int(B), int(N), int(W.shape[0]), T, dA2, device=Z2.device)
+
+
 def _pool_layer_backward(Z2, tab2, asum, W, gamma, sel, dout, B, N):
     """ops/pointnet_pool.py::pool_backward with its two 256 x 256 GEMMs over the points on the library's own kernels: the Gram
     matrix of the centred activations (pl_wgrad_kernel, gram form) and -C (A_2 - m) - const (pl_gemm_kernel with a row
@@ -163,18 +168,16 @@ def _pool_layer_backward(Z2, tab2, asum, W, gamma, sel, dout, B, N):
     S = asum.double().sum(0)
     sc, sh = tab2[:, 0], tab2[:, 1]
     tabc = _table(sc, sh, (S / M).to(sc.dtype))
-    gidx = idx.unsqueeze(1).expand(B, Cin, idx.shape[1])                            # (B,Cin,C)
     Gc = _wgrad(Cin, Cin, 1, LD_AFFINE, Z2, None, tabc, None, None, B, N)
-    hsel_rows = torch.relu_(torch.gather(Z2, 2, gidx) * sc.view(1, Cin, 1) + sh.view(1, Cin, 1))     # A_2 at the selected points
-    T = torch.einsum('bc,bkc->ck', coef, hsel_rows)
-    Sf = S.to(Z2.dtype)
-    dW = T - (a1 * inv).unsqueeze(1) * Sf.unsqueeze(0) - (a2 * inv * inv).unsqueeze(1) * torch.matmul(W, Gc)
     w_scaled = W * (a2 * inv * inv).unsqueeze(1)
     negC = -torch.matmul(W.t(), w_scaled)                                           # -(W^T diag(a2 / sigma^2) W)
     negconst = -torch.mv(W.t(), a1 * inv)
     dA2, _ = _gemm(LD_AFFINE, Cin, Z2, None, tabc, _image(negC.contiguous(), Cin, Cin, False), B, N, Cin, row_off=negconst.contiguous())
-    contrib = coef.unsqueeze(1) * W.t().unsqueeze(0)                                # (B,Cin,C): coef[b,c] W[c,k]
-    dA2.scatter_add_(2, gidx, contrib)
+    # the sparse part (one selected point per (shape, channel)): T = sum_b coef a(n*) and dA2[.., n*] += coef W, one kernel
+    T = torch.zeros((W.shape[0], Cin), dtype=Z2.dtype, device=dev)
+    _sparse_backward(Z2, tab2, idx, coef.contiguous(), W, B, N, T, dA2)
+    Sf = S.to(Z2.dtype)
+    dW = T - (a1 * inv).unsqueeze(1) * Sf.unsqueeze(0) - (a2 * inv * inv).unsqueeze(1) * torch.matmul(W, Gc)
     return dA2, dW, dgamma, dbeta
 
 

@@ -217,6 +217,10 @@ int dpf_pointnet_bwd_finalize(const double* sums, const float* tab_fwd, const fl
                               float* tab_bwd, float* dgamma, float* dbeta, void* stream);
 int dpf_pointnet_layer0_bwd_finalize(const double* sums4, const double* moments, const float* W0, const float* gamma, const float* stats,
                                      int C, int B, int N, float* dW0, float* dgamma, float* dbeta, void* stream);
+/* the sparse part of the pooled last layer's backward (the max-pool routes each (shape, channel) cotangent to one point):
+ * T (C,256) += sum_b coef[b][c] relu(sc Z[b][:][n*] + sh) (zero it first), dA (B,256,N) += coef[b][c] W[c][:] at n* = idx[b][c] */
+int dpf_pointnet_pool_sparse_backward(const float* Z, const float* tab, const long long* idx, const float* coef, const float* W,
+                                      int B, int N, int C, float* T, float* dA, void* stream);
 
 
 /* ---- Latent-side fused blocks -------------------------------------------
